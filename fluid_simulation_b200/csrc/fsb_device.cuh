@@ -1,0 +1,151 @@
+// Device-side arithmetic shared by the kernels.  Everything here reproduces the
+// reference's fp32 expression order exactly (compiled with -fmad=false and
+// IEEE division), so gather-type stages are bit-identical to the CPU path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct GridDims
+{
+  int nx, ny, ld; // ld: row pitch in elements
+  float dx, dy;   // deltas used for index computation
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi)
+{
+  // include/MathDefinitions.h:16-19 clamps through float; for |v| < 2^24 and
+  // hi < 2^24 that is the integer clamp.
+  return min(max(v, lo), hi);
+}
+
+// include/Grid.h:117-144  Grid<T>::valueInterpolated.
+// Truncating index, fraction taken BEFORE the index clamp, i+1 from the
+// clamped i, x interpolated first, then y.
+__device__ __forceinline__ float grid_interp(const float* __restrict__ g, const GridDims d,
+                                             float x, float y)
+{
+  const float xd = x / d.dx;
+  const float yd = y / d.dy;
+  int i = (int)xd;
+  int j = (int)yd;
+  const float fi = xd - (float)i;
+  const float fj = yd - (float)j;
+  i = clampi(i, 0, d.nx - 1);
+  j = clampi(j, 0, d.ny - 1);
+  const int i1 = clampi(i + 1, 0, d.nx - 1);
+  const int j1 = clampi(j + 1, 0, d.ny - 1);
+  const float v00 = __ldg(g + i + (size_t)j * d.ld);
+  const float v10 = __ldg(g + i1 + (size_t)j * d.ld);
+  const float v01 = __ldg(g + i + (size_t)j1 * d.ld);
+  const float v11 = __ldg(g + i1 + (size_t)j1 * d.ld);
+  const float v0 = (1.0f - fi) * v00 + fi * v10;
+  const float v1 = (1.0f - fi) * v01 + fi * v11;
+  return (1.0f - fj) * v0 + fj * v1;
+}
+
+// Same, on the difference of two grids taken tap by tap: identical to
+// interpolating MacGrid's diff buffer (src/MacGrid.cpp:64-67).
+__device__ __forceinline__ float grid_interp_diff(const float* __restrict__ a,
+                                                  const float* __restrict__ b, const GridDims d,
+                                                  float x, float y)
+{
+  const float xd = x / d.dx;
+  const float yd = y / d.dy;
+  int i = (int)xd;
+  int j = (int)yd;
+  const float fi = xd - (float)i;
+  const float fj = yd - (float)j;
+  i = clampi(i, 0, d.nx - 1);
+  j = clampi(j, 0, d.ny - 1);
+  const int i1 = clampi(i + 1, 0, d.nx - 1);
+  const int j1 = clampi(j + 1, 0, d.ny - 1);
+  const size_t k00 = i + (size_t)j * d.ld, k10 = i1 + (size_t)j * d.ld;
+  const size_t k01 = i + (size_t)j1 * d.ld, k11 = i1 + (size_t)j1 * d.ld;
+  const float v00 = __ldg(a + k00) - __ldg(b + k00);
+  const float v10 = __ldg(a + k10) - __ldg(b + k10);
+  const float v01 = __ldg(a + k01) - __ldg(b + k01);
+  const float v11 = __ldg(a + k11) - __ldg(b + k11);
+  const float v0 = (1.0f - fi) * v00 + fi * v10;
+  const float v1 = (1.0f - fi) * v01 + fi * v11;
+  return (1.0f - fj) * v0 + fj * v1;
+}
+
+// include/MacGrid.h:66-79: u lives at (i dx, (j+1/2) dy), v at ((i+1/2) dx, j dy).
+// The reference forms the half-cell shift in double (`_DELTA_Y * 0.5`) and
+// rounds once; 0.5*d is exact and the fp32 subtraction rounds the same exact
+// difference, so fp32 gives the same bits (probe A).
+__device__ __forceinline__ float vel_x_interp(const float* __restrict__ u, const GridDims d,
+                                              float x, float y)
+{
+  return grid_interp(u, d, x, y - d.dy * 0.5f);
+}
+__device__ __forceinline__ float vel_y_interp(const float* __restrict__ v, const GridDims d,
+                                              float x, float y)
+{
+  return grid_interp(v, d, x - d.dx * 0.5f, y);
+}
+
+__device__ __forceinline__ int cell_type(const uint8_t* __restrict__ cell, const GridDims d, int i,
+                                         int j)
+{
+  // include/MacGrid.h:92-97: index-clamped
+  i = clampi(i, 0, d.nx - 1);
+  j = clampi(j, 0, d.ny - 1);
+  return cell[i + (size_t)j * d.ld];
+}
+
+// src/FluidSolver.cpp:793-814 + include/OdeSolver.h:78-86,102-113 with the
+// Vec2 operators of include/FluidSolver.h:119-141.  `h` is +dt or -dt.
+__device__ __forceinline__ void advected_position(const float* __restrict__ u,
+                                                  const float* __restrict__ v, const GridDims d,
+                                                  int integrator, float x, float y, float h,
+                                                  float* xo, float* yo)
+{
+  float ddx, ddy;
+  if (integrator == 1)
+  {
+    // EulerExplicit: f(x + h) * h, where Vec2 + scalar adds h to BOTH coordinates
+    const float ax = x + h, ay = y + h;
+    ddx = vel_x_interp(u, d, ax, ay) * h;
+    ddy = vel_y_interp(v, d, ax, ay) * h;
+  }
+  else
+  {
+    // RK3: k2 at x + k1*h*1.0/2, k3 at x + k2*h*3.0/4, (k1*2 + k2*3 + k3*4)*h*1.0/9
+    const float k1x = vel_x_interp(u, d, x, y);
+    const float k1y = vel_y_interp(v, d, x, y);
+    const float ax = x + ((k1x * h) * 1.0f) / 2.0f;
+    const float ay = y + ((k1y * h) * 1.0f) / 2.0f;
+    const float k2x = vel_x_interp(u, d, ax, ay);
+    const float k2y = vel_y_interp(v, d, ax, ay);
+    const float bx = x + ((k2x * h) * 3.0f) / 4.0f;
+    const float by = y + ((k2y * h) * 3.0f) / 4.0f;
+    const float k3x = vel_x_interp(u, d, bx, by);
+    const float k3y = vel_y_interp(v, d, bx, by);
+    ddx = ((((k1x * 2.0f + k2x * 3.0f) + k3x * 4.0f) * h) * 1.0f) / 9.0f;
+    ddy = ((((k1y * 2.0f + k2y * 3.0f) + k3y * 4.0f) * h) * 1.0f) / 9.0f;
+  }
+  *xo = x + ddx;
+  *yo = y + ddy;
+}
+
+// block-wide sum of doubles; result valid in thread 0.  blockDim.x <= 1024.
+__device__ __forceinline__ double block_sum(double v)
+{
+  __shared__ double s_part[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads(); // protect s_part against a previous call
+  if (lane == 0) s_part[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? s_part[threadIdx.x] : 0.0;
+  if (wid == 0)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  return v;
+}

@@ -1,0 +1,309 @@
+// Grid-side stages of the step: cell classification, previous/diff buffers,
+// external acceleration, Dirichlet walls, velocity extension, semi-Lagrangian
+// velocity advection.  One thread per cell, rows padded to `ld`.
+#include "fsb_device.cuh"
+#include "fsb_internal.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ bool cell_of_thread(const GridDims d, int* i, int* j)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  *i = (int)(t % d.ld);
+  *j = (int)(t / d.ld);
+  return *i < d.nx && *j < d.ny;
+}
+
+inline int cell_grid(const fsb_ctx* c) { return fsb_div_up((int64_t)c->ld * c->ny, kBlock); }
+inline GridDims dims(const fsb_ctx* c) { return GridDims{c->nx, c->ny, c->ld, c->dx, c->dy}; }
+
+// src/MacGrid.cpp:32-50 clearCellTypeBuffer + the border reset of
+// src/FluidDomain.cpp:169-179 (the border is SOLID before and after marking).
+__global__ void k_fill_labels(uint8_t* __restrict__ cell, const GridDims d)
+{
+  int i, j;
+  if (!cell_of_thread(d, &i, &j)) return;
+  const bool border = (i == 0 || j == 0 || i == d.nx - 1 || j == d.ny - 1);
+  cell[i + (size_t)j * d.ld] = border ? FSB_SOLID : FSB_AIR;
+}
+
+// src/FluidDomain.cpp:157-167: cell = (int)((pos / length) * size), clamped.
+// lengthX() is recomputed as size * delta in float (include/Grid.h:54-55).
+// Marking a border cell is undone by the border reset, so it is skipped; the
+// store is idempotent, hence race-free without atomics.
+__global__ void k_mark_liquid(const float4* __restrict__ part, int64_t n,
+                              uint8_t* __restrict__ cell, const GridDims d)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const float4 p = part[k];
+  const float len_x = (float)d.nx * d.dx;
+  const float len_y = (float)d.ny * d.dy;
+  int x = (int)((p.x / len_x) * (float)d.nx);
+  int y = (int)((p.y / len_y) * (float)d.ny);
+  x = clampi(x, 0, d.nx - 1);
+  y = clampi(y, 0, d.ny - 1);
+  if (x == 0 || y == 0 || x == d.nx - 1 || y == d.ny - 1) return;
+  cell[x + (size_t)y * d.ld] = FSB_LIQUID;
+}
+
+// src/MacGrid.cpp:58-70
+__global__ void k_update_diff(const float* __restrict__ uf, const float* __restrict__ vf,
+                              const float* __restrict__ up, const float* __restrict__ vp,
+                              float* __restrict__ ud, float* __restrict__ vd, const GridDims d)
+{
+  int i, j;
+  if (!cell_of_thread(d, &i, &j)) return;
+  const size_t k = i + (size_t)j * d.ld;
+  ud[k] = uf[k] - up[k];
+  vd[k] = vf[k] - vp[k];
+}
+
+// src/FluidSolver.cpp:276-295: only the left and bottom faces of LIQUID cells
+__global__ void k_add_acceleration(float* __restrict__ uf, float* __restrict__ vf,
+                                   const uint8_t* __restrict__ cell, const GridDims d, float ax,
+                                   float ay, float dt)
+{
+  int i, j;
+  if (!cell_of_thread(d, &i, &j)) return;
+  const size_t k = i + (size_t)j * d.ld;
+  if (cell[k] == FSB_LIQUID)
+  {
+    uf[k] = uf[k] + ax * dt;
+    vf[k] = vf[k] + ay * dt;
+  }
+}
+
+// src/FluidSolver.cpp:297-321: one-sided wall condition
+__global__ void k_enforce_dirichlet(float* __restrict__ uf, float* __restrict__ vf,
+                                    const uint8_t* __restrict__ cell, const GridDims d)
+{
+  int i, j;
+  if (!cell_of_thread(d, &i, &j)) return;
+  const size_t k = i + (size_t)j * d.ld;
+  const int im1 = clampi(i - 1, 0, d.nx - 1);
+  const int jm1 = clampi(j - 1, 0, d.ny - 1);
+  const int c = cell[k];
+  const int cw = cell[im1 + (size_t)j * d.ld];
+  const int cs = cell[i + (size_t)jm1 * d.ld];
+  const float u = uf[k], v = vf[k];
+  if ((cw == FSB_SOLID && u < 0.0f) || (c == FSB_SOLID && u > 0.0f)) uf[k] = 0.0f;
+  if ((cs == FSB_SOLID && v < 0.0f) || (c == FSB_SOLID && v > 0.0f)) vf[k] = 0.0f;
+}
+
+// src/FluidSolver.cpp:490-530: validity masks and the front->back copy,
+// including the line-527 typo (an invalid v-face zeroes the front U).
+__global__ void k_extend_init(float* __restrict__ uf, const float* __restrict__ vf,
+                              float* __restrict__ ub, float* __restrict__ vb,
+                              uint8_t* __restrict__ mxf, uint8_t* __restrict__ mxb,
+                              uint8_t* __restrict__ myf, uint8_t* __restrict__ myb,
+                              const uint8_t* __restrict__ cell, const GridDims d)
+{
+  int i, j;
+  if (!cell_of_thread(d, &i, &j)) return;
+  const size_t k = i + (size_t)j * d.ld;
+  const bool liq = cell[k] == FSB_LIQUID;
+  const bool u_valid = liq || cell_type(cell, d, i - 1, j) == FSB_LIQUID;
+  const bool v_valid = liq || cell_type(cell, d, i, j - 1) == FSB_LIQUID;
+  const float u = uf[k];
+  mxf[k] = u_valid;
+  mxb[k] = u_valid;
+  ub[k] = u_valid ? u : 0.0f;
+  myf[k] = v_valid;
+  myb[k] = v_valid;
+  vb[k] = v_valid ? vf[k] : 0.0f;
+  if (!u_valid || !v_valid) uf[k] = 0.0f;
+}
+
+// src/FluidSolver.cpp:533-620, one sweep.  Reads only faces whose FRONT mask
+// is 1 and writes only faces whose front mask is 0, so updating the back
+// velocity buffer in place is race-free and order-independent; the four-term
+// sum keeps the reference's order (i-1,j),(i,j-1),(i,j+1),(i+1,j).
+__global__ void k_extend_sweep(float* __restrict__ ub, float* __restrict__ vb,
+                               const uint8_t* __restrict__ mxf, uint8_t* __restrict__ mxb,
+                               const uint8_t* __restrict__ myf, uint8_t* __restrict__ myb,
+                               const uint8_t* __restrict__ cell, const GridDims d)
+{
+  int i, j;
+  if (!cell_of_thread(d, &i, &j)) return;
+  // a face that passes the tests below has a non-SOLID cell on both sides, so
+  // 1 <= i,j <= size-2 there and the four neighbours exist
+  if (i < 1 || j < 1 || i > d.nx - 2 || j > d.ny - 2) return;
+  const size_t k = i + (size_t)j * d.ld;
+  const size_t kw = k - 1, ke = k + 1, ks = k - d.ld, kn = k + d.ld;
+  const bool not_solid = cell[k] != FSB_SOLID;
+  if (mxf[k] == 0 && not_solid && cell[kw] != FSB_SOLID)
+  {
+    float nv = 0.0f;
+    int n = 0;
+    if (mxf[kw] == 1) { nv += ub[kw]; n++; }
+    if (mxf[ks] == 1) { nv += ub[ks]; n++; }
+    if (mxf[kn] == 1) { nv += ub[kn]; n++; }
+    if (mxf[ke] == 1) { nv += ub[ke]; n++; }
+    if (n > 0)
+    {
+      ub[k] = nv / (float)n;
+      mxb[k] = 1;
+    }
+  }
+  if (myf[k] == 0 && not_solid && cell[ks] != FSB_SOLID)
+  {
+    float nv = 0.0f;
+    int n = 0;
+    if (myf[kw] == 1) { nv += vb[kw]; n++; }
+    if (myf[ks] == 1) { nv += vb[ks]; n++; }
+    if (myf[kn] == 1) { nv += vb[kn]; n++; }
+    if (myf[ke] == 1) { nv += vb[ke]; n++; }
+    if (n > 0)
+    {
+      vb[k] = nv / (float)n;
+      myb[k] = 1;
+    }
+  }
+}
+
+// include/Grid.h:152-184 as a scatter with float atomics (order of the sums
+// differs from the reference's face order: within 1e-5 of the field maximum).
+__device__ __forceinline__ void grid_splat_atomic(float* __restrict__ g, const GridDims d, float x,
+                                                  float y, float value)
+{
+  const float xd = x / d.dx;
+  const float yd = y / d.dy;
+  int i = (int)xd;
+  int j = (int)yd;
+  int i1 = i + 1;
+  int j1 = j + 1;
+  const float fi = xd - (float)i;
+  const float fj = yd - (float)j;
+  i = clampi(i, 0, d.nx - 1);
+  j = clampi(j, 0, d.ny - 1);
+  i1 = clampi(i1, 0, d.nx - 1);
+  j1 = clampi(j1, 0, d.ny - 1);
+  const float v0 = (1.0f - fj) * value;
+  const float v1 = fj * value;
+  atomicAdd(g + i + (size_t)j * d.ld, (1.0f - fi) * v0);
+  atomicAdd(g + i1 + (size_t)j * d.ld, fi * v0);
+  atomicAdd(g + i + (size_t)j1 * d.ld, (1.0f - fi) * v1);
+  atomicAdd(g + i1 + (size_t)j1 * d.ld, fi * v1);
+}
+
+// src/FluidSolver.cpp:721-771: forward splat of each liquid-adjacent face value
+// to its back-traced position, into the zeroed BACK buffer; no swap.
+__global__ void k_advect_velocity_sl(const float* __restrict__ uf, const float* __restrict__ vf,
+                                     float* __restrict__ ub, float* __restrict__ vb,
+                                     const uint8_t* __restrict__ cell, const GridDims d, float dt,
+                                     int integrator)
+{
+  int i, j;
+  if (!cell_of_thread(d, &i, &j)) return;
+  const bool liq = cell[i + (size_t)j * d.ld] == FSB_LIQUID;
+  if (liq || cell_type(cell, d, i - 1, j) == FSB_LIQUID)
+  {
+    const float x_pos = (float)i * d.dx;
+    const float y_pos = ((float)j + 0.5f) * d.dy;
+    float xq, yq;
+    advected_position(uf, vf, d, integrator, x_pos, y_pos, -dt, &xq, &yq);
+    const float val = vel_x_interp(uf, d, x_pos, y_pos);
+    grid_splat_atomic(ub, d, xq, yq - 0.5f * d.dy, val);
+  }
+  if (liq || cell_type(cell, d, i, j - 1) == FSB_LIQUID)
+  {
+    const float x_pos = ((float)i + 0.5f) * d.dx;
+    const float y_pos = (float)j * d.dy;
+    float xq, yq;
+    advected_position(uf, vf, d, integrator, x_pos, y_pos, -dt, &xq, &yq);
+    const float val = vel_y_interp(vf, d, x_pos, y_pos);
+    grid_splat_atomic(vb, d, xq - 0.5f * d.dx, yq, val);
+  }
+}
+
+} // namespace
+
+int fsb_k_classify(fsb_ctx* c)
+{
+  fsb_prof_begin(c, FSB_PROF_CLASSIFY);
+  k_fill_labels<<<cell_grid(c), kBlock, 0, c->stream>>>(c->cell, dims(c));
+  FSB_LAUNCHED(c);
+  if (c->n > 0)
+  {
+    k_mark_liquid<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(c->part[c->pcur], c->n,
+                                                                       c->cell, dims(c));
+    FSB_LAUNCHED(c);
+  }
+  fsb_prof_end(c, FSB_PROF_CLASSIFY);
+  return FSB_OK;
+}
+
+int fsb_k_save_previous(fsb_ctx* c)
+{
+  const size_t bytes = (size_t)c->ld * c->ny * sizeof(float);
+  fsb_prof_begin(c, FSB_PROF_GRID_PRE);
+  FSB_CUDA(c, cudaMemcpyAsync(c->u_prev, fsb_uf(c), bytes, cudaMemcpyDeviceToDevice, c->stream));
+  FSB_CUDA(c, cudaMemcpyAsync(c->v_prev, fsb_vf(c), bytes, cudaMemcpyDeviceToDevice, c->stream));
+  fsb_prof_end(c, FSB_PROF_GRID_PRE);
+  return FSB_OK;
+}
+
+int fsb_k_update_diff(fsb_ctx* c)
+{
+  k_update_diff<<<cell_grid(c), kBlock, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->u_prev, c->v_prev,
+                                                        c->u_diff, c->v_diff, dims(c));
+  FSB_LAUNCHED(c);
+  return FSB_OK;
+}
+
+int fsb_k_add_acceleration(fsb_ctx* c, float ax, float ay, float dt)
+{
+  fsb_prof_begin(c, FSB_PROF_GRID_PRE);
+  k_add_acceleration<<<cell_grid(c), kBlock, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell, dims(c),
+                                                             ax, ay, dt);
+  FSB_LAUNCHED(c);
+  fsb_prof_end(c, FSB_PROF_GRID_PRE);
+  return FSB_OK;
+}
+
+int fsb_k_enforce_dirichlet(fsb_ctx* c)
+{
+  fsb_prof_begin(c, FSB_PROF_GRID_PRE);
+  k_enforce_dirichlet<<<cell_grid(c), kBlock, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell,
+                                                              dims(c));
+  FSB_LAUNCHED(c);
+  fsb_prof_end(c, FSB_PROF_GRID_PRE);
+  return FSB_OK;
+}
+
+int fsb_k_extend_velocity(fsb_ctx* c, int n_iter)
+{
+  fsb_prof_begin(c, FSB_PROF_EXTEND);
+  k_extend_init<<<cell_grid(c), kBlock, 0, c->stream>>>(
+      fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), c->mask_x[c->mask_front],
+      c->mask_x[c->mask_front ^ 1], c->mask_y[c->mask_front], c->mask_y[c->mask_front ^ 1], c->cell,
+      dims(c));
+  FSB_LAUNCHED(c);
+  for (int it = 0; it < n_iter; ++it)
+  {
+    k_extend_sweep<<<cell_grid(c), kBlock, 0, c->stream>>>(
+        fsb_ub(c), fsb_vb(c), c->mask_x[c->mask_front], c->mask_x[c->mask_front ^ 1],
+        c->mask_y[c->mask_front], c->mask_y[c->mask_front ^ 1], c->cell, dims(c));
+    FSB_LAUNCHED(c);
+    c->mask_front ^= 1; // swapValidMaskBuffer, src/FluidSolver.cpp:619
+  }
+  c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:621
+  fsb_prof_end(c, FSB_PROF_EXTEND);
+  return FSB_OK;
+}
+
+int fsb_k_advect_velocity_sl(fsb_ctx* c, float dt)
+{
+  const size_t bytes = (size_t)c->ld * c->ny * sizeof(float);
+  fsb_prof_begin(c, FSB_PROF_ADVECT_SL);
+  FSB_CUDA(c, cudaMemsetAsync(fsb_ub(c), 0, bytes, c->stream));
+  FSB_CUDA(c, cudaMemsetAsync(fsb_vb(c), 0, bytes, c->stream));
+  k_advect_velocity_sl<<<cell_grid(c), kBlock, 0, c->stream>>>(
+      fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), c->cell, dims(c), dt, c->integrator);
+  FSB_LAUNCHED(c);
+  fsb_prof_end(c, FSB_PROF_ADVECT_SL);
+  return FSB_OK;
+}

@@ -1,0 +1,170 @@
+// Internal declarations shared by the libfsb.so translation units.
+// Product code: never includes or links anything under oracle/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "fsb.h"
+
+// ---------------------------------------------------------------------------
+// Data layout in HBM
+//   * every grid (u, v, prev, diff, CG vectors: fp32; labels, masks, stencil
+//     codes: u8) is stored row-major with a padded row pitch `ld` (elements),
+//     ld = nx rounded up to 32, so every row starts on a 128-byte boundary and
+//     every kernel can use 16-byte vector accesses.  Pad columns hold zeros /
+//     non-liquid codes and are never copied to the host.
+//   * particles: AoS float4 {pos_x,pos_y,vel_x,vel_y} (one 16-byte access per
+//     particle), kept SORTED by cell on the device, with `orig[k]` = index the
+//     caller knows the particle by.  cell_start[c] .. cell_start[c+1] is the
+//     range of cell c (dense index i + j*nx).
+// ---------------------------------------------------------------------------
+
+struct CgScalars
+{
+  double rhs2; // |b|^2
+  double pq;   // p . A p
+  double r2;   // |r|^2 after the update
+  double rz;   // r . z
+  float abs_new, abs_old, beta, thr, tol;
+  int iter;      // Eigen's `i`
+  int done;      // 1: converged or capped; all later CG launches are no-ops
+  int max_iters;
+  int n_liquid;
+  unsigned int ticket[4]; // last-block counters, one per reducing kernel
+};
+
+struct CgCoef
+{
+  float off;        // (float)(1 / pow(dx, 2))           src/FluidSolver.cpp:382
+  float diag[5];    // (float)(-n / pow(dx, 2)), n=0..4  src/FluidSolver.cpp:409-410
+  float invdiag[5]; // Eigen DiagonalPreconditioner: diag != 0 ? 1/diag : 1
+};
+
+struct fsb_ctx
+{
+  int nx = 0, ny = 0, ld = 0;
+  float dx = 0, dy = 0;           // MacGrid deltas (src/MacGrid.cpp:8)
+  float pool_dx = 0, pool_dy = 0; // FluidSolverMemoryPool deltas (src/FluidSolver.cpp:56-65)
+  float density = 0, pic_ratio = 0;
+  float grav_x = 0, grav_y = 0;
+  int integrator = FSB_INTEGRATOR_RK3;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+
+  // MacGrid
+  float* u[2] = {nullptr, nullptr};
+  float* v[2] = {nullptr, nullptr};
+  int front = 0;
+  float *u_prev = nullptr, *v_prev = nullptr, *u_diff = nullptr, *v_diff = nullptr;
+  uint8_t* cell = nullptr;
+  // FluidSolverMemoryPool: extension masks
+  uint8_t* mask_x[2] = {nullptr, nullptr};
+  uint8_t* mask_y[2] = {nullptr, nullptr};
+  int mask_front = 0;
+
+  // particles (double-buffered for the cell sort)
+  float4* part[2] = {nullptr, nullptr};
+  int* orig[2] = {nullptr, nullptr};
+  int pcur = 0;
+  int64_t n = 0, cap = 0;
+  bool sort_valid = false;
+  int* cell_start = nullptr; // nx*ny + 1
+  int* cell_count = nullptr; // nx*ny
+  int* sort_key = nullptr;   // cap
+  int* sort_rank = nullptr;  // cap
+  int* sort_idx = nullptr;   // cap
+  int* scan_block = nullptr; // block sums for the scan
+  float* stage = nullptr;    // device staging for host copies (dense), grown on demand
+  size_t stage_bytes = 0;
+
+  // CG
+  float *cg_x = nullptr, *cg_r = nullptr, *cg_q = nullptr;
+  float* cg_p[2] = {nullptr, nullptr}; // search direction, ping-pong
+  uint8_t* cg_code = nullptr;
+  double* partials = nullptr;
+  int partials_cap = 0;
+  CgScalars* scal = nullptr;   // device
+  CgScalars* scal_h = nullptr; // pinned host mirror
+  int max_iters = 100;
+  float tol = 1.1920929e-7f;
+  int iters = 0;
+  float err = 0;
+  bool pressure_valid = false;
+  // fused FLIP steps interpolate (front - previous) per tap; the diff buffer is
+  // materialised only when somebody reads it
+  bool diff_pending = false;
+
+  // measurement
+  bool profiling = false;
+  static constexpr int kProfPool = 512; // event pairs recorded between two drains
+  cudaEvent_t prof_ev[kProfPool][2];
+  int prof_stage[kProfPool];
+  int prof_used = 0;
+  bool prof_made = false;
+  float prof_ms[FSB_PROF_COUNT];
+  int prof_calls[FSB_PROF_COUNT];
+  cudaEvent_t timer_ev[2] = {nullptr, nullptr};
+  int64_t launches = 0;
+  int sm_count = 148;
+
+  std::string err_msg;
+};
+
+// error plumbing ------------------------------------------------------------
+int fsb_fail(fsb_ctx* ctx, int code, const char* fmt, ...);
+#define FSB_CUDA(ctx, expr)                                                          \
+  do                                                                                 \
+  {                                                                                  \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess)                                                           \
+      return fsb_fail((ctx), FSB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,           \
+                      cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+  } while (0)
+#define FSB_TRY(expr)                 \
+  do                                  \
+  {                                   \
+    int _rc = (expr);                 \
+    if (_rc != FSB_OK) return _rc;    \
+  } while (0)
+// after a kernel launch
+#define FSB_LAUNCHED(ctx)                    \
+  do                                         \
+  {                                          \
+    (ctx)->launches++;                       \
+    FSB_CUDA((ctx), cudaGetLastError());     \
+  } while (0)
+
+static inline int fsb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline float* fsb_uf(fsb_ctx* c) { return c->u[c->front]; }
+static inline float* fsb_vf(fsb_ctx* c) { return c->v[c->front]; }
+static inline float* fsb_ub(fsb_ctx* c) { return c->u[c->front ^ 1]; }
+static inline float* fsb_vb(fsb_ctx* c) { return c->v[c->front ^ 1]; }
+
+void fsb_prof_begin(fsb_ctx* ctx, int stage);
+void fsb_prof_end(fsb_ctx* ctx, int stage);
+
+// stage launchers (each returns FSB_OK or an error code) ----------------------
+// grid stages: fsb_grid.cu
+int fsb_k_classify(fsb_ctx* c);
+int fsb_k_save_previous(fsb_ctx* c);
+int fsb_k_update_diff(fsb_ctx* c);
+int fsb_k_add_acceleration(fsb_ctx* c, float ax, float ay, float dt);
+int fsb_k_enforce_dirichlet(fsb_ctx* c);
+int fsb_k_extend_velocity(fsb_ctx* c, int n_iter);
+int fsb_k_advect_velocity_sl(fsb_ctx* c, float dt);
+// particle stages: fsb_particles.cu
+int fsb_k_sort_particles(fsb_ctx* c);
+int fsb_k_p2g(fsb_ctx* c);
+int fsb_k_g2p(fsb_ctx* c, int mode, float pic_ratio);
+int fsb_k_advect_particles(fsb_ctx* c, float dt, int ensure_outside);
+int fsb_k_g2p_advect(fsb_ctx* c, int mode, float pic_ratio, float dt, int ensure_outside);
+int fsb_k_advect_particles_grid(fsb_ctx* c, float dt);
+int fsb_k_unpermute(fsb_ctx* c, float4* dst_dense);
+int fsb_k_emit_source_dev(fsb_ctx* c, int64_t first, const float* xs_dev, const float* ys_dev,
+                          int64_t count_x, int64_t count_y, float vel_x, float vel_y);
+// pressure: fsb_cg.cu
+int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt);

@@ -1,0 +1,515 @@
+// Particle-side stages: cell-binned stable sort, particle-to-grid transfer as
+// an atomics-free gather over the sorted particles, grid-to-particle transfer
+// fused with the PIC/FLIP blend and the advection, RK3 particle tracing.
+#include "fsb_device.cuh"
+#include "fsb_internal.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+inline GridDims dims(const fsb_ctx* c) { return GridDims{c->nx, c->ny, c->ld, c->dx, c->dy}; }
+// the P2G accumulators carry the memory pool's deltas (src/FluidSolver.cpp:13-16)
+inline GridDims pool_dims(const fsb_ctx* c)
+{
+  return GridDims{c->nx, c->ny, c->ld, c->pool_dx, c->pool_dy};
+}
+
+// ------------------------------------------------------------------ sort --
+// Key = the particle's interpolation base cell (int)(pos/delta), index-clamped
+// (formula 3 of SURVEY.md A.4), dense index ci + cj*nx.  Runs of equal keys
+// inside a warp are aggregated so that only the run head touches the counter.
+__global__ void k_sort_count(const float4* __restrict__ part, int64_t n, const GridDims d,
+                             int* __restrict__ count, int* __restrict__ key_out,
+                             int* __restrict__ rank_out)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31;
+  const bool live = k < n;
+  int key = -1 - (int)lane; // distinct per lane, never equal to a real key
+  if (live)
+  {
+    const float4 p = part[k];
+    const int ci = clampi((int)(p.x / d.dx), 0, d.nx - 1);
+    const int cj = clampi((int)(p.y / d.dy), 0, d.ny - 1);
+    key = ci + cj * d.nx;
+  }
+  const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (key != prev);
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  const unsigned below = heads & (0xffffffffu >> (31 - lane)); // heads at lanes <= mine
+  const int start = 31 - __clz(below);
+  const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
+  const int len = above ? __ffs(above) : (32 - (int)lane); // run length seen from a head
+  int base = 0;
+  if (head && live) base = atomicAdd(count + key, len);
+  base = __shfl_sync(0xffffffffu, base, start);
+  if (live)
+  {
+    key_out[k] = key;
+    rank_out[k] = base + ((int)lane - start);
+  }
+}
+
+// exclusive scan of count[0..m) into start[0..m], three small kernels
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 16; // per thread
+constexpr int kScanTile = kScanBlock * kScanItems;
+
+__device__ __forceinline__ int block_scan_excl(int v, int* total)
+{
+  // exclusive scan of one int per thread over the block
+  __shared__ int s_warp[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0)
+  {
+    const int nw = blockDim.x >> 5;
+    int w = (lane < nw) ? s_warp[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    s_warp[lane] = wi - w; // exclusive warp offsets
+    if (lane == nw - 1) s_warp[31] = (nw == 32) ? wi : wi; // total (overwritten below if nw==32)
+  }
+  __syncthreads();
+  const int off = s_warp[wid];
+  // total = offset of last warp + its inclusive sum: recompute cheaply
+  __shared__ int s_total;
+  if (threadIdx.x == blockDim.x - 1) s_total = off + incl;
+  __syncthreads();
+  *total = s_total;
+  return off + incl - v;
+}
+
+__global__ void k_scan_reduce(const int* __restrict__ count, int m, int* __restrict__ block_sum)
+{
+  const int base = blockIdx.x * kScanTile;
+  int s = 0;
+  for (int t = threadIdx.x; t < kScanTile; t += kScanBlock)
+  {
+    const int idx = base + t;
+    if (idx < m) s += count[idx];
+  }
+  // block reduce
+  __shared__ int s_w[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) s_w[wid] = s;
+  __syncthreads();
+  if (wid == 0)
+  {
+    s = (lane < (kScanBlock >> 5)) ? s_w[lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) block_sum[blockIdx.x] = s;
+  }
+}
+
+// single block: in-place exclusive scan of the block sums
+__global__ void k_scan_blocks(int* __restrict__ block_sum, int nb)
+{
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += blockDim.x)
+  {
+    const int idx = base + threadIdx.x;
+    const int v = (idx < nb) ? block_sum[idx] : 0;
+    int total;
+    const int ex = block_scan_excl(v, &total);
+    const int carry = s_carry;
+    if (idx < nb) block_sum[idx] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+}
+
+__global__ void k_scan_apply(const int* __restrict__ count, int m,
+                             const int* __restrict__ block_sum, int* __restrict__ start)
+{
+  // each thread owns kScanItems consecutive entries
+  const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int s = 0;
+#pragma unroll
+  for (int t = 0; t < kScanItems; ++t)
+  {
+    const int idx = base + t;
+    v[t] = (idx < m) ? count[idx] : 0;
+    s += v[t];
+  }
+  int total;
+  int run = block_sum[blockIdx.x] + block_scan_excl(s, &total);
+#pragma unroll
+  for (int t = 0; t < kScanItems; ++t)
+  {
+    const int idx = base + t;
+    if (idx < m) start[idx] = run;
+    run += v[t];
+  }
+  // the grand total goes to start[m]
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanBlock - 1) start[m] = run;
+}
+
+__global__ void k_sort_place(const int* __restrict__ key, const int* __restrict__ rank, int64_t n,
+                             const int* __restrict__ start, int* __restrict__ idx)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  idx[start[key[k]] + rank[k]] = (int)k;
+}
+
+// Make the order inside each cell canonical (ascending source position), which
+// turns the atomic ranking into a STABLE counting sort: the device order, and
+// with it every floating-point sum over a cell's particles, is reproducible.
+__global__ void k_sort_canon(const int* __restrict__ start, int m, int* __restrict__ idx)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m) return;
+  const int a = start[c], b = start[c + 1];
+  for (int s = a + 1; s < b; ++s)
+  {
+    const int v = idx[s];
+    int t = s - 1;
+    while (t >= a && idx[t] > v)
+    {
+      idx[t + 1] = idx[t];
+      --t;
+    }
+    idx[t + 1] = v;
+  }
+}
+
+__global__ void k_sort_gather(const float4* __restrict__ src, const int* __restrict__ src_orig,
+                              const int* __restrict__ idx, int64_t n, float4* __restrict__ dst,
+                              int* __restrict__ dst_orig)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int s = idx[k];
+  dst[k] = src[s];
+  dst_orig[k] = src_orig[s];
+}
+
+// ------------------------------------------------------------------- P2G --
+// src/FluidSolver.cpp:873-919 as a gather.  One thread per cell (i,j) owns
+// the faces u(i,j) and v(i,j).  A particle whose sort cell is (ci,cj) splats u
+// onto nodes {ci,ci+1} x {bj,bj+1} with bj in {cj-1,cj}, and v onto
+// {bi,bi+1} x {cj,cj+1} with bi in {ci-1,ci} (include/Grid.h:152-184 with the
+// MAC half-cell shift), so both faces only receive from the 3x3 cells around
+// (i,j).  Every visited particle recomputes its own four target nodes exactly
+// as the reference does (truncation, fraction before clamping, independent
+// clamps) and contributes where a target equals this face, so clamped
+// duplicates and out-of-domain particles land where the reference puts them.
+// face = sum / weight where weight > 1e-6, else the back buffer keeps its stale
+// value (:902-915).  No accumulator grids, no atomics, deterministic.
+__global__ void k_p2g_gather(const float4* __restrict__ part, const int* __restrict__ cell_start,
+                             float* __restrict__ ub, float* __restrict__ vb, const GridDims d,
+                             float half_dx, float half_dy)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(t % d.ld);
+  const int j = (int)(t / d.ld);
+  if (i >= d.nx || j >= d.ny) return;
+
+  float su = 0.0f, wu = 0.0f, sv = 0.0f, wv = 0.0f;
+  const int ia = max(i - 1, 0), ib = min(i + 1, d.nx - 1);
+  const int ja = max(j - 1, 0), jb = min(j + 1, d.ny - 1);
+  for (int jj = ja; jj <= jb; ++jj)
+  {
+    const int p0 = cell_start[ia + jj * d.nx];
+    const int p1 = cell_start[ib + jj * d.nx + 1];
+    for (int k = p0; k < p1; ++k)
+    {
+      const float4 p = __ldg(part + k);
+      // ---- u: splat (vel_x, 1) at (px, py - dy/2)
+      {
+        const float xd = p.x / d.dx;
+        const float yd = (p.y - half_dy) / d.dy;
+        const int bi = (int)xd, bj = (int)yd;
+        const float fi = xd - (float)bi, fj = yd - (float)bj;
+        const int i0 = clampi(bi, 0, d.nx - 1), i1 = clampi(bi + 1, 0, d.nx - 1);
+        const int j0 = clampi(bj, 0, d.ny - 1), j1 = clampi(bj + 1, 0, d.ny - 1);
+        if ((i0 == i || i1 == i) && (j0 == j || j1 == j))
+        {
+          const float v0 = (1.0f - fj) * p.z, v1 = fj * p.z;
+          const float w0 = (1.0f - fj) * 1.0f, w1 = fj * 1.0f;
+          if (i0 == i && j0 == j) { su += (1.0f - fi) * v0; wu += (1.0f - fi) * w0; }
+          if (i1 == i && j0 == j) { su += fi * v0; wu += fi * w0; }
+          if (i0 == i && j1 == j) { su += (1.0f - fi) * v1; wu += (1.0f - fi) * w1; }
+          if (i1 == i && j1 == j) { su += fi * v1; wu += fi * w1; }
+        }
+      }
+      // ---- v: splat (vel_y, 1) at (px - dx/2, py)
+      {
+        const float xd = (p.x - half_dx) / d.dx;
+        const float yd = p.y / d.dy;
+        const int bi = (int)xd, bj = (int)yd;
+        const float fi = xd - (float)bi, fj = yd - (float)bj;
+        const int i0 = clampi(bi, 0, d.nx - 1), i1 = clampi(bi + 1, 0, d.nx - 1);
+        const int j0 = clampi(bj, 0, d.ny - 1), j1 = clampi(bj + 1, 0, d.ny - 1);
+        if ((i0 == i || i1 == i) && (j0 == j || j1 == j))
+        {
+          const float v0 = (1.0f - fj) * p.w, v1 = fj * p.w;
+          const float w0 = (1.0f - fj) * 1.0f, w1 = fj * 1.0f;
+          if (i0 == i && j0 == j) { sv += (1.0f - fi) * v0; wv += (1.0f - fi) * w0; }
+          if (i1 == i && j0 == j) { sv += fi * v0; wv += fi * w0; }
+          if (i0 == i && j1 == j) { sv += (1.0f - fi) * v1; wv += (1.0f - fi) * w1; }
+          if (i1 == i && j1 == j) { sv += fi * v1; wv += fi * w1; }
+        }
+      }
+    }
+  }
+  const size_t o = i + (size_t)j * d.ld;
+  if ((double)wu > 0.000001) ub[o] = su / wu;
+  if ((double)wv > 0.000001) vb[o] = sv / wv;
+}
+
+// ------------------------------------------------------------------- G2P --
+// src/FluidSolver.cpp:921-963 fused with src/MarkerParticleSet.cpp:40-62.
+// mode < 0: advect only.  dt_advect == 0 && !do_advect: transfer only.
+template <bool DO_G2P, bool DO_ADVECT>
+__global__ void k_g2p_advect(float4* __restrict__ part, int64_t n, const float* __restrict__ uf,
+                             const float* __restrict__ vf, const float* __restrict__ ud_or_prev,
+                             const float* __restrict__ vd_or_prev, int diff_is_prev,
+                             const uint8_t* __restrict__ cell, const GridDims d, int mode,
+                             float pic_ratio, float dt, int ensure_outside)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  float4 p = part[k];
+  if (DO_G2P)
+  {
+    float nvx, nvy;
+    if (mode == FSB_G2P_PIC)
+    {
+      nvx = vel_x_interp(uf, d, p.x, p.y);
+      nvy = vel_y_interp(vf, d, p.x, p.y);
+    }
+    else
+    {
+      float dvx, dvy;
+      if (diff_is_prev)
+      {
+        dvx = grid_interp_diff(uf, ud_or_prev, d, p.x, p.y - d.dy * 0.5f);
+        dvy = grid_interp_diff(vf, vd_or_prev, d, p.x - d.dx * 0.5f, p.y);
+      }
+      else
+      {
+        dvx = vel_x_interp(ud_or_prev, d, p.x, p.y);
+        dvy = vel_y_interp(vd_or_prev, d, p.x, p.y);
+      }
+      const float flip_x = p.z + dvx;
+      const float flip_y = p.w + dvy;
+      if (mode == FSB_G2P_FLIP)
+      {
+        nvx = flip_x;
+        nvy = flip_y;
+      }
+      else
+      {
+        const float pic_x = vel_x_interp(uf, d, p.x, p.y);
+        const float pic_y = vel_y_interp(vf, d, p.x, p.y);
+        nvx = pic_x * pic_ratio + flip_x * (1.0f - pic_ratio);
+        nvy = pic_y * pic_ratio + flip_y * (1.0f - pic_ratio);
+      }
+    }
+    p.z = nvx;
+    p.w = nvy;
+  }
+  if (DO_ADVECT)
+  {
+    // include/MarkerParticleSet.h:37-41
+    p.x += p.z * dt;
+    p.y += p.w * dt;
+    if (ensure_outside)
+    {
+      // src/MarkerParticleSet.cpp:55-60: the roll-back is a second advect(-dt)
+      const int x = (int)(p.x / d.dx);
+      const int y = (int)(p.y / d.dy);
+      if (cell_type(cell, d, x, y) == FSB_SOLID)
+      {
+        const float mdt = -dt;
+        p.x += p.z * mdt;
+        p.y += p.w * mdt;
+      }
+    }
+  }
+  part[k] = p;
+}
+
+// src/FluidSolver.cpp:774-791
+__global__ void k_advect_particles_grid(float4* __restrict__ part, int64_t n,
+                                        const float* __restrict__ uf, const float* __restrict__ vf,
+                                        const GridDims d, float dt, int integrator)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  float4 p = part[k];
+  float xn, yn;
+  advected_position(uf, vf, d, integrator, p.x, p.y, dt, &xn, &yn);
+  p.x = xn;
+  p.y = yn;
+  part[k] = p;
+}
+
+__global__ void k_unpermute(const float4* __restrict__ part, const int* __restrict__ orig,
+                            int64_t n, float4* __restrict__ dst)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  dst[orig[k]] = part[k];
+}
+
+// src/FluidDomain.cpp:39-46: lattice in y-outer / x-inner order; the coordinate
+// sequences (repeated float additions) are produced on the host.
+__global__ void k_emit_source(float4* __restrict__ part, int* __restrict__ orig, int64_t first,
+                              const float* __restrict__ xs, const float* __restrict__ ys,
+                              int64_t count_x, int64_t count_y, float vel_x, float vel_y)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count_x * count_y) return;
+  const int64_t ix = k % count_x, iy = k / count_x;
+  part[first + k] = make_float4(xs[ix], ys[iy], vel_x, vel_y);
+  orig[first + k] = (int)(first + k);
+}
+
+} // namespace
+
+int fsb_k_sort_particles(fsb_ctx* c)
+{
+  if (c->sort_valid) return FSB_OK;
+  const int m = c->nx * c->ny;
+  fsb_prof_begin(c, FSB_PROF_SORT);
+  FSB_CUDA(c, cudaMemsetAsync(c->cell_count, 0, (size_t)m * sizeof(int), c->stream));
+  if (c->n > 0)
+  {
+    k_sort_count<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+        c->part[c->pcur], c->n, pool_dims(c), c->cell_count, c->sort_key, c->sort_rank);
+    FSB_LAUNCHED(c);
+  }
+  const int nb = fsb_div_up(m, kScanTile);
+  k_scan_reduce<<<nb, kScanBlock, 0, c->stream>>>(c->cell_count, m, c->scan_block);
+  FSB_LAUNCHED(c);
+  k_scan_blocks<<<1, 1024, 0, c->stream>>>(c->scan_block, nb);
+  FSB_LAUNCHED(c);
+  k_scan_apply<<<nb, kScanBlock, 0, c->stream>>>(c->cell_count, m, c->scan_block, c->cell_start);
+  FSB_LAUNCHED(c);
+  if (c->n > 0)
+  {
+    k_sort_place<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+        c->sort_key, c->sort_rank, c->n, c->cell_start, c->sort_idx);
+    FSB_LAUNCHED(c);
+    k_sort_canon<<<fsb_div_up(m, kBlock), kBlock, 0, c->stream>>>(c->cell_start, m, c->sort_idx);
+    FSB_LAUNCHED(c);
+    k_sort_gather<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+        c->part[c->pcur], c->orig[c->pcur], c->sort_idx, c->n, c->part[c->pcur ^ 1],
+        c->orig[c->pcur ^ 1]);
+    FSB_LAUNCHED(c);
+    c->pcur ^= 1;
+  }
+  c->sort_valid = true;
+  fsb_prof_end(c, FSB_PROF_SORT);
+  return FSB_OK;
+}
+
+int fsb_k_p2g(fsb_ctx* c)
+{
+  FSB_TRY(fsb_k_sort_particles(c));
+  fsb_prof_begin(c, FSB_PROF_P2G);
+  const GridDims d = pool_dims(c);
+  k_p2g_gather<<<fsb_div_up((int64_t)c->ld * c->ny, kBlock), kBlock, 0, c->stream>>>(
+      c->part[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), d, 0.5f * c->dx, 0.5f * c->dy);
+  FSB_LAUNCHED(c);
+  c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:918
+  fsb_prof_end(c, FSB_PROF_P2G);
+  return FSB_OK;
+}
+
+int fsb_k_g2p(fsb_ctx* c, int mode, float pic_ratio)
+{
+  if (c->n == 0) return FSB_OK;
+  fsb_prof_begin(c, FSB_PROF_G2P);
+  k_g2p_advect<true, false><<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+      c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c), c->u_diff, c->v_diff, 0, c->cell, dims(c), mode,
+      pic_ratio, 0.0f, 0);
+  FSB_LAUNCHED(c);
+  fsb_prof_end(c, FSB_PROF_G2P);
+  return FSB_OK;
+}
+
+int fsb_k_advect_particles(fsb_ctx* c, float dt, int ensure_outside)
+{
+  if (c->n == 0) return FSB_OK;
+  fsb_prof_begin(c, FSB_PROF_G2P);
+  k_g2p_advect<false, true><<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+      c->part[c->pcur], c->n, nullptr, nullptr, nullptr, nullptr, 0, c->cell, dims(c), 0, 0.0f, dt,
+      ensure_outside);
+  FSB_LAUNCHED(c);
+  c->sort_valid = false;
+  fsb_prof_end(c, FSB_PROF_G2P);
+  return FSB_OK;
+}
+
+// G2P on (front - previous) taken per tap + blend + advect in one pass: the
+// diff buffer is never materialised (src/MacGrid.cpp:58-70 folded in).
+int fsb_k_g2p_advect(fsb_ctx* c, int mode, float pic_ratio, float dt, int ensure_outside)
+{
+  if (c->n == 0) return FSB_OK;
+  fsb_prof_begin(c, FSB_PROF_G2P);
+  k_g2p_advect<true, true><<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+      c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c), c->u_prev, c->v_prev, 1, c->cell, dims(c), mode,
+      pic_ratio, dt, ensure_outside);
+  FSB_LAUNCHED(c);
+  c->sort_valid = false;
+  fsb_prof_end(c, FSB_PROF_G2P);
+  return FSB_OK;
+}
+
+int fsb_k_advect_particles_grid(fsb_ctx* c, float dt)
+{
+  if (c->n == 0) return FSB_OK;
+  fsb_prof_begin(c, FSB_PROF_ADVECT_PART);
+  k_advect_particles_grid<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+      c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c), dims(c), dt, c->integrator);
+  FSB_LAUNCHED(c);
+  c->sort_valid = false;
+  fsb_prof_end(c, FSB_PROF_ADVECT_PART);
+  return FSB_OK;
+}
+
+int fsb_k_unpermute(fsb_ctx* c, float4* dst_dense)
+{
+  if (c->n == 0) return FSB_OK;
+  k_unpermute<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(c->part[c->pcur],
+                                                                  c->orig[c->pcur], c->n, dst_dense);
+  FSB_LAUNCHED(c);
+  return FSB_OK;
+}
+
+int fsb_k_emit_source_dev(fsb_ctx* c, int64_t first, const float* xs_dev, const float* ys_dev,
+                          int64_t count_x, int64_t count_y, float vel_x, float vel_y)
+{
+  const int64_t total = count_x * count_y;
+  if (total == 0) return FSB_OK;
+  k_emit_source<<<fsb_div_up(total, kBlock), kBlock, 0, c->stream>>>(
+      c->part[c->pcur], c->orig[c->pcur], first, xs_dev, ys_dev, count_x, count_y, vel_x, vel_y);
+  FSB_LAUNCHED(c);
+  return FSB_OK;
+}

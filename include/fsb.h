@@ -1,0 +1,181 @@
+/* fsb.h -- C ABI of the B200-native PIC/FLIP hot path (libfsb.so).
+ *
+ * Drop-in boundary for the per-step path of kbladin/Fluid_Simulation.  The
+ * reference has no FFI: its boundary is the public C++ class surface of
+ * fluidsim_lib (include/FluidSolver.h:45-54, include/FluidDomain.h:40-68,
+ * include/MacGrid.h:19-159, include/MarkerParticleSet.h:53-74).  The C++ host
+ * classes in include/fsb/ keep those class and method names and forward every
+ * call to the functions below; each entry point cites the reference routine it
+ * replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no CUDA or torch types in any signature
+ *    (a CUDA stream is passed as void*).
+ *  - every function returns FSB_OK or an FSB_ERR_* code; fsb_last_error()
+ *    gives the text.  The C++ wrappers rethrow std::runtime_error, which is
+ *    what the reference's step* functions throw (src/FluidSolver.cpp:101-107).
+ *  - one context = one simulation domain on one CUDA device, one stream.  Calls
+ *    are asynchronous on that stream; fsb_get_* and fsb_synchronize wait.
+ *    A context is not thread-safe (neither is the reference).
+ *  - all state lives in HBM.  Host buffers are caller-owned, dense row-major
+ *    `i + j*size_x` exactly like Grid<T> (include/Grid.h:27-31); particles are
+ *    AoS {pos_x,pos_y,vel_x,vel_y} like MarkerParticle
+ *    (include/MarkerParticleSet.h:43-50) and always in the caller's original
+ *    order, whatever ordering the device uses internally.
+ *  - cell labels: 0 LIQUID, 1 AIR, 2 SOLID (include/MacGrid.h:14-17), one
+ *    byte per cell.
+ *  - there is no CPU fallback: every entry point fails with FSB_ERR_CUDA when
+ *    no sm_100 device is usable.
+ */
+#ifndef FSB_H
+#define FSB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fsb_ctx fsb_ctx;
+
+enum {
+  FSB_OK = 0,
+  FSB_ERR_INVALID = 1, /* bad argument, or the reference's validate() mismatch */
+  FSB_ERR_CUDA = 2,    /* CUDA runtime failure (incl. no device) */
+  FSB_ERR_NOMEM = 3,
+  FSB_ERR_COMM = 4     /* multi-GPU exchange failure / timeout */
+};
+
+/* MacGrid buffers (include/MacGrid.h:164-174) */
+enum {
+  FSB_U_FRONT = 0, FSB_V_FRONT = 1, FSB_U_BACK = 2, FSB_V_BACK = 3,
+  FSB_U_PREV = 4, FSB_V_PREV = 5, FSB_U_DIFF = 6, FSB_V_DIFF = 7
+};
+enum { FSB_LIQUID = 0, FSB_AIR = 1, FSB_SOLID = 2 };
+enum { FSB_G2P_PIC = 0, FSB_G2P_FLIP = 1, FSB_G2P_PICFLIP = 2 };
+enum { FSB_STEP_SEMILAGRANGIAN = 0, FSB_STEP_PIC = 1, FSB_STEP_FLIP = 2, FSB_STEP_PICFLIP = 3 };
+/* include/OdeSolver.h: RK3 :102-113 (the reference's hard-wired choice,
+ * include/FluidSolver.h:144), EulerExplicit :78-86 */
+enum { FSB_INTEGRATOR_RK3 = 0, FSB_INTEGRATOR_EULER = 1 };
+
+/* ---- life cycle ------------------------------------------------------- */
+
+/* FluidDomain(size_x,size_y,length_x,length_y,density,pic_ratio)
+ * (src/FluidDomain.cpp:54-68) + FluidSolverMemoryPool(domain)
+ * (src/FluidSolver.cpp:28-54) + FluidSolver(pool) (:78-82) in one object.
+ * `device` is the CUDA ordinal.  Labels start SOLID-border / AIR-interior
+ * (src/MacGrid.cpp:24), velocities zero, no particles, CG cap 100 and
+ * tolerance FLT_EPSILON (src/FluidSolver.cpp:81 and Eigen's default). */
+int fsb_create(fsb_ctx** out, int size_x, int size_y, float length_x, float length_y,
+               float density, float pic_ratio, int device);
+void fsb_destroy(fsb_ctx* ctx);
+/* Text of the last error on this context (ctx may be NULL: last create error). */
+const char* fsb_last_error(const fsb_ctx* ctx);
+const char* fsb_version(void);
+/* Run all later work of this context on `cuda_stream` (a cudaStream_t). */
+int fsb_set_stream(fsb_ctx* ctx, void* cuda_stream);
+int fsb_synchronize(fsb_ctx* ctx);
+
+/* GridInterface getters (include/Grid.h:50-55) */
+int fsb_size_x(const fsb_ctx* ctx);
+int fsb_size_y(const fsb_ctx* ctx);
+float fsb_delta_x(const fsb_ctx* ctx);
+float fsb_delta_y(const fsb_ctx* ctx);
+
+/* ---- parameters ------------------------------------------------------- */
+
+/* _cg_solver.setMaxIterations / setTolerance (src/FluidSolver.cpp:81).
+ * max_iters < 0 means Eigen's default cap (2 * unknowns). */
+int fsb_set_cg(fsb_ctx* ctx, int max_iters, float tol);
+/* iterations() and error() of the last solve */
+int fsb_get_cg_info(const fsb_ctx* ctx, int* iterations, float* error);
+/* FluidDomain::setPicRatio (src/FluidDomain.cpp:99-102): clamped to [0,1] */
+int fsb_set_pic_ratio(fsb_ctx* ctx, float pic_ratio);
+int fsb_set_density(fsb_ctx* ctx, float density);
+int fsb_set_integrator(fsb_ctx* ctx, int integrator);
+/* gravity used by the fused steps; default (0, (float)-9.82)
+ * (src/FluidSolver.cpp:115,154,192,232) */
+int fsb_set_gravity(fsb_ctx* ctx, float ax, float ay);
+
+/* ---- state transfer --------------------------------------------------- */
+
+/* MarkerParticleSet::clear + addParticle (include/MarkerParticleSet.h:56-58) */
+int fsb_set_particles(fsb_ctx* ctx, const float* aos4, int64_t n);
+int fsb_append_particles(fsb_ctx* ctx, const float* aos4, int64_t n);
+int64_t fsb_num_particles(const fsb_ctx* ctx);
+/* iteration over the set (include/MarkerParticleSet.h:68-74), original order */
+int fsb_get_particles(fsb_ctx* ctx, float* aos4);
+/* FluidSource::update spawn branch (src/FluidDomain.cpp:34-50) executed on the
+ * device: appends the delta/2.5 lattice over [x_min,x_max) x [y_min,y_max)
+ * in the reference's order.  *n_added receives the count (may be NULL). */
+int fsb_emit_source(fsb_ctx* ctx, float x_min, float x_max, float y_min, float y_max,
+                    float delta_x, float delta_y, float vel_x, float vel_y,
+                    int64_t* n_added);
+
+int fsb_set_grid(fsb_ctx* ctx, int which, const float* src);
+int fsb_get_grid(fsb_ctx* ctx, int which, float* dst);
+/* MacGrid::setCellType / cellType (include/MacGrid.h:92-97,140-143) */
+int fsb_set_cell_types(fsb_ctx* ctx, const uint8_t* src);
+int fsb_get_cell_types(fsb_ctx* ctx, uint8_t* dst);
+/* the CG solution of the last pressure solve on the full grid (0 where not
+ * LIQUID); the reference discards it (src/FluidSolver.cpp:423-460) */
+int fsb_get_pressure(fsb_ctx* ctx, float* dst);
+
+/* ---- one entry per reference stage ----------------------------------- */
+
+/* FluidDomain::classifyCells(MarkerParticleSet&) src/FluidDomain.cpp:150-180 */
+int fsb_classify_cells(fsb_ctx* ctx);
+/* FluidSolver::transferVelocityToGridSpread src/FluidSolver.cpp:873-919 */
+int fsb_p2g_spread(fsb_ctx* ctx);
+/* MacGrid::updatePreviousVelocityBuffer src/MacGrid.cpp:52-56 */
+int fsb_save_previous(fsb_ctx* ctx);
+/* FluidSolver::addExternalAcceleration src/FluidSolver.cpp:276-295 */
+int fsb_add_acceleration(fsb_ctx* ctx, float ax, float ay, float dt);
+/* FluidSolver::enforceDirichlet src/FluidSolver.cpp:297-321 */
+int fsb_enforce_dirichlet(fsb_ctx* ctx);
+/* FluidSolver::extendVelocityIndividual src/FluidSolver.cpp:485-622 */
+int fsb_extend_velocity(fsb_ctx* ctx, int n_iterations);
+/* FluidSolver::pressureSolve src/FluidSolver.cpp:323-483 (Eigen CG replaced by
+ * the matrix-free Jacobi-PCG kernels) */
+int fsb_pressure_solve(fsb_ctx* ctx, float density, float dt);
+/* MacGrid::updateVelocityDiffBuffer src/MacGrid.cpp:58-70 */
+int fsb_update_diff(fsb_ctx* ctx);
+/* FluidSolver::transferVelocityToParticles{PIC,FLIP,PICFLIP} src/FluidSolver.cpp:921-963 */
+int fsb_g2p(fsb_ctx* ctx, int mode, float pic_ratio);
+/* MarkerParticleSet::advect / advectAndEnsureOutsideObstacles src/MarkerParticleSet.cpp:40-62 */
+int fsb_advect_particles(fsb_ctx* ctx, float dt, int ensure_outside_obstacles);
+/* FluidSolver::advectVelocitySemiLagrangian src/FluidSolver.cpp:709-772 */
+int fsb_advect_velocity_sl(fsb_ctx* ctx, float dt);
+/* FluidSolver::advectParticlesWithGrid src/FluidSolver.cpp:774-791 */
+int fsb_advect_particles_grid(fsb_ctx* ctx, float dt);
+
+/* ---- fused steps: FluidSolver::step* src/FluidSolver.cpp:99-251 ------- */
+
+/* kind = FSB_STEP_*.  Uses the context's density and pic ratio the way the
+ * reference reads them from the FluidDomain.  FSB_ERR_INVALID when the
+ * reference's validate() (src/FluidSolver.cpp:89-97) would throw. */
+int fsb_step(fsb_ctx* ctx, int kind, float dt);
+
+/* ---- measurement ------------------------------------------------------ */
+
+/* Per-stage CUDA-event timing on the context's stream.  Enabling it makes
+ * every stage record an event pair; fsb_profile_read drains them (this
+ * synchronises).  Stage ids: FSB_PROF_*. */
+enum {
+  FSB_PROF_CLASSIFY = 0, FSB_PROF_SORT, FSB_PROF_P2G, FSB_PROF_GRID_PRE,
+  FSB_PROF_EXTEND, FSB_PROF_RHS, FSB_PROF_CG, FSB_PROF_PATCH, FSB_PROF_G2P,
+  FSB_PROF_ADVECT_SL, FSB_PROF_ADVECT_PART, FSB_PROF_COUNT
+};
+int fsb_profile_enable(fsb_ctx* ctx, int on);
+/* ms[FSB_PROF_COUNT], calls[FSB_PROF_COUNT]: totals since the last read */
+int fsb_profile_read(fsb_ctx* ctx, float* ms, int* calls);
+/* number of kernels this library launched on the context since creation */
+int64_t fsb_launch_count(const fsb_ctx* ctx);
+/* a pair of events around an arbitrary region of this context's stream */
+int fsb_timer_start(fsb_ctx* ctx);
+int fsb_timer_stop(fsb_ctx* ctx, float* elapsed_ms); /* synchronises */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSB_H */

@@ -1,0 +1,358 @@
+"""GPU parity: every stage of the CUDA path, called through the C ABI, against
+the CPU checkers on the same seeded inputs.
+
+Bars (BASELINE.json north_star / SURVEY.md 8d):
+  * cell labels and anything integer: bit-exact
+  * gather-type stages (Dirichlet, gravity, extension, pressure patch given p,
+    G2P, particle advection, RK3 tracing): bit-exact (required: <= 1e-5)
+  * scatter stages (P2G, semi-Lagrangian velocity advection): max|a-b| <= 1e-5 * max|ref|
+  * CG: same stopping rule; iterations within 10 %; pressure within the solver tolerance
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import scenes
+from oracle_lib import (G2P_FLIP, G2P_PIC, G2P_PICFLIP, STEP_FLIP, STEP_PIC, STEP_PICFLIP, STEP_SL,
+                        U_BACK, U_DIFF, U_FRONT, U_PREV, V_BACK, V_DIFF, V_FRONT, V_PREV)
+
+pytestmark = pytest.mark.gpu
+
+SCATTER_TOL = 1e-5
+SIZES = [(64, 64), (37, 53), (96, 40), (130, 67)]
+
+
+def make_pair(capi, checker, nx, ny, density=0.01, pic_ratio=0.05):
+    lx, ly = 1.0, float(np.float32(ny) / np.float32(nx))  # square cells
+    g = capi.Sim(nx, ny, lx, ly, density, pic_ratio)
+    c = checker.sim(nx, ny, lx, ly, density, pic_ratio)
+    assert g.dx == c.dx and g.dy == c.dy
+    return g, c
+
+
+def load_state(sims, rng, nx, ny, with_particles=True, per_cell=4):
+    lab = scenes.random_labels(nx, ny, rng)
+    fields = {w: scenes.random_field(nx, ny, rng) for w in
+              (U_FRONT, V_FRONT, U_BACK, V_BACK, U_PREV, V_PREV, U_DIFF, V_DIFF)}
+    parts = scenes.particles_in_liquid(lab, sims[0].dx, rng, per_cell) if with_particles else None
+    for s in sims:
+        s.set_cell_types(lab)
+        for w, f in fields.items():
+            s.set_grid(w, f)
+        if parts is not None:
+            s.set_particles(parts)
+    return lab, fields, parts
+
+
+def assert_grids_equal(g, c, which=(U_FRONT, V_FRONT, U_BACK, V_BACK)):
+    for w in which:
+        a, b = g.get_grid(w), c.get_grid(w)
+        assert np.array_equal(a, b), f"grid {w}: {np.abs(a - b).max()} max abs diff"
+
+
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_classify_cells_bit_exact(capi, checkers, nx, ny):
+    rng = np.random.default_rng(1)
+    for chk in checkers:
+        g, c = make_pair(capi, chk, nx, ny)
+        lx, ly = nx * g.dx, ny * g.dy
+        n = 5000
+        p = np.zeros((n, 4), dtype=np.float32)
+        # inside, on cell boundaries, on the border cells, and outside the domain
+        p[:, 0] = rng.uniform(-0.1 * lx, 1.1 * lx, n)
+        p[:, 1] = rng.uniform(-0.1 * ly, 1.1 * ly, n)
+        k = n // 4
+        p[:k, 0] = (rng.integers(0, nx + 1, k) * np.float32(g.dx)).astype(np.float32)
+        p[k:2 * k, 1] = (rng.integers(0, ny + 1, k) * np.float32(g.dy)).astype(np.float32)
+        for s in (g, c):
+            s.set_particles(p)
+            s.classify_cells()
+        assert np.array_equal(g.get_cell_types(), c.get_cell_types())
+        # empty particle set: SOLID border, AIR interior
+        for s in (g, c):
+            s.set_particles(np.zeros((0, 4), dtype=np.float32))
+            s.classify_cells()
+        lab = g.get_cell_types()
+        assert np.array_equal(lab, c.get_cell_types())
+        assert (lab[1:-1, 1:-1] == scenes.AIR).all() and (lab[0] == scenes.SOLID).all()
+
+
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_p2g_spread(capi, checkers, nx, ny):
+    rng = np.random.default_rng(2)
+    for chk in checkers:
+        g, c = make_pair(capi, chk, nx, ny)
+        lab, fields, parts = load_state((g, c), rng, nx, ny)
+        # a few particles outside the domain and exactly on grid lines (clamped duplicates)
+        extra = np.array([[-0.01, 0.3, 1, 2], [0.5, -0.02, 3, 4], [nx * g.dx + 0.01, 0.2, 5, 6],
+                          [0.25, ny * g.dy + 0.01, 7, 8], [3 * g.dx, 5 * g.dy, 1, 1],
+                          [0.0, 0.0, 2, 2]], dtype=np.float32)
+        for s in (g, c):
+            s.append_particles(extra)
+            s.p2g_spread()
+        for wf, wb in ((U_FRONT, U_BACK), (V_FRONT, V_BACK)):
+            a, b = g.get_grid(wf), c.get_grid(wf)
+            assert scenes.field_rel_err(a, b) <= SCATTER_TOL
+            # faces that received no weight keep the stale back-buffer value, bit for bit
+            stale = b == fields[wb]
+            assert stale.any() and np.array_equal(a[stale], b[stale])
+            # the old front is now the back buffer, untouched
+            assert np.array_equal(g.get_grid(wb), fields[wf])
+
+
+def test_p2g_is_deterministic_and_order_independent(capi):
+    rng = np.random.default_rng(3)
+    nx = ny = 64
+    lab = scenes.random_labels(nx, ny, rng)
+    g1 = capi.Sim(nx, ny)
+    parts = scenes.particles_in_liquid(lab, g1.dx, rng, 6)
+    out = []
+    for rep in range(3):
+        g = capi.Sim(nx, ny)
+        p = parts if rep < 2 else parts[rng.permutation(parts.shape[0])]
+        g.set_particles(p)
+        g.p2g_spread()
+        out.append((g.get_grid(U_FRONT), g.get_grid(V_FRONT)))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    # a different host order only changes the summation order inside a cell
+    assert scenes.field_rel_err(out[2][0], out[0][0]) <= SCATTER_TOL
+
+
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_grid_stages_bit_exact(capi, checkers, nx, ny):
+    rng = np.random.default_rng(4)
+    for chk in checkers:
+        g, c = make_pair(capi, chk, nx, ny)
+        load_state((g, c), rng, nx, ny, with_particles=False)
+        for s in (g, c):
+            s.save_previous()
+            s.add_acceleration(0.0, float(np.float32(-9.82)), 0.01)
+            s.enforce_dirichlet()
+        assert_grids_equal(g, c, (U_FRONT, V_FRONT, U_BACK, V_BACK, U_PREV, V_PREV))
+        for s in (g, c):
+            s.add_acceleration(1.5, 0.25, 0.003)
+            s.update_diff()
+        assert_grids_equal(g, c, (U_FRONT, V_FRONT, U_DIFF, V_DIFF))
+
+
+@pytest.mark.parametrize("nx,ny", SIZES)
+@pytest.mark.parametrize("n_iter", [0, 1, 2, 3])
+def test_extend_velocity_bit_exact(capi, checkers, nx, ny, n_iter):
+    rng = np.random.default_rng(5 + n_iter)
+    for chk in checkers:
+        g, c = make_pair(capi, chk, nx, ny)
+        load_state((g, c), rng, nx, ny, with_particles=False)
+        for s in (g, c):
+            s.extend_velocity(n_iter)
+        assert_grids_equal(g, c)
+        # twice in a row exercises the mask double-buffer state
+        for s in (g, c):
+            s.extend_velocity(n_iter)
+        assert_grids_equal(g, c)
+
+
+@pytest.mark.parametrize("mode", [G2P_PIC, G2P_FLIP, G2P_PICFLIP])
+@pytest.mark.parametrize("nx,ny", SIZES[:2])
+def test_g2p_and_advect_bit_exact(capi, checkers, nx, ny, mode):
+    rng = np.random.default_rng(6)
+    for chk in checkers:
+        g, c = make_pair(capi, chk, nx, ny)
+        lab, fields, parts = load_state((g, c), rng, nx, ny)
+        outside = np.array([[-0.01, 0.3, 1, 2], [0.5, ny * g.dy + 0.02, 3, 4]], dtype=np.float32)
+        for s in (g, c):
+            s.append_particles(outside)
+            s.g2p(mode, 0.05)
+        assert np.array_equal(g.get_particles(), c.get_particles())
+        for ensure in (True, False):
+            for s in (g, c):
+                s.advect_particles(0.01, ensure)
+            assert np.array_equal(g.get_particles(), c.get_particles())
+
+
+@pytest.mark.parametrize("nx,ny", SIZES[:2])
+def test_advect_particles_grid_bit_exact(capi, checkers, nx, ny):
+    rng = np.random.default_rng(7)
+    for chk in checkers:
+        g, c = make_pair(capi, chk, nx, ny)
+        load_state((g, c), rng, nx, ny)
+        for dt in (0.01, -0.004):
+            for s in (g, c):
+                s.advect_particles_grid(dt)
+            assert np.array_equal(g.get_particles(), c.get_particles())
+
+
+def test_euler_integrator_matches_port(capi, port):
+    rng = np.random.default_rng(8)
+    g, c = make_pair(capi, port, 64, 64)
+    load_state((g, c), rng, 64, 64)
+    g.set_integrator(capi.INTEGRATOR_EULER)
+    port.lib.fso_set_integrator.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    port.lib.fso_set_integrator(c.h, 1)
+    for s in (g, c):
+        s.advect_particles_grid(0.01)
+        s.advect_velocity_sl(0.01)
+    assert np.array_equal(g.get_particles(), c.get_particles())
+    assert scenes.field_rel_err(g.get_grid(U_BACK), c.get_grid(U_BACK)) <= SCATTER_TOL
+
+
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_advect_velocity_sl(capi, checkers, nx, ny):
+    rng = np.random.default_rng(9)
+    for chk in checkers:
+        g, c = make_pair(capi, chk, nx, ny)
+        lab, fields, _ = load_state((g, c), rng, nx, ny, with_particles=False)
+        dt = 0.25 * g.dx  # |u| ~ 1-3 -> back-trace of up to ~1 cell
+        for s in (g, c):
+            s.advect_velocity_sl(dt)
+        # the front buffer is untouched and there is NO swap
+        assert np.array_equal(g.get_grid(U_FRONT), fields[U_FRONT])
+        assert np.array_equal(g.get_grid(V_FRONT), fields[V_FRONT])
+        for w in (U_BACK, V_BACK):
+            assert scenes.field_rel_err(g.get_grid(w), c.get_grid(w)) <= SCATTER_TOL
+
+
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_pressure_solve(capi, checkers, nx, ny):
+    rng = np.random.default_rng(10)
+    for chk in checkers:
+        for max_iters, tol in ((100, float(np.finfo(np.float32).eps)), (5000, 1e-6)):
+            g, c = make_pair(capi, chk, nx, ny)
+            lab, fields, parts = load_state((g, c), rng, nx, ny)
+            for s in (g, c):
+                s.set_cg(max_iters, tol)
+                s.pressure_solve(0.01, 0.01)
+            ig, eg = g.cg_info()
+            ic, ec = c.cg_info()
+            assert abs(ig - ic) <= max(2, 0.1 * ic), (ig, ic)
+            pg, pc = g.get_pressure(), c.get_pressure()
+            denom = np.linalg.norm(pc.astype(np.float64))
+            rel = np.linalg.norm(pg.astype(np.float64) - pc) / denom
+            if ic < max_iters:  # both converged: solutions agree to the solver tolerance x kappa
+                assert rel < 2e-3, rel
+                assert eg < tol and ec < tol
+            else:  # both capped mid-way: same iterate up to fp32 rounding growth
+                assert rel < 5e-2, rel
+            # faces that do not touch a liquid cell keep the old back buffer, bit for bit
+            liq = lab == 0
+            touch = liq.copy()
+            touch[:, 1:] |= liq[:, :-1]
+            touch[1:, :] |= liq[:-1, :]
+            for wf, wb in ((U_FRONT, U_BACK), (V_FRONT, V_BACK)):
+                a = g.get_grid(wf)
+                assert np.array_equal(a[~touch], fields[wb][~touch])
+                assert np.array_equal(g.get_grid(wb), fields[wf])  # swapped
+
+
+def test_pressure_patch_exact_given_same_pressure(capi, port):
+    """With zero divergence-free input (rhs == 0) the solve returns x = 0 in 0 iterations and
+    the patch copies front to back on liquid-touching faces: bit-exact on both sides."""
+    rng = np.random.default_rng(11)
+    g, c = make_pair(capi, port, 48, 48)
+    lab = scenes.random_labels(48, 48, rng)
+    const = np.full((48, 48), 0.5, dtype=np.float32)
+    back = scenes.random_field(48, 48, rng)
+    for s in (g, c):
+        s.set_cell_types(lab)
+        for w in (U_FRONT, V_FRONT):
+            s.set_grid(w, const)
+        for w in (U_BACK, V_BACK):
+            s.set_grid(w, back)
+        s.pressure_solve(0.01, 0.01)
+    assert g.cg_info() == c.cg_info() == (0, 0.0)
+    assert_grids_equal(g, c)
+
+
+def test_pressure_no_liquid_is_a_no_op(capi, port):
+    g, c = make_pair(capi, port, 32, 32)
+    rng = np.random.default_rng(12)
+    f = {w: scenes.random_field(32, 32, rng) for w in (U_FRONT, V_FRONT, U_BACK, V_BACK)}
+    for s in (g, c):
+        for w, a in f.items():
+            s.set_grid(w, a)
+        s.pressure_solve(0.01, 0.01)  # no LIQUID cell: returns before touching anything, no swap
+    assert_grids_equal(g, c)
+    assert np.array_equal(g.get_grid(U_FRONT), f[U_FRONT])
+
+
+@pytest.mark.parametrize("kind", [STEP_PICFLIP, STEP_FLIP, STEP_PIC, STEP_SL])
+def test_full_steps_config0(capi, checkers, kind):
+    """examples/simple.cpp scene (64x64, 7 800 particles, dt 0.01)."""
+    n = 64
+    for chk in checkers:
+        g, c = make_pair(capi, chk, n, n)
+        args = scenes.dam_break_args(n)
+        assert g.emit_source(*args) == c.emit_source(*args) == 7800
+        assert np.array_equal(g.get_particles(), c.get_particles())
+        n_steps = 20
+        for step in range(n_steps):
+            for s in (g, c):
+                s.step(kind, 0.01)
+            lg, lc = g.get_cell_types(), c.get_cell_types()
+            pg, pc = g.get_particles(), c.get_particles()
+            if step < 3:
+                # labels and particle->cell indexing stay bit-exact while the fields agree
+                assert np.array_equal(lg, lc), f"labels differ at step {step}"
+            err = np.abs(pg[:, :2] - pc[:, :2]).max()
+            # positions (same original order!) track the reference; chaos grows slowly
+            assert err < 2e-3 * (step + 1), (step, err)
+            assert abs(int((lg == 0).sum()) - int((lc == 0).sum())) <= 0.02 * (lc == 0).sum() + 2
+
+
+def test_first_step_stage_by_stage_config0(capi, ref):
+    """Buffer-state contract of SURVEY.md A.8 after every stage of the first two PIC/FLIP steps."""
+    n = 64
+    g, c = make_pair(capi, ref, n, n)
+    args = scenes.dam_break_args(n)
+    g.emit_source(*args)
+    c.emit_source(*args)
+    grav = float(np.float32(-9.82))
+    for step in range(2):
+        stages = [
+            ("classify", lambda s: s.classify_cells()),
+            ("p2g", lambda s: s.p2g_spread()),
+            ("prev", lambda s: s.save_previous()),
+            ("gravity", lambda s: s.add_acceleration(0.0, grav, 0.01)),
+            ("dirichlet", lambda s: s.enforce_dirichlet()),
+            ("extend", lambda s: s.extend_velocity(2)),
+            ("pressure", lambda s: s.pressure_solve(0.01, 0.01)),
+            ("dirichlet2", lambda s: s.enforce_dirichlet()),
+            ("diff", lambda s: s.update_diff()),
+            ("g2p", lambda s: s.g2p(G2P_PICFLIP, 0.05)),
+            ("advect", lambda s: s.advect_particles(0.01, True)),
+        ]
+        for name, fn in stages:
+            fn(g)
+            fn(c)
+            assert np.array_equal(g.get_cell_types(), c.get_cell_types()), (step, name)
+            tol = 1e-5 if step == 0 and name in ("classify", "p2g", "prev", "gravity", "dirichlet",
+                                                  "extend") else 5e-3
+            for w in (U_FRONT, V_FRONT, U_BACK, V_BACK, U_PREV, V_PREV):
+                e = scenes.field_rel_err(g.get_grid(w), c.get_grid(w))
+                assert e <= tol, (step, name, w, e)
+            e = np.abs(g.get_particles() - c.get_particles()).max()
+            assert e <= 5e-3, (step, name, e)
+
+
+def test_particle_order_is_the_callers(capi):
+    rng = np.random.default_rng(13)
+    g = capi.Sim(64, 64)
+    lab = scenes.random_labels(64, 64, rng)
+    parts = scenes.particles_in_liquid(lab, g.dx, rng, 3)
+    g.set_particles(parts)
+    g.p2g_spread()  # sorts on the device
+    assert np.array_equal(g.get_particles(), parts)
+    more = parts[:100] + np.float32(0.001)
+    g.append_particles(more)
+    g.p2g_spread()
+    assert np.array_equal(g.get_particles(), np.concatenate([parts, more]))
+
+
+def test_errors(capi):
+    with pytest.raises(RuntimeError):
+        capi.Sim(2, 2)
+    g = capi.Sim(32, 16, 1.0, 1.0)  # dx != dy: the reference's validate() throws in every step
+    with pytest.raises(RuntimeError, match="Memory pool and fluid domain does not match"):
+        g.step(STEP_PICFLIP, 0.01)
+    with pytest.raises(RuntimeError):
+        g.g2p(7)
