@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native PIC/FLIP hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload picflip4096|sl1024|...] [--no-cpu-baseline]
+
+A "step" is one full pass of the hot path (FluidSolver::stepPICFLIP, reference
+src/FluidSolver.cpp:211-251) over the whole grid and particle set.
+
+Workload (N = 1): BASELINE.json configs[2] -- 4096^2 PIC/FLIP (pic_ratio 0.02), 4 particles
+per cell in a 15/16-full tank (6.29e7 particles), swirl initial velocity, dt = 0.01*64/4096,
+density = dt (dt/rho = 1 as in the reference's example), CG run to a 1e-6 relative residual.
+This is the configuration BASELINE.json's north_star quotes its single-GPU target on.
+
+value   cell-updates/s = size_x*size_y*steps / device time, state resident in HBM
+e2e     same metric through the C ABI with HOST buffers: every step uploads the particle set
+        from pinned host memory, runs fsb_step, and downloads the particle set again
+roofline  the CG iteration (k_cg_dir_spmv + k_cg_update), which is >95 % of the step:
+        algorithmic bytes = 45 B x cells per iteration / CUDA-event time of the
+        CG loop on the library's stream / iterations, against MEASURED_PEAKS.json hbm_gbs
+cpu_baseline  the reference's own sources (oracle/_ref) or the C restatement (oracle port) on one
+        host core, bounded sample (see `sample`), reported only
+
+Only the cpu_baseline / --impl reference legs touch oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ALG_BYTES_CG_PER_CELL = 45.0  # bytes per cell per CG iteration
+
+WORKLOADS = {
+    # name: (n, step kind, pic_ratio, cg tol, cg cap, particles per cell side)
+    "picflip4096": dict(n=4096, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
+    "picflip2048": dict(n=2048, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
+    "picflip1024": dict(n=1024, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
+    "sl1024": dict(n=1024, kind="sl", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
+    "picflip256": dict(n=256, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
+}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def tank_particles(n, per_side, seed=1234):
+    import scenes
+    return scenes.tank_particles(n, np.random.default_rng(seed), per_side)
+
+
+def step_kind(mod, name):
+    return {"picflip": mod.STEP_PICFLIP, "sl": mod.STEP_SL, "flip": mod.STEP_FLIP,
+            "pic": mod.STEP_PIC}[name]
+
+
+# --------------------------------------------------------------------------- reference arm --
+def run_cpu_reference(wl, name, steps, warmup, gpu_iters_hint=None):
+    """Times the reference's CPU implementation (one core: the reference is single-threaded,
+    src/FluidSolver.cpp:3,418-420) on a bounded sample of the workload.
+
+    Sample: the same scene at the workload's grid size when that fits a ~30 s budget, else at the
+    largest power-of-two size that does; the step is run stage by stage with the CG capped at
+    `cg_sample_iters` iterations, and the converged-step time is extrapolated as
+    t_non_cg + iterations_to_tol * t_per_iteration with iterations_to_tol taken from the GPU run
+    (or the O(N) law measured at 256^2 when no GPU figure is given).  Labelled as extrapolated."""
+    import oracle_lib as ol
+    import scenes
+    kind_name = "reference" if ol.available("fsr") else "port"
+    lib = ol.OracleLib("fsr" if kind_name == "reference" else "fso")
+    n = wl["n"]
+    budget_cells = 1024 * 1024  # ~20-30 s of single-core work per sampled step
+    n_s = n
+    while n_s * n_s > budget_cells:
+        n_s //= 2
+    dt = np.float32(0.01 * 64.0 / n_s)
+    s = lib.sim(n_s, n_s, 1.0, 1.0, float(dt), wl["pic_ratio"])
+    parts = scenes.tank_particles(n_s, np.random.default_rng(1234), wl["per_side"])
+    s.set_particles(parts)
+    cg_sample_iters = 20
+    s.set_cg(cg_sample_iters, wl["tol"])
+    grav = float(np.float32(-9.82))
+    results = []
+    for it in range(max(1, min(steps, 2)) + min(warmup, 1)):
+        t0 = time.perf_counter()
+        if wl["kind"] == "sl":
+            s.classify_cells(); s.advect_velocity_sl(float(dt)); s.add_acceleration(0.0, grav, float(dt))
+            s.enforce_dirichlet()
+            t1 = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
+            s.enforce_dirichlet(); s.advect_particles_grid(float(dt))
+        else:
+            s.classify_cells(); s.p2g_spread(); s.save_previous()
+            s.add_acceleration(0.0, grav, float(dt)); s.enforce_dirichlet(); s.extend_velocity(2)
+            t1 = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
+            s.enforce_dirichlet(); s.update_diff(); s.g2p(ol.G2P_PICFLIP, wl["pic_ratio"])
+            s.advect_particles(float(dt), True)
+        t3 = time.perf_counter()
+        iters_done = max(1, s.cg_info()[0])
+        results.append((t3 - t0, t2 - t1, iters_done))
+    tot, solve, iters_done = results[-1]
+    # assembly + patch share of the solve: time a zero-iteration solve
+    s.set_cg(0, wl["tol"])
+    t1 = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
+    solve0 = t2 - t1
+    t_iter = max(solve - solve0, 1e-9) / iters_done
+    t_non_cg = tot - solve + solve0
+    scale = (n * n) / float(n_s * n_s)
+    iters_to_tol = gpu_iters_hint if gpu_iters_hint else int(3.2 * n)  # O(N): ~800 at 256^2
+    step_time_full = scale * (t_non_cg + iters_to_tol * t_iter)
+    value = n * n / step_time_full
+    sample = (f"{kind_name} build, 1 thread: one {wl['kind']} step of the tank scene at {n_s}^2 "
+              f"({parts.shape[0]} particles) run stage by stage with CG capped at {cg_sample_iters} "
+              f"iterations: non-CG {t_non_cg:.2f} s, {t_iter * 1e3:.2f} ms per CG iteration; "
+              f"scaled x{scale:.0f} in cells to {n}^2 and extrapolated to {iters_to_tol} CG "
+              f"iterations (time-to-1e-6 is EXTRAPOLATED, not run)")
+    return {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": kind_name,
+            "sample": sample, "host_cores_available": os.cpu_count(),
+            "cg_iters_per_s": (1.0 / (t_iter * scale))}
+
+
+# ------------------------------------------------------------------------------- our arm --
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="picflip4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cg-cap", type=int, default=None, help="override the CG iteration cap (debug)")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.cg_cap is not None:
+        wl["cap"] = args.cg_cap
+    n = wl["n"]
+    t_start = time.perf_counter()
+
+    def log(msg):
+        if args.verbose:
+            print(f"[bench +{time.perf_counter() - t_start:7.2f}s] {msg}", file=sys.stderr, flush=True)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg_name = (f"{n}^2 {wl['kind']} full step, tank scene {wl['per_side']**2} particles/cell, "
+                f"pic_ratio {wl['pic_ratio']}, CG to {wl['tol']:g} relative residual")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        hint = None
+        hp = os.path.join(ROOT, "gpurun_out", "last_gpu_iters.json")
+        if os.path.exists(hp):
+            try:
+                hint = json.load(open(hp)).get(args.workload)
+            except Exception:
+                hint = None
+        cb = run_cpu_reference(wl, args.workload, args.steps, args.warmup, hint)
+        line = {"impl": "reference", "metric": "cell_updates_per_s", "value": cb["value"],
+                "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * n * n / cb["value"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": cfg_name},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from fluid_simulation_b200 import capi
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    dt = float(np.float32(0.01 * 64.0 / n))
+    sim = capi.Sim(n, n, 1.0, 1.0, dt, wl["pic_ratio"], device=local_rank)
+    sim.set_cg(wl["cap"], wl["tol"])
+    parts = tank_particles(n, wl["per_side"])
+    n_part = parts.shape[0]
+    host = torch.empty((n_part, 4), dtype=torch.float32, pin_memory=True)
+    host.numpy()[:] = parts
+    del parts
+    log(f"scene ready: {n_part} particles")
+    sim.set_particles_ptr(host.data_ptr(), n_part)
+    sim.synchronize()
+    log("particles uploaded")
+    kind = step_kind(capi, wl["kind"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        sim.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        sim.step(kind, dt)
+        sim.synchronize()
+        log(f"warm-up step done, cg {sim.cg_info()}")
+    barrier()
+
+    # ---- timed region: K steps, state resident in HBM
+    sim.profile_enable(True)
+    sim.profile_read()
+    launches0 = sim.launch_count()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    iters_total = 0
+    barrier()
+    sim.timer_start()
+    for _ in range(args.steps):
+        sim.step(kind, dt)
+        iters_total += sim.cg_info()[0]
+        log(f"timed step done, cg {sim.cg_info()}")
+    ms = sim.timer_stop()
+    barrier()
+    clock_info = clocks.stop()
+    launches = sim.launch_count() - launches0
+    prof = sim.profile_read()
+    sim.profile_enable(False)
+    relres = sim.cg_info()[1]
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    # N > 1: independent replicas of the single-GPU step (the sharded CG is reported separately)
+    value = world * n * n * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers in and out every step
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sim.set_particles_ptr(host.data_ptr(), n_part)
+            sim.step(kind, dt)
+            sim.get_particles_ptr(host.data_ptr())
+        barrier()
+        t1 = time.perf_counter()
+        et = t1 - t0
+        if world > 1:
+            t = torch.tensor([et], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            et = float(t.item())
+        e2e = {"value": world * n * n * args.steps / et, "unit": "cell-updates/s",
+               "h2d_bytes_per_step": int(n_part * 16), "d2h_bytes_per_step": int(n_part * 16)}
+
+    if rank != 0:
+        return 0
+
+    peak, peak_src = measured_peak_gbs()
+    cg_ms, _ = prof["cg"]
+    it_ms = cg_ms / max(iters_total, 1)
+    achieved = ALG_BYTES_CG_PER_CELL * n * n / (it_ms * 1e-3) / 1e9 if iters_total else 0.0
+    stages = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "kernel": "CG iteration = k_cg_dir_spmv + k_cg_update (2 launches)",
+                "algorithmic_bytes_per_launch_pair": ALG_BYTES_CG_PER_CELL * n * n,
+                "avg_iteration_us": it_ms * 1e3, "peak_source": peak_src,
+                "cg_share_of_step": cg_ms / ms if ms else None}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    try:
+        json.dump({args.workload: int(round(iters_total / args.steps))},
+                  open(os.path.join(ROOT, "gpurun_out", "last_gpu_iters.json"), "w"))
+    except Exception:
+        pass
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = run_cpu_reference(wl, args.workload, 1, 0, int(round(iters_total / args.steps)))
+
+    line = {
+        "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak" if world > 1 else "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg_name, "particles": int(n_part), "dt": dt,
+                   "l2": "inputs larger than L2 (1.0 GB particles, 64 MB per grid)"
+                   if n >= 4096 else "working set may fit L2: latency-bound, see DESIGN.md",
+                   "parallelism": "replicas" if world > 1 else "single GPU"},
+        "cg_iters_per_step": iters_total / args.steps,
+        "cg_iters_per_s": iters_total / (cg_ms * 1e-3) if cg_ms else None,
+        "cg_relres": relres,
+        "stage_ms_per_step": stages,
+        "gpu_launches": int(launches),
+        "clocks": clock_info,
+        "e2e": e2e,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

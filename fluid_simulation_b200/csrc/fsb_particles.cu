@@ -58,8 +58,8 @@ constexpr int kScanTile = kScanBlock * kScanItems;
 
 __device__ __forceinline__ int block_scan_excl(int v, int* total)
 {
-  // exclusive scan of one int per thread over the block
-  __shared__ int s_warp[32];
+  // exclusive scan of one int per thread over the block (blockDim.x a multiple of 32)
+  __shared__ int s_warp[33];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int incl = v;
 #pragma unroll
@@ -68,13 +68,13 @@ __device__ __forceinline__ int block_scan_excl(int v, int* total)
     const int t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  __syncthreads();
+  __syncthreads(); // s_warp may still be read by a previous call
   if (lane == 31) s_warp[wid] = incl;
   __syncthreads();
   if (wid == 0)
   {
     const int nw = blockDim.x >> 5;
-    int w = (lane < nw) ? s_warp[lane] : 0;
+    const int w = (lane < nw) ? s_warp[lane] : 0;
     int wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -82,17 +82,12 @@ __device__ __forceinline__ int block_scan_excl(int v, int* total)
       const int t = __shfl_up_sync(0xffffffffu, wi, o);
       if (lane >= o) wi += t;
     }
-    s_warp[lane] = wi - w; // exclusive warp offsets
-    if (lane == nw - 1) s_warp[31] = (nw == 32) ? wi : wi; // total (overwritten below if nw==32)
+    s_warp[lane] = wi - w;       // exclusive offset of warp `lane`
+    if (lane == 31) s_warp[32] = wi; // block total (lanes >= nw contribute 0)
   }
   __syncthreads();
-  const int off = s_warp[wid];
-  // total = offset of last warp + its inclusive sum: recompute cheaply
-  __shared__ int s_total;
-  if (threadIdx.x == blockDim.x - 1) s_total = off + incl;
-  __syncthreads();
-  *total = s_total;
-  return off + incl - v;
+  *total = s_warp[32];
+  return s_warp[wid] + incl - v;
 }
 
 __global__ void k_scan_reduce(const int* __restrict__ count, int m, int* __restrict__ block_sum)
