@@ -377,12 +377,17 @@ def test_large_grid_sort_and_p2g(capi, port):
     for w in (U_FRONT, V_FRONT):
         assert scenes.field_rel_err(g.get_grid(w), c.get_grid(w)) <= SCATTER_TOL
     assert np.array_equal(g.get_particles(), p)
-    # second sort from the already-sorted device order (the per-step path)
+    # second sort from the already-sorted device order (the per-step path).  Give both sides the
+    # SAME grid first: at this size one ulp of a particle position is 1.4e-4 of a cell, so
+    # 1e-7-level velocity differences inherited from the first P2G would be amplified to 1e-4 in
+    # the bilinear weights (the reference has the same conditioning; it is not a GPU effect).
+    for w in (U_FRONT, V_FRONT):
+        c.set_grid(w, g.get_grid(w))
     for s in (g, c):
         s.g2p(G2P_PIC)
         s.advect_particles(0.3 * g.dx, True)
+    assert np.array_equal(g.get_particles(), c.get_particles())  # gathers: bit-exact
+    for s in (g, c):
         s.p2g_spread()
-    # the gathered velocities inherit the 1e-7-level P2G summation-order differences
-    assert scenes.field_rel_err(g.get_particles(), c.get_particles()) <= SCATTER_TOL
     for w in (U_FRONT, V_FRONT):
-        assert scenes.field_rel_err(g.get_grid(w), c.get_grid(w)) <= 2 * SCATTER_TOL
+        assert scenes.field_rel_err(g.get_grid(w), c.get_grid(w)) <= SCATTER_TOL
