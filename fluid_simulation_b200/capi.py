@@ -48,6 +48,9 @@ SIGNATURES = {
     "fsb_set_density": (_i, [_p, _f]),
     "fsb_set_integrator": (_i, [_p, _i]),
     "fsb_set_gravity": (_i, [_p, _f, _f]),
+    "fsb_set_pool": (_i, [_p, _i, _i, _f, _f]),
+    "fsb_clear_cell_types": (_i, [_p]),
+    "fsb_swap_velocity_buffers": (_i, [_p]),
     "fsb_set_particles": (_i, [_p, _p, _l]),
     "fsb_append_particles": (_i, [_p, _p, _l]),
     "fsb_num_particles": (_l, [_p]),
@@ -139,6 +142,15 @@ class Sim:
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(_lib.fsb_set_stream(self.h, _p(cuda_stream_ptr)))
+
+    def set_pool(self, nx, ny, dx, dy):
+        self._ck(_lib.fsb_set_pool(self.h, nx, ny, dx, dy))
+
+    def clear_cell_types(self):
+        self._ck(_lib.fsb_clear_cell_types(self.h))
+
+    def swap_velocity_buffers(self):
+        self._ck(_lib.fsb_swap_velocity_buffers(self.h))
 
     def synchronize(self):
         self._ck(_lib.fsb_synchronize(self.h))

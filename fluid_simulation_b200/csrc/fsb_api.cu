@@ -228,6 +228,8 @@ int fsb_create(fsb_ctx** out, int size_x, int size_y, float length_x, float leng
   c->dy = length_y / size_y;
   c->pool_dx = c->dx; // src/FluidSolver.cpp:56-65: the solver's pool copy passes deltaX twice
   c->pool_dy = c->dx;
+  c->pool_nx = size_x;
+  c->pool_ny = size_y;
   c->density = density;
   c->pic_ratio = pic_ratio;
   c->grav_x = 0.0f;
@@ -264,16 +266,17 @@ int fsb_create(fsb_ctx** out, int size_x, int size_y, float length_x, float leng
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cg_r, cells);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cg_p[0], cells);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cg_p[1], cells);
-  if (rc == FSB_OK) rc = dev_alloc(c, &c->cg_q, cells);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cg_code, cells);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cell_start, (size_t)size_x * size_y + 1);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cell_count, (size_t)size_x * size_y);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->scan_block, (size_t)size_x * size_y / 4096 + 2);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->scal, 1);
   if (rc != FSB_OK) return fail(rc);
-  if (cudaMallocHost((void**)&c->scal_h, sizeof(CgScalars)) != cudaSuccess)
+  if (cudaMallocHost((void**)&c->scal_h, 2 * sizeof(CgScalars)) != cudaSuccess)
     return fail(fsb_fail(c, FSB_ERR_NOMEM, "cudaMallocHost failed"));
-  memset(c->scal_h, 0, sizeof(CgScalars));
+  memset(c->scal_h, 0, 2 * sizeof(CgScalars));
+  cudaEventCreateWithFlags(&c->cg_ev[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->cg_ev[1], cudaEventDisableTiming);
   // labels: pad columns SOLID, then the constructor's clearCellTypeBuffer (src/MacGrid.cpp:24)
   k_fill_u8<<<fsb_div_up((int64_t)cells, 256), 256, 0, c->stream>>>(c->cell, FSB_SOLID,
                                                                     (int64_t)cells);
@@ -299,11 +302,14 @@ void fsb_destroy(fsb_ctx* c)
     cudaFree(c->part[k]); cudaFree(c->orig[k]);
   }
   cudaFree(c->u_prev); cudaFree(c->v_prev); cudaFree(c->u_diff); cudaFree(c->v_diff);
-  cudaFree(c->cell); cudaFree(c->cg_x); cudaFree(c->cg_r); cudaFree(c->cg_p[0]); cudaFree(c->cg_p[1]); cudaFree(c->cg_q);
+  cudaFree(c->cell); cudaFree(c->cg_x); cudaFree(c->cg_r); cudaFree(c->cg_p[0]); cudaFree(c->cg_p[1]);
   cudaFree(c->cg_code); cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->scan_block);
   cudaFree(c->sort_key); cudaFree(c->sort_rank); cudaFree(c->sort_idx);
   cudaFree(c->partials); cudaFree(c->scal); cudaFree(c->stage);
   if (c->scal_h) cudaFreeHost(c->scal_h);
+  if (c->cg_graph) cudaGraphExecDestroy(c->cg_graph);
+  if (c->cg_ev[0]) cudaEventDestroy(c->cg_ev[0]);
+  if (c->cg_ev[1]) cudaEventDestroy(c->cg_ev[1]);
   if (c->timer_ev[0]) cudaEventDestroy(c->timer_ev[0]);
   if (c->timer_ev[1]) cudaEventDestroy(c->timer_ev[1]);
   if (c->prof_made)
@@ -371,6 +377,15 @@ int fsb_set_integrator(fsb_ctx* c, int integrator)
   if (integrator != FSB_INTEGRATOR_RK3 && integrator != FSB_INTEGRATOR_EULER)
     return fsb_fail(c, FSB_ERR_INVALID, "unknown integrator %d", integrator);
   c->integrator = integrator;
+  return FSB_OK;
+}
+int fsb_set_pool(fsb_ctx* c, int size_x, int size_y, float delta_x, float delta_y)
+{
+  CHECK_CTX(c);
+  c->pool_nx = size_x;
+  c->pool_ny = size_y;
+  c->pool_dx = delta_x;
+  c->pool_dy = delta_y;
   return FSB_OK;
 }
 int fsb_set_gravity(fsb_ctx* c, float ax, float ay)
@@ -509,7 +524,8 @@ static int square_cells(fsb_ctx* c)
 {
   // the particle-to-grid gather window assumes the reference's own validity
   // condition (src/FluidSolver.cpp:89-97)
-  if (!(std::fabs(c->dx - c->pool_dx) < 0.0000001 && std::fabs(c->dy - c->pool_dy) < 0.0000001))
+  if (!(c->nx == c->pool_nx && c->ny == c->pool_ny && std::fabs(c->dx - c->pool_dx) < 0.0000001 &&
+        std::fabs(c->dy - c->pool_dy) < 0.0000001))
     return fsb_fail(c, FSB_ERR_INVALID,
                     "Memory pool and fluid domain does not match. Initialize the fluid solver "
                     "with a memory pool corresponding to the right fluid domain!");
@@ -520,6 +536,18 @@ int fsb_classify_cells(fsb_ctx* c)
 {
   CHECK_CTX(c);
   return fsb_k_classify(c);
+}
+int fsb_clear_cell_types(fsb_ctx* c)
+{
+  CHECK_CTX(c);
+  return fsb_k_clear_labels(c);
+}
+int fsb_swap_velocity_buffers(fsb_ctx* c)
+{
+  CHECK_CTX(c);
+  FSB_TRY(flush_diff(c));
+  c->front ^= 1;
+  return FSB_OK;
 }
 int fsb_p2g_spread(fsb_ctx* c)
 {

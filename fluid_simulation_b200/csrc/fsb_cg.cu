@@ -10,19 +10,23 @@
 // sum, so the operator needs no neighbour bits.
 //
 // One CG iteration = two kernels (Eigen's statement order is kept):
-//   k_cg_dir_spmv : p = z + beta p (z = invdiag r; p = z on the first pass),
-//                   q = A p computed from p in registers (3-row sliding window),
-//                   partial p.q           -> 9 B read + 8 B written per cell
-//   k_cg_update   : alpha = absNew / p.q; x += alpha p; r -= alpha q;
-//                   partial |r|^2 and r.z -> 17 B read + 8 B written per cell
-// The last block to finish each kernel folds the per-block partials in a fixed
-// order (deterministic) and advances the device-resident scalars, so there is
-// no host round trip inside the loop; the host polls `done` every
-// kCheckEvery iterations.  Once `done` is set every later launch returns
-// immediately, so x and the iteration count are exactly those of the
+//   k_cg_direction : p = z + beta p (z = invdiag r; p = z on the first pass) on a
+//                    tile and its halo, q = A p in registers, partial p.q
+//                    -> 9 B read + 4 B written per cell (q is never stored)
+//   k_cg_update    : alpha = absNew / p.q; q = A p recomputed from the staged
+//                    p tile; x += alpha p; r -= alpha q; partial |r|^2, r.z
+//                    -> 13 B read + 8 B written per cell
+// 34 B of HBM traffic per cell and iteration against the 45 B of the textbook
+// formulation.  The last block to finish each kernel folds the
+// per-block partials in a fixed order (deterministic) and advances the
+// device-resident scalars, so there is no host round trip inside the loop;
+// the loop is a CUDA graph of kCheckEvery iterations and the host polls
+// `done` one chunk behind the GPU.  Once `done` is set every later launch
+// returns immediately, so x and the iteration count are exactly those of the
 // converging iteration.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "fsb_device.cuh"
 #include "fsb_internal.cuh"
@@ -133,140 +137,212 @@ __global__ void k_cg_build(const float* __restrict__ uf, const float* __restrict
   }
 }
 
-// --------------------------------------------------- direction + product --
-// Strip-marching stencil: each thread owns 4 consecutive columns and walks
-// down kRows rows keeping the new search direction of three rows in registers,
-// so p and r are read once per band (plus two halo rows) and q never needs p
-// from memory.  West/east neighbours come from the adjacent lanes; the two
-// edge lanes of a warp recompute their outer neighbour from r, p and code.
-// The old direction is read from `p` and the new one written to `p_out`
-// (ping-pong): halo rows and edge columns belong to other blocks, which may
-// already have produced their new values.
-constexpr int kSpmvThreads = 128;
-constexpr int kRows = 32;
+// ------------------------------------------------------------ tile frame --
+// Both iteration kernels work on tiles of kTileW columns x TH rows.  A CTA of
+// 256 threads = 8 warps; lane l owns the four columns 4l..4l+3 of the tile
+// (one 16-byte access per row), warp w owns rows w, w+8, ... of the tile.
+// The search direction of the tile and of its one-cell halo is staged in
+// shared memory (row pitch kPitch floats, interior starts at word 4 so the
+// float4 stores stay 16-byte aligned); north/south neighbours are read from
+// there, west/east neighbours come from the adjacent lanes (shuffle) and from
+// the halo columns for lanes 0 and 31.  CTAs walk the tile list with a grid
+// stride, so the number of per-CTA partial sums is bounded by the grid size.
+constexpr int kTileW = 128;
+constexpr int kPitch = kTileW + 8;
+constexpr int kCgThreads = 256;
+constexpr int kCgWarps = kCgThreads / 32;
 
-struct Row4
+// Per-cell coefficients come from a 2 x 8 shared-memory table indexed by the
+// stencil code (0 = not liquid -> coefficient 0, 1 + n -> n non-SOLID
+// neighbours): [0][code] = Jacobi inverse diagonal, [1][code] = diagonal.  A
+// dynamically indexed kernel-parameter array would compile to indexed LDC,
+// which issues on the slow XU pipe (measured: 78 % XU-bound, profiles/r01b).
+struct CgLut
 {
-  float4 p; // new direction
-  float w, e; // west neighbour of p.x, east neighbour of p.w
-  uint32_t code;
+  float inv[8];
+  float diag[8];
 };
 
-__device__ __forceinline__ float dir_value(float r, float p_old, uint32_t cd, const CgCoef& coef,
+__device__ __forceinline__ void load_lut(CgLut* lut, const CgCoef& coef)
+{
+  if (threadIdx.x < 8)
+  {
+    const int t = threadIdx.x;
+    float iv = 0.0f, dg = 0.0f;
+    if (t >= 1 && t <= 5)
+    {
+      iv = coef.invdiag[t - 1];
+      dg = coef.diag[t - 1];
+    }
+    lut->inv[t] = iv;
+    lut->diag[t] = dg;
+  }
+}
+
+// r and p_old are exactly zero on non-liquid cells and inv[0] = 0, so the
+// result is exactly zero there without a branch.
+__device__ __forceinline__ float dir_value(float r, float p_old, uint32_t cd, const CgLut* lut,
                                            float beta, bool first)
 {
-  if (cd == 0) return 0.0f;
-  const float z = coef.invdiag[cd - 1] * r;
+  const float z = lut->inv[cd] * r;
   return first ? z : z + beta * p_old;
 }
 
-__device__ __forceinline__ void load_row(Row4& row, const float* __restrict__ r,
-                                         const float* __restrict__ p,
-                                         const uint8_t* __restrict__ code, int ci, int jj, int ld,
-                                         int ny, const CgCoef& coef, float beta, bool first,
-                                         unsigned lane)
+__device__ __forceinline__ float4 dir_value4(const float4 r4, const float4 p4, uint32_t c4,
+                                             const CgLut* lut, float beta, bool first)
 {
-  row.p = make_float4(0.f, 0.f, 0.f, 0.f);
-  row.w = 0.f;
-  row.e = 0.f;
-  row.code = 0;
-  const bool row_ok = (jj >= 0 && jj < ny);
-  const bool col_ok = ci < ld;
-  float edge = 0.0f;
-  if (row_ok)
-  {
-    const size_t base = (size_t)jj * ld;
-    if (col_ok)
-    {
-      const float4 r4 = *reinterpret_cast<const float4*>(r + base + ci);
-      float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!first) p4 = *reinterpret_cast<const float4*>(p + base + ci);
-      const uint32_t c4 = *reinterpret_cast<const uint32_t*>(code + base + ci);
-      row.code = c4;
-      row.p.x = dir_value(r4.x, p4.x, c4 & 0xff, coef, beta, first);
-      row.p.y = dir_value(r4.y, p4.y, (c4 >> 8) & 0xff, coef, beta, first);
-      row.p.z = dir_value(r4.z, p4.z, (c4 >> 16) & 0xff, coef, beta, first);
-      row.p.w = dir_value(r4.w, p4.w, (c4 >> 24) & 0xff, coef, beta, first);
-    }
-    // outer neighbour of the warp's 128-column span: lane 0 -> column ci-1,
-    // lane 31 -> column ci+4
-    if (lane == 0 || lane == 31)
-    {
-      const int ce = (lane == 0) ? ci - 1 : ci + 4;
-      if (ce >= 0 && ce < ld)
-      {
-        const uint32_t cd = code[base + ce];
-        if (cd) edge = dir_value(r[base + ce], first ? 0.0f : p[base + ce], cd, coef, beta, first);
-      }
-    }
-  }
-  float w = __shfl_up_sync(0xffffffffu, row.p.w, 1);
-  float e = __shfl_down_sync(0xffffffffu, row.p.x, 1);
-  if (lane == 0) w = edge;
-  if (lane == 31) e = edge;
-  row.w = w;
-  row.e = e;
+  float4 o;
+  o.x = dir_value(r4.x, p4.x, c4 & 0xff, lut, beta, first);
+  o.y = dir_value(r4.y, p4.y, (c4 >> 8) & 0xff, lut, beta, first);
+  o.z = dir_value(r4.z, p4.z, (c4 >> 16) & 0xff, lut, beta, first);
+  o.w = dir_value(r4.w, p4.w, c4 >> 24, lut, beta, first);
+  return o;
 }
 
 __device__ __forceinline__ float apply_a(float c, float w, float e, float s, float n, uint32_t cd,
-                                         const CgCoef& coef)
+                                         float off, const CgLut* lut)
 {
-  if (cd == 0) return 0.0f;
   // each coefficient multiplies its own operand, as a sparse product does
-  float acc = coef.off * w;
-  acc += coef.off * e;
-  acc += coef.off * s;
-  acc += coef.off * n;
-  acc += coef.diag[cd - 1] * c;
-  return acc;
+  float acc = off * w;
+  acc += off * e;
+  acc += off * s;
+  acc += off * n;
+  acc += lut->diag[cd] * c;
+  return cd ? acc : 0.0f;
 }
 
-__global__ void __launch_bounds__(kSpmvThreads)
-k_cg_dir_spmv(const float* __restrict__ p, float* __restrict__ p_out, float* __restrict__ q,
-              const float* __restrict__ r, const uint8_t* __restrict__ code, int ld, int ny,
-              const CgCoef coef, CgScalars* __restrict__ s, double* __restrict__ partials)
+// q = A p for the four cells of one lane in tile row `tr` (0-based inside the
+// tile); `pc` is the lane's own direction, sp the staged tile.
+__device__ __forceinline__ float4 apply_a4(const float* __restrict__ sp, int tr, unsigned lane,
+                                           const float4 pc, uint32_t c4, float off,
+                                           const CgLut* lut)
+{
+  const float* row = sp + (tr + 1) * kPitch + 4 + lane * 4;
+  const float4 s4 = *reinterpret_cast<const float4*>(row - kPitch);
+  const float4 n4 = *reinterpret_cast<const float4*>(row + kPitch);
+  float w = __shfl_up_sync(0xffffffffu, pc.w, 1);
+  float e = __shfl_down_sync(0xffffffffu, pc.x, 1);
+  if (lane == 0) w = row[-1];
+  if (lane == 31) e = row[4];
+  float4 q;
+  q.x = apply_a(pc.x, w, pc.y, s4.x, n4.x, c4 & 0xff, off, lut);
+  q.y = apply_a(pc.y, pc.x, pc.z, s4.y, n4.y, (c4 >> 8) & 0xff, off, lut);
+  q.z = apply_a(pc.z, pc.y, pc.w, s4.z, n4.z, (c4 >> 16) & 0xff, off, lut);
+  q.w = apply_a(pc.w, pc.z, e, s4.w, n4.w, c4 >> 24, off, lut);
+  return q;
+}
+
+// ------------------------------------------------- direction + p.Ap dot --
+// p_new = z + beta p_old on the tile and its halo (the halo is RE-COMPUTED
+// from r, p_old and code, so no other CTA's output is needed and p_new can be
+// produced and consumed in the same kernel); q = A p_new stays in registers
+// and only feeds the dot product.  13 B of HBM traffic per cell: r, p_old,
+// code in, p_new out (ping-pong with p_old because neighbours still need the
+// old halo).
+template <int TH>
+__global__ void __launch_bounds__(kCgThreads, 4)
+k_cg_direction(const float* __restrict__ p_old, float* __restrict__ p_new,
+               const float* __restrict__ r, const uint8_t* __restrict__ code, int ld, int ny,
+               int tiles_x, int n_tiles, const CgCoef coef, CgScalars* __restrict__ s,
+               double* __restrict__ partials)
 {
   if (s->done) return;
+  __shared__ __align__(16) float sp[(TH + 2) * kPitch];
+  __shared__ CgLut lut;
+  load_lut(&lut, coef);
+  __syncthreads();
+  const float off = coef.off;
+  constexpr int RPW = TH / kCgWarps; // rows per warp
   const bool first = (s->iter == 0);
   const float beta = s->beta;
-  const unsigned lane = threadIdx.x & 31;
-  const int ci = (blockIdx.x * kSpmvThreads + threadIdx.x) * 4;
-  const int j0 = blockIdx.y * kRows;
-  const int j1 = min(j0 + kRows, ny);
-  const bool col_ok = ci < ld;
-
-  Row4 a, b, c; // rows jj-2, jj-1, jj
-  load_row(a, r, p, code, ci, j0 - 1, ld, ny, coef, beta, first, lane);
-  load_row(b, r, p, code, ci, j0, ld, ny, coef, beta, first, lane);
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   double acc = 0.0;
-  for (int jj = j0 + 1; jj <= j1; ++jj)
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
   {
-    load_row(c, r, p, code, ci, jj, ld, ny, coef, beta, first, lane);
-    // finish row jj-1 (= b): its south is a, its north is c
-    if (col_ok)
+    const int c0 = (tile % tiles_x) * kTileW;
+    const int j0 = (tile / tiles_x) * TH;
+    const int ci = c0 + (int)lane * 4;
+    const bool col_ok = ci < ld;
+    float4 pn[RPW];
+    uint32_t cd[RPW];
+    // owned rows
+#pragma unroll
+    for (int k = 0; k < RPW; ++k)
     {
-      const size_t o = (size_t)(jj - 1) * ld + ci;
-      float4 qv;
-      qv.x = apply_a(b.p.x, b.w, b.p.y, a.p.x, c.p.x, b.code & 0xff, coef);
-      qv.y = apply_a(b.p.y, b.p.x, b.p.z, a.p.y, c.p.y, (b.code >> 8) & 0xff, coef);
-      qv.z = apply_a(b.p.z, b.p.y, b.p.w, a.p.z, c.p.z, (b.code >> 16) & 0xff, coef);
-      qv.w = apply_a(b.p.w, b.p.z, b.e, a.p.w, c.p.w, (b.code >> 24) & 0xff, coef);
-      *reinterpret_cast<float4*>(p_out + o) = b.p;
-      *reinterpret_cast<float4*>(q + o) = qv;
-      acc += (double)b.p.x * (double)qv.x + (double)b.p.y * (double)qv.y +
-             (double)b.p.z * (double)qv.z + (double)b.p.w * (double)qv.w;
+      const int tr = (int)warp + k * kCgWarps;
+      const int j = j0 + tr;
+      pn[k] = zero4;
+      cd[k] = 0;
+      if (col_ok && j < ny)
+      {
+        const size_t o = (size_t)j * ld + ci;
+        const uint32_t c4 = *reinterpret_cast<const uint32_t*>(code + o);
+        const float4 r4 = *reinterpret_cast<const float4*>(r + o);
+        float4 p4 = zero4;
+        if (!first) p4 = *reinterpret_cast<const float4*>(p_old + o);
+        cd[k] = c4;
+        pn[k] = dir_value4(r4, p4, c4, &lut, beta, first);
+      }
+      *reinterpret_cast<float4*>(sp + (tr + 1) * kPitch + 4 + lane * 4) = pn[k];
     }
-    a = b;
-    b = c;
+    // halo rows j0-1 (warp 0) and j0+TH (warp 1)
+    if (warp < 2)
+    {
+      const int j = (warp == 0) ? j0 - 1 : j0 + TH;
+      float4 h = zero4;
+      if (col_ok && j >= 0 && j < ny)
+      {
+        const size_t o = (size_t)j * ld + ci;
+        const uint32_t c4 = *reinterpret_cast<const uint32_t*>(code + o);
+        if (c4)
+        {
+          const float4 r4 = *reinterpret_cast<const float4*>(r + o);
+          float4 p4 = zero4;
+          if (!first) p4 = *reinterpret_cast<const float4*>(p_old + o);
+          h = dir_value4(r4, p4, c4, &lut, beta, first);
+        }
+      }
+      *reinterpret_cast<float4*>(sp + ((warp == 0) ? 0 : (TH + 1)) * kPitch + 4 + lane * 4) = h;
+    }
+    // halo columns c0-1 and c0+kTileW of the TH tile rows: threads 64 .. 64+2*TH-1
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * TH)
+    {
+      const int t = threadIdx.x - 64;
+      const int tr = t >> 1, side = t & 1;
+      const int j = j0 + tr;
+      const int cc = side ? c0 + kTileW : c0 - 1;
+      float h = 0.0f;
+      if (j < ny && cc >= 0 && cc < ld)
+      {
+        const size_t o = (size_t)j * ld + cc;
+        const uint32_t c1 = code[o];
+        if (c1) h = dir_value(r[o], first ? 0.0f : p_old[o], c1, &lut, beta, first);
+      }
+      sp[(tr + 1) * kPitch + (side ? 4 + kTileW : 3)] = h;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RPW; ++k)
+    {
+      const int tr = (int)warp + k * kCgWarps;
+      const int j = j0 + tr;
+      const float4 q = apply_a4(sp, tr, lane, pn[k], cd[k], off, &lut);
+      if (col_ok && j < ny)
+      {
+        *reinterpret_cast<float4*>(p_new + (size_t)j * ld + ci) = pn[k];
+        acc += (double)((pn[k].x * q.x + pn[k].y * q.y) + (pn[k].z * q.z + pn[k].w * q.w));
+      }
+    }
+    __syncthreads(); // the tile buffer is reused
   }
 
-  const unsigned int nblocks = gridDim.x * gridDim.y;
-  const unsigned int bid = blockIdx.y * gridDim.x + blockIdx.x;
   const double tot = block_sum(acc);
-  if (threadIdx.x == 0) partials[bid] = tot;
-  if (last_block_done(&s->ticket[1], nblocks))
+  if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+  if (last_block_done(&s->ticket[1], gridDim.x))
   {
-    const double pq = fold_partials(partials, (int)nblocks);
+    const double pq = fold_partials(partials, (int)gridDim.x);
     if (threadIdx.x == 0)
     {
       s->pq = pq;
@@ -276,39 +352,103 @@ k_cg_dir_spmv(const float* __restrict__ p, float* __restrict__ p_out, float* __r
 }
 
 // ------------------------------------------------------------ the update --
-constexpr int kUpdThreads = 256;
-
-__global__ void __launch_bounds__(kUpdThreads)
+// alpha = absNew / p.Ap; x += alpha p; r -= alpha A p with A p RE-COMPUTED
+// from the staged p tile (q is never stored); partial |r|^2 and r.z.
+// 21 B of HBM traffic per cell: p, code, x, r in; x, r out.
+template <int TH>
+__global__ void __launch_bounds__(kCgThreads, TH >= 32 ? 3 : 4)
 k_cg_update(float* __restrict__ x, float* __restrict__ r, const float* __restrict__ p,
-            const float* __restrict__ q, const uint8_t* __restrict__ code, int64_t n4,
+            const uint8_t* __restrict__ code, int ld, int ny, int tiles_x, int n_tiles,
             const CgCoef coef, CgScalars* __restrict__ s, double* __restrict__ partials)
 {
   if (s->done) return;
+  __shared__ __align__(16) float sp[(TH + 2) * kPitch];
+  __shared__ CgLut lut;
+  load_lut(&lut, coef);
+  __syncthreads();
+  const float off = coef.off;
+  constexpr int RPW = TH / kCgWarps;
   const float alpha = s->abs_new / (float)s->pq; // Eigen: alpha = absNew / p.dot(tmp)
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   double acc_r2 = 0.0, acc_rz = 0.0;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4;
-       t += (int64_t)gridDim.x * blockDim.x)
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
   {
-    const uint32_t c4 = reinterpret_cast<const uint32_t*>(code)[t];
-    if (c4 == 0) continue; // four non-liquid cells: x, r stay exactly zero
-    float4 xv = reinterpret_cast<float4*>(x)[t];
-    float4 rv = reinterpret_cast<float4*>(r)[t];
-    const float4 pv = reinterpret_cast<const float4*>(p)[t];
-    const float4 qv = reinterpret_cast<const float4*>(q)[t];
-    xv.x = xv.x + alpha * pv.x; rv.x = rv.x - alpha * qv.x;
-    xv.y = xv.y + alpha * pv.y; rv.y = rv.y - alpha * qv.y;
-    xv.z = xv.z + alpha * pv.z; rv.z = rv.z - alpha * qv.z;
-    xv.w = xv.w + alpha * pv.w; rv.w = rv.w - alpha * qv.w;
-    reinterpret_cast<float4*>(x)[t] = xv;
-    reinterpret_cast<float4*>(r)[t] = rv;
-    const uint32_t c0 = c4 & 0xff, c1 = (c4 >> 8) & 0xff, c2 = (c4 >> 16) & 0xff, c3 = c4 >> 24;
-    const float z0 = c0 ? coef.invdiag[c0 - 1] * rv.x : 0.0f;
-    const float z1 = c1 ? coef.invdiag[c1 - 1] * rv.y : 0.0f;
-    const float z2 = c2 ? coef.invdiag[c2 - 1] * rv.z : 0.0f;
-    const float z3 = c3 ? coef.invdiag[c3 - 1] * rv.w : 0.0f;
-    acc_r2 += (double)rv.x * rv.x + (double)rv.y * rv.y + (double)rv.z * rv.z + (double)rv.w * rv.w;
-    acc_rz += (double)rv.x * z0 + (double)rv.y * z1 + (double)rv.z * z2 + (double)rv.w * z3;
+    const int c0 = (tile % tiles_x) * kTileW;
+    const int j0 = (tile / tiles_x) * TH;
+    const int ci = c0 + (int)lane * 4;
+    const bool col_ok = ci < ld;
+    float4 pc[RPW], xv[RPW], rv[RPW];
+    uint32_t cd[RPW];
+#pragma unroll
+    for (int k = 0; k < RPW; ++k)
+    {
+      const int tr = (int)warp + k * kCgWarps;
+      const int j = j0 + tr;
+      pc[k] = zero4;
+      xv[k] = zero4;
+      rv[k] = zero4;
+      cd[k] = 0;
+      if (col_ok && j < ny)
+      {
+        const size_t o = (size_t)j * ld + ci;
+        cd[k] = *reinterpret_cast<const uint32_t*>(code + o);
+        pc[k] = *reinterpret_cast<const float4*>(p + o);
+        if (cd[k])
+        {
+          xv[k] = *reinterpret_cast<const float4*>(x + o);
+          rv[k] = *reinterpret_cast<const float4*>(r + o);
+        }
+      }
+      *reinterpret_cast<float4*>(sp + (tr + 1) * kPitch + 4 + lane * 4) = pc[k];
+    }
+    if (warp < 2)
+    {
+      const int j = (warp == 0) ? j0 - 1 : j0 + TH;
+      float4 h = zero4;
+      if (col_ok && j >= 0 && j < ny) h = *reinterpret_cast<const float4*>(p + (size_t)j * ld + ci);
+      *reinterpret_cast<float4*>(sp + ((warp == 0) ? 0 : (TH + 1)) * kPitch + 4 + lane * 4) = h;
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * TH)
+    {
+      const int t = threadIdx.x - 64;
+      const int tr = t >> 1, side = t & 1;
+      const int j = j0 + tr;
+      const int cc = side ? c0 + kTileW : c0 - 1;
+      float h = 0.0f;
+      if (j < ny && cc >= 0 && cc < ld) h = p[(size_t)j * ld + cc];
+      sp[(tr + 1) * kPitch + (side ? 4 + kTileW : 3)] = h;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RPW; ++k)
+    {
+      const int tr = (int)warp + k * kCgWarps;
+      const int j = j0 + tr;
+      const uint32_t c4 = cd[k];
+      const float4 q = apply_a4(sp, tr, lane, pc[k], c4, off, &lut); // shuffles: whole warp takes part
+      if (c4 != 0 && col_ok && j < ny) // four non-liquid cells: x, r stay exactly zero
+      {
+        float4 xo = xv[k], ro = rv[k];
+        xo.x = xo.x + alpha * pc[k].x; ro.x = ro.x - alpha * q.x;
+        xo.y = xo.y + alpha * pc[k].y; ro.y = ro.y - alpha * q.y;
+        xo.z = xo.z + alpha * pc[k].z; ro.z = ro.z - alpha * q.z;
+        xo.w = xo.w + alpha * pc[k].w; ro.w = ro.w - alpha * q.w;
+        const size_t o = (size_t)j * ld + ci;
+        *reinterpret_cast<float4*>(x + o) = xo;
+        *reinterpret_cast<float4*>(r + o) = ro;
+        const float z0 = lut.inv[c4 & 0xff] * ro.x;
+        const float z1 = lut.inv[(c4 >> 8) & 0xff] * ro.y;
+        const float z2 = lut.inv[(c4 >> 16) & 0xff] * ro.z;
+        const float z3 = lut.inv[c4 >> 24] * ro.w;
+        acc_r2 += (double)((ro.x * ro.x + ro.y * ro.y) + (ro.z * ro.z + ro.w * ro.w));
+        acc_rz += (double)((ro.x * z0 + ro.y * z1) + (ro.z * z2 + ro.w * z3));
+      }
+    }
+    __syncthreads();
   }
+
   const double r2 = block_sum(acc_r2);
   const double rz = block_sum(acc_rz);
   if (threadIdx.x == 0)
@@ -371,9 +511,10 @@ __global__ void k_pressure_patch(const float* __restrict__ uf, const float* __re
 
 } // namespace
 
-int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
+namespace {
+
+CgCoef make_coef(const fsb_ctx* c)
 {
-  const GridDims d{c->nx, c->ny, c->ld, c->dx, c->dy};
   CgCoef coef;
   const double dx2 = std::pow((double)c->dx, 2);
   coef.off = (float)(1 / dx2);
@@ -382,16 +523,120 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
     coef.diag[n] = (float)(-n / dx2);
     coef.invdiag[n] = (coef.diag[n] != 0.0f) ? 1.0f / coef.diag[n] : 1.0f;
   }
+  return coef;
+}
+
+// Tile height: the tallest of 32/16/8 rows that still gives every SM several tiles.
+int pick_tile_rows(const fsb_ctx* c)
+{
+  if (const char* e = getenv("FSB_CG_TILE_ROWS")) // tuning knob for profiling runs
+  {
+    const int th = atoi(e);
+    if (th == 8 || th == 16 || th == 32) return th;
+  }
+  const int tiles_x = fsb_div_up(c->ld, kTileW);
+  for (int th = 32; th > 8; th >>= 1)
+    if ((int64_t)tiles_x * fsb_div_up(c->ny, th) >= (int64_t)4 * c->sm_count) return th;
+  return 8;
+}
+
+// persistent-style grids: exactly the CTAs that are co-resident (one wave), each walking the
+// tile list with a grid stride
+template <int TH>
+void resident_grids(fsb_ctx* c, int64_t n_tiles)
+{
+  int occ_dir = 4, occ_upd = 3;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dir, k_cg_direction<TH>, kCgThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, k_cg_update<TH>, kCgThreads, 0);
+  c->cg_grid_dir = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count * std::max(occ_dir, 1));
+  c->cg_grid_upd = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count * std::max(occ_upd, 1));
+}
+
+// one CG iteration = two launches; `cur` selects the ping-pong direction buffer
+int launch_iteration(fsb_ctx* c, const CgCoef& coef, int cur)
+{
+  const int th = c->cg_tile_rows;
+  const int tiles_x = fsb_div_up(c->ld, kTileW);
+  const int n_tiles = tiles_x * fsb_div_up(c->ny, th);
+#define FSB_CG_LAUNCH(TH)                                                                          \
+  k_cg_direction<TH><<<c->cg_grid_dir, kCgThreads, 0, c->stream>>>(                                \
+      c->cg_p[cur], c->cg_p[cur ^ 1], c->cg_r, c->cg_code, c->ld, c->ny, tiles_x, n_tiles, coef,   \
+      c->scal, c->partials);                                                                       \
+  k_cg_update<TH><<<c->cg_grid_upd, kCgThreads, 0, c->stream>>>(                                   \
+      c->cg_x, c->cg_r, c->cg_p[cur ^ 1], c->cg_code, c->ld, c->ny, tiles_x, n_tiles, coef,        \
+      c->scal, c->partials)
+  if (th == 32) { FSB_CG_LAUNCH(32); }
+  else if (th == 16) { FSB_CG_LAUNCH(16); }
+  else { FSB_CG_LAUNCH(8); }
+#undef FSB_CG_LAUNCH
+  FSB_CUDA(c, cudaGetLastError());
+  return FSB_OK;
+}
+
+// kCheckEvery iterations captured once per context into a CUDA graph (all
+// arguments are fixed for the life of the context; alpha, beta, the first-pass
+// flag and `done` live in device memory).
+int ensure_cg_graph(fsb_ctx* c, const CgCoef& coef)
+{
+  if (c->cg_graph_state != 0) return FSB_OK;
+  c->cg_graph_state = -1; // direct launches unless the capture below succeeds
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return FSB_OK;
+  }
+  int rc = FSB_OK;
+  for (int k = 0; k < kCheckEvery && rc == FSB_OK; ++k) rc = launch_iteration(c, coef, k & 1);
+  const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+  if (rc != FSB_OK || e != cudaSuccess || !graph)
+  {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    return FSB_OK;
+  }
+  if (cudaGraphInstantiate(&c->cg_graph, graph, 0) == cudaSuccess) c->cg_graph_state = 1;
+  else cudaGetLastError();
+  cudaGraphDestroy(graph);
+  return FSB_OK;
+}
+
+int launch_chunk(fsb_ctx* c, const CgCoef& coef)
+{
+  static_assert(kCheckEvery % 2 == 0, "a chunk must leave the ping-pong where it started");
+  if (c->cg_graph_state == 1)
+  {
+    FSB_CUDA(c, cudaGraphLaunch(c->cg_graph, c->stream));
+  }
+  else
+  {
+    for (int k = 0; k < kCheckEvery; ++k) FSB_TRY(launch_iteration(c, coef, k & 1));
+  }
+  c->launches += 2 * kCheckEvery;
+  return FSB_OK;
+}
+
+} // namespace
+
+int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
+{
+  const GridDims d{c->nx, c->ny, c->ld, c->dx, c->dy};
+  const CgCoef coef = make_coef(c);
 
   // ---- build
   fsb_prof_begin(c, FSB_PROF_RHS);
   const int64_t total = (int64_t)c->ld * c->ny;
   const int build_blocks = (int)std::min<int64_t>(fsb_div_up(total, 256), c->sm_count * 8);
-  const dim3 spmv_grid(fsb_div_up(c->ld, kSpmvThreads * 4), fsb_div_up(c->ny, kRows));
-  const int64_t n4 = total / 4;
-  const int upd_blocks = (int)std::min<int64_t>(fsb_div_up(n4, kUpdThreads), c->sm_count * 8);
-  const int need = std::max(std::max(3 * build_blocks, (int)(spmv_grid.x * spmv_grid.y)),
-                            2 * upd_blocks);
+  if (c->cg_tile_rows == 0)
+  {
+    c->cg_tile_rows = pick_tile_rows(c);
+    const int64_t n_tiles =
+        (int64_t)fsb_div_up(c->ld, kTileW) * fsb_div_up(c->ny, c->cg_tile_rows);
+    if (c->cg_tile_rows == 32) resident_grids<32>(c, n_tiles);
+    else if (c->cg_tile_rows == 16) resident_grids<16>(c, n_tiles);
+    else resident_grids<8>(c, n_tiles);
+  }
+  const int need = std::max(3 * build_blocks, std::max(c->cg_grid_dir, 2 * c->cg_grid_upd));
   if (need > c->partials_cap)
   {
     if (c->partials) cudaFree(c->partials);
@@ -403,38 +648,53 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
                                                   c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
                                                   c->tol, c->max_iters);
   FSB_LAUNCHED(c);
-  FSB_CUDA(c, cudaMemcpyAsync(c->scal_h, c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
+  FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[0], c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
                               c->stream));
   fsb_prof_end(c, FSB_PROF_RHS);
   FSB_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (c->scal_h->n_liquid == 0) return FSB_OK; // :347-350: nothing touched, no swap
+  if (c->scal_h[0].n_liquid == 0) return FSB_OK; // :347-350: nothing touched, no swap
 
-  // ---- iterate
+  // ---- iterate: chunks of kCheckEvery iterations; the host reads the device
+  // scalars of chunk k while chunk k+1 is already queued, so the GPU never
+  // waits for the poll.  Launches after convergence return immediately.
   fsb_prof_begin(c, FSB_PROF_CG);
-  int cur = 0; // cg_p[cur] holds the previous direction
-  while (!c->scal_h->done)
+  CgScalars fin = c->scal_h[0];
+  if (!fin.done)
   {
-    for (int k = 0; k < kCheckEvery; ++k)
+    FSB_TRY(ensure_cg_graph(c, coef));
+    const int max_chunks = fsb_div_up(std::max(fin.max_iters, 1), kCheckEvery);
+    int queued = 0, slot = 0;
+    auto queue_chunk = [&]() -> int {
+      FSB_TRY(launch_chunk(c, coef));
+      FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[slot], c->scal, sizeof(CgScalars),
+                                  cudaMemcpyDeviceToHost, c->stream));
+      FSB_CUDA(c, cudaEventRecord(c->cg_ev[slot], c->stream));
+      slot ^= 1;
+      ++queued;
+      return FSB_OK;
+    };
+    FSB_TRY(queue_chunk());
+    for (;;)
     {
-      k_cg_dir_spmv<<<spmv_grid, kSpmvThreads, 0, c->stream>>>(
-          c->cg_p[cur], c->cg_p[cur ^ 1], c->cg_q, c->cg_r, c->cg_code, c->ld, c->ny, coef, c->scal,
-          c->partials);
-      FSB_LAUNCHED(c);
-      k_cg_update<<<upd_blocks, kUpdThreads, 0, c->stream>>>(c->cg_x, c->cg_r, c->cg_p[cur ^ 1],
-                                                             c->cg_q, c->cg_code, n4, coef, c->scal,
-                                                             c->partials);
-      FSB_LAUNCHED(c);
-      cur ^= 1;
+      const bool more = queued < max_chunks;
+      if (more) FSB_TRY(queue_chunk());
+      // the older of the (up to) two chunks in flight
+      const int wait_slot = more ? slot : slot ^ 1;
+      FSB_CUDA(c, cudaEventSynchronize(c->cg_ev[wait_slot]));
+      fin = c->scal_h[wait_slot];
+      if (fin.done) break;
+      if (!more)
+      {
+        // cannot happen: max_chunks chunks always reach the iteration cap
+        return fsb_fail(c, FSB_ERR_CUDA, "CG did not terminate after %d chunks", queued);
+      }
     }
-    FSB_CUDA(c, cudaMemcpyAsync(c->scal_h, c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
-                                c->stream));
-    FSB_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   fsb_prof_end(c, FSB_PROF_CG);
-  c->iters = c->scal_h->iter;
-  c->err = (c->scal_h->rhs2 == 0.0 || (float)c->scal_h->rhs2 == 0.0f)
+  c->iters = fin.iter;
+  c->err = (fin.rhs2 == 0.0 || (float)fin.rhs2 == 0.0f)
                ? 0.0f
-               : std::sqrt((float)c->scal_h->r2 / (float)c->scal_h->rhs2);
+               : std::sqrt((float)fin.r2 / (float)fin.rhs2);
   c->pressure_valid = true;
 
   // ---- patch + swap

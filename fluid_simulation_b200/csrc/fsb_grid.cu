@@ -236,6 +236,13 @@ int fsb_k_classify(fsb_ctx* c)
   return FSB_OK;
 }
 
+int fsb_k_clear_labels(fsb_ctx* c)
+{
+  k_fill_labels<<<cell_grid(c), kBlock, 0, c->stream>>>(c->cell, dims(c));
+  FSB_LAUNCHED(c);
+  return FSB_OK;
+}
+
 int fsb_k_save_previous(fsb_ctx* c)
 {
   const size_t bytes = (size_t)c->ld * c->ny * sizeof(float);

@@ -48,6 +48,7 @@ struct fsb_ctx
   int nx = 0, ny = 0, ld = 0;
   float dx = 0, dy = 0;           // MacGrid deltas (src/MacGrid.cpp:8)
   float pool_dx = 0, pool_dy = 0; // FluidSolverMemoryPool deltas (src/FluidSolver.cpp:56-65)
+  int pool_nx = 0, pool_ny = 0;
   float density = 0, pic_ratio = 0;
   float grav_x = 0, grav_y = 0;
   int integrator = FSB_INTEGRATOR_RK3;
@@ -82,13 +83,17 @@ struct fsb_ctx
   size_t stage_bytes = 0;
 
   // CG
-  float *cg_x = nullptr, *cg_r = nullptr, *cg_q = nullptr;
+  float *cg_x = nullptr, *cg_r = nullptr;
   float* cg_p[2] = {nullptr, nullptr}; // search direction, ping-pong
   uint8_t* cg_code = nullptr;
   double* partials = nullptr;
   int partials_cap = 0;
   CgScalars* scal = nullptr;   // device
-  CgScalars* scal_h = nullptr; // pinned host mirror
+  CgScalars* scal_h = nullptr; // pinned host mirror, two slots (poll runs one chunk behind)
+  cudaEvent_t cg_ev[2] = {nullptr, nullptr};
+  cudaGraphExec_t cg_graph = nullptr;
+  int cg_graph_state = 0; // 0: not built, 1: usable, -1: capture unavailable (direct launches)
+  int cg_tile_rows = 0, cg_grid_dir = 0, cg_grid_upd = 0;
   int max_iters = 100;
   float tol = 1.1920929e-7f;
   int iters = 0;
@@ -150,6 +155,7 @@ void fsb_prof_end(fsb_ctx* ctx, int stage);
 // stage launchers (each returns FSB_OK or an error code) ----------------------
 // grid stages: fsb_grid.cu
 int fsb_k_classify(fsb_ctx* c);
+int fsb_k_clear_labels(fsb_ctx* c);
 int fsb_k_save_previous(fsb_ctx* c);
 int fsb_k_update_diff(fsb_ctx* c);
 int fsb_k_add_acceleration(fsb_ctx* c, float ax, float ay, float dt);

@@ -93,6 +93,12 @@ int fsb_get_cg_info(const fsb_ctx* ctx, int* iterations, float* error);
 int fsb_set_pic_ratio(fsb_ctx* ctx, float pic_ratio);
 int fsb_set_density(fsb_ctx* ctx, float density);
 int fsb_set_integrator(fsb_ctx* ctx, int integrator);
+/* FluidSolverMemoryPool(size_x,size_y,delta_x,delta_y) as held by the FluidSolver
+ * (src/FluidSolver.cpp:5-26,56-65): the step functions compare it with the domain
+ * (validate(), :89-97) and the P2G accumulators carry its deltas.  The default is
+ * the pool FluidSolver(FluidSolverMemoryPool(domain)) ends up with: the domain's
+ * sizes and delta_x for BOTH deltas (the copy constructor passes deltaX twice). */
+int fsb_set_pool(fsb_ctx* ctx, int size_x, int size_y, float delta_x, float delta_y);
 /* gravity used by the fused steps; default (0, (float)-9.82)
  * (src/FluidSolver.cpp:115,154,192,232) */
 int fsb_set_gravity(fsb_ctx* ctx, float ax, float ay);
@@ -129,6 +135,10 @@ int fsb_classify_cells(fsb_ctx* ctx);
 int fsb_p2g_spread(fsb_ctx* ctx);
 /* MacGrid::updatePreviousVelocityBuffer src/MacGrid.cpp:52-56 */
 int fsb_save_previous(fsb_ctx* ctx);
+/* MacGrid::clearCellTypeBuffer src/MacGrid.cpp:32-50: border SOLID, interior AIR */
+int fsb_clear_cell_types(fsb_ctx* ctx);
+/* MacGrid::swapVelocityBuffers src/MacGrid.cpp:89-93 */
+int fsb_swap_velocity_buffers(fsb_ctx* ctx);
 /* FluidSolver::addExternalAcceleration src/FluidSolver.cpp:276-295 */
 int fsb_add_acceleration(fsb_ctx* ctx, float ax, float ay, float dt);
 /* FluidSolver::enforceDirichlet src/FluidSolver.cpp:297-321 */
