@@ -27,6 +27,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "fsb_device.cuh"
 #include "fsb_internal.cuh"
@@ -138,330 +139,481 @@ __global__ void k_cg_build(const float* __restrict__ uf, const float* __restrict
 }
 
 // ------------------------------------------------------------ tile frame --
-// Both iteration kernels work on tiles of kTileW columns x TH rows.  A CTA of
-// 256 threads = 8 warps; lane l owns the four columns 4l..4l+3 of the tile
-// (one 16-byte access per row), warp w owns rows w, w+8, ... of the tile.
-// The search direction of the tile and of its one-cell halo is staged in
-// shared memory (row pitch kPitch floats, interior starts at word 4 so the
-// float4 stores stay 16-byte aligned); north/south neighbours are read from
-// there, west/east neighbours come from the adjacent lanes (shuffle) and from
-// the halo columns for lanes 0 and 31.  CTAs walk the tile list with a grid
-// stride, so the number of per-CTA partial sums is bounded by the grid size.
+// Both iteration kernels are TMA-fed, warp-specialised, persistent kernels:
+//   * one CTA per SM; TH consumer warps + 1 producer warp; tiles of kTileW = 128
+//     columns x TH rows; consumer warp w owns tile row w, lane l its columns
+//     4l..4l+3 (one 16-byte shared-memory access).
+//   * the producer's elected lane walks the CTA's tile list and issues
+//     cp.async.bulk.tensor (TMA) box loads into a kStages-deep shared-memory
+//     ring, completion on full[stage] (mbarrier, expect_tx); consumers release a
+//     stage by arriving on empty[stage].  Boxes include the one-cell halo
+//     (fp32: 136 x (TH+2) starting at (c0-4, j0-1); code bytes: 160 x (TH+2)
+//     starting at (c0-16, j0-1)); TMA zero-fills everything outside the grid,
+//     so the kernels have no bounds logic on the load side and the pipeline
+//     keeps (kStages-1) tiles of loads in flight per SM regardless of what the
+//     consumer warps are doing.
+//   * per-cell coefficients come from a shared-memory table of float4
+//     {inverse diagonal, diagonal, off-diagonal, 0} indexed by the stencil code
+//     (code 0 -> all zero, so masked cells come out exactly 0 without branches);
+//     one LDS.128 per cell.  (An indexed kernel-parameter array compiles to
+//     indexed LDC on the XU pipe: measured 78 % XU-bound, profiles/r01b.)
+//   * arithmetic uses explicit FMA: the CG is held to the solver tolerance and
+//     comparable iteration counts, not to Eigen's rounding.
 constexpr int kTileW = 128;
-constexpr int kPitch = kTileW + 8;
-constexpr int kCgThreads = 256;
-constexpr int kCgWarps = kCgThreads / 32;
+constexpr int kHaloW = kTileW + 8;  // fp32 halo box width: columns c0-4 .. c0+131
+constexpr int kCodeW = kTileW + 32; // code halo box width: columns c0-16 .. c0+143
+constexpr int kStages = 4;
 
-// Per-cell coefficients come from a 2 x 8 shared-memory table indexed by the
-// stencil code (0 = not liquid -> coefficient 0, 1 + n -> n non-SOLID
-// neighbours): [0][code] = Jacobi inverse diagonal, [1][code] = diagonal.  A
-// dynamically indexed kernel-parameter array would compile to indexed LDC,
-// which issues on the slow XU pipe (measured: 78 % XU-bound, profiles/r01b).
-struct CgLut
+__host__ __device__ constexpr int align128(int x) { return (x + 127) / 128 * 128; }
+
+template <int TH>
+struct DirStage // k_cg_direction: r, p_old (both with halo), code (with halo)
 {
-  float inv[8];
-  float diag[8];
+  static constexpr int kF32 = kHaloW * (TH + 2) * 4;
+  static constexpr int kCode = kCodeW * (TH + 2);
+  static constexpr int oR = 0, oP = align128(kF32), oC = 2 * align128(kF32);
+  static constexpr int kBytes = align128(oC + kCode);
+  static constexpr int kTx = 2 * kF32 + kCode;
+};
+template <int TH>
+struct UpdStage // k_cg_update: p (with halo), x, r (interior), code (with halo)
+{
+  static constexpr int kHalo = kHaloW * (TH + 2) * 4;
+  static constexpr int kInner = kTileW * TH * 4;
+  static constexpr int kCode = kCodeW * (TH + 2);
+  static constexpr int oP = 0, oX = align128(kHalo), oR = oX + kInner, oC = oR + kInner;
+  static constexpr int kBytes = align128(oC + kCode);
+  static constexpr int kTx = kHalo + 2 * kInner + kCode;
 };
 
-__device__ __forceinline__ void load_lut(CgLut* lut, const CgCoef& coef)
+struct CgMaps
+{
+  CUtensorMap halo_a; // fp32, box kHaloW x (TH+2)
+  CUtensorMap halo_b; // fp32, box kHaloW x (TH+2)
+  CUtensorMap inner_a; // fp32, box kTileW x TH
+  CUtensorMap inner_b; // fp32, box kTileW x TH
+  CUtensorMap code;    // u8,   box kCodeW x (TH+2)
+};
+
+// ---- PTX wrappers: mbarrier + TMA (sm_90+ forms, SASS: SYNCS / UTMALDG)
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void consumer_sync(int n_threads) // named barrier 1: consumer warps only
+{
+  asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
+}
+
+// coefficient table: [code] -> {inv diag, diag, off, 0}; code 0 (not liquid) -> zeros
+__device__ __forceinline__ void load_lut(float4* lut, const CgCoef& coef)
 {
   if (threadIdx.x < 8)
   {
     const int t = threadIdx.x;
-    float iv = 0.0f, dg = 0.0f;
-    if (t >= 1 && t <= 5)
-    {
-      iv = coef.invdiag[t - 1];
-      dg = coef.diag[t - 1];
-    }
-    lut->inv[t] = iv;
-    lut->diag[t] = dg;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 1 && t <= 5) v = make_float4(coef.invdiag[t - 1], coef.diag[t - 1], coef.off, 0.f);
+    lut[t] = v;
   }
 }
 
-// r and p_old are exactly zero on non-liquid cells and inv[0] = 0, so the
-// result is exactly zero there without a branch.
-__device__ __forceinline__ float dir_value(float r, float p_old, uint32_t cd, const CgLut* lut,
-                                           float beta, bool first)
+// q = A p for the four cells of one lane.  `prow` points at the lane's first
+// cell in the staged halo tile of p (row pitch kHaloW); pc is that float4.
+__device__ __forceinline__ float4 apply_a4(const float* __restrict__ prow, unsigned lane,
+                                           const float4 pc, const float4 k0, const float4 k1,
+                                           const float4 k2, const float4 k3)
 {
-  const float z = lut->inv[cd] * r;
-  return first ? z : z + beta * p_old;
-}
-
-__device__ __forceinline__ float4 dir_value4(const float4 r4, const float4 p4, uint32_t c4,
-                                             const CgLut* lut, float beta, bool first)
-{
-  float4 o;
-  o.x = dir_value(r4.x, p4.x, c4 & 0xff, lut, beta, first);
-  o.y = dir_value(r4.y, p4.y, (c4 >> 8) & 0xff, lut, beta, first);
-  o.z = dir_value(r4.z, p4.z, (c4 >> 16) & 0xff, lut, beta, first);
-  o.w = dir_value(r4.w, p4.w, c4 >> 24, lut, beta, first);
-  return o;
-}
-
-__device__ __forceinline__ float apply_a(float c, float w, float e, float s, float n, uint32_t cd,
-                                         float off, const CgLut* lut)
-{
-  // each coefficient multiplies its own operand, as a sparse product does
-  float acc = off * w;
-  acc += off * e;
-  acc += off * s;
-  acc += off * n;
-  acc += lut->diag[cd] * c;
-  return cd ? acc : 0.0f;
-}
-
-// q = A p for the four cells of one lane in tile row `tr` (0-based inside the
-// tile); `pc` is the lane's own direction, sp the staged tile.
-__device__ __forceinline__ float4 apply_a4(const float* __restrict__ sp, int tr, unsigned lane,
-                                           const float4 pc, uint32_t c4, float off,
-                                           const CgLut* lut)
-{
-  const float* row = sp + (tr + 1) * kPitch + 4 + lane * 4;
-  const float4 s4 = *reinterpret_cast<const float4*>(row - kPitch);
-  const float4 n4 = *reinterpret_cast<const float4*>(row + kPitch);
+  const float4 s4 = *reinterpret_cast<const float4*>(prow - kHaloW);
+  const float4 n4 = *reinterpret_cast<const float4*>(prow + kHaloW);
   float w = __shfl_up_sync(0xffffffffu, pc.w, 1);
   float e = __shfl_down_sync(0xffffffffu, pc.x, 1);
-  if (lane == 0) w = row[-1];
-  if (lane == 31) e = row[4];
+  if (lane == 0) w = prow[-1];
+  if (lane == 31) e = prow[4];
   float4 q;
-  q.x = apply_a(pc.x, w, pc.y, s4.x, n4.x, c4 & 0xff, off, lut);
-  q.y = apply_a(pc.y, pc.x, pc.z, s4.y, n4.y, (c4 >> 8) & 0xff, off, lut);
-  q.z = apply_a(pc.z, pc.y, pc.w, s4.z, n4.z, (c4 >> 16) & 0xff, off, lut);
-  q.w = apply_a(pc.w, pc.z, e, s4.w, n4.w, c4 >> 24, off, lut);
+  q.x = fmaf(k0.y, pc.x, k0.z * ((w + pc.y) + (s4.x + n4.x)));
+  q.y = fmaf(k1.y, pc.y, k1.z * ((pc.x + pc.z) + (s4.y + n4.y)));
+  q.z = fmaf(k2.y, pc.z, k2.z * ((pc.y + pc.w) + (s4.z + n4.z)));
+  q.w = fmaf(k3.y, pc.w, k3.z * ((pc.z + e) + (s4.w + n4.w)));
   return q;
 }
 
+__device__ __forceinline__ float dot4(const float4 a, const float4 b)
+{
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
 // ------------------------------------------------- direction + p.Ap dot --
-// p_new = z + beta p_old on the tile and its halo (the halo is RE-COMPUTED
-// from r, p_old and code, so no other CTA's output is needed and p_new can be
-// produced and consumed in the same kernel); q = A p_new stays in registers
-// and only feeds the dot product.  13 B of HBM traffic per cell: r, p_old,
-// code in, p_new out (ping-pong with p_old because neighbours still need the
-// old halo).
+// p_new = z + beta p_old on the tile AND on its one-cell halo ring (recomputed
+// from the staged r, p_old, code, so no other CTA's output is needed), written
+// over p_old in the stage buffer; q = A p_new from shared memory / shuffles,
+// kept in registers for the dot product only.  HBM traffic 13 B per cell:
+// r, p_old, code in (TMA), p_new out (STG.128; ping-pong with p_old because
+// other CTAs still read the old halo).
 template <int TH>
-__global__ void __launch_bounds__(kCgThreads, 4)
-k_cg_direction(const float* __restrict__ p_old, float* __restrict__ p_new,
-               const float* __restrict__ r, const uint8_t* __restrict__ code, int ld, int ny,
+__global__ void __launch_bounds__((TH + 1) * 32, 1)
+k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, int ld, int ny,
                int tiles_x, int n_tiles, const CgCoef coef, CgScalars* __restrict__ s,
                double* __restrict__ partials)
 {
   if (s->done) return;
-  __shared__ __align__(16) float sp[(TH + 2) * kPitch];
-  __shared__ CgLut lut;
-  load_lut(&lut, coef);
-  __syncthreads();
-  const float off = coef.off;
-  constexpr int RPW = TH / kCgWarps; // rows per warp
-  const bool first = (s->iter == 0);
-  const float beta = s->beta;
+  using St = DirStage<TH>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full[kStages], empty[kStages];
+  __shared__ float4 lut[8];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  double acc = 0.0;
+  const bool first = (s->iter == 0);
+  const float beta = first ? 0.0f : s->beta;
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  load_lut(lut, coef);
+  if (threadIdx.x == 0)
   {
-    const int c0 = (tile % tiles_x) * kTileW;
-    const int j0 = (tile / tiles_x) * TH;
-    const int ci = c0 + (int)lane * 4;
-    const bool col_ok = ci < ld;
-    float4 pn[RPW];
-    uint32_t cd[RPW];
-    // owned rows
-#pragma unroll
-    for (int k = 0; k < RPW; ++k)
+    for (int k = 0; k < kStages; ++k)
     {
-      const int tr = (int)warp + k * kCgWarps;
-      const int j = j0 + tr;
-      pn[k] = zero4;
-      cd[k] = 0;
-      if (col_ok && j < ny)
-      {
-        const size_t o = (size_t)j * ld + ci;
-        const uint32_t c4 = *reinterpret_cast<const uint32_t*>(code + o);
-        const float4 r4 = *reinterpret_cast<const float4*>(r + o);
-        float4 p4 = zero4;
-        if (!first) p4 = *reinterpret_cast<const float4*>(p_old + o);
-        cd[k] = c4;
-        pn[k] = dir_value4(r4, p4, c4, &lut, beta, first);
-      }
-      *reinterpret_cast<float4*>(sp + (tr + 1) * kPitch + 4 + lane * 4) = pn[k];
+      mbar_init(&full[k], 1);
+      mbar_init(&empty[k], TH);
     }
-    // halo rows j0-1 (warp 0) and j0+TH (warp 1)
-    if (warp < 2)
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == TH)
+  {
+    // ---- producer
+    if (lane == 0)
     {
-      const int j = (warp == 0) ? j0 - 1 : j0 + TH;
-      float4 h = zero4;
-      if (col_ok && j >= 0 && j < ny)
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it)
       {
-        const size_t o = (size_t)j * ld + ci;
-        const uint32_t c4 = *reinterpret_cast<const uint32_t*>(code + o);
-        if (c4)
-        {
-          const float4 r4 = *reinterpret_cast<const float4*>(r + o);
-          float4 p4 = zero4;
-          if (!first) p4 = *reinterpret_cast<const float4*>(p_old + o);
-          h = dir_value4(r4, p4, c4, &lut, beta, first);
-        }
-      }
-      *reinterpret_cast<float4*>(sp + ((warp == 0) ? 0 : (TH + 1)) * kPitch + 4 + lane * 4) = h;
-    }
-    // halo columns c0-1 and c0+kTileW of the TH tile rows: threads 64 .. 64+2*TH-1
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * TH)
-    {
-      const int t = threadIdx.x - 64;
-      const int tr = t >> 1, side = t & 1;
-      const int j = j0 + tr;
-      const int cc = side ? c0 + kTileW : c0 - 1;
-      float h = 0.0f;
-      if (j < ny && cc >= 0 && cc < ld)
-      {
-        const size_t o = (size_t)j * ld + cc;
-        const uint32_t c1 = code[o];
-        if (c1) h = dir_value(r[o], first ? 0.0f : p_old[o], c1, &lut, beta, first);
-      }
-      sp[(tr + 1) * kPitch + (side ? 4 + kTileW : 3)] = h;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < RPW; ++k)
-    {
-      const int tr = (int)warp + k * kCgWarps;
-      const int j = j0 + tr;
-      const float4 q = apply_a4(sp, tr, lane, pn[k], cd[k], off, &lut);
-      if (col_ok && j < ny)
-      {
-        *reinterpret_cast<float4*>(p_new + (size_t)j * ld + ci) = pn[k];
-        acc += (double)((pn[k].x * q.x + pn[k].y * q.y) + (pn[k].z * q.z + pn[k].w * q.w));
+        const int st = it % kStages;
+        if (it >= kStages) mbar_wait(&empty[st], ((it / kStages) - 1) & 1);
+        const int c0 = (tile % tiles_x) * kTileW;
+        const int j0 = (tile / tiles_x) * TH;
+        unsigned char* base = smem + st * St::kBytes;
+        mbar_expect_tx(&full[st], first ? St::kTx - St::kF32 : St::kTx);
+        tma_load_2d(base + St::oR, &maps.halo_a, c0 - 4, j0 - 1, &full[st]);
+        if (!first) tma_load_2d(base + St::oP, &maps.halo_b, c0 - 4, j0 - 1, &full[st]);
+        tma_load_2d(base + St::oC, &maps.code, c0 - 16, j0 - 1, &full[st]);
       }
     }
-    __syncthreads(); // the tile buffer is reused
+    return;
   }
 
-  const double tot = block_sum(acc);
-  if (threadIdx.x == 0) partials[blockIdx.x] = tot;
-  if (last_block_done(&s->ticket[1], gridDim.x))
+  // ---- consumers
+  double acc = 0.0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it)
   {
-    const double pq = fold_partials(partials, (int)gridDim.x);
+    const int st = it % kStages;
+    const int c0 = (tile % tiles_x) * kTileW;
+    const int j0 = (tile / tiles_x) * TH;
+    unsigned char* base = smem + st * St::kBytes;
+    const float* sr = reinterpret_cast<const float*>(base + St::oR);
+    float* sp = reinterpret_cast<float*>(base + St::oP);
+    const unsigned char* sc = base + St::oC;
+    mbar_wait(&full[st], (it / kStages) & 1);
+
+    // direction on the owned row (stage row warp+1) ...
+    const int row = (int)warp + 1;
+    const int fo = row * kHaloW + 4 + (int)lane * 4;
+    const uint32_t c4 = *reinterpret_cast<const uint32_t*>(sc + row * kCodeW + 16 + lane * 4);
+    const float4 k0 = lut[c4 & 0xff], k1 = lut[(c4 >> 8) & 0xff], k2 = lut[(c4 >> 16) & 0xff],
+                 k3 = lut[c4 >> 24];
+    const float4 r4 = *reinterpret_cast<const float4*>(sr + fo);
+    float4 pn;
+    if (first)
+    {
+      pn = make_float4(k0.x * r4.x, k1.x * r4.y, k2.x * r4.z, k3.x * r4.w);
+    }
+    else
+    {
+      const float4 p4 = *reinterpret_cast<const float4*>(sp + fo);
+      pn.x = fmaf(beta, p4.x, k0.x * r4.x);
+      pn.y = fmaf(beta, p4.y, k1.x * r4.y);
+      pn.z = fmaf(beta, p4.z, k2.x * r4.z);
+      pn.w = fmaf(beta, p4.w, k3.x * r4.w);
+    }
+    *reinterpret_cast<float4*>(sp + fo) = pn;
+    // ... on its west / east halo cells (lanes 0 and 31) ...
+    if (lane == 0 || lane == 31)
+    {
+      const int ho = row * kHaloW + (lane == 0 ? 3 : 4 + kTileW);
+      const float inv = lut[sc[row * kCodeW + (lane == 0 ? 15 : 16 + kTileW)]].x;
+      sp[ho] = first ? inv * sr[ho] : fmaf(beta, sp[ho], inv * sr[ho]);
+    }
+    // ... and on the south / north halo rows (warps 0 and 1)
+    if (warp < 2)
+    {
+      const int hrow = (warp == 0) ? 0 : TH + 1;
+      const int ho = hrow * kHaloW + 4 + (int)lane * 4;
+      const uint32_t h4 = *reinterpret_cast<const uint32_t*>(sc + hrow * kCodeW + 16 + lane * 4);
+      const float4 hr = *reinterpret_cast<const float4*>(sr + ho);
+      float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!first) hp = *reinterpret_cast<const float4*>(sp + ho);
+      float4 hn;
+      hn.x = fmaf(beta, hp.x, lut[h4 & 0xff].x * hr.x);
+      hn.y = fmaf(beta, hp.y, lut[(h4 >> 8) & 0xff].x * hr.y);
+      hn.z = fmaf(beta, hp.z, lut[(h4 >> 16) & 0xff].x * hr.z);
+      hn.w = fmaf(beta, hp.w, lut[h4 >> 24].x * hr.w);
+      *reinterpret_cast<float4*>(sp + ho) = hn;
+    }
+    consumer_sync(TH * 32);
+
+    const float4 q = apply_a4(sp + fo, lane, pn, k0, k1, k2, k3);
+    acc += (double)dot4(pn, q);
+    const int j = j0 + (int)warp, ci = c0 + (int)lane * 4;
+    if (j < ny && ci < ld) *reinterpret_cast<float4*>(p_new + (size_t)j * ld + ci) = pn;
+
+    // the stage was written through the generic proxy; the next TMA load into
+    // it goes through the async proxy
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+
+  // ---- reduction over the consumer warps, then over the CTAs (last one folds)
+  __shared__ double s_part[32];
+  __shared__ bool s_last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) s_part[warp] = acc;
+  consumer_sync(TH * 32);
+  if (warp == 0)
+  {
+    double v = (lane < TH) ? s_part[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0)
+    {
+      partials[blockIdx.x] = v;
+      __threadfence();
+      s_last = (atomicAdd(&s->ticket[1], 1u) == gridDim.x - 1);
+    }
+  }
+  consumer_sync(TH * 32);
+  if (s_last)
+  {
+    __threadfence();
+    double v = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += TH * 32)
+      v += reinterpret_cast<const volatile double*>(partials)[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_part[warp] = v;
+    consumer_sync(TH * 32);
     if (threadIdx.x == 0)
     {
-      s->pq = pq;
+      double t = 0.0;
+      for (int k = 0; k < TH; ++k) t += s_part[k];
+      s->pq = t;
       s->ticket[1] = 0;
     }
   }
 }
 
 // ------------------------------------------------------------ the update --
-// alpha = absNew / p.Ap; x += alpha p; r -= alpha A p with A p RE-COMPUTED
-// from the staged p tile (q is never stored); partial |r|^2 and r.z.
-// 21 B of HBM traffic per cell: p, code, x, r in; x, r out.
+// alpha = absNew / p.Ap; q = A p RE-COMPUTED from the staged p tile (q is
+// never stored); x += alpha p; r -= alpha q; partial |r|^2 and r.z.
+// HBM traffic 21 B per cell: p, code, x, r in (TMA), x, r out (STG.128).
+// No CTA-level barrier inside the tile loop: a warp only needs the TMA data.
 template <int TH>
-__global__ void __launch_bounds__(kCgThreads, TH >= 32 ? 3 : 4)
-k_cg_update(float* __restrict__ x, float* __restrict__ r, const float* __restrict__ p,
-            const uint8_t* __restrict__ code, int ld, int ny, int tiles_x, int n_tiles,
-            const CgCoef coef, CgScalars* __restrict__ s, double* __restrict__ partials)
+__global__ void __launch_bounds__((TH + 1) * 32, 1)
+k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* __restrict__ r,
+            int ld, int ny, int tiles_x, int n_tiles, const CgCoef coef,
+            CgScalars* __restrict__ s, double* __restrict__ partials)
 {
   if (s->done) return;
-  __shared__ __align__(16) float sp[(TH + 2) * kPitch];
-  __shared__ CgLut lut;
-  load_lut(&lut, coef);
-  __syncthreads();
-  const float off = coef.off;
-  constexpr int RPW = TH / kCgWarps;
-  const float alpha = s->abs_new / (float)s->pq; // Eigen: alpha = absNew / p.dot(tmp)
+  using St = UpdStage<TH>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full[kStages], empty[kStages];
+  __shared__ float4 lut[8];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  double acc_r2 = 0.0, acc_rz = 0.0;
+  const float alpha = s->abs_new / (float)s->pq; // Eigen: alpha = absNew / p.dot(tmp)
+  const float nalpha = -alpha;
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-  {
-    const int c0 = (tile % tiles_x) * kTileW;
-    const int j0 = (tile / tiles_x) * TH;
-    const int ci = c0 + (int)lane * 4;
-    const bool col_ok = ci < ld;
-    float4 pc[RPW], xv[RPW], rv[RPW];
-    uint32_t cd[RPW];
-#pragma unroll
-    for (int k = 0; k < RPW; ++k)
-    {
-      const int tr = (int)warp + k * kCgWarps;
-      const int j = j0 + tr;
-      pc[k] = zero4;
-      xv[k] = zero4;
-      rv[k] = zero4;
-      cd[k] = 0;
-      if (col_ok && j < ny)
-      {
-        const size_t o = (size_t)j * ld + ci;
-        cd[k] = *reinterpret_cast<const uint32_t*>(code + o);
-        pc[k] = *reinterpret_cast<const float4*>(p + o);
-        if (cd[k])
-        {
-          xv[k] = *reinterpret_cast<const float4*>(x + o);
-          rv[k] = *reinterpret_cast<const float4*>(r + o);
-        }
-      }
-      *reinterpret_cast<float4*>(sp + (tr + 1) * kPitch + 4 + lane * 4) = pc[k];
-    }
-    if (warp < 2)
-    {
-      const int j = (warp == 0) ? j0 - 1 : j0 + TH;
-      float4 h = zero4;
-      if (col_ok && j >= 0 && j < ny) h = *reinterpret_cast<const float4*>(p + (size_t)j * ld + ci);
-      *reinterpret_cast<float4*>(sp + ((warp == 0) ? 0 : (TH + 1)) * kPitch + 4 + lane * 4) = h;
-    }
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * TH)
-    {
-      const int t = threadIdx.x - 64;
-      const int tr = t >> 1, side = t & 1;
-      const int j = j0 + tr;
-      const int cc = side ? c0 + kTileW : c0 - 1;
-      float h = 0.0f;
-      if (j < ny && cc >= 0 && cc < ld) h = p[(size_t)j * ld + cc];
-      sp[(tr + 1) * kPitch + (side ? 4 + kTileW : 3)] = h;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < RPW; ++k)
-    {
-      const int tr = (int)warp + k * kCgWarps;
-      const int j = j0 + tr;
-      const uint32_t c4 = cd[k];
-      const float4 q = apply_a4(sp, tr, lane, pc[k], c4, off, &lut); // shuffles: whole warp takes part
-      if (c4 != 0 && col_ok && j < ny) // four non-liquid cells: x, r stay exactly zero
-      {
-        float4 xo = xv[k], ro = rv[k];
-        xo.x = xo.x + alpha * pc[k].x; ro.x = ro.x - alpha * q.x;
-        xo.y = xo.y + alpha * pc[k].y; ro.y = ro.y - alpha * q.y;
-        xo.z = xo.z + alpha * pc[k].z; ro.z = ro.z - alpha * q.z;
-        xo.w = xo.w + alpha * pc[k].w; ro.w = ro.w - alpha * q.w;
-        const size_t o = (size_t)j * ld + ci;
-        *reinterpret_cast<float4*>(x + o) = xo;
-        *reinterpret_cast<float4*>(r + o) = ro;
-        const float z0 = lut.inv[c4 & 0xff] * ro.x;
-        const float z1 = lut.inv[(c4 >> 8) & 0xff] * ro.y;
-        const float z2 = lut.inv[(c4 >> 16) & 0xff] * ro.z;
-        const float z3 = lut.inv[c4 >> 24] * ro.w;
-        acc_r2 += (double)((ro.x * ro.x + ro.y * ro.y) + (ro.z * ro.z + ro.w * ro.w));
-        acc_rz += (double)((ro.x * z0 + ro.y * z1) + (ro.z * z2 + ro.w * z3));
-      }
-    }
-    __syncthreads();
-  }
-
-  const double r2 = block_sum(acc_r2);
-  const double rz = block_sum(acc_rz);
+  load_lut(lut, coef);
   if (threadIdx.x == 0)
   {
-    partials[blockIdx.x] = r2;
-    partials[gridDim.x + blockIdx.x] = rz;
+    for (int k = 0; k < kStages; ++k)
+    {
+      mbar_init(&full[k], 1);
+      mbar_init(&empty[k], TH);
+    }
+    fence_barrier_init();
   }
-  if (last_block_done(&s->ticket[2], gridDim.x))
+  __syncthreads();
+
+  if (warp == TH)
   {
-    const double tr2 = fold_partials(partials, gridDim.x);
-    const double trz = fold_partials(partials + gridDim.x, gridDim.x);
+    if (lane == 0)
+    {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it)
+      {
+        const int st = it % kStages;
+        if (it >= kStages) mbar_wait(&empty[st], ((it / kStages) - 1) & 1);
+        const int c0 = (tile % tiles_x) * kTileW;
+        const int j0 = (tile / tiles_x) * TH;
+        unsigned char* base = smem + st * St::kBytes;
+        mbar_expect_tx(&full[st], St::kTx);
+        tma_load_2d(base + St::oP, &maps.halo_a, c0 - 4, j0 - 1, &full[st]);
+        tma_load_2d(base + St::oX, &maps.inner_a, c0, j0, &full[st]);
+        tma_load_2d(base + St::oR, &maps.inner_b, c0, j0, &full[st]);
+        tma_load_2d(base + St::oC, &maps.code, c0 - 16, j0 - 1, &full[st]);
+      }
+    }
+    return;
+  }
+
+  double acc_r2 = 0.0, acc_rz = 0.0;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it)
+  {
+    const int st = it % kStages;
+    const int c0 = (tile % tiles_x) * kTileW;
+    const int j0 = (tile / tiles_x) * TH;
+    unsigned char* base = smem + st * St::kBytes;
+    const float* sp = reinterpret_cast<const float*>(base + St::oP);
+    const float* sx = reinterpret_cast<const float*>(base + St::oX);
+    const float* sr = reinterpret_cast<const float*>(base + St::oR);
+    const unsigned char* sc = base + St::oC;
+    mbar_wait(&full[st], (it / kStages) & 1);
+
+    const int row = (int)warp + 1;
+    const int fo = row * kHaloW + 4 + (int)lane * 4;
+    const uint32_t c4 = *reinterpret_cast<const uint32_t*>(sc + row * kCodeW + 16 + lane * 4);
+    const float4 pc = *reinterpret_cast<const float4*>(sp + fo);
+    const float4 k0 = lut[c4 & 0xff], k1 = lut[(c4 >> 8) & 0xff], k2 = lut[(c4 >> 16) & 0xff],
+                 k3 = lut[c4 >> 24];
+    const float4 q = apply_a4(sp + fo, lane, pc, k0, k1, k2, k3);
+    float4 xo = *reinterpret_cast<const float4*>(sx + warp * kTileW + lane * 4);
+    float4 ro = *reinterpret_cast<const float4*>(sr + warp * kTileW + lane * 4);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]); // everything this warp needs is in registers
+
+    if (c4 != 0) // four non-liquid cells: x and r stay exactly zero, nothing to write
+    {
+      xo.x = fmaf(alpha, pc.x, xo.x); ro.x = fmaf(nalpha, q.x, ro.x);
+      xo.y = fmaf(alpha, pc.y, xo.y); ro.y = fmaf(nalpha, q.y, ro.y);
+      xo.z = fmaf(alpha, pc.z, xo.z); ro.z = fmaf(nalpha, q.z, ro.z);
+      xo.w = fmaf(alpha, pc.w, xo.w); ro.w = fmaf(nalpha, q.w, ro.w);
+      const int j = j0 + (int)warp, ci = c0 + (int)lane * 4; // c4 != 0 implies inside the grid
+      const size_t o = (size_t)j * ld + ci;
+      *reinterpret_cast<float4*>(x + o) = xo;
+      *reinterpret_cast<float4*>(r + o) = ro;
+      const float4 z = make_float4(k0.x * ro.x, k1.x * ro.y, k2.x * ro.z, k3.x * ro.w);
+      acc_r2 += (double)dot4(ro, ro);
+      acc_rz += (double)dot4(ro, z);
+    }
+  }
+
+  __shared__ double s_part[2][32];
+  __shared__ bool s_last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    acc_r2 += __shfl_down_sync(0xffffffffu, acc_r2, o);
+    acc_rz += __shfl_down_sync(0xffffffffu, acc_rz, o);
+  }
+  if (lane == 0)
+  {
+    s_part[0][warp] = acc_r2;
+    s_part[1][warp] = acc_rz;
+  }
+  consumer_sync(TH * 32);
+  if (warp == 0)
+  {
+    double v0 = (lane < TH) ? s_part[0][lane] : 0.0;
+    double v1 = (lane < TH) ? s_part[1][lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      v0 += __shfl_down_sync(0xffffffffu, v0, o);
+      v1 += __shfl_down_sync(0xffffffffu, v1, o);
+    }
+    if (lane == 0)
+    {
+      partials[blockIdx.x] = v0;
+      partials[gridDim.x + blockIdx.x] = v1;
+      __threadfence();
+      s_last = (atomicAdd(&s->ticket[2], 1u) == gridDim.x - 1);
+    }
+  }
+  consumer_sync(TH * 32);
+  if (s_last)
+  {
+    __threadfence();
+    const volatile double* part = partials;
+    double v0 = 0.0, v1 = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += TH * 32)
+    {
+      v0 += part[k];
+      v1 += part[gridDim.x + k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      v0 += __shfl_down_sync(0xffffffffu, v0, o);
+      v1 += __shfl_down_sync(0xffffffffu, v1, o);
+    }
+    if (lane == 0)
+    {
+      s_part[0][warp] = v0;
+      s_part[1][warp] = v1;
+    }
+    consumer_sync(TH * 32);
     if (threadIdx.x == 0)
     {
+      double tr2 = 0.0, trz = 0.0;
+      for (int k = 0; k < TH; ++k)
+      {
+        tr2 += s_part[0][k];
+        trz += s_part[1][k];
+      }
       s->r2 = tr2;
       s->rz = trz;
       if ((float)tr2 < s->thr)
@@ -526,30 +678,105 @@ CgCoef make_coef(const fsb_ctx* c)
   return coef;
 }
 
-// Tile height: the tallest of 32/16/8 rows that still gives every SM several tiles.
+// Tile height = consumer warps per CTA: 16 rows when that still gives every SM
+// several tiles, else 8.
 int pick_tile_rows(const fsb_ctx* c)
 {
   if (const char* e = getenv("FSB_CG_TILE_ROWS")) // tuning knob for profiling runs
   {
     const int th = atoi(e);
-    if (th == 8 || th == 16 || th == 32) return th;
+    if (th == 8 || th == 16) return th;
   }
   const int tiles_x = fsb_div_up(c->ld, kTileW);
-  for (int th = 32; th > 8; th >>= 1)
-    if ((int64_t)tiles_x * fsb_div_up(c->ny, th) >= (int64_t)4 * c->sm_count) return th;
+  if ((int64_t)tiles_x * fsb_div_up(c->ny, 16) >= (int64_t)4 * c->sm_count) return 16;
   return 8;
 }
 
-// persistent-style grids: exactly the CTAs that are co-resident (one wave), each walking the
-// tile list with a grid stride
-template <int TH>
-void resident_grids(fsb_ctx* c, int64_t n_tiles)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D tiled tensor map over a pitched grid; out-of-range box elements read as zero
+int make_map(fsb_ctx* c, EncodeTiledFn encode, CUtensorMap* map, void* base, bool is_f32,
+             int box_w, int box_h)
 {
-  int occ_dir = 4, occ_upd = 3;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dir, k_cg_direction<TH>, kCgThreads, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, k_cg_update<TH>, kCgThreads, 0);
-  c->cg_grid_dir = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count * std::max(occ_dir, 1));
-  c->cg_grid_upd = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count * std::max(occ_upd, 1));
+  const cuuint64_t esz = is_f32 ? 4 : 1;
+  const cuuint64_t gdim[2] = {(cuuint64_t)c->ld, (cuuint64_t)c->ny};
+  const cuuint64_t gstride[1] = {(cuuint64_t)c->ld * esz};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = encode(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8,
+                            2, base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fsb_fail(c, FSB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d box", (int)r,
+                    box_w, box_h);
+  return FSB_OK;
+}
+
+template <int TH>
+int configure_kernels(fsb_ctx* c, int64_t n_tiles)
+{
+  const int threads = (TH + 1) * 32;
+  const int smem_dir = kStages * DirStage<TH>::kBytes, smem_upd = kStages * UpdStage<TH>::kBytes;
+  FSB_CUDA(c, cudaFuncSetAttribute(k_cg_direction<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   smem_dir));
+  FSB_CUDA(c, cudaFuncSetAttribute(k_cg_update<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   smem_upd));
+  int occ_dir = 1, occ_upd = 1;
+  FSB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dir, k_cg_direction<TH>, threads,
+                                                            smem_dir));
+  FSB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, k_cg_update<TH>, threads,
+                                                            smem_upd));
+  int cap = 2; // CTAs per SM worth keeping resident (each already keeps kStages-1 tiles in flight)
+  if (const char* e = getenv("FSB_CG_CTAS_PER_SM")) cap = std::max(1, atoi(e));
+  occ_dir = std::max(1, std::min(occ_dir, cap));
+  occ_upd = std::max(1, std::min(occ_upd, cap));
+  // persistent-style grids: exactly one resident wave, each CTA walks the tile list
+  c->cg_grid_dir = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count * occ_dir);
+  c->cg_grid_upd = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count * occ_upd);
+  return FSB_OK;
+}
+
+int configure_cg(fsb_ctx* c)
+{
+  if (c->cg_tile_rows != 0) return FSB_OK;
+  const int th = pick_tile_rows(c);
+  const int64_t n_tiles = (int64_t)fsb_div_up(c->ld, kTileW) * fsb_div_up(c->ny, th);
+  if (th == 16) FSB_TRY(configure_kernels<16>(c, n_tiles));
+  else FSB_TRY(configure_kernels<8>(c, n_tiles));
+
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  FSB_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess)
+    return fsb_fail(c, FSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+  EncodeTiledFn encode = (EncodeTiledFn)fn;
+  CUtensorMap halo_r, halo_p[2], inner_x, inner_r, code;
+  FSB_TRY(make_map(c, encode, &halo_r, c->cg_r, true, kHaloW, th + 2));
+  FSB_TRY(make_map(c, encode, &halo_p[0], c->cg_p[0], true, kHaloW, th + 2));
+  FSB_TRY(make_map(c, encode, &halo_p[1], c->cg_p[1], true, kHaloW, th + 2));
+  FSB_TRY(make_map(c, encode, &inner_x, c->cg_x, true, kTileW, th));
+  FSB_TRY(make_map(c, encode, &inner_r, c->cg_r, true, kTileW, th));
+  FSB_TRY(make_map(c, encode, &code, c->cg_code, false, kCodeW, th + 2));
+  for (int cur = 0; cur < 2; ++cur)
+  {
+    CgMaps* d = reinterpret_cast<CgMaps*>(c->cg_maps_dir[cur]);
+    CgMaps* u = reinterpret_cast<CgMaps*>(c->cg_maps_upd[cur]);
+    memset(d, 0, sizeof(CgMaps));
+    memset(u, 0, sizeof(CgMaps));
+    d->halo_a = halo_r;          // direction: r and the OLD direction p[cur]
+    d->halo_b = halo_p[cur];
+    d->code = code;
+    u->halo_a = halo_p[cur ^ 1]; // update: the NEW direction p[cur^1], x, r
+    u->inner_a = inner_x;
+    u->inner_b = inner_r;
+    u->code = code;
+  }
+  c->cg_tile_rows = th;
+  return FSB_OK;
 }
 
 // one CG iteration = two launches; `cur` selects the ping-pong direction buffer
@@ -558,15 +785,14 @@ int launch_iteration(fsb_ctx* c, const CgCoef& coef, int cur)
   const int th = c->cg_tile_rows;
   const int tiles_x = fsb_div_up(c->ld, kTileW);
   const int n_tiles = tiles_x * fsb_div_up(c->ny, th);
+  const CgMaps& md = *reinterpret_cast<const CgMaps*>(c->cg_maps_dir[cur]);
+  const CgMaps& mu = *reinterpret_cast<const CgMaps*>(c->cg_maps_upd[cur]);
 #define FSB_CG_LAUNCH(TH)                                                                          \
-  k_cg_direction<TH><<<c->cg_grid_dir, kCgThreads, 0, c->stream>>>(                                \
-      c->cg_p[cur], c->cg_p[cur ^ 1], c->cg_r, c->cg_code, c->ld, c->ny, tiles_x, n_tiles, coef,   \
-      c->scal, c->partials);                                                                       \
-  k_cg_update<TH><<<c->cg_grid_upd, kCgThreads, 0, c->stream>>>(                                   \
-      c->cg_x, c->cg_r, c->cg_p[cur ^ 1], c->cg_code, c->ld, c->ny, tiles_x, n_tiles, coef,        \
-      c->scal, c->partials)
-  if (th == 32) { FSB_CG_LAUNCH(32); }
-  else if (th == 16) { FSB_CG_LAUNCH(16); }
+  k_cg_direction<TH><<<c->cg_grid_dir, (TH + 1) * 32, kStages * DirStage<TH>::kBytes, c->stream>>>( \
+      md, c->cg_p[cur ^ 1], c->ld, c->ny, tiles_x, n_tiles, coef, c->scal, c->partials);           \
+  k_cg_update<TH><<<c->cg_grid_upd, (TH + 1) * 32, kStages * UpdStage<TH>::kBytes, c->stream>>>(   \
+      mu, c->cg_x, c->cg_r, c->ld, c->ny, tiles_x, n_tiles, coef, c->scal, c->partials)
+  if (th == 16) { FSB_CG_LAUNCH(16); }
   else { FSB_CG_LAUNCH(8); }
 #undef FSB_CG_LAUNCH
   FSB_CUDA(c, cudaGetLastError());
@@ -620,22 +846,14 @@ int launch_chunk(fsb_ctx* c, const CgCoef& coef)
 
 int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
 {
-  const GridDims d{c->nx, c->ny, c->ld, c->dx, c->dy};
+  const GridDims d = make_grid_dims(c->nx, c->ny, c->ld, c->dx, c->dy);
   const CgCoef coef = make_coef(c);
 
   // ---- build
   fsb_prof_begin(c, FSB_PROF_RHS);
   const int64_t total = (int64_t)c->ld * c->ny;
   const int build_blocks = (int)std::min<int64_t>(fsb_div_up(total, 256), c->sm_count * 8);
-  if (c->cg_tile_rows == 0)
-  {
-    c->cg_tile_rows = pick_tile_rows(c);
-    const int64_t n_tiles =
-        (int64_t)fsb_div_up(c->ld, kTileW) * fsb_div_up(c->ny, c->cg_tile_rows);
-    if (c->cg_tile_rows == 32) resident_grids<32>(c, n_tiles);
-    else if (c->cg_tile_rows == 16) resident_grids<16>(c, n_tiles);
-    else resident_grids<8>(c, n_tiles);
-  }
+  FSB_TRY(configure_cg(c));
   const int need = std::max(3 * build_blocks, std::max(c->cg_grid_dir, 2 * c->cg_grid_upd));
   if (need > c->partials_cap)
   {

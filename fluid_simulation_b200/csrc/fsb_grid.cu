@@ -17,7 +17,7 @@ __device__ __forceinline__ bool cell_of_thread(const GridDims d, int* i, int* j)
 }
 
 inline int cell_grid(const fsb_ctx* c) { return fsb_div_up((int64_t)c->ld * c->ny, kBlock); }
-inline GridDims dims(const fsb_ctx* c) { return GridDims{c->nx, c->ny, c->ld, c->dx, c->dy}; }
+inline GridDims dims(const fsb_ctx* c) { return make_grid_dims(c->nx, c->ny, c->ld, c->dx, c->dy); }
 
 // src/MacGrid.cpp:32-50 clearCellTypeBuffer + the border reset of
 // src/FluidDomain.cpp:169-179 (the border is SOLID before and after marking).
@@ -33,16 +33,15 @@ __global__ void k_fill_labels(uint8_t* __restrict__ cell, const GridDims d)
 // lengthX() is recomputed as size * delta in float (include/Grid.h:54-55).
 // Marking a border cell is undone by the border reset, so it is skipped; the
 // store is idempotent, hence race-free without atomics.
+// `len` carries lengthX / lengthY in its dx / dy slots (with the power-of-two fast path).
 __global__ void k_mark_liquid(const float4* __restrict__ part, int64_t n,
-                              uint8_t* __restrict__ cell, const GridDims d)
+                              uint8_t* __restrict__ cell, const GridDims d, const GridDims len)
 {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const float4 p = part[k];
-  const float len_x = (float)d.nx * d.dx;
-  const float len_y = (float)d.ny * d.dy;
-  int x = (int)((p.x / len_x) * (float)d.nx);
-  int y = (int)((p.y / len_y) * (float)d.ny);
+  int x = (int)(div_dx(len, p.x) * (float)d.nx);
+  int y = (int)(div_dy(len, p.y) * (float)d.ny);
   x = clampi(x, 0, d.nx - 1);
   y = clampi(y, 0, d.ny - 1);
   if (x == 0 || y == 0 || x == d.nx - 1 || y == d.ny - 1) return;
@@ -169,8 +168,8 @@ __global__ void k_extend_sweep(float* __restrict__ ub, float* __restrict__ vb,
 __device__ __forceinline__ void grid_splat_atomic(float* __restrict__ g, const GridDims d, float x,
                                                   float y, float value)
 {
-  const float xd = x / d.dx;
-  const float yd = y / d.dy;
+  const float xd = div_dx(d, x);
+  const float yd = div_dy(d, y);
   int i = (int)xd;
   int j = (int)yd;
   int i1 = i + 1;
@@ -228,8 +227,11 @@ int fsb_k_classify(fsb_ctx* c)
   FSB_LAUNCHED(c);
   if (c->n > 0)
   {
+    // lengthX() is recomputed as size * delta in float (include/Grid.h:54-55)
+    const GridDims len =
+        make_grid_dims(c->nx, c->ny, c->ld, (float)c->nx * c->dx, (float)c->ny * c->dy);
     k_mark_liquid<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(c->part[c->pcur], c->n,
-                                                                       c->cell, dims(c));
+                                                                       c->cell, dims(c), len);
     FSB_LAUNCHED(c);
   }
   fsb_prof_end(c, FSB_PROF_CLASSIFY);

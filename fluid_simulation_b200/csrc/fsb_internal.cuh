@@ -2,6 +2,7 @@
 // Product code: never includes or links anything under oracle/.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -94,6 +95,9 @@ struct fsb_ctx
   cudaGraphExec_t cg_graph = nullptr;
   int cg_graph_state = 0; // 0: not built, 1: usable, -1: capture unavailable (direct launches)
   int cg_tile_rows = 0, cg_grid_dir = 0, cg_grid_upd = 0;
+  // TMA descriptors of the two iteration kernels for both ping-pong phases (CgMaps in fsb_cg.cu)
+  alignas(64) unsigned char cg_maps_dir[2][5 * sizeof(CUtensorMap)];
+  alignas(64) unsigned char cg_maps_upd[2][5 * sizeof(CUtensorMap)];
   int max_iters = 100;
   float tol = 1.1920929e-7f;
   int iters = 0;

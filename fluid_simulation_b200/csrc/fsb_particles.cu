@@ -8,11 +8,11 @@ namespace {
 
 constexpr int kBlock = 256;
 
-inline GridDims dims(const fsb_ctx* c) { return GridDims{c->nx, c->ny, c->ld, c->dx, c->dy}; }
+inline GridDims dims(const fsb_ctx* c) { return make_grid_dims(c->nx, c->ny, c->ld, c->dx, c->dy); }
 // the P2G accumulators carry the memory pool's deltas (src/FluidSolver.cpp:13-16)
 inline GridDims pool_dims(const fsb_ctx* c)
 {
-  return GridDims{c->nx, c->ny, c->ld, c->pool_dx, c->pool_dy};
+  return make_grid_dims(c->nx, c->ny, c->ld, c->pool_dx, c->pool_dy);
 }
 
 // ------------------------------------------------------------------ sort --
@@ -30,8 +30,8 @@ __global__ void k_sort_count(const float4* __restrict__ part, int64_t n, const G
   if (live)
   {
     const float4 p = part[k];
-    const int ci = clampi((int)(p.x / d.dx), 0, d.nx - 1);
-    const int cj = clampi((int)(p.y / d.dy), 0, d.ny - 1);
+    const int ci = clampi((int)div_dx(d, p.x), 0, d.nx - 1);
+    const int cj = clampi((int)div_dy(d, p.y), 0, d.ny - 1);
     key = ci + cj * d.nx;
   }
   const int prev = __shfl_up_sync(0xffffffffu, key, 1);
@@ -203,77 +203,190 @@ __global__ void k_sort_gather(const float4* __restrict__ src, const int* __restr
 }
 
 // ------------------------------------------------------------------- P2G --
-// src/FluidSolver.cpp:873-919 as a gather.  One thread per cell (i,j) owns
-// the faces u(i,j) and v(i,j).  A particle whose sort cell is (ci,cj) splats u
-// onto nodes {ci,ci+1} x {bj,bj+1} with bj in {cj-1,cj}, and v onto
-// {bi,bi+1} x {cj,cj+1} with bi in {ci-1,ci} (include/Grid.h:152-184 with the
-// MAC half-cell shift), so both faces only receive from the 3x3 cells around
-// (i,j).  Every visited particle recomputes its own four target nodes exactly
-// as the reference does (truncation, fraction before clamping, independent
-// clamps) and contributes where a target equals this face, so clamped
-// duplicates and out-of-domain particles land where the reference puts them.
-// face = sum / weight where weight > 1e-6, else the back buffer keeps its stale
-// value (:902-915).  No accumulator grids, no atomics, deterministic.
-__global__ void k_p2g_gather(const float4* __restrict__ part, const int* __restrict__ cell_start,
-                             float* __restrict__ ub, float* __restrict__ vb, const GridDims d,
-                             float half_dx, float half_dy)
-{
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = (int)(t % d.ld);
-  const int j = (int)(t / d.ld);
-  if (i >= d.nx || j >= d.ny) return;
+// src/FluidSolver.cpp:873-919 as a register-streaming, atomics-free,
+// deterministic transfer over the cell-sorted particles.
+//
+// A warp owns a strip of 32 cell columns (lane = column; lanes 1..30 produce
+// output, lanes 0 and 31 are the halo columns) and walks up a chunk of
+// kP2gRows output rows.  In every cell row each lane visits ITS OWN cell's
+// particles once, computes the reference's four splat targets and weights
+// (include/Grid.h:152-184: truncation, fraction before clamping, independent
+// clamps, y-split then x-split) and adds them into rolling per-lane node
+// accumulators:  u targets lie in columns {ci, ci+1} and rows {c-1, c, c+1}
+// of the particle's sort cell (ci, c), v targets in columns {ci-1, ci, ci+1}
+// and rows {c, c+1}.  After cell row c the u nodes of row c-1 and the v nodes
+// of row c are complete: the cross-column parts move one lane over by warp
+// shuffle, the face is written as sum / weight where weight > 1e-6 (else the
+// back buffer keeps its stale value, :902-915), and the accumulators rotate.
+// Each particle is read 1.13 times (halo columns / rows); no shared memory,
+// no atomics, and the summation order is fixed.
+constexpr int kP2gRows = 32;
+constexpr int kP2gCols = 30;
 
-  float su = 0.0f, wu = 0.0f, sv = 0.0f, wv = 0.0f;
-  const int ia = max(i - 1, 0), ib = min(i + 1, d.nx - 1);
-  const int ja = max(j - 1, 0), jb = min(j + 1, d.ny - 1);
-  for (int jj = ja; jj <= jb; ++jj)
+struct P2gAcc
+{
+  // u: [row slot 0..2 = c-1, c, c+1][column offset 0..1]; v: [row slot 0..1 = c, c+1][column offset -1..1]
+  float us[3][2], uw[3][2];
+  float vs[2][3], vw[2][3];
+};
+
+// generic (border / out-of-domain) accumulation: target node (it, jt) -> slot by comparison
+__device__ __forceinline__ void p2g_add_u(P2gAcc& a, int di, int dj, float val, float w)
+{
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (dj == r - 1 && di == q)
+      {
+        a.us[r][q] += val;
+        a.uw[r][q] += w;
+      }
+}
+__device__ __forceinline__ void p2g_add_v(P2gAcc& a, int di, int dj, float val, float w)
+{
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (dj == r && di == q - 1)
+      {
+        a.vs[r][q] += val;
+        a.vw[r][q] += w;
+      }
+}
+
+__device__ __forceinline__ void p2g_particle(P2gAcc& a, const float4 p, const GridDims& d, int ci,
+                                             int c, float half_dx, float half_dy)
+{
+  // ---- u: splat (vel_x, 1) at (px, py - dy/2)
   {
-    const int p0 = cell_start[ia + jj * d.nx];
-    const int p1 = cell_start[ib + jj * d.nx + 1];
-    for (int k = p0; k < p1; ++k)
+    const float xd = div_dx(d, p.x);
+    const float yd = div_dy(d, p.y - half_dy);
+    const int bi = (int)xd, bj = (int)yd;
+    const float fi = xd - (float)bi, fj = yd - (float)bj;
+    const float v0 = (1.0f - fj) * p.z, v1 = fj * p.z;
+    const float w0 = (1.0f - fj) * 1.0f, w1 = fj * 1.0f;
+    const float s00 = (1.0f - fi) * v0, s10 = fi * v0, s01 = (1.0f - fi) * v1, s11 = fi * v1;
+    const float t00 = (1.0f - fi) * w0, t10 = fi * w0, t01 = (1.0f - fi) * w1, t11 = fi * w1;
+    const bool regular = bi == ci && bi + 1 < d.nx && bj >= 0 && bj + 1 < d.ny;
+    if (regular && bj == c - 1)
     {
-      const float4 p = __ldg(part + k);
-      // ---- u: splat (vel_x, 1) at (px, py - dy/2)
-      {
-        const float xd = p.x / d.dx;
-        const float yd = (p.y - half_dy) / d.dy;
-        const int bi = (int)xd, bj = (int)yd;
-        const float fi = xd - (float)bi, fj = yd - (float)bj;
-        const int i0 = clampi(bi, 0, d.nx - 1), i1 = clampi(bi + 1, 0, d.nx - 1);
-        const int j0 = clampi(bj, 0, d.ny - 1), j1 = clampi(bj + 1, 0, d.ny - 1);
-        if ((i0 == i || i1 == i) && (j0 == j || j1 == j))
-        {
-          const float v0 = (1.0f - fj) * p.z, v1 = fj * p.z;
-          const float w0 = (1.0f - fj) * 1.0f, w1 = fj * 1.0f;
-          if (i0 == i && j0 == j) { su += (1.0f - fi) * v0; wu += (1.0f - fi) * w0; }
-          if (i1 == i && j0 == j) { su += fi * v0; wu += fi * w0; }
-          if (i0 == i && j1 == j) { su += (1.0f - fi) * v1; wu += (1.0f - fi) * w1; }
-          if (i1 == i && j1 == j) { su += fi * v1; wu += fi * w1; }
-        }
-      }
-      // ---- v: splat (vel_y, 1) at (px - dx/2, py)
-      {
-        const float xd = (p.x - half_dx) / d.dx;
-        const float yd = p.y / d.dy;
-        const int bi = (int)xd, bj = (int)yd;
-        const float fi = xd - (float)bi, fj = yd - (float)bj;
-        const int i0 = clampi(bi, 0, d.nx - 1), i1 = clampi(bi + 1, 0, d.nx - 1);
-        const int j0 = clampi(bj, 0, d.ny - 1), j1 = clampi(bj + 1, 0, d.ny - 1);
-        if ((i0 == i || i1 == i) && (j0 == j || j1 == j))
-        {
-          const float v0 = (1.0f - fj) * p.w, v1 = fj * p.w;
-          const float w0 = (1.0f - fj) * 1.0f, w1 = fj * 1.0f;
-          if (i0 == i && j0 == j) { sv += (1.0f - fi) * v0; wv += (1.0f - fi) * w0; }
-          if (i1 == i && j0 == j) { sv += fi * v0; wv += fi * w0; }
-          if (i0 == i && j1 == j) { sv += (1.0f - fi) * v1; wv += (1.0f - fi) * w1; }
-          if (i1 == i && j1 == j) { sv += fi * v1; wv += fi * w1; }
-        }
-      }
+      a.us[0][0] += s00; a.uw[0][0] += t00; a.us[0][1] += s10; a.uw[0][1] += t10;
+      a.us[1][0] += s01; a.uw[1][0] += t01; a.us[1][1] += s11; a.uw[1][1] += t11;
+    }
+    else if (regular && bj == c)
+    {
+      a.us[1][0] += s00; a.uw[1][0] += t00; a.us[1][1] += s10; a.uw[1][1] += t10;
+      a.us[2][0] += s01; a.uw[2][0] += t01; a.us[2][1] += s11; a.uw[2][1] += t11;
+    }
+    else
+    {
+      const int i0 = clampi(bi, 0, d.nx - 1) - ci, i1 = clampi(bi + 1, 0, d.nx - 1) - ci;
+      const int j0 = clampi(bj, 0, d.ny - 1) - c, j1 = clampi(bj + 1, 0, d.ny - 1) - c;
+      p2g_add_u(a, i0, j0, s00, t00);
+      p2g_add_u(a, i1, j0, s10, t10);
+      p2g_add_u(a, i0, j1, s01, t01);
+      p2g_add_u(a, i1, j1, s11, t11);
     }
   }
-  const size_t o = i + (size_t)j * d.ld;
-  if ((double)wu > 0.000001) ub[o] = su / wu;
-  if ((double)wv > 0.000001) vb[o] = sv / wv;
+  // ---- v: splat (vel_y, 1) at (px - dx/2, py)
+  {
+    const float xd = div_dx(d, p.x - half_dx);
+    const float yd = div_dy(d, p.y);
+    const int bi = (int)xd, bj = (int)yd;
+    const float fi = xd - (float)bi, fj = yd - (float)bj;
+    const float v0 = (1.0f - fj) * p.w, v1 = fj * p.w;
+    const float w0 = (1.0f - fj) * 1.0f, w1 = fj * 1.0f;
+    const float s00 = (1.0f - fi) * v0, s10 = fi * v0, s01 = (1.0f - fi) * v1, s11 = fi * v1;
+    const float t00 = (1.0f - fi) * w0, t10 = fi * w0, t01 = (1.0f - fi) * w1, t11 = fi * w1;
+    const bool regular = bj == c && bj + 1 < d.ny && bi >= 0 && bi + 1 < d.nx;
+    if (regular && bi == ci - 1)
+    {
+      a.vs[0][0] += s00; a.vw[0][0] += t00; a.vs[0][1] += s10; a.vw[0][1] += t10;
+      a.vs[1][0] += s01; a.vw[1][0] += t01; a.vs[1][1] += s11; a.vw[1][1] += t11;
+    }
+    else if (regular && bi == ci)
+    {
+      a.vs[0][1] += s00; a.vw[0][1] += t00; a.vs[0][2] += s10; a.vw[0][2] += t10;
+      a.vs[1][1] += s01; a.vw[1][1] += t01; a.vs[1][2] += s11; a.vw[1][2] += t11;
+    }
+    else
+    {
+      const int i0 = clampi(bi, 0, d.nx - 1) - ci, i1 = clampi(bi + 1, 0, d.nx - 1) - ci;
+      const int j0 = clampi(bj, 0, d.ny - 1) - c, j1 = clampi(bj + 1, 0, d.ny - 1) - c;
+      p2g_add_v(a, i0, j0, s00, t00);
+      p2g_add_v(a, i1, j0, s10, t10);
+      p2g_add_v(a, i0, j1, s01, t01);
+      p2g_add_v(a, i1, j1, s11, t11);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_p2g_stream(const float4* __restrict__ part, const int* __restrict__ cell_start,
+             float* __restrict__ ub, float* __restrict__ vb, const GridDims d, float half_dx,
+             float half_dy, int strips_x, int n_warps)
+{
+  const int warp_id = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (warp_id >= n_warps) return; // whole warps leave together
+  const int lane = threadIdx.x & 31;
+  const int ci = (warp_id % strips_x) * kP2gCols - 1 + lane;
+  const int ja = (warp_id / strips_x) * kP2gRows;
+  const int jb = min(ja + kP2gRows, d.ny);
+  const bool col_ok = ci >= 0 && ci < d.nx;
+  const bool writer = col_ok && lane >= 1 && lane <= kP2gCols;
+
+  P2gAcc a;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) a.us[r][q] = a.uw[r][q] = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) a.vs[r][q] = a.vw[r][q] = 0.0f;
+
+  for (int c = ja - 1; c <= jb; ++c)
+  {
+    if (col_ok && c >= 0 && c < d.ny)
+    {
+      const int p0 = __ldg(cell_start + ci + c * d.nx);
+      const int p1 = __ldg(cell_start + ci + c * d.nx + 1);
+      for (int k = p0; k < p1; ++k) p2g_particle(a, __ldg(part + k), d, ci, c, half_dx, half_dy);
+    }
+    // u nodes of row c-1: own column + the part the west neighbour lane holds for us
+    {
+      const float s_w = __shfl_up_sync(0xffffffffu, a.us[0][1], 1);
+      const float w_w = __shfl_up_sync(0xffffffffu, a.uw[0][1], 1);
+      const float su = a.us[0][0] + s_w, wu = a.uw[0][0] + w_w;
+      const int j = c - 1;
+      if (writer && j >= ja && j < jb && (double)wu > 0.000001) ub[ci + (size_t)j * d.ld] = su / wu;
+    }
+    // v nodes of row c: own column + west neighbour's east part + east neighbour's west part
+    {
+      const float s_w = __shfl_up_sync(0xffffffffu, a.vs[0][2], 1);
+      const float w_w = __shfl_up_sync(0xffffffffu, a.vw[0][2], 1);
+      const float s_e = __shfl_down_sync(0xffffffffu, a.vs[0][0], 1);
+      const float w_e = __shfl_down_sync(0xffffffffu, a.vw[0][0], 1);
+      const float sv = (a.vs[0][1] + s_w) + s_e, wv = (a.vw[0][1] + w_w) + w_e;
+      if (writer && c >= ja && c < jb && (double)wv > 0.000001) vb[ci + (size_t)c * d.ld] = sv / wv;
+    }
+    // rotate the row slots
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+    {
+      a.us[0][q] = a.us[1][q]; a.uw[0][q] = a.uw[1][q];
+      a.us[1][q] = a.us[2][q]; a.uw[1][q] = a.uw[2][q];
+      a.us[2][q] = 0.0f; a.uw[2][q] = 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+    {
+      a.vs[0][q] = a.vs[1][q]; a.vw[0][q] = a.vw[1][q];
+      a.vs[1][q] = 0.0f; a.vw[1][q] = 0.0f;
+    }
+  }
 }
 
 // ------------------------------------------------------------------- G2P --
@@ -336,8 +449,8 @@ __global__ void k_g2p_advect(float4* __restrict__ part, int64_t n, const float* 
     if (ensure_outside)
     {
       // src/MarkerParticleSet.cpp:55-60: the roll-back is a second advect(-dt)
-      const int x = (int)(p.x / d.dx);
-      const int y = (int)(p.y / d.dy);
+      const int x = (int)div_dx(d, p.x);
+      const int y = (int)div_dy(d, p.y);
       if (cell_type(cell, d, x, y) == FSB_SOLID)
       {
         const float mdt = -dt;
@@ -429,8 +542,11 @@ int fsb_k_p2g(fsb_ctx* c)
   FSB_TRY(fsb_k_sort_particles(c));
   fsb_prof_begin(c, FSB_PROF_P2G);
   const GridDims d = pool_dims(c);
-  k_p2g_gather<<<fsb_div_up((int64_t)c->ld * c->ny, kBlock), kBlock, 0, c->stream>>>(
-      c->part[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), d, 0.5f * c->dx, 0.5f * c->dy);
+  const int strips_x = fsb_div_up(c->nx, kP2gCols);
+  const int64_t n_warps = (int64_t)strips_x * fsb_div_up(c->ny, kP2gRows);
+  k_p2g_stream<<<fsb_div_up(n_warps * 32, 256), 256, 0, c->stream>>>(
+      c->part[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), d, 0.5f * c->dx, 0.5f * c->dy,
+      strips_x, (int)n_warps);
   FSB_LAUNCHED(c);
   c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:918
   fsb_prof_end(c, FSB_PROF_P2G);
