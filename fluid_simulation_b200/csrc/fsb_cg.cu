@@ -140,29 +140,36 @@ __global__ void k_cg_build(const float* __restrict__ uf, const float* __restrict
 
 // ------------------------------------------------------------ tile frame --
 // Both iteration kernels are TMA-fed, warp-specialised, persistent kernels:
-//   * one CTA per SM; TH consumer warps + 1 producer warp; tiles of kTileW = 128
-//     columns x TH rows; consumer warp w owns tile row w, lane l its columns
-//     4l..4l+3 (one 16-byte shared-memory access).
+//   * CTA = NW consumer warps + 1 producer warp; tiles of kTileW = 128 columns
+//     x TH = NW * RPW rows.  Consumer warp w owns the RPW consecutive tile rows
+//     w*RPW ..; lane l owns columns 4l..4l+3 (one 16-byte shared-memory access).
 //   * the producer's elected lane walks the CTA's tile list and issues
-//     cp.async.bulk.tensor (TMA) box loads into a kStages-deep shared-memory
-//     ring, completion on full[stage] (mbarrier, expect_tx); consumers release a
-//     stage by arriving on empty[stage].  Boxes include the one-cell halo
-//     (fp32: 136 x (TH+2) starting at (c0-4, j0-1); code bytes: 160 x (TH+2)
-//     starting at (c0-16, j0-1)); TMA zero-fills everything outside the grid,
-//     so the kernels have no bounds logic on the load side and the pipeline
-//     keeps (kStages-1) tiles of loads in flight per SM regardless of what the
-//     consumer warps are doing.
-//   * per-cell coefficients come from a shared-memory table of float4
+//     cp.async.bulk.tensor (TMA) box loads into a STAGES-deep shared-memory
+//     ring, completion on full[stage] (mbarrier, expect_tx); a consumer warp
+//     releases a stage (arrive on empty[stage]) as soon as it has pulled what it
+//     needs into registers.  Boxes include the one-cell halo (fp32: 136 x (TH+2)
+//     starting at (c0-4, j0-1); code bytes: 160 x (TH+2) starting at (c0-16,
+//     j0-1)); TMA zero-fills everything outside the grid, so there is no bounds
+//     logic on the load side, and (STAGES-1) tiles of loads stay in flight per
+//     CTA regardless of what the consumer warps are doing.
+//   * consumers never write shared memory and never synchronise with each
+//     other inside the tile loop: k_cg_direction re-computes the new direction
+//     on the two halo rows and two halo columns of a warp's row block from the
+//     staged r / p_old / code instead of exchanging it between warps.
+//   * coefficients: a float4 group whose four cells are all liquid with four
+//     non-SOLID neighbours (code word 0x05050505, the bulk of any scene) uses
+//     register constants; other groups read a shared-memory table of float4
 //     {inverse diagonal, diagonal, off-diagonal, 0} indexed by the stencil code
-//     (code 0 -> all zero, so masked cells come out exactly 0 without branches);
-//     one LDS.128 per cell.  (An indexed kernel-parameter array compiles to
-//     indexed LDC on the XU pipe: measured 78 % XU-bound, profiles/r01b.)
+//     (code 0 -> zeros, so masked cells come out exactly 0 without branches).
+//     (An indexed kernel-parameter array compiles to indexed LDC on the XU
+//     pipe: measured 78 % XU-bound, profiles/r01b.)
 //   * arithmetic uses explicit FMA: the CG is held to the solver tolerance and
 //     comparable iteration counts, not to Eigen's rounding.
 constexpr int kTileW = 128;
 constexpr int kHaloW = kTileW + 8;  // fp32 halo box width: columns c0-4 .. c0+131
 constexpr int kCodeW = kTileW + 32; // code halo box width: columns c0-16 .. c0+143
-constexpr int kStages = 4;
+constexpr uint32_t kInterior4 = 0x05050505u;
+constexpr int kMaxStages = 8;
 
 __host__ __device__ constexpr int align128(int x) { return (x + 127) / 128 * 128; }
 
@@ -241,10 +248,6 @@ __device__ __forceinline__ void fence_barrier_init()
 {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async()
-{
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void consumer_sync(int n_threads) // named barrier 1: consumer warps only
 {
   asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
@@ -262,24 +265,62 @@ __device__ __forceinline__ void load_lut(float4* lut, const CgCoef& coef)
   }
 }
 
-// q = A p for the four cells of one lane.  `prow` points at the lane's first
-// cell in the staged halo tile of p (row pitch kHaloW); pc is that float4.
-__device__ __forceinline__ float4 apply_a4(const float* __restrict__ prow, unsigned lane,
-                                           const float4 pc, const float4 k0, const float4 k1,
-                                           const float4 k2, const float4 k3)
+// walk of the CTA's tile list (tile = blockIdx.x, += gridDim.x) without a division per tile
+struct TileWalk
 {
-  const float4 s4 = *reinterpret_cast<const float4*>(prow - kHaloW);
-  const float4 n4 = *reinterpret_cast<const float4*>(prow + kHaloW);
-  float w = __shfl_up_sync(0xffffffffu, pc.w, 1);
-  float e = __shfl_down_sync(0xffffffffu, pc.x, 1);
-  if (lane == 0) w = prow[-1];
-  if (lane == 31) e = prow[4];
-  float4 q;
-  q.x = fmaf(k0.y, pc.x, k0.z * ((w + pc.y) + (s4.x + n4.x)));
-  q.y = fmaf(k1.y, pc.y, k1.z * ((pc.x + pc.z) + (s4.y + n4.y)));
-  q.z = fmaf(k2.y, pc.z, k2.z * ((pc.y + pc.w) + (s4.z + n4.z)));
-  q.w = fmaf(k3.y, pc.w, k3.z * ((pc.z + e) + (s4.w + n4.w)));
-  return q;
+  int tx, ty, step_x, step_y, tiles_x;
+  __device__ __forceinline__ TileWalk(int first_tile, int stride, int tiles_x_)
+  {
+    tiles_x = tiles_x_;
+    tx = first_tile % tiles_x;
+    ty = first_tile / tiles_x;
+    step_x = stride % tiles_x;
+    step_y = stride / tiles_x;
+  }
+  __device__ __forceinline__ void next()
+  {
+    tx += step_x;
+    ty += step_y;
+    if (tx >= tiles_x)
+    {
+      tx -= tiles_x;
+      ++ty;
+    }
+  }
+};
+
+// new direction for four cells: z + beta p_old with z = invdiag r
+__device__ __forceinline__ float4 direction4(const float4 r4, const float4 p4, uint32_t c4,
+                                             const float4* lut, float inv5, float beta)
+{
+  float i0 = inv5, i1 = inv5, i2 = inv5, i3 = inv5;
+  if (c4 != kInterior4)
+  {
+    i0 = lut[c4 & 0xff].x;
+    i1 = lut[(c4 >> 8) & 0xff].x;
+    i2 = lut[(c4 >> 16) & 0xff].x;
+    i3 = lut[c4 >> 24].x;
+  }
+  return make_float4(fmaf(beta, p4.x, i0 * r4.x), fmaf(beta, p4.y, i1 * r4.y),
+                     fmaf(beta, p4.z, i2 * r4.z), fmaf(beta, p4.w, i3 * r4.w));
+}
+
+// q = A p for four cells: centre pc, west / east scalars, south / north float4
+__device__ __forceinline__ float4 apply_a4(const float4 pc, float w, float e, const float4 s4,
+                                           const float4 n4, uint32_t c4, const float4* lut,
+                                           float diag5, float off)
+{
+  const float a0 = (w + pc.y) + (s4.x + n4.x);
+  const float a1 = (pc.x + pc.z) + (s4.y + n4.y);
+  const float a2 = (pc.y + pc.w) + (s4.z + n4.z);
+  const float a3 = (pc.z + e) + (s4.w + n4.w);
+  if (c4 == kInterior4)
+    return make_float4(fmaf(diag5, pc.x, off * a0), fmaf(diag5, pc.y, off * a1),
+                       fmaf(diag5, pc.z, off * a2), fmaf(diag5, pc.w, off * a3));
+  const float4 k0 = lut[c4 & 0xff], k1 = lut[(c4 >> 8) & 0xff], k2 = lut[(c4 >> 16) & 0xff],
+               k3 = lut[c4 >> 24];
+  return make_float4(fmaf(k0.y, pc.x, k0.z * a0), fmaf(k1.y, pc.y, k1.z * a1),
+                     fmaf(k2.y, pc.z, k2.z * a2), fmaf(k3.y, pc.w, k3.z * a3));
 }
 
 __device__ __forceinline__ float dot4(const float4 a, const float4 b)
@@ -287,23 +328,85 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b)
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 
+// block-level sum of NW consumer warps' doubles (N values each), then the
+// grid-level fold by the last CTA to finish; returns true in the threads of
+// that last CTA, with the totals in out[] (valid in thread 0).
+template <int NW, int N>
+__device__ __forceinline__ bool fold_consumers(double (&acc)[N], unsigned int* ticket,
+                                               double* __restrict__ partials, double (&out)[N])
+{
+  __shared__ double s_part[N][32];
+  __shared__ bool s_last;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_down_sync(0xffffffffu, acc[n], o);
+    if (lane == 0) s_part[n][warp] = acc[n];
+  }
+  consumer_sync(NW * 32);
+  if (warp == 0)
+  {
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+    {
+      double v = (lane < NW) ? s_part[n][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) partials[n * gridDim.x + blockIdx.x] = v;
+    }
+    if (lane == 0)
+    {
+      __threadfence();
+      s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+  }
+  consumer_sync(NW * 32);
+  if (!s_last) return false;
+  __threadfence();
+  const volatile double* part = partials;
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+  {
+    double v = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += NW * 32) v += part[n * gridDim.x + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_part[n][warp] = v;
+  }
+  consumer_sync(NW * 32);
+  if (threadIdx.x == 0)
+  {
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+    {
+      double t = 0.0;
+      for (int k = 0; k < NW; ++k) t += s_part[n][k];
+      out[n] = t;
+    }
+    *ticket = 0;
+  }
+  return true;
+}
+
 // ------------------------------------------------- direction + p.Ap dot --
-// p_new = z + beta p_old on the tile AND on its one-cell halo ring (recomputed
-// from the staged r, p_old, code, so no other CTA's output is needed), written
-// over p_old in the stage buffer; q = A p_new from shared memory / shuffles,
-// kept in registers for the dot product only.  HBM traffic 13 B per cell:
-// r, p_old, code in (TMA), p_new out (STG.128; ping-pong with p_old because
-// other CTAs still read the old halo).
-template <int TH>
-__global__ void __launch_bounds__((TH + 1) * 32, 1)
+// p_new = z + beta p_old on the warp's RPW rows and on their one-cell halo
+// (re-computed from the staged r, p_old, code: no other warp's or CTA's output
+// is needed), q = A p_new from registers and shuffles, kept for the dot product
+// only.  HBM traffic 13 B per cell: r, p_old, code in (TMA), p_new out
+// (STG.128; ping-pong with p_old because other CTAs still read the old halo).
+template <int NW, int RPW>
+__global__ void __launch_bounds__((NW + 1) * 32)
 k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, int ld, int ny,
-               int tiles_x, int n_tiles, const CgCoef coef, CgScalars* __restrict__ s,
-               double* __restrict__ partials)
+               int tiles_x, int n_tiles, int stages, const CgCoef coef,
+               CgScalars* __restrict__ s, double* __restrict__ partials)
 {
   if (s->done) return;
+  constexpr int TH = NW * RPW;
   using St = DirStage<TH>;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t full[kStages], empty[kStages];
+  __shared__ uint64_t full[kMaxStages], empty[kMaxStages];
   __shared__ float4 lut[8];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool first = (s->iter == 0);
@@ -312,164 +415,116 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
   load_lut(lut, coef);
   if (threadIdx.x == 0)
   {
-    for (int k = 0; k < kStages; ++k)
+    for (int k = 0; k < stages; ++k)
     {
       mbar_init(&full[k], 1);
-      mbar_init(&empty[k], TH);
+      mbar_init(&empty[k], NW);
     }
     fence_barrier_init();
   }
   __syncthreads();
 
-  if (warp == TH)
+  if (warp == NW)
   {
     // ---- producer
     if (lane == 0)
     {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it)
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+      int st = 0, round = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
       {
-        const int st = it % kStages;
-        if (it >= kStages) mbar_wait(&empty[st], ((it / kStages) - 1) & 1);
-        const int c0 = (tile % tiles_x) * kTileW;
-        const int j0 = (tile / tiles_x) * TH;
+        if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
+        const int c0 = t.tx * kTileW, j0 = t.ty * TH;
         unsigned char* base = smem + st * St::kBytes;
         mbar_expect_tx(&full[st], first ? St::kTx - St::kF32 : St::kTx);
         tma_load_2d(base + St::oR, &maps.halo_a, c0 - 4, j0 - 1, &full[st]);
         if (!first) tma_load_2d(base + St::oP, &maps.halo_b, c0 - 4, j0 - 1, &full[st]);
         tma_load_2d(base + St::oC, &maps.code, c0 - 16, j0 - 1, &full[st]);
+        if (++st == stages) { st = 0; ++round; }
       }
     }
     return;
   }
 
   // ---- consumers
-  double acc = 0.0;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it)
+  const float inv5 = coef.invdiag[4], diag5 = coef.diag[4], off = coef.off;
+  // stage-relative offsets of this lane: fp32 element (row r0 of the halo box), code byte
+  const int r0 = (int)warp * RPW; // first own row; halo-box rows r0 .. r0+RPW+1
+  const int fo = r0 * kHaloW + 4 + (int)lane * 4;
+  const int co = r0 * kCodeW + 16 + (int)lane * 4;
+  // lanes 0 / 31 also own the west / east halo cell of every row
+  const int hfo = r0 * kHaloW + (lane == 31 ? 4 + kTileW : 3);
+  const int hco = r0 * kCodeW + (lane == 31 ? 16 + kTileW : 15);
+  const bool edge = (lane == 0 || lane == 31);
+  double acc[1] = {0.0};
+  TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+  int st = 0, round = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
   {
-    const int st = it % kStages;
-    const int c0 = (tile % tiles_x) * kTileW;
-    const int j0 = (tile / tiles_x) * TH;
-    unsigned char* base = smem + st * St::kBytes;
+    const unsigned char* base = smem + st * St::kBytes;
     const float* sr = reinterpret_cast<const float*>(base + St::oR);
-    float* sp = reinterpret_cast<float*>(base + St::oP);
+    const float* sp = reinterpret_cast<const float*>(base + St::oP);
     const unsigned char* sc = base + St::oC;
-    mbar_wait(&full[st], (it / kStages) & 1);
+    mbar_wait(&full[st], round & 1);
 
-    // direction on the owned row (stage row warp+1) ...
-    const int row = (int)warp + 1;
-    const int fo = row * kHaloW + 4 + (int)lane * 4;
-    const uint32_t c4 = *reinterpret_cast<const uint32_t*>(sc + row * kCodeW + 16 + lane * 4);
-    const float4 k0 = lut[c4 & 0xff], k1 = lut[(c4 >> 8) & 0xff], k2 = lut[(c4 >> 16) & 0xff],
-                 k3 = lut[c4 >> 24];
-    const float4 r4 = *reinterpret_cast<const float4*>(sr + fo);
-    float4 pn;
-    if (first)
+    float4 pn[RPW + 2];
+    uint32_t cd[RPW + 2];
+    float he[RPW + 2]; // lanes 0 / 31: new direction of the west / east halo cell
+#pragma unroll
+    for (int k = 0; k < RPW + 2; ++k)
     {
-      pn = make_float4(k0.x * r4.x, k1.x * r4.y, k2.x * r4.z, k3.x * r4.w);
+      cd[k] = *reinterpret_cast<const uint32_t*>(sc + co + k * kCodeW);
+      const float4 r4 = *reinterpret_cast<const float4*>(sr + fo + k * kHaloW);
+      float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!first) p4 = *reinterpret_cast<const float4*>(sp + fo + k * kHaloW);
+      pn[k] = direction4(r4, p4, cd[k], lut, inv5, beta);
+      he[k] = 0.0f;
+      if (edge && k >= 1 && k <= RPW)
+      {
+        const float inv = lut[sc[hco + k * kCodeW]].x;
+        const float hp = first ? 0.0f : sp[hfo + k * kHaloW];
+        he[k] = fmaf(beta, hp, inv * sr[hfo + k * kHaloW]);
+      }
     }
-    else
-    {
-      const float4 p4 = *reinterpret_cast<const float4*>(sp + fo);
-      pn.x = fmaf(beta, p4.x, k0.x * r4.x);
-      pn.y = fmaf(beta, p4.y, k1.x * r4.y);
-      pn.z = fmaf(beta, p4.z, k2.x * r4.z);
-      pn.w = fmaf(beta, p4.w, k3.x * r4.w);
-    }
-    *reinterpret_cast<float4*>(sp + fo) = pn;
-    // ... on its west / east halo cells (lanes 0 and 31) ...
-    if (lane == 0 || lane == 31)
-    {
-      const int ho = row * kHaloW + (lane == 0 ? 3 : 4 + kTileW);
-      const float inv = lut[sc[row * kCodeW + (lane == 0 ? 15 : 16 + kTileW)]].x;
-      sp[ho] = first ? inv * sr[ho] : fmaf(beta, sp[ho], inv * sr[ho]);
-    }
-    // ... and on the south / north halo rows (warps 0 and 1)
-    if (warp < 2)
-    {
-      const int hrow = (warp == 0) ? 0 : TH + 1;
-      const int ho = hrow * kHaloW + 4 + (int)lane * 4;
-      const uint32_t h4 = *reinterpret_cast<const uint32_t*>(sc + hrow * kCodeW + 16 + lane * 4);
-      const float4 hr = *reinterpret_cast<const float4*>(sr + ho);
-      float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!first) hp = *reinterpret_cast<const float4*>(sp + ho);
-      float4 hn;
-      hn.x = fmaf(beta, hp.x, lut[h4 & 0xff].x * hr.x);
-      hn.y = fmaf(beta, hp.y, lut[(h4 >> 8) & 0xff].x * hr.y);
-      hn.z = fmaf(beta, hp.z, lut[(h4 >> 16) & 0xff].x * hr.z);
-      hn.w = fmaf(beta, hp.w, lut[h4 >> 24].x * hr.w);
-      *reinterpret_cast<float4*>(sp + ho) = hn;
-    }
-    consumer_sync(TH * 32);
-
-    const float4 q = apply_a4(sp + fo, lane, pn, k0, k1, k2, k3);
-    acc += (double)dot4(pn, q);
-    const int j = j0 + (int)warp, ci = c0 + (int)lane * 4;
-    if (j < ny && ci < ld) *reinterpret_cast<float4*>(p_new + (size_t)j * ld + ci) = pn;
-
-    // the stage was written through the generic proxy; the next TMA load into
-    // it goes through the async proxy
-    fence_proxy_async();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);
+    if (lane == 0) mbar_arrive(&empty[st]); // everything is in registers
+    if (++st == stages) { st = 0; ++round; }
+
+    const int ci = t.tx * kTileW + (int)lane * 4;
+    const int jb = t.ty * TH + r0;
+#pragma unroll
+    for (int k = 1; k <= RPW; ++k)
+    {
+      float w = __shfl_up_sync(0xffffffffu, pn[k].w, 1);
+      float e = __shfl_down_sync(0xffffffffu, pn[k].x, 1);
+      if (lane == 0) w = he[k];
+      if (lane == 31) e = he[k];
+      const float4 q = apply_a4(pn[k], w, e, pn[k - 1], pn[k + 1], cd[k], lut, diag5, off);
+      acc[0] += (double)dot4(pn[k], q);
+      const int j = jb + k - 1;
+      if (j < ny && ci < ld) *reinterpret_cast<float4*>(p_new + (size_t)j * ld + ci) = pn[k];
+    }
   }
 
-  // ---- reduction over the consumer warps, then over the CTAs (last one folds)
-  __shared__ double s_part[32];
-  __shared__ bool s_last;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-  if (lane == 0) s_part[warp] = acc;
-  consumer_sync(TH * 32);
-  if (warp == 0)
-  {
-    double v = (lane < TH) ? s_part[lane] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0)
-    {
-      partials[blockIdx.x] = v;
-      __threadfence();
-      s_last = (atomicAdd(&s->ticket[1], 1u) == gridDim.x - 1);
-    }
-  }
-  consumer_sync(TH * 32);
-  if (s_last)
-  {
-    __threadfence();
-    double v = 0.0;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += TH * 32)
-      v += reinterpret_cast<const volatile double*>(partials)[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) s_part[warp] = v;
-    consumer_sync(TH * 32);
-    if (threadIdx.x == 0)
-    {
-      double t = 0.0;
-      for (int k = 0; k < TH; ++k) t += s_part[k];
-      s->pq = t;
-      s->ticket[1] = 0;
-    }
-  }
+  double tot[1];
+  if (fold_consumers<NW, 1>(acc, &s->ticket[1], partials, tot) && threadIdx.x == 0) s->pq = tot[0];
 }
 
 // ------------------------------------------------------------ the update --
 // alpha = absNew / p.Ap; q = A p RE-COMPUTED from the staged p tile (q is
 // never stored); x += alpha p; r -= alpha q; partial |r|^2 and r.z.
 // HBM traffic 21 B per cell: p, code, x, r in (TMA), x, r out (STG.128).
-// No CTA-level barrier inside the tile loop: a warp only needs the TMA data.
-template <int TH>
-__global__ void __launch_bounds__((TH + 1) * 32, 1)
+template <int NW, int RPW>
+__global__ void __launch_bounds__((NW + 1) * 32)
 k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* __restrict__ r,
-            int ld, int ny, int tiles_x, int n_tiles, const CgCoef coef,
+            int ld, int ny, int tiles_x, int n_tiles, int stages, const CgCoef coef,
             CgScalars* __restrict__ s, double* __restrict__ partials)
 {
   if (s->done) return;
+  constexpr int TH = NW * RPW;
   using St = UpdStage<TH>;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t full[kStages], empty[kStages];
+  __shared__ uint64_t full[kMaxStages], empty[kMaxStages];
   __shared__ float4 lut[8];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float alpha = s->abs_new / (float)s->pq; // Eigen: alpha = absNew / p.dot(tmp)
@@ -478,157 +533,123 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
   load_lut(lut, coef);
   if (threadIdx.x == 0)
   {
-    for (int k = 0; k < kStages; ++k)
+    for (int k = 0; k < stages; ++k)
     {
       mbar_init(&full[k], 1);
-      mbar_init(&empty[k], TH);
+      mbar_init(&empty[k], NW);
     }
     fence_barrier_init();
   }
   __syncthreads();
 
-  if (warp == TH)
+  if (warp == NW)
   {
     if (lane == 0)
     {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it)
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+      int st = 0, round = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
       {
-        const int st = it % kStages;
-        if (it >= kStages) mbar_wait(&empty[st], ((it / kStages) - 1) & 1);
-        const int c0 = (tile % tiles_x) * kTileW;
-        const int j0 = (tile / tiles_x) * TH;
+        if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
+        const int c0 = t.tx * kTileW, j0 = t.ty * TH;
         unsigned char* base = smem + st * St::kBytes;
         mbar_expect_tx(&full[st], St::kTx);
         tma_load_2d(base + St::oP, &maps.halo_a, c0 - 4, j0 - 1, &full[st]);
         tma_load_2d(base + St::oX, &maps.inner_a, c0, j0, &full[st]);
         tma_load_2d(base + St::oR, &maps.inner_b, c0, j0, &full[st]);
         tma_load_2d(base + St::oC, &maps.code, c0 - 16, j0 - 1, &full[st]);
+        if (++st == stages) { st = 0; ++round; }
       }
     }
     return;
   }
 
-  double acc_r2 = 0.0, acc_rz = 0.0;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it)
+  const float inv5 = coef.invdiag[4], diag5 = coef.diag[4], off = coef.off;
+  const int r0 = (int)warp * RPW;
+  const int fo = r0 * kHaloW + 4 + (int)lane * 4;
+  const int co = (r0 + 1) * kCodeW + 16 + (int)lane * 4;
+  const int io = r0 * kTileW + (int)lane * 4;
+  const int hfo = r0 * kHaloW + (lane == 31 ? 4 + kTileW : 3);
+  const bool edge = (lane == 0 || lane == 31);
+  double acc[2] = {0.0, 0.0};
+  TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+  int st = 0, round = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
   {
-    const int st = it % kStages;
-    const int c0 = (tile % tiles_x) * kTileW;
-    const int j0 = (tile / tiles_x) * TH;
-    unsigned char* base = smem + st * St::kBytes;
+    const unsigned char* base = smem + st * St::kBytes;
     const float* sp = reinterpret_cast<const float*>(base + St::oP);
     const float* sx = reinterpret_cast<const float*>(base + St::oX);
     const float* sr = reinterpret_cast<const float*>(base + St::oR);
     const unsigned char* sc = base + St::oC;
-    mbar_wait(&full[st], (it / kStages) & 1);
+    mbar_wait(&full[st], round & 1);
 
-    const int row = (int)warp + 1;
-    const int fo = row * kHaloW + 4 + (int)lane * 4;
-    const uint32_t c4 = *reinterpret_cast<const uint32_t*>(sc + row * kCodeW + 16 + lane * 4);
-    const float4 pc = *reinterpret_cast<const float4*>(sp + fo);
-    const float4 k0 = lut[c4 & 0xff], k1 = lut[(c4 >> 8) & 0xff], k2 = lut[(c4 >> 16) & 0xff],
-                 k3 = lut[c4 >> 24];
-    const float4 q = apply_a4(sp + fo, lane, pc, k0, k1, k2, k3);
-    float4 xo = *reinterpret_cast<const float4*>(sx + warp * kTileW + lane * 4);
-    float4 ro = *reinterpret_cast<const float4*>(sr + warp * kTileW + lane * 4);
+    float4 pc[RPW + 2], xo[RPW], ro[RPW];
+    uint32_t cd[RPW];
+    float he[RPW];
+#pragma unroll
+    for (int k = 0; k < RPW + 2; ++k) pc[k] = *reinterpret_cast<const float4*>(sp + fo + k * kHaloW);
+#pragma unroll
+    for (int k = 0; k < RPW; ++k)
+    {
+      cd[k] = *reinterpret_cast<const uint32_t*>(sc + co + k * kCodeW);
+      xo[k] = *reinterpret_cast<const float4*>(sx + io + k * kTileW);
+      ro[k] = *reinterpret_cast<const float4*>(sr + io + k * kTileW);
+      he[k] = edge ? sp[hfo + (k + 1) * kHaloW] : 0.0f;
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]); // everything this warp needs is in registers
+    if (++st == stages) { st = 0; ++round; }
 
-    if (c4 != 0) // four non-liquid cells: x and r stay exactly zero, nothing to write
+    const int ci = t.tx * kTileW + (int)lane * 4;
+    const int jb = t.ty * TH + r0;
+#pragma unroll
+    for (int k = 0; k < RPW; ++k)
     {
-      xo.x = fmaf(alpha, pc.x, xo.x); ro.x = fmaf(nalpha, q.x, ro.x);
-      xo.y = fmaf(alpha, pc.y, xo.y); ro.y = fmaf(nalpha, q.y, ro.y);
-      xo.z = fmaf(alpha, pc.z, xo.z); ro.z = fmaf(nalpha, q.z, ro.z);
-      xo.w = fmaf(alpha, pc.w, xo.w); ro.w = fmaf(nalpha, q.w, ro.w);
-      const int j = j0 + (int)warp, ci = c0 + (int)lane * 4; // c4 != 0 implies inside the grid
-      const size_t o = (size_t)j * ld + ci;
-      *reinterpret_cast<float4*>(x + o) = xo;
-      *reinterpret_cast<float4*>(r + o) = ro;
-      const float4 z = make_float4(k0.x * ro.x, k1.x * ro.y, k2.x * ro.z, k3.x * ro.w);
-      acc_r2 += (double)dot4(ro, ro);
-      acc_rz += (double)dot4(ro, z);
+      const float4 p4 = pc[k + 1];
+      float w = __shfl_up_sync(0xffffffffu, p4.w, 1);
+      float e = __shfl_down_sync(0xffffffffu, p4.x, 1);
+      if (lane == 0) w = he[k];
+      if (lane == 31) e = he[k];
+      const uint32_t c4 = cd[k];
+      if (c4 != 0) // four non-liquid cells: x and r stay exactly zero, nothing to write
+      {
+        const float4 q = apply_a4(p4, w, e, pc[k], pc[k + 2], c4, lut, diag5, off);
+        float4 xn, rn;
+        xn.x = fmaf(alpha, p4.x, xo[k].x); rn.x = fmaf(nalpha, q.x, ro[k].x);
+        xn.y = fmaf(alpha, p4.y, xo[k].y); rn.y = fmaf(nalpha, q.y, ro[k].y);
+        xn.z = fmaf(alpha, p4.z, xo[k].z); rn.z = fmaf(nalpha, q.z, ro[k].z);
+        xn.w = fmaf(alpha, p4.w, xo[k].w); rn.w = fmaf(nalpha, q.w, ro[k].w);
+        const size_t o = (size_t)(jb + k) * ld + ci; // c4 != 0 implies inside the grid
+        *reinterpret_cast<float4*>(x + o) = xn;
+        *reinterpret_cast<float4*>(r + o) = rn;
+        float4 z;
+        if (c4 == kInterior4) z = make_float4(inv5 * rn.x, inv5 * rn.y, inv5 * rn.z, inv5 * rn.w);
+        else
+          z = make_float4(lut[c4 & 0xff].x * rn.x, lut[(c4 >> 8) & 0xff].x * rn.y,
+                          lut[(c4 >> 16) & 0xff].x * rn.z, lut[c4 >> 24].x * rn.w);
+        acc[0] += (double)dot4(rn, rn);
+        acc[1] += (double)dot4(rn, z);
+      }
     }
   }
 
-  __shared__ double s_part[2][32];
-  __shared__ bool s_last;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
+  double tot[2];
+  if (fold_consumers<NW, 2>(acc, &s->ticket[2], partials, tot) && threadIdx.x == 0)
   {
-    acc_r2 += __shfl_down_sync(0xffffffffu, acc_r2, o);
-    acc_rz += __shfl_down_sync(0xffffffffu, acc_rz, o);
-  }
-  if (lane == 0)
-  {
-    s_part[0][warp] = acc_r2;
-    s_part[1][warp] = acc_rz;
-  }
-  consumer_sync(TH * 32);
-  if (warp == 0)
-  {
-    double v0 = (lane < TH) ? s_part[0][lane] : 0.0;
-    double v1 = (lane < TH) ? s_part[1][lane] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    const double tr2 = tot[0], trz = tot[1];
+    s->r2 = tr2;
+    s->rz = trz;
+    if ((float)tr2 < s->thr)
     {
-      v0 += __shfl_down_sync(0xffffffffu, v0, o);
-      v1 += __shfl_down_sync(0xffffffffu, v1, o);
+      s->done = 1; // converged: Eigen breaks before i++
     }
-    if (lane == 0)
+    else
     {
-      partials[blockIdx.x] = v0;
-      partials[gridDim.x + blockIdx.x] = v1;
-      __threadfence();
-      s_last = (atomicAdd(&s->ticket[2], 1u) == gridDim.x - 1);
-    }
-  }
-  consumer_sync(TH * 32);
-  if (s_last)
-  {
-    __threadfence();
-    const volatile double* part = partials;
-    double v0 = 0.0, v1 = 0.0;
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += TH * 32)
-    {
-      v0 += part[k];
-      v1 += part[gridDim.x + k];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-    {
-      v0 += __shfl_down_sync(0xffffffffu, v0, o);
-      v1 += __shfl_down_sync(0xffffffffu, v1, o);
-    }
-    if (lane == 0)
-    {
-      s_part[0][warp] = v0;
-      s_part[1][warp] = v1;
-    }
-    consumer_sync(TH * 32);
-    if (threadIdx.x == 0)
-    {
-      double tr2 = 0.0, trz = 0.0;
-      for (int k = 0; k < TH; ++k)
-      {
-        tr2 += s_part[0][k];
-        trz += s_part[1][k];
-      }
-      s->r2 = tr2;
-      s->rz = trz;
-      if ((float)tr2 < s->thr)
-      {
-        s->done = 1; // converged: Eigen breaks before i++
-      }
-      else
-      {
-        s->abs_old = s->abs_new;
-        s->abs_new = (float)trz;
-        s->beta = s->abs_new / s->abs_old;
-        s->iter = s->iter + 1;
-        if (s->iter >= s->max_iters) s->done = 1;
-      }
-      s->ticket[2] = 0;
+      s->abs_old = s->abs_new;
+      s->abs_new = (float)trz;
+      s->beta = s->abs_new / s->abs_old;
+      s->iter = s->iter + 1;
+      if (s->iter >= s->max_iters) s->done = 1;
     }
   }
 }
@@ -678,14 +699,17 @@ CgCoef make_coef(const fsb_ctx* c)
   return coef;
 }
 
-// Tile height = consumer warps per CTA: 16 rows when that still gives every SM
-// several tiles, else 8.
+// Kernel shapes: 8 consumer warps x RPW rows.  RPW = 2 (16-row tiles) when that still
+// gives every SM several tiles, else RPW = 1 (8-row tiles, small grids).
+constexpr int kNW = 8;
+
+
 int pick_tile_rows(const fsb_ctx* c)
 {
   if (const char* e = getenv("FSB_CG_TILE_ROWS")) // tuning knob for profiling runs
   {
     const int th = atoi(e);
-    if (th == 8 || th == 16) return th;
+    if (th == 8 || th == 16 || th == 32) return th;
   }
   const int tiles_x = fsb_div_up(c->ld, kTileW);
   if ((int64_t)tiles_x * fsb_div_up(c->ny, 16) >= (int64_t)4 * c->sm_count) return 16;
@@ -716,21 +740,33 @@ int make_map(fsb_ctx* c, EncodeTiledFn encode, CUtensorMap* map, void* base, boo
   return FSB_OK;
 }
 
-template <int TH>
+template <int RPW>
 int configure_kernels(fsb_ctx* c, int64_t n_tiles)
 {
-  const int threads = (TH + 1) * 32;
-  const int smem_dir = kStages * DirStage<TH>::kBytes, smem_upd = kStages * UpdStage<TH>::kBytes;
-  FSB_CUDA(c, cudaFuncSetAttribute(k_cg_direction<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   smem_dir));
-  FSB_CUDA(c, cudaFuncSetAttribute(k_cg_update<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   smem_upd));
+  constexpr int TH = kNW * RPW;
+  const int threads = (kNW + 1) * 32;
+  // ring depth: as many stages as two resident CTAs per SM allow (at least 2, at most kMaxStages)
+  const int budget = (227 * 1024 - 2 * 2048) / 2;
+  c->cg_stages_dir = std::max(2, std::min(kMaxStages, budget / DirStage<TH>::kBytes));
+  c->cg_stages_upd = std::max(2, std::min(kMaxStages, budget / UpdStage<TH>::kBytes));
+  if (const char* e = getenv("FSB_CG_STAGES")) // tuning knob for profiling runs
+  {
+    const int v = atoi(e);
+    if (v >= 2 && v <= kMaxStages) c->cg_stages_dir = c->cg_stages_upd = v;
+  }
+  const int smem_dir = c->cg_stages_dir * DirStage<TH>::kBytes;
+  const int smem_upd = c->cg_stages_upd * UpdStage<TH>::kBytes;
+  if (smem_dir > 227 * 1024 - 2048 || smem_upd > 227 * 1024 - 2048)
+    return fsb_fail(c, FSB_ERR_INVALID, "CG ring of %d/%d stages does not fit shared memory",
+                    c->cg_stages_dir, c->cg_stages_upd);
+  auto kd = k_cg_direction<kNW, RPW>;
+  auto ku = k_cg_update<kNW, RPW>;
+  FSB_CUDA(c, cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dir));
+  FSB_CUDA(c, cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_upd));
   int occ_dir = 1, occ_upd = 1;
-  FSB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dir, k_cg_direction<TH>, threads,
-                                                            smem_dir));
-  FSB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, k_cg_update<TH>, threads,
-                                                            smem_upd));
-  int cap = 2; // CTAs per SM worth keeping resident (each already keeps kStages-1 tiles in flight)
+  FSB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dir, kd, threads, smem_dir));
+  FSB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, ku, threads, smem_upd));
+  int cap = 4; // CTAs per SM worth keeping resident (each already keeps STAGES-1 tiles in flight)
   if (const char* e = getenv("FSB_CG_CTAS_PER_SM")) cap = std::max(1, atoi(e));
   occ_dir = std::max(1, std::min(occ_dir, cap));
   occ_upd = std::max(1, std::min(occ_upd, cap));
@@ -745,8 +781,9 @@ int configure_cg(fsb_ctx* c)
   if (c->cg_tile_rows != 0) return FSB_OK;
   const int th = pick_tile_rows(c);
   const int64_t n_tiles = (int64_t)fsb_div_up(c->ld, kTileW) * fsb_div_up(c->ny, th);
-  if (th == 16) FSB_TRY(configure_kernels<16>(c, n_tiles));
-  else FSB_TRY(configure_kernels<8>(c, n_tiles));
+  if (th == 32) FSB_TRY(configure_kernels<4>(c, n_tiles));
+  else if (th == 16) FSB_TRY(configure_kernels<2>(c, n_tiles));
+  else FSB_TRY(configure_kernels<1>(c, n_tiles));
 
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -787,13 +824,18 @@ int launch_iteration(fsb_ctx* c, const CgCoef& coef, int cur)
   const int n_tiles = tiles_x * fsb_div_up(c->ny, th);
   const CgMaps& md = *reinterpret_cast<const CgMaps*>(c->cg_maps_dir[cur]);
   const CgMaps& mu = *reinterpret_cast<const CgMaps*>(c->cg_maps_upd[cur]);
-#define FSB_CG_LAUNCH(TH)                                                                          \
-  k_cg_direction<TH><<<c->cg_grid_dir, (TH + 1) * 32, kStages * DirStage<TH>::kBytes, c->stream>>>( \
-      md, c->cg_p[cur ^ 1], c->ld, c->ny, tiles_x, n_tiles, coef, c->scal, c->partials);           \
-  k_cg_update<TH><<<c->cg_grid_upd, (TH + 1) * 32, kStages * UpdStage<TH>::kBytes, c->stream>>>(   \
-      mu, c->cg_x, c->cg_r, c->ld, c->ny, tiles_x, n_tiles, coef, c->scal, c->partials)
-  if (th == 16) { FSB_CG_LAUNCH(16); }
-  else { FSB_CG_LAUNCH(8); }
+#define FSB_CG_LAUNCH(RPW)                                                                         \
+  k_cg_direction<kNW, RPW><<<c->cg_grid_dir, (kNW + 1) * 32,                                       \
+                             c->cg_stages_dir * DirStage<kNW * RPW>::kBytes, c->stream>>>(         \
+      md, c->cg_p[cur ^ 1], c->ld, c->ny, tiles_x, n_tiles, c->cg_stages_dir, coef, c->scal,       \
+      c->partials);                                                                                \
+  k_cg_update<kNW, RPW><<<c->cg_grid_upd, (kNW + 1) * 32,                                          \
+                          c->cg_stages_upd * UpdStage<kNW * RPW>::kBytes, c->stream>>>(            \
+      mu, c->cg_x, c->cg_r, c->ld, c->ny, tiles_x, n_tiles, c->cg_stages_upd, coef, c->scal,       \
+      c->partials)
+  if (th == 32) { FSB_CG_LAUNCH(4); }
+  else if (th == 16) { FSB_CG_LAUNCH(2); }
+  else { FSB_CG_LAUNCH(1); }
 #undef FSB_CG_LAUNCH
   FSB_CUDA(c, cudaGetLastError());
   return FSB_OK;

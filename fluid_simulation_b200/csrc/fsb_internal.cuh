@@ -94,7 +94,7 @@ struct fsb_ctx
   cudaEvent_t cg_ev[2] = {nullptr, nullptr};
   cudaGraphExec_t cg_graph = nullptr;
   int cg_graph_state = 0; // 0: not built, 1: usable, -1: capture unavailable (direct launches)
-  int cg_tile_rows = 0, cg_grid_dir = 0, cg_grid_upd = 0;
+  int cg_tile_rows = 0, cg_grid_dir = 0, cg_grid_upd = 0, cg_stages_dir = 0, cg_stages_upd = 0;
   // TMA descriptors of the two iteration kernels for both ping-pong phases (CgMaps in fsb_cg.cu)
   alignas(64) unsigned char cg_maps_dir[2][5 * sizeof(CUtensorMap)];
   alignas(64) unsigned char cg_maps_upd[2][5 * sizeof(CUtensorMap)];
