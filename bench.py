@@ -38,6 +38,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 ALG_BYTES_CG_PER_CELL = 45.0  # bytes per cell per CG iteration
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_cg_direction + k_cg_update pair, from the
+# committed ncu --set full capture (bytes per iteration)
+NCU_TRAFFIC = {("picflip4096", 1): 491.7e6}
+NCU_TRAFFIC_SOURCE = "profiles/r01d_cg_ncu_full.md"
 
 WORKLOADS = {
     # name: (n, step kind, pic_ratio, cg tol, cg cap, particles per cell side)
@@ -46,6 +50,10 @@ WORKLOADS = {
     "picflip1024": dict(n=1024, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
     "sl1024": dict(n=1024, kind="sl", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
     "picflip256": dict(n=256, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
+    # BASELINE.json configs[3]: pressure Poisson CG only, tank labels, swirl + gravity velocities
+    "cg8192": dict(n=8192, kind="cg", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=0),
+    "cg4096": dict(n=4096, kind="cg", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=0),
+    "cg1024": dict(n=1024, kind="cg", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=0),
 }
 
 
@@ -112,6 +120,22 @@ def tank_particles(n, per_side, seed=1234):
     return scenes.tank_particles(n, np.random.default_rng(seed), per_side)
 
 
+def tank_fields(n):
+    """CG-only workloads: labels of the tank scene (SOLID border, LIQUID below 15/16, AIR cap) and a
+    velocity field = analytic swirl + one gravity kick, sampled at the MAC face positions."""
+    dx = 1.0 / n
+    lab = np.full((n, n), 1, dtype=np.uint8)
+    lab[1:int(15.0 / 16.0 * n), 1:-1] = 0
+    lab[0, :] = lab[-1, :] = 2
+    lab[:, 0] = lab[:, -1] = 2
+    i = np.arange(n, dtype=np.float64)
+    xu, yu = (i * dx)[None, :], ((i + 0.5) * dx)[:, None]
+    xv, yv = ((i + 0.5) * dx)[None, :], (i * dx)[:, None]
+    u = (np.sin(np.pi * xu) * np.cos(np.pi * yu)).astype(np.float32)
+    v = (-np.cos(np.pi * xv) * np.sin(np.pi * yv) - 9.82 * 0.01 * 64.0 / n).astype(np.float32)
+    return lab, u, v
+
+
 def step_kind(mod, name):
     return {"picflip": mod.STEP_PICFLIP, "sl": mod.STEP_SL, "flip": mod.STEP_FLIP,
             "pic": mod.STEP_PIC}[name]
@@ -138,15 +162,24 @@ def run_cpu_reference(wl, name, steps, warmup, gpu_iters_hint=None):
         n_s //= 2
     dt = np.float32(0.01 * 64.0 / n_s)
     s = lib.sim(n_s, n_s, 1.0, 1.0, float(dt), wl["pic_ratio"])
-    parts = scenes.tank_particles(n_s, np.random.default_rng(1234), wl["per_side"])
-    s.set_particles(parts)
     cg_sample_iters = 20
     s.set_cg(cg_sample_iters, wl["tol"])
     grav = float(np.float32(-9.82))
+    if wl["kind"] == "cg":
+        lab, u0, v0 = tank_fields(n_s)
+        s.set_cell_types(lab)
+        parts = np.zeros((0, 4), dtype=np.float32)
+    else:
+        parts = scenes.tank_particles(n_s, np.random.default_rng(1234), wl["per_side"])
+        s.set_particles(parts)
     results = []
     for it in range(max(1, min(steps, 2)) + min(warmup, 1)):
         t0 = time.perf_counter()
-        if wl["kind"] == "sl":
+        if wl["kind"] == "cg":
+            s.set_grid(ol.U_FRONT, u0); s.set_grid(ol.V_FRONT, v0)
+            t0 = time.perf_counter()
+            t1 = t0; s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
+        elif wl["kind"] == "sl":
             s.classify_cells(); s.advect_velocity_sl(float(dt)); s.add_acceleration(0.0, grav, float(dt))
             s.enforce_dirichlet()
             t1 = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
@@ -163,6 +196,8 @@ def run_cpu_reference(wl, name, steps, warmup, gpu_iters_hint=None):
     tot, solve, iters_done = results[-1]
     # assembly + patch share of the solve: time a zero-iteration solve
     s.set_cg(0, wl["tol"])
+    if wl["kind"] == "cg":
+        s.set_grid(ol.U_FRONT, u0); s.set_grid(ol.V_FRONT, v0)
     t1 = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
     solve0 = t2 - t1
     t_iter = max(solve - solve0, 1e-9) / iters_done
@@ -171,7 +206,8 @@ def run_cpu_reference(wl, name, steps, warmup, gpu_iters_hint=None):
     iters_to_tol = gpu_iters_hint if gpu_iters_hint else int(3.2 * n)  # O(N): ~800 at 256^2
     step_time_full = scale * (t_non_cg + iters_to_tol * t_iter)
     value = n * n / step_time_full
-    sample = (f"{kind_name} build, 1 thread: one {wl['kind']} step of the tank scene at {n_s}^2 "
+    what = "pressure solve" if wl["kind"] == "cg" else f"{wl['kind']} step"
+    sample = (f"{kind_name} build, 1 thread: one {what} of the tank scene at {n_s}^2 "
               f"({parts.shape[0]} particles) run stage by stage with CG capped at {cg_sample_iters} "
               f"iterations: non-CG {t_non_cg:.2f} s, {t_iter * 1e3:.2f} ms per CG iteration; "
               f"scaled x{scale:.0f} in cells to {n}^2 and extrapolated to {iters_to_tol} CG "
@@ -206,8 +242,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cfg_name = (f"{n}^2 {wl['kind']} full step, tank scene {wl['per_side']**2} particles/cell, "
-                f"pic_ratio {wl['pic_ratio']}, CG to {wl['tol']:g} relative residual")
+    if wl["kind"] == "cg":
+        cfg_name = (f"{n}^2 pressure Poisson solve only (tank labels, swirl + gravity field), "
+                    f"Jacobi-PCG to {wl['tol']:g} relative residual")
+    else:
+        cfg_name = (f"{n}^2 {wl['kind']} full step, tank scene {wl['per_side']**2} particles/cell, "
+                    f"pic_ratio {wl['pic_ratio']}, CG to {wl['tol']:g} relative residual")
 
     if args.impl == "reference":
         if rank != 0:
@@ -233,25 +273,41 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from fluid_simulation_b200 import capi
+    from fluid_simulation_b200 import capi, sharding
 
+    torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
 
     dt = float(np.float32(0.01 * 64.0 / n))
     sim = capi.Sim(n, n, 1.0, 1.0, dt, wl["pic_ratio"], device=local_rank)
     sim.set_cg(wl["cap"], wl["tol"])
-    parts = tank_particles(n, wl["per_side"])
-    n_part = parts.shape[0]
-    host = torch.empty((n_part, 4), dtype=torch.float32, pin_memory=True)
-    host.numpy()[:] = parts
-    del parts
-    log(f"scene ready: {n_part} particles")
-    sim.set_particles_ptr(host.data_ptr(), n_part)
+    cg_only = wl["kind"] == "cg"
+    if cg_only:
+        lab, u0, v0 = tank_fields(n)
+        hu = torch.empty((n, n), dtype=torch.float32, pin_memory=True); hu.numpy()[:] = u0
+        hv = torch.empty((n, n), dtype=torch.float32, pin_memory=True); hv.numpy()[:] = v0
+        hp = torch.empty((n, n), dtype=torch.float32, pin_memory=True)
+        sim.set_cell_types(lab)
+        n_part = 0
+        del u0, v0
+        log("fields ready")
+    else:
+        parts = tank_particles(n, wl["per_side"])
+        n_part = parts.shape[0]
+        host = torch.empty((n_part, 4), dtype=torch.float32, pin_memory=True)
+        host.numpy()[:] = parts
+        del parts
+        log(f"scene ready: {n_part} particles")
+        sim.set_particles_ptr(host.data_ptr(), n_part)
+        kind = step_kind(capi, wl["kind"])
     sim.synchronize()
-    log("particles uploaded")
-    kind = step_kind(capi, wl["kind"])
+    rows = (0, n)
+    if world > 1:
+        # every stage but the CG runs replicated (deterministic kernels, identical on all ranks);
+        # the CG iterates on row slabs with peer-memory halos and mailbox reductions
+        rows = sharding.connect(sim, dist, torch.device("cuda", local_rank))
+    log(f"state uploaded, rows {rows}")
 
     def barrier():
         torch.cuda.synchronize()
@@ -259,9 +315,20 @@ def main():
         if world > 1:
             dist.barrier()
 
+    def one_step():
+        """One pass of the hot path with state resident in HBM."""
+        if cg_only:
+            # the solve consumes its input (it projects the field): restore it from HBM-resident
+            # copies is not possible through the ABI, so re-upload; only the solve is timed below
+            sim.set_grid_ptr(capi.U_FRONT, hu.data_ptr())
+            sim.set_grid_ptr(capi.V_FRONT, hv.data_ptr())
+            sim.pressure_solve(dt, dt)
+        else:
+            sim.step(kind, dt)
+
     # ---- warm-up
     for _ in range(args.warmup):
-        sim.step(kind, dt)
+        one_step()
         sim.synchronize()
         log(f"warm-up step done, cg {sim.cg_info()}")
     barrier()
@@ -276,7 +343,7 @@ def main():
     barrier()
     sim.timer_start()
     for _ in range(args.steps):
-        sim.step(kind, dt)
+        one_step()
         iters_total += sim.cg_info()[0]
         log(f"timed step done, cg {sim.cg_info()}")
     ms = sim.timer_stop()
@@ -286,13 +353,17 @@ def main():
     prof = sim.profile_read()
     sim.profile_enable(False)
     relres = sim.cg_info()[1]
+    if cg_only:
+        # device time of the solves only (build + CG loop + patch), not the input re-upload
+        ms = prof["rhs"][0] + prof["cg"][0] + prof["patch"][0]
     if world > 1:
-        t = torch.tensor([ms], device="cuda")
+        t = torch.tensor([ms, prof["cg"][0]], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, cg_ms_max = float(t[0].item()), float(t[1].item())
+        prof["cg"] = (cg_ms_max, prof["cg"][1])
     ms_per_step = ms / args.steps
-    # N > 1: independent replicas of the single-GPU step (the sharded CG is reported separately)
-    value = world * n * n * args.steps / (ms * 1e-3)
+    # N > 1 is STRONG scaling of the same workload: total work fixed, CG rows split over N GPUs
+    value = n * n * args.steps / (ms * 1e-3)
 
     # ---- e2e: host buffers in and out every step
     e2e = None
@@ -300,31 +371,48 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            sim.set_particles_ptr(host.data_ptr(), n_part)
-            sim.step(kind, dt)
-            sim.get_particles_ptr(host.data_ptr())
+            if cg_only:
+                sim.set_grid_ptr(capi.U_FRONT, hu.data_ptr())
+                sim.set_grid_ptr(capi.V_FRONT, hv.data_ptr())
+                sim.pressure_solve(dt, dt)
+                sim.get_pressure_ptr(hp.data_ptr())
+            else:
+                sim.set_particles_ptr(host.data_ptr(), n_part)
+                sim.step(kind, dt)
+                sim.get_particles_ptr(host.data_ptr())
         barrier()
         t1 = time.perf_counter()
         et = t1 - t0
         if world > 1:
-            t = torch.tensor([et], device="cuda")
+            t = torch.tensor([et], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             et = float(t.item())
-        e2e = {"value": world * n * n * args.steps / et, "unit": "cell-updates/s",
-               "h2d_bytes_per_step": int(n_part * 16), "d2h_bytes_per_step": int(n_part * 16)}
+        h2d = 2 * n * n * 4 if cg_only else n_part * 16
+        d2h = n * n * 4 if cg_only else n_part * 16
+        e2e = {"value": n * n * args.steps / et, "unit": "cell-updates/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
+    if world > 1:
+        sim.shard_disconnect()
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
 
     peak, peak_src = measured_peak_gbs()
     cg_ms, _ = prof["cg"]
     it_ms = cg_ms / max(iters_total, 1)
-    achieved = ALG_BYTES_CG_PER_CELL * n * n / (it_ms * 1e-3) / 1e9 if iters_total else 0.0
+    # per GPU: each rank sweeps 1/world of the rows per iteration
+    alg_bytes = ALG_BYTES_CG_PER_CELL * n * n / world
+    achieved = alg_bytes / (it_ms * 1e-3) / 1e9 if iters_total else 0.0
     stages = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
-                "kernel": "CG iteration = k_cg_dir_spmv + k_cg_update (2 launches)",
-                "algorithmic_bytes_per_launch_pair": ALG_BYTES_CG_PER_CELL * n * n,
+                "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, world)),
+                "traffic_source": NCU_TRAFFIC_SOURCE if (args.workload, world) in NCU_TRAFFIC else None,
+                "kernel": "CG iteration = k_cg_direction + k_cg_update (2 launches"
+                          + (" + 2 one-warp mailbox combines" if world > 1 else "") + "), per GPU",
+                "algorithmic_bytes_per_launch_pair": alg_bytes,
+                "design_bytes_per_launch_pair": 34.0 * n * n / world,
                 "avg_iteration_us": it_ms * 1e3, "peak_source": peak_src,
                 "cg_share_of_step": cg_ms / ms if ms else None}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -341,12 +429,14 @@ def main():
     line = {
         "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak" if world > 1 else "strong",
+        "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg_name, "particles": int(n_part), "dt": dt,
                    "l2": "inputs larger than L2 (1.0 GB particles, 64 MB per grid)"
                    if n >= 4096 else "working set may fit L2: latency-bound, see DESIGN.md",
-                   "parallelism": "replicas" if world > 1 else "single GPU"},
+                   "parallelism": (f"CG sharded over {world} row slabs (peer-memory halo stores + mailbox "
+                                   f"reductions over NVLink), other stages replicated")
+                   if world > 1 else "single GPU"},
         "cg_iters_per_step": iters_total / args.steps,
         "cg_iters_per_s": iters_total / (cg_ms * 1e-3) if cg_ms else None,
         "cg_relres": relres,

@@ -25,6 +25,7 @@ LIQUID, AIR, SOLID = 0, 1, 2
 G2P_PIC, G2P_FLIP, G2P_PICFLIP = range(3)
 STEP_SL, STEP_PIC, STEP_FLIP, STEP_PICFLIP = range(4)
 INTEGRATOR_RK3, INTEGRATOR_EULER = 0, 1
+SHARD_BLOB_BYTES = 512
 PROF_NAMES = ["classify", "sort", "p2g", "grid_pre", "extend", "rhs", "cg", "patch", "g2p",
               "advect_sl", "advect_part"]
 
@@ -74,6 +75,10 @@ SIGNATURES = {
     "fsb_advect_velocity_sl": (_i, [_p, _f]),
     "fsb_advect_particles_grid": (_i, [_p, _f]),
     "fsb_step": (_i, [_p, _i, _f]),
+    "fsb_shard_export": (_i, [_p, _p]),
+    "fsb_shard_connect": (_i, [_p, _i, _i, _p]),
+    "fsb_shard_disconnect": (_i, [_p]),
+    "fsb_shard_rows": (_i, [_p, C.POINTER(_i), C.POINTER(_i)]),
     "fsb_profile_enable": (_i, [_p, _i]),
     "fsb_profile_read": (_i, [_p, _p, _p]),
     "fsb_launch_count": (_l, [_p]),
@@ -190,6 +195,13 @@ class Sim:
         a = np.ascontiguousarray(a, dtype=np.float32).reshape(self.ny, self.nx)
         self._ck(_lib.fsb_set_grid(self.h, which, _ptr(a)))
 
+    def set_grid_ptr(self, which, host_ptr):
+        """host_ptr: address of ny*nx dense floats (e.g. a pinned torch tensor's data_ptr())."""
+        self._ck(_lib.fsb_set_grid(self.h, which, _p(host_ptr)))
+
+    def get_pressure_ptr(self, host_ptr):
+        self._ck(_lib.fsb_get_pressure(self.h, _p(host_ptr)))
+
     def get_grid(self, which):
         a = np.empty((self.ny, self.nx), dtype=np.float32)
         self._ck(_lib.fsb_get_grid(self.h, which, _ptr(a)))
@@ -248,6 +260,24 @@ class Sim:
 
     def step(self, kind, dt):
         self._ck(_lib.fsb_step(self.h, kind, dt))
+
+    # multi-GPU row-slab sharding of the pressure solve
+    def shard_export(self):
+        blob = np.zeros(SHARD_BLOB_BYTES, dtype=np.uint8)
+        self._ck(_lib.fsb_shard_export(self.h, _ptr(blob)))
+        return blob
+
+    def shard_connect(self, rank, world, all_blobs):
+        a = np.ascontiguousarray(all_blobs, dtype=np.uint8).reshape(world, SHARD_BLOB_BYTES)
+        self._ck(_lib.fsb_shard_connect(self.h, rank, world, _ptr(a)))
+
+    def shard_disconnect(self):
+        self._ck(_lib.fsb_shard_disconnect(self.h))
+
+    def shard_rows(self):
+        lo, hi = _i(), _i()
+        self._ck(_lib.fsb_shard_rows(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
 
     # measurement
     def profile_enable(self, on=True):

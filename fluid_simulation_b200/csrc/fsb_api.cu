@@ -305,6 +305,8 @@ void fsb_destroy(fsb_ctx* c)
   cudaFree(c->cell); cudaFree(c->cg_x); cudaFree(c->cg_r); cudaFree(c->cg_p[0]); cudaFree(c->cg_p[1]);
   cudaFree(c->cg_code); cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->scan_block);
   cudaFree(c->sort_key); cudaFree(c->sort_rank); cudaFree(c->sort_idx);
+  for (int k = 0; k < c->n_ipc_opened; ++k) cudaIpcCloseMemHandle(c->ipc_opened[k]);
+  cudaFree(c->peer_x_dev); cudaFree(c->mail_local);
   cudaFree(c->partials); cudaFree(c->scal); cudaFree(c->stage);
   if (c->scal_h) cudaFreeHost(c->scal_h);
   if (c->cg_graph) cudaGraphExecDestroy(c->cg_graph);
@@ -660,6 +662,119 @@ int fsb_step(fsb_ctx* c, int kind, float dt)
     if (kind == FSB_STEP_FLIP) FSB_TRY(fsb_k_g2p_advect(c, FSB_G2P_FLIP, 0.0f, dt, 0));
     else FSB_TRY(fsb_k_g2p_advect(c, FSB_G2P_PICFLIP, c->pic_ratio, dt, 1));
   }
+  return FSB_OK;
+}
+
+// ------------------------------------------------------------------ sharding
+namespace {
+struct ShardBlob
+{
+  uint32_t magic;
+  int nx, ny, ld;
+  cudaIpcMemHandle_t h[5]; // r, p[0], p[1], x, mailbox
+};
+static_assert(sizeof(ShardBlob) <= FSB_SHARD_BLOB_BYTES, "blob too large");
+constexpr uint32_t kBlobMagic = 0x46534231u; // "FSB1"
+} // namespace
+
+int fsb_shard_export(fsb_ctx* c, void* blob)
+{
+  CHECK_CTX(c);
+  if (!blob) return fsb_fail(c, FSB_ERR_INVALID, "null blob");
+  if (!c->mail_local)
+  {
+    FSB_TRY(dev_alloc(c, &c->mail_local, (size_t)kMailTypes * kMaxRanks));
+    FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  ShardBlob b;
+  memset(&b, 0, sizeof b);
+  b.magic = kBlobMagic;
+  b.nx = c->nx; b.ny = c->ny; b.ld = c->ld;
+  void* ptrs[5] = {c->cg_r, c->cg_p[0], c->cg_p[1], c->cg_x, c->mail_local};
+  for (int k = 0; k < 5; ++k) FSB_CUDA(c, cudaIpcGetMemHandle(&b.h[k], ptrs[k]));
+  memset(blob, 0, FSB_SHARD_BLOB_BYTES);
+  memcpy(blob, &b, sizeof b);
+  return FSB_OK;
+}
+
+int fsb_shard_disconnect(fsb_ctx* c)
+{
+  CHECK_CTX(c);
+  FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < c->n_ipc_opened; ++k) cudaIpcCloseMemHandle(c->ipc_opened[k]);
+  c->n_ipc_opened = 0;
+  if (c->peer_x_dev) cudaFree(c->peer_x_dev);
+  c->peer_x_dev = nullptr;
+  for (int q = 0; q < kMaxRanks; ++q)
+  {
+    c->peer_r[q] = c->peer_p[0][q] = c->peer_p[1][q] = c->peer_x[q] = nullptr;
+    c->shard.mail[q] = nullptr;
+  }
+  c->shard.world = 1;
+  c->shard.rank = 0;
+  fsb_cg_reconfigure(c);
+  return FSB_OK;
+}
+
+int fsb_shard_connect(fsb_ctx* c, int rank, int world, const void* all_blobs)
+{
+  CHECK_CTX(c);
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !all_blobs)
+    return fsb_fail(c, FSB_ERR_INVALID, "bad shard arguments (rank %d of %d)", rank, world);
+  if (!c->mail_local) return fsb_fail(c, FSB_ERR_INVALID, "call fsb_shard_export first");
+  if (c->ny < 4 * world) return fsb_fail(c, FSB_ERR_INVALID, "grid too small for %d slabs", world);
+  FSB_TRY(fsb_shard_disconnect(c));
+  if (world == 1) return FSB_OK;
+  const char* base = (const char*)all_blobs;
+  float* peers_x[kMaxRanks];
+  int n_peers = 0;
+  for (int q = 0; q < world; ++q)
+  {
+    if (q == rank)
+    {
+      c->shard.mail[q] = c->mail_local;
+      continue;
+    }
+    ShardBlob b;
+    memcpy(&b, base + (size_t)q * FSB_SHARD_BLOB_BYTES, sizeof b);
+    if (b.magic != kBlobMagic || b.nx != c->nx || b.ny != c->ny || b.ld != c->ld)
+      return fsb_fail(c, FSB_ERR_INVALID, "rank %d exported a different domain", q);
+    void* opened[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const bool neighbour = (q == rank - 1 || q == rank + 1);
+    for (int k = 0; k < 5; ++k)
+    {
+      if (k < 3 && !neighbour) continue; // r and p are only needed from the adjacent slabs
+      cudaError_t e = cudaIpcOpenMemHandle(&opened[k], b.h[k], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        return fsb_fail(c, FSB_ERR_COMM, "cudaIpcOpenMemHandle(rank %d, buffer %d): %s", q, k,
+                        cudaGetErrorString(e));
+      c->ipc_opened[c->n_ipc_opened++] = opened[k];
+    }
+    c->peer_r[q] = (float*)opened[0];
+    c->peer_p[0][q] = (float*)opened[1];
+    c->peer_p[1][q] = (float*)opened[2];
+    c->peer_x[q] = (float*)opened[3];
+    c->shard.mail[q] = (MailSlot*)opened[4];
+    peers_x[n_peers++] = c->peer_x[q];
+  }
+  FSB_TRY(dev_alloc(c, &c->peer_x_dev, (size_t)kMaxRanks, 0));
+  FSB_CUDA(c, cudaMemcpyAsync(c->peer_x_dev, peers_x, sizeof(float*) * n_peers,
+                              cudaMemcpyHostToDevice, c->stream));
+  FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->shard.world = world;
+  c->shard.rank = rank;
+  // even split of the rows; the slabs need not be multiples of the tile height
+  c->shard.row_lo = (int)((int64_t)c->ny * rank / world);
+  c->shard.row_hi = (int)((int64_t)c->ny * (rank + 1) / world);
+  fsb_cg_reconfigure(c);
+  return FSB_OK;
+}
+
+int fsb_shard_rows(const fsb_ctx* c, int* row_lo, int* row_hi)
+{
+  if (!c) return FSB_ERR_INVALID;
+  if (row_lo) *row_lo = c->shard.world > 1 ? c->shard.row_lo : 0;
+  if (row_hi) *row_hi = c->shard.world > 1 ? c->shard.row_hi : c->ny;
   return FSB_OK;
 }
 

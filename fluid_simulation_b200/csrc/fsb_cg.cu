@@ -69,13 +69,16 @@ __global__ void k_cg_build(const float* __restrict__ uf, const float* __restrict
                            const CgCoef coef, CgScalars* __restrict__ s,
                            double* __restrict__ partials, float tol, int max_iters)
 {
-  const int64_t total = (int64_t)d.ld * d.ny;
+  // blocks walk (row, 256-column segment) pairs: no per-cell integer division
+  const int segs = (d.ld + 255) / 256;
+  const int n_work = segs * d.ny;
   double acc_b2 = 0.0, acc_bz = 0.0, acc_n = 0.0;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x)
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x)
   {
-    const int i = (int)(t % d.ld);
-    const int j = (int)(t / d.ld);
+    const int j = w / segs;
+    const int i = (w - j * segs) * 256 + threadIdx.x;
+    if (i >= d.ld) continue;
+    const size_t t = i + (size_t)j * d.ld;
     uint8_t cd = 0;
     float b = 0.0f;
     if (i < d.nx && j < d.ny && cell[t] == FSB_LIQUID)
@@ -328,12 +331,130 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b)
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 
+// ---- scalar updates shared by the single-GPU last-CTA path and the combine kernels
+__device__ __forceinline__ void finalize_update(CgScalars* s, double tr2, double trz)
+{
+  s->r2 = tr2;
+  s->rz = trz;
+  if ((float)tr2 < s->thr)
+  {
+    s->done = 1; // converged: Eigen breaks before i++
+  }
+  else
+  {
+    s->abs_old = s->abs_new;
+    s->abs_new = (float)trz;
+    s->beta = s->abs_new / s->abs_old;
+    s->iter = s->iter + 1;
+    if (s->iter >= s->max_iters) s->done = 1;
+  }
+}
+
+// ---- peer-memory mailbox (row-slab sharding, see fsb_internal.cuh)
+// Called by ONE thread after the values are final: write them into every rank's
+// mailbox, fence at system scope, then publish the sequence number.
+__device__ __forceinline__ void mail_post(const ShardArgs& sh, int type, double v0, double v1,
+                                          unsigned long long seq)
+{
+  for (int q = 0; q < sh.world; ++q)
+  {
+    volatile MailSlot* slot = sh.mail[q] + type * kMaxRanks + sh.rank;
+    slot->v[0] = v0;
+    slot->v[1] = v1;
+  }
+  __threadfence_system();
+  for (int q = 0; q < sh.world; ++q)
+  {
+    volatile MailSlot* slot = sh.mail[q] + type * kMaxRanks + sh.rank;
+    slot->seq = seq;
+  }
+}
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One warp: lane q waits for rank q's entry of `type` with sequence number
+// seq[type] + 1, lane 0 adds the entries in rank order (identical on every rank).
+// TYPE 0: p.Ap -> s->pq.  TYPE 1: (|r|^2, r.z) -> convergence test, beta, iteration
+// counter.  TYPE 2: barrier only.  A peer that stays silent for kMailTimeoutNs raises
+// comm_error and ends the solve instead of hanging the GPU.
+constexpr unsigned long long kMailTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+template <int TYPE>
+__global__ void k_cg_combine(const ShardArgs sh, CgScalars* __restrict__ s)
+{
+  if (TYPE != 2 && s->done) return;
+  const int lane = threadIdx.x;
+  const unsigned long long want = s->seq[TYPE] + 1;
+  volatile MailSlot* mine = sh.mail[sh.rank] + TYPE * kMaxRanks;
+  bool ok = true;
+  if (lane < sh.world)
+  {
+    const unsigned long long t0 = global_ns();
+    while (mine[lane].seq != want)
+    {
+      if (global_ns() - t0 > kMailTimeoutNs)
+      {
+        ok = false;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0)
+  {
+    double v0 = 0.0, v1 = 0.0;
+    for (int q = 0; q < sh.world; ++q)
+    {
+      v0 += mine[q].v[0];
+      v1 += mine[q].v[1];
+    }
+    s->seq[TYPE] = want;
+    if (!ok)
+    {
+      s->comm_error = 1;
+      s->done = 1;
+    }
+    else if (TYPE == 0) s->pq = v0;
+    else if (TYPE == 1) finalize_update(s, v0, v1);
+  }
+}
+
+// end of a sharded solve: every rank stores its rows of x into every peer's copy
+__global__ void k_shard_scatter_rows(const float* __restrict__ src, float* const* __restrict__ dst,
+                                     int n_dst, int64_t first, int64_t count4)
+{
+  const float4* s4 = reinterpret_cast<const float4*>(src + first);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count4;
+       t += (int64_t)gridDim.x * blockDim.x)
+  {
+    const float4 v = s4[t];
+    for (int q = 0; q < n_dst; ++q) reinterpret_cast<float4*>(dst[q] + first)[t] = v;
+  }
+}
+
+__global__ void k_shard_post_barrier(const ShardArgs sh, CgScalars* __restrict__ s)
+{
+  if (threadIdx.x == 0)
+  {
+    __threadfence_system();
+    mail_post(sh, 2, 0.0, 0.0, s->seq[2] + 1);
+  }
+}
+
 // block-level sum of NW consumer warps' doubles (N values each), then the
 // grid-level fold by the last CTA to finish; returns true in the threads of
 // that last CTA, with the totals in out[] (valid in thread 0).
 template <int NW, int N>
 __device__ __forceinline__ bool fold_consumers(double (&acc)[N], unsigned int* ticket,
-                                               double* __restrict__ partials, double (&out)[N])
+                                               double* __restrict__ partials, double (&out)[N],
+                                               bool sharded)
 {
   __shared__ double s_part[N][32];
   __shared__ bool s_last;
@@ -358,7 +479,10 @@ __device__ __forceinline__ bool fold_consumers(double (&acc)[N], unsigned int* t
     }
     if (lane == 0)
     {
-      __threadfence();
+      // sharded: this CTA's stores into peer memory must be visible to the peers before the
+      // mailbox entry that follows the last CTA's fold
+      if (sharded) __threadfence_system();
+      else __threadfence();
       s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
   }
@@ -398,9 +522,11 @@ __device__ __forceinline__ bool fold_consumers(double (&acc)[N], unsigned int* t
 // (STG.128; ping-pong with p_old because other CTAs still read the old halo).
 template <int NW, int RPW>
 __global__ void __launch_bounds__((NW + 1) * 32)
-k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, int ld, int ny,
+k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, int ld,
                int tiles_x, int n_tiles, int stages, const CgCoef coef,
-               CgScalars* __restrict__ s, double* __restrict__ partials)
+               CgScalars* __restrict__ s, double* __restrict__ partials,
+               const __grid_constant__ ShardArgs sh, float* __restrict__ push_lo,
+               float* __restrict__ push_hi)
 {
   if (s->done) return;
   constexpr int TH = NW * RPW;
@@ -434,7 +560,7 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
       {
         if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
-        const int c0 = t.tx * kTileW, j0 = t.ty * TH;
+        const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
         unsigned char* base = smem + st * St::kBytes;
         mbar_expect_tx(&full[st], first ? St::kTx - St::kF32 : St::kTx);
         tma_load_2d(base + St::oR, &maps.halo_a, c0 - 4, j0 - 1, &full[st]);
@@ -491,7 +617,7 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
     if (++st == stages) { st = 0; ++round; }
 
     const int ci = t.tx * kTileW + (int)lane * 4;
-    const int jb = t.ty * TH + r0;
+    const int jb = sh.row_lo + t.ty * TH + r0;
 #pragma unroll
     for (int k = 1; k <= RPW; ++k)
     {
@@ -500,14 +626,24 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
       if (lane == 0) w = he[k];
       if (lane == 31) e = he[k];
       const float4 q = apply_a4(pn[k], w, e, pn[k - 1], pn[k + 1], cd[k], lut, diag5, off);
-      acc[0] += (double)dot4(pn[k], q);
       const int j = jb + k - 1;
-      if (j < ny && ci < ld) *reinterpret_cast<float4*>(p_new + (size_t)j * ld + ci) = pn[k];
+      if (j < sh.row_hi && ci < ld)
+      {
+        acc[0] += (double)dot4(pn[k], q);
+        *reinterpret_cast<float4*>(p_new + (size_t)j * ld + ci) = pn[k];
+        // slab boundary rows also go straight into the neighbour's ghost row (NVLink store)
+        if (j == sh.row_lo && push_lo) *reinterpret_cast<float4*>(push_lo + ci) = pn[k];
+        if (j == sh.row_hi - 1 && push_hi) *reinterpret_cast<float4*>(push_hi + ci) = pn[k];
+      }
     }
   }
 
   double tot[1];
-  if (fold_consumers<NW, 1>(acc, &s->ticket[1], partials, tot) && threadIdx.x == 0) s->pq = tot[0];
+  if (fold_consumers<NW, 1>(acc, &s->ticket[1], partials, tot, sh.world > 1) && threadIdx.x == 0)
+  {
+    if (sh.world > 1) mail_post(sh, 0, tot[0], 0.0, s->seq[0] + 1);
+    else s->pq = tot[0];
+  }
 }
 
 // ------------------------------------------------------------ the update --
@@ -517,8 +653,10 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
 template <int NW, int RPW>
 __global__ void __launch_bounds__((NW + 1) * 32)
 k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* __restrict__ r,
-            int ld, int ny, int tiles_x, int n_tiles, int stages, const CgCoef coef,
-            CgScalars* __restrict__ s, double* __restrict__ partials)
+            int ld, int tiles_x, int n_tiles, int stages, const CgCoef coef,
+            CgScalars* __restrict__ s, double* __restrict__ partials,
+            const __grid_constant__ ShardArgs sh, float* __restrict__ push_lo,
+            float* __restrict__ push_hi)
 {
   if (s->done) return;
   constexpr int TH = NW * RPW;
@@ -551,7 +689,7 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
       {
         if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
-        const int c0 = t.tx * kTileW, j0 = t.ty * TH;
+        const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
         unsigned char* base = smem + st * St::kBytes;
         mbar_expect_tx(&full[st], St::kTx);
         tma_load_2d(base + St::oP, &maps.halo_a, c0 - 4, j0 - 1, &full[st]);
@@ -601,7 +739,7 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
     if (++st == stages) { st = 0; ++round; }
 
     const int ci = t.tx * kTileW + (int)lane * 4;
-    const int jb = t.ty * TH + r0;
+    const int jb = sh.row_lo + t.ty * TH + r0;
 #pragma unroll
     for (int k = 0; k < RPW; ++k)
     {
@@ -611,7 +749,10 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
       if (lane == 0) w = he[k];
       if (lane == 31) e = he[k];
       const uint32_t c4 = cd[k];
-      if (c4 != 0) // four non-liquid cells: x and r stay exactly zero, nothing to write
+      const int j = jb + k;
+      // four non-liquid cells: x and r stay exactly zero, nothing to write; rows past the
+      // slab end belong to the neighbour
+      if (c4 != 0 && j < sh.row_hi)
       {
         const float4 q = apply_a4(p4, w, e, pc[k], pc[k + 2], c4, lut, diag5, off);
         float4 xn, rn;
@@ -619,9 +760,11 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
         xn.y = fmaf(alpha, p4.y, xo[k].y); rn.y = fmaf(nalpha, q.y, ro[k].y);
         xn.z = fmaf(alpha, p4.z, xo[k].z); rn.z = fmaf(nalpha, q.z, ro[k].z);
         xn.w = fmaf(alpha, p4.w, xo[k].w); rn.w = fmaf(nalpha, q.w, ro[k].w);
-        const size_t o = (size_t)(jb + k) * ld + ci; // c4 != 0 implies inside the grid
+        const size_t o = (size_t)j * ld + ci; // c4 != 0 implies inside the grid
         *reinterpret_cast<float4*>(x + o) = xn;
         *reinterpret_cast<float4*>(r + o) = rn;
+        if (j == sh.row_lo && push_lo) *reinterpret_cast<float4*>(push_lo + ci) = rn;
+        if (j == sh.row_hi - 1 && push_hi) *reinterpret_cast<float4*>(push_hi + ci) = rn;
         float4 z;
         if (c4 == kInterior4) z = make_float4(inv5 * rn.x, inv5 * rn.y, inv5 * rn.z, inv5 * rn.w);
         else
@@ -634,23 +777,10 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
   }
 
   double tot[2];
-  if (fold_consumers<NW, 2>(acc, &s->ticket[2], partials, tot) && threadIdx.x == 0)
+  if (fold_consumers<NW, 2>(acc, &s->ticket[2], partials, tot, sh.world > 1) && threadIdx.x == 0)
   {
-    const double tr2 = tot[0], trz = tot[1];
-    s->r2 = tr2;
-    s->rz = trz;
-    if ((float)tr2 < s->thr)
-    {
-      s->done = 1; // converged: Eigen breaks before i++
-    }
-    else
-    {
-      s->abs_old = s->abs_new;
-      s->abs_new = (float)trz;
-      s->beta = s->abs_new / s->abs_old;
-      s->iter = s->iter + 1;
-      if (s->iter >= s->max_iters) s->done = 1;
-    }
+    if (sh.world > 1) mail_post(sh, 1, tot[0], tot[1], s->seq[1] + 1);
+    else finalize_update(s, tot[0], tot[1]);
   }
 }
 
@@ -663,13 +793,12 @@ __global__ void k_pressure_patch(const float* __restrict__ uf, const float* __re
                                  const float* __restrict__ x, const uint8_t* __restrict__ code,
                                  const GridDims d, float dt, float density)
 {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = (int)(t % d.ld);
-  const int j = (int)(t / d.ld);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
   if (i >= d.nx || j >= d.ny) return;
   const int im1 = clampi(i - 1, 0, d.nx - 1);
   const int jm1 = clampi(j - 1, 0, d.ny - 1);
-  const size_t k = t, kw = im1 + (size_t)j * d.ld, ks = i + (size_t)jm1 * d.ld;
+  const size_t k = i + (size_t)j * d.ld, kw = im1 + (size_t)j * d.ld, ks = i + (size_t)jm1 * d.ld;
   const bool l = code[k] != 0, lw = code[kw] != 0, ls = code[ks] != 0;
   if (!(l || lw || ls)) return;
   // the particle-pressure terms are k * n with k = 0.0 (:443-453): exactly +0
@@ -712,7 +841,8 @@ int pick_tile_rows(const fsb_ctx* c)
     if (th == 8 || th == 16 || th == 32) return th;
   }
   const int tiles_x = fsb_div_up(c->ld, kTileW);
-  if ((int64_t)tiles_x * fsb_div_up(c->ny, 16) >= (int64_t)4 * c->sm_count) return 16;
+  const int rows = c->shard.row_hi - c->shard.row_lo;
+  if ((int64_t)tiles_x * fsb_div_up(rows, 16) >= (int64_t)4 * c->sm_count) return 16;
   return 8;
 }
 
@@ -779,8 +909,14 @@ int configure_kernels(fsb_ctx* c, int64_t n_tiles)
 int configure_cg(fsb_ctx* c)
 {
   if (c->cg_tile_rows != 0) return FSB_OK;
+  if (c->shard.world == 1)
+  {
+    c->shard.row_lo = 0;
+    c->shard.row_hi = c->ny;
+  }
   const int th = pick_tile_rows(c);
-  const int64_t n_tiles = (int64_t)fsb_div_up(c->ld, kTileW) * fsb_div_up(c->ny, th);
+  const int64_t n_tiles = (int64_t)fsb_div_up(c->ld, kTileW) *
+                          fsb_div_up(c->shard.row_hi - c->shard.row_lo, th);
   if (th == 32) FSB_TRY(configure_kernels<4>(c, n_tiles));
   else if (th == 16) FSB_TRY(configure_kernels<2>(c, n_tiles));
   else FSB_TRY(configure_kernels<1>(c, n_tiles));
@@ -821,18 +957,28 @@ int launch_iteration(fsb_ctx* c, const CgCoef& coef, int cur)
 {
   const int th = c->cg_tile_rows;
   const int tiles_x = fsb_div_up(c->ld, kTileW);
-  const int n_tiles = tiles_x * fsb_div_up(c->ny, th);
+  const ShardArgs& sh = c->shard;
+  const int n_tiles = tiles_x * fsb_div_up(sh.row_hi - sh.row_lo, th);
   const CgMaps& md = *reinterpret_cast<const CgMaps*>(c->cg_maps_dir[cur]);
   const CgMaps& mu = *reinterpret_cast<const CgMaps*>(c->cg_maps_upd[cur]);
+  // slab boundary rows are stored into the neighbours' copies of the same rows
+  const bool south = sh.world > 1 && sh.rank > 0, north = sh.world > 1 && sh.rank < sh.world - 1;
+  const size_t lo_off = (size_t)sh.row_lo * c->ld, hi_off = (size_t)(sh.row_hi - 1) * c->ld;
+  float* p_lo = south ? c->peer_p[cur ^ 1][sh.rank - 1] + lo_off : nullptr;
+  float* p_hi = north ? c->peer_p[cur ^ 1][sh.rank + 1] + hi_off : nullptr;
+  float* r_lo = south ? c->peer_r[sh.rank - 1] + lo_off : nullptr;
+  float* r_hi = north ? c->peer_r[sh.rank + 1] + hi_off : nullptr;
 #define FSB_CG_LAUNCH(RPW)                                                                         \
   k_cg_direction<kNW, RPW><<<c->cg_grid_dir, (kNW + 1) * 32,                                       \
                              c->cg_stages_dir * DirStage<kNW * RPW>::kBytes, c->stream>>>(         \
-      md, c->cg_p[cur ^ 1], c->ld, c->ny, tiles_x, n_tiles, c->cg_stages_dir, coef, c->scal,       \
-      c->partials);                                                                                \
+      md, c->cg_p[cur ^ 1], c->ld, tiles_x, n_tiles, c->cg_stages_dir, coef, c->scal, c->partials, \
+      sh, p_lo, p_hi);                                                                             \
+  if (sh.world > 1) k_cg_combine<0><<<1, 32, 0, c->stream>>>(sh, c->scal);                         \
   k_cg_update<kNW, RPW><<<c->cg_grid_upd, (kNW + 1) * 32,                                          \
                           c->cg_stages_upd * UpdStage<kNW * RPW>::kBytes, c->stream>>>(            \
-      mu, c->cg_x, c->cg_r, c->ld, c->ny, tiles_x, n_tiles, c->cg_stages_upd, coef, c->scal,       \
-      c->partials)
+      mu, c->cg_x, c->cg_r, c->ld, tiles_x, n_tiles, c->cg_stages_upd, coef, c->scal, c->partials, \
+      sh, r_lo, r_hi);                                                                             \
+  if (sh.world > 1) k_cg_combine<1><<<1, 32, 0, c->stream>>>(sh, c->scal)
   if (th == 32) { FSB_CG_LAUNCH(4); }
   else if (th == 16) { FSB_CG_LAUNCH(2); }
   else { FSB_CG_LAUNCH(1); }
@@ -880,11 +1026,19 @@ int launch_chunk(fsb_ctx* c, const CgCoef& coef)
   {
     for (int k = 0; k < kCheckEvery; ++k) FSB_TRY(launch_iteration(c, coef, k & 1));
   }
-  c->launches += 2 * kCheckEvery;
+  c->launches += (c->shard.world > 1 ? 4 : 2) * kCheckEvery;
   return FSB_OK;
 }
 
 } // namespace
+
+void fsb_cg_reconfigure(fsb_ctx* c)
+{
+  c->cg_tile_rows = 0;
+  if (c->cg_graph) cudaGraphExecDestroy(c->cg_graph);
+  c->cg_graph = nullptr;
+  c->cg_graph_state = 0;
+}
 
 int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
 {
@@ -950,6 +1104,31 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
       }
     }
   }
+  if (c->shard.world > 1)
+  {
+    // every rank needs the whole pressure field for the (replicated) velocity patch
+    const ShardArgs& sh = c->shard;
+    const int64_t first = (int64_t)sh.row_lo * c->ld;
+    const int64_t count4 = (int64_t)(sh.row_hi - sh.row_lo) * c->ld / 4;
+    if (count4 > 0)
+    {
+      k_shard_scatter_rows<<<c->sm_count * 2, 256, 0, c->stream>>>(c->cg_x, c->peer_x_dev,
+                                                                   sh.world - 1, first, count4);
+      FSB_LAUNCHED(c);
+    }
+    k_shard_post_barrier<<<1, 32, 0, c->stream>>>(sh, c->scal);
+    FSB_LAUNCHED(c);
+    k_cg_combine<2><<<1, 32, 0, c->stream>>>(sh, c->scal);
+    FSB_LAUNCHED(c);
+    FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[0], c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
+                                c->stream));
+    FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->scal_h[0].comm_error || fin.comm_error)
+    {
+      FSB_CUDA(c, cudaMemsetAsync(&c->scal->comm_error, 0, sizeof(int), c->stream));
+      return fsb_fail(c, FSB_ERR_COMM, "a peer rank did not answer within the mailbox time-out");
+    }
+  }
   fsb_prof_end(c, FSB_PROF_CG);
   c->iters = fin.iter;
   c->err = (fin.rhs2 == 0.0 || (float)fin.rhs2 == 0.0f)
@@ -959,7 +1138,7 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
 
   // ---- patch + swap
   fsb_prof_begin(c, FSB_PROF_PATCH);
-  k_pressure_patch<<<fsb_div_up(total, 256), 256, 0, c->stream>>>(
+  k_pressure_patch<<<dim3(fsb_div_up(c->ld, 256), c->ny), 256, 0, c->stream>>>(
       fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), c->cg_x, c->cg_code, d, dt, density);
   FSB_LAUNCHED(c);
   c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:482

@@ -8,15 +8,16 @@ namespace {
 
 constexpr int kBlock = 256;
 
+// one thread per cell: blockIdx.y is the row, so no integer division is needed (runtime
+// div / mod issue on the slow XU pipe)
 __device__ __forceinline__ bool cell_of_thread(const GridDims d, int* i, int* j)
 {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  *i = (int)(t % d.ld);
-  *j = (int)(t / d.ld);
+  *i = blockIdx.x * blockDim.x + threadIdx.x;
+  *j = blockIdx.y;
   return *i < d.nx && *j < d.ny;
 }
 
-inline int cell_grid(const fsb_ctx* c) { return fsb_div_up((int64_t)c->ld * c->ny, kBlock); }
+inline dim3 cell_grid(const fsb_ctx* c) { return dim3(fsb_div_up(c->ld, kBlock), c->ny); }
 inline GridDims dims(const fsb_ctx* c) { return make_grid_dims(c->nx, c->ny, c->ld, c->dx, c->dy); }
 
 // src/MacGrid.cpp:32-50 clearCellTypeBuffer + the border reset of

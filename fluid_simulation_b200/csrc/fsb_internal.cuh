@@ -35,6 +35,38 @@ struct CgScalars
   int max_iters;
   int n_liquid;
   unsigned int ticket[4]; // last-block counters, one per reducing kernel
+  // row-slab sharding: sequence numbers of the peer-memory mailbox reductions (one per type),
+  // and a flag raised when a peer did not answer in time
+  unsigned long long seq[4];
+  int comm_error;
+};
+
+// ---------------------------------------------------------------------------
+// Row-slab sharding of the CG across GPUs (one process per GPU).
+//   Every rank holds the full-size vectors; rank q iterates on rows
+//   [row_lo, row_hi) and keeps the two ghost rows row_lo-1 and row_hi current:
+//   the kernel that produces a boundary row (k_cg_direction: p, k_cg_update: r)
+//   also stores it straight into the neighbour's copy over NVLink (peer pointers
+//   from CUDA IPC).  The two dot products per iteration are combined through a
+//   mailbox in each rank's HBM: the last CTA of the producing kernel writes its
+//   partial sums and a sequence number into EVERY rank's mailbox, a one-warp
+//   combine kernel waits for all `world` entries and adds them in rank order, so
+//   all ranks derive bit-identical alpha / beta / `done`.  No NCCL call in the loop.
+constexpr int kMaxRanks = 8;
+constexpr int kMailTypes = 4; // 0: p.Ap, 1: (|r|^2, r.z), 2: end-of-solve barrier
+
+struct MailSlot
+{
+  double v[2];
+  unsigned long long seq;
+  unsigned long long pad;
+};
+
+struct ShardArgs
+{
+  int world, rank;
+  int row_lo, row_hi;         // rows this rank iterates on
+  MailSlot* mail[kMaxRanks];  // mail[q]: rank q's mailbox (kMailTypes x kMaxRanks slots)
 };
 
 struct CgCoef
@@ -107,6 +139,16 @@ struct fsb_ctx
   // materialised only when somebody reads it
   bool diff_pending = false;
 
+  // row-slab sharding (fsb_shard_*); world == 1: not sharded
+  ShardArgs shard = {1, 0, 0, 0, {nullptr}};
+  MailSlot* mail_local = nullptr;
+  float* peer_r[kMaxRanks] = {nullptr};
+  float* peer_p[2][kMaxRanks] = {{nullptr}};
+  float* peer_x[kMaxRanks] = {nullptr};
+  float** peer_x_dev = nullptr; // device array of the world-1 peer x pointers
+  void* ipc_opened[5 * kMaxRanks] = {nullptr};
+  int n_ipc_opened = 0;
+
   // measurement
   bool profiling = false;
   static constexpr int kProfPool = 512; // event pairs recorded between two drains
@@ -178,3 +220,4 @@ int fsb_k_emit_source_dev(fsb_ctx* c, int64_t first, const float* xs_dev, const 
                           int64_t count_x, int64_t count_y, float vel_x, float vel_y);
 // pressure: fsb_cg.cu
 int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt);
+void fsb_cg_reconfigure(fsb_ctx* c); // drop the CG launch configuration and graph (sharding changed)

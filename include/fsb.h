@@ -166,6 +166,26 @@ int fsb_advect_particles_grid(fsb_ctx* ctx, float dt);
  * reference's validate() (src/FluidSolver.cpp:89-97) would throw. */
 int fsb_step(fsb_ctx* ctx, int kind, float dt);
 
+/* ---- multi-GPU: row-slab sharding of the pressure solve ---------------- */
+
+/* One process per GPU, each holding the same domain (every stage except the CG
+ * runs replicated and is deterministic); the CG iterates on `world` row slabs.
+ * Slab halos travel as direct peer-memory stores over NVLink and the dot
+ * products through peer-memory mailboxes (CUDA IPC), so an iteration issues no
+ * collective call.  The host exchanges the handle blobs once (any transport:
+ * torch.distributed, MPI, files):
+ *   fsb_shard_export  on every rank -> blob of FSB_SHARD_BLOB_BYTES
+ *   all-gather the blobs in rank order
+ *   fsb_shard_connect(rank, world, all_blobs)
+ * After that fsb_pressure_solve / fsb_step on every rank cooperate; every rank
+ * must make the same sequence of calls.  FSB_ERR_COMM: a peer did not answer. */
+#define FSB_SHARD_BLOB_BYTES 512
+int fsb_shard_export(fsb_ctx* ctx, void* blob);
+int fsb_shard_connect(fsb_ctx* ctx, int rank, int world, const void* all_blobs);
+int fsb_shard_disconnect(fsb_ctx* ctx);
+/* rows [*row_lo, *row_hi) of the grid this rank iterates on */
+int fsb_shard_rows(const fsb_ctx* ctx, int* row_lo, int* row_hi);
+
 /* ---- measurement ------------------------------------------------------ */
 
 /* Per-stage CUDA-event timing on the context's stream.  Enabling it makes
