@@ -644,9 +644,8 @@ int fsb_step(fsb_ctx* c, int kind, float dt)
   if (kind == FSB_STEP_PIC) FSB_TRY(flush_diff(c));
   FSB_TRY(fsb_k_classify(c));
   FSB_TRY(fsb_k_p2g(c));
-  if (kind != FSB_STEP_PIC) FSB_TRY(fsb_k_save_previous(c));
-  FSB_TRY(fsb_k_add_acceleration(c, gx, gy, dt));
-  FSB_TRY(fsb_k_enforce_dirichlet(c));
+  // updatePreviousVelocityBuffer + addExternalAcceleration + enforceDirichlet in one pass
+  FSB_TRY(fsb_k_prev_gravity_dirichlet(c, gx, gy, dt, kind != FSB_STEP_PIC));
   FSB_TRY(fsb_k_extend_velocity(c, 2));
   FSB_TRY(fsb_k_pressure_solve(c, c->density, dt));
   FSB_TRY(fsb_k_enforce_dirichlet(c));

@@ -137,6 +137,8 @@ __global__ void k_cg_build(const float* __restrict__ uf, const float* __restrict
       // maxIters == 0 -> the while loop never runs
       s->done = (rhs2 == 0.0f || rhs2 < thr || s->max_iters <= 0) ? 1 : 0;
       s->ticket[0] = 0;
+      s->bar_count = 0;
+      s->bar_release = 0;
     }
   }
 }
@@ -351,24 +353,40 @@ __device__ __forceinline__ void finalize_update(CgScalars* s, double tr2, double
 }
 
 // ---- peer-memory mailbox (row-slab sharding, see fsb_internal.cuh)
-// Called by ONE thread after the values are final: write them into every rank's
-// mailbox, fence at system scope, then publish the sequence number.
+// Every 8-byte word of a slot is self-validating: 32 bits of payload + the low 32 bits of the
+// sequence number.  8-byte stores are single transactions, so the reader needs no flag that is
+// ordered after the payload and the writer needs no fence between them (a system-scope fence
+// costs an NVLink round trip).  One double = two words.
+__device__ __forceinline__ unsigned long long mail_word(unsigned int payload, unsigned long long seq)
+{
+  return (unsigned long long)payload | (seq << 32);
+}
+
+// Called by ONE thread after the values are final (and after a system-scope fence if peer rows
+// were stored by this kernel): write them into every rank's mailbox.
 __device__ __forceinline__ void mail_post(const ShardArgs& sh, int type, double v0, double v1,
                                           unsigned long long seq)
 {
+  const unsigned long long b0 = (unsigned long long)__double_as_longlong(v0);
+  const unsigned long long b1 = (unsigned long long)__double_as_longlong(v1);
   for (int q = 0; q < sh.world; ++q)
   {
-    volatile MailSlot* slot = sh.mail[q] + type * kMaxRanks + sh.rank;
-    slot->v[0] = v0;
-    slot->v[1] = v1;
-  }
-  __threadfence_system();
-  for (int q = 0; q < sh.world; ++q)
-  {
-    volatile MailSlot* slot = sh.mail[q] + type * kMaxRanks + sh.rank;
-    slot->seq = seq;
+    volatile unsigned long long* w =
+        reinterpret_cast<volatile unsigned long long*>(sh.mail[q] + type * kMaxRanks + sh.rank);
+    w[0] = mail_word((unsigned int)b0, seq);
+    w[1] = mail_word((unsigned int)(b0 >> 32), seq);
+    w[2] = mail_word((unsigned int)b1, seq);
+    w[3] = mail_word((unsigned int)(b1 >> 32), seq);
   }
 }
+
+__device__ __forceinline__ unsigned long long global_ns();
+
+// Called by ONE thread right after mail_post: wait until every rank's entry of `type` carries
+// `seq`, then add the entries in rank order (the same order on every rank -> bit-identical
+// totals).  Returns false after kMailTimeoutNs without an answer.
+__device__ __forceinline__ bool mail_collect(const ShardArgs& sh, int type, unsigned long long seq,
+                                             double* v0, double* v1);
 
 __device__ __forceinline__ unsigned long long global_ns()
 {
@@ -377,53 +395,49 @@ __device__ __forceinline__ unsigned long long global_ns()
   return t;
 }
 
-// One warp: lane q waits for rank q's entry of `type` with sequence number
-// seq[type] + 1, lane 0 adds the entries in rank order (identical on every rank).
-// TYPE 0: p.Ap -> s->pq.  TYPE 1: (|r|^2, r.z) -> convergence test, beta, iteration
-// counter.  TYPE 2: barrier only.  A peer that stays silent for kMailTimeoutNs raises
-// comm_error and ends the solve instead of hanging the GPU.
+// A peer that stays silent for kMailTimeoutNs raises comm_error and ends the solve instead of
+// hanging the GPU.
 constexpr unsigned long long kMailTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
+__device__ __forceinline__ bool mail_collect(const ShardArgs& sh, int type, unsigned long long seq,
+                                             double* v0, double* v1)
+{
+  const unsigned long long tag = seq & 0xffffffffull;
+  const unsigned long long t0 = global_ns();
+  double a = 0.0, b = 0.0;
+  for (int q = 0; q < sh.world; ++q) // rank order: identical totals on every rank
+  {
+    volatile unsigned long long* w =
+        reinterpret_cast<volatile unsigned long long*>(sh.mail[sh.rank] + type * kMaxRanks + q);
+    unsigned long long w0, w1, w2, w3;
+    for (;;)
+    {
+      w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3];
+      if ((w0 >> 32) == tag && (w1 >> 32) == tag && (w2 >> 32) == tag && (w3 >> 32) == tag) break;
+      if (global_ns() - t0 > kMailTimeoutNs) return false;
+    }
+    a += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    b += __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
+  }
+  __threadfence_system(); // acquire: the peers' boundary rows were stored before their entries
+  *v0 = a;
+  *v1 = b;
+  return true;
+}
+
+// end-of-solve barrier (TYPE 2): one thread waits for every rank's entry
 template <int TYPE>
 __global__ void k_cg_combine(const ShardArgs sh, CgScalars* __restrict__ s)
 {
-  if (TYPE != 2 && s->done) return;
-  const int lane = threadIdx.x;
+  if (threadIdx.x != 0) return;
   const unsigned long long want = s->seq[TYPE] + 1;
-  volatile MailSlot* mine = sh.mail[sh.rank] + TYPE * kMaxRanks;
-  bool ok = true;
-  if (lane < sh.world)
+  double v0, v1;
+  if (!mail_collect(sh, TYPE, want, &v0, &v1))
   {
-    const unsigned long long t0 = global_ns();
-    while (mine[lane].seq != want)
-    {
-      if (global_ns() - t0 > kMailTimeoutNs)
-      {
-        ok = false;
-        break;
-      }
-      __nanosleep(200);
-    }
+    s->comm_error = 1;
+    s->done = 1;
   }
-  __threadfence_system();
-  ok = __all_sync(0xffffffffu, ok);
-  if (lane == 0)
-  {
-    double v0 = 0.0, v1 = 0.0;
-    for (int q = 0; q < sh.world; ++q)
-    {
-      v0 += mine[q].v[0];
-      v1 += mine[q].v[1];
-    }
-    s->seq[TYPE] = want;
-    if (!ok)
-    {
-      s->comm_error = 1;
-      s->done = 1;
-    }
-    else if (TYPE == 0) s->pq = v0;
-    else if (TYPE == 1) finalize_update(s, v0, v1);
-  }
+  s->seq[TYPE] = want;
 }
 
 // end of a sharded solve: every rank stores its rows of x into every peer's copy
@@ -454,7 +468,7 @@ __global__ void k_shard_post_barrier(const ShardArgs sh, CgScalars* __restrict__
 template <int NW, int N>
 __device__ __forceinline__ bool fold_consumers(double (&acc)[N], unsigned int* ticket,
                                                double* __restrict__ partials, double (&out)[N],
-                                               bool sharded)
+                                               bool pushed)
 {
   __shared__ double s_part[N][32];
   __shared__ bool s_last;
@@ -479,9 +493,9 @@ __device__ __forceinline__ bool fold_consumers(double (&acc)[N], unsigned int* t
     }
     if (lane == 0)
     {
-      // sharded: this CTA's stores into peer memory must be visible to the peers before the
-      // mailbox entry that follows the last CTA's fold
-      if (sharded) __threadfence_system();
+      // a CTA that stored slab boundary rows into peer memory makes them visible at system
+      // scope before it checks in; the mailbox entry follows the last CTA's fold
+      if (pushed) __threadfence_system();
       else __threadfence();
       s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
@@ -585,12 +599,15 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
   double acc[1] = {0.0};
   TileWalk t(blockIdx.x, gridDim.x, tiles_x);
   int st = 0, round = 0;
+  bool pushed = false; // CTA-uniform: one of this CTA's tiles holds a slab boundary row with a peer
+  const int last_ty = n_tiles / tiles_x - 1;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
   {
     const unsigned char* base = smem + st * St::kBytes;
     const float* sr = reinterpret_cast<const float*>(base + St::oR);
     const float* sp = reinterpret_cast<const float*>(base + St::oP);
     const unsigned char* sc = base + St::oC;
+    pushed |= (push_lo && t.ty == 0) || (push_hi && t.ty == last_ty);
     mbar_wait(&full[st], round & 1);
 
     float4 pn[RPW + 2];
@@ -639,10 +656,23 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
   }
 
   double tot[1];
-  if (fold_consumers<NW, 1>(acc, &s->ticket[1], partials, tot, sh.world > 1) && threadIdx.x == 0)
+  if (fold_consumers<NW, 1>(acc, &s->ticket[1], partials, tot, pushed) && threadIdx.x == 0)
   {
-    if (sh.world > 1) mail_post(sh, 0, tot[0], 0.0, s->seq[0] + 1);
-    else s->pq = tot[0];
+    double pq = tot[0], unused = 0.0;
+    if (sh.world > 1)
+    {
+      __threadfence_system(); // every CTA's check-in (and its peer rows) precedes the entry
+      // the last CTA of every rank publishes its slab's sum to all ranks and collects theirs
+      const unsigned long long seq = s->seq[0] + 1;
+      mail_post(sh, 0, pq, 0.0, seq);
+      if (!mail_collect(sh, 0, seq, &pq, &unused))
+      {
+        s->comm_error = 1;
+        s->done = 1;
+      }
+      s->seq[0] = seq;
+    }
+    s->pq = pq;
   }
 }
 
@@ -712,6 +742,8 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
   double acc[2] = {0.0, 0.0};
   TileWalk t(blockIdx.x, gridDim.x, tiles_x);
   int st = 0, round = 0;
+  bool pushed = false;
+  const int last_ty = n_tiles / tiles_x - 1;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
   {
     const unsigned char* base = smem + st * St::kBytes;
@@ -719,6 +751,7 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
     const float* sx = reinterpret_cast<const float*>(base + St::oX);
     const float* sr = reinterpret_cast<const float*>(base + St::oR);
     const unsigned char* sc = base + St::oC;
+    pushed |= (push_lo && t.ty == 0) || (push_hi && t.ty == last_ty);
     mbar_wait(&full[st], round & 1);
 
     float4 pc[RPW + 2], xo[RPW], ro[RPW];
@@ -777,10 +810,391 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
   }
 
   double tot[2];
-  if (fold_consumers<NW, 2>(acc, &s->ticket[2], partials, tot, sh.world > 1) && threadIdx.x == 0)
+  if (fold_consumers<NW, 2>(acc, &s->ticket[2], partials, tot, pushed) && threadIdx.x == 0)
   {
-    if (sh.world > 1) mail_post(sh, 1, tot[0], tot[1], s->seq[1] + 1);
-    else finalize_update(s, tot[0], tot[1]);
+    double tr2 = tot[0], trz = tot[1];
+    bool ok = true;
+    if (sh.world > 1)
+    {
+      __threadfence_system();
+      const unsigned long long seq = s->seq[1] + 1;
+      mail_post(sh, 1, tr2, trz, seq);
+      ok = mail_collect(sh, 1, seq, &tr2, &trz);
+      s->seq[1] = seq;
+    }
+    if (ok) finalize_update(s, tr2, trz);
+    else
+    {
+      s->comm_error = 1;
+      s->done = 1;
+    }
+  }
+}
+
+// ------------------------------------------------ persistent fused solve --
+// The whole CG loop as ONE cooperative kernel: every CTA stays resident, runs the
+// direction phase and the update phase of every iteration over its tile list
+// (same TMA ring, same per-tile code as the two kernels above) and meets the
+// other CTAs at a software grid barrier after each phase.  The barrier carries
+// the reduction: every CTA stores its partial sums, the LAST CTA to arrive folds
+// them in index order, (sharded: exchanges the slab sums with the peer GPUs
+// through the mailboxes,) updates the device scalars and releases the others.
+// This removes two kernel boundaries (launch gap + pipeline prologue + last-CTA
+// tail, ~6 us each) per iteration, which is what bounds small grids and the
+// multi-GPU slabs; it also needs no host polling: the kernel returns when the
+// solve is done.
+struct SolveMaps
+{
+  CUtensorMap halo_r, halo_p[2], inner_x, inner_r, code;
+};
+struct SolvePush // peer rows receiving this rank's slab boundary rows (null: no neighbour)
+{
+  float *p_lo[2], *p_hi[2], *r_lo, *r_hi;
+};
+
+__device__ __forceinline__ void fence_proxy_async_all()
+{
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+struct PhaseState // broadcast of the device scalars after a barrier
+{
+  int done, first;
+  float beta, alpha;
+};
+
+// Barrier + reduction for the NW consumer warps of every CTA (see above).  TYPE 0: p.Ap,
+// TYPE 1: (|r|^2, r.z).  Returns with `ps` filled from the released scalars.
+template <int NW, int N, int TYPE>
+__device__ __forceinline__ void grid_reduce(double (&acc)[N], CgScalars* s,
+                                            double* __restrict__ partials, unsigned phase_id,
+                                            const ShardArgs& sh, PhaseState* ps)
+{
+  __shared__ double s_part[N][32];
+  __shared__ bool s_last;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  volatile CgScalars* vs = s;
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_down_sync(0xffffffffu, acc[n], o);
+    if (lane == 0) s_part[n][warp] = acc[n];
+  }
+  consumer_sync(NW * 32);
+  if (warp == 0)
+  {
+    // the CTA's global stores (p / x / r rows, peer rows) must be visible to the TMA loads of
+    // the next phase on every SM (and GPU): one thread fences after the CTA barrier
+    if (lane == 0)
+    {
+      fence_proxy_async_all();
+      if (sh.world > 1) __threadfence_system();
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+    {
+      double v = (lane < NW) ? s_part[n][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) partials[n * gridDim.x + blockIdx.x] = v;
+    }
+    if (lane == 0)
+    {
+      __threadfence();
+      s_last = (atomicAdd(&s->bar_count, 1u) == phase_id * gridDim.x - 1);
+    }
+  }
+  consumer_sync(NW * 32);
+  if (s_last)
+  {
+    __threadfence();
+    const volatile double* part = partials;
+    double tot[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+    {
+      double v = 0.0;
+      for (int k = threadIdx.x; k < (int)gridDim.x; k += NW * 32) v += part[n * gridDim.x + k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) s_part[n][warp] = v;
+    }
+    consumer_sync(NW * 32);
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+      for (int n = 0; n < N; ++n)
+      {
+        double t = 0.0;
+        for (int k = 0; k < NW; ++k) t += s_part[n][k];
+        tot[n] = t;
+      }
+      double v0 = tot[0], v1 = (N > 1) ? tot[N - 1] : 0.0;
+      bool ok = true;
+      if (sh.world > 1)
+      {
+        const unsigned long long seq = s->seq[TYPE] + 1;
+        mail_post(sh, TYPE, v0, v1, seq);
+        ok = mail_collect(sh, TYPE, seq, &v0, &v1);
+        s->seq[TYPE] = seq;
+      }
+      if (!ok)
+      {
+        s->comm_error = 1;
+        s->done = 1;
+      }
+      else if (TYPE == 0) s->pq = v0;
+      else finalize_update(s, v0, v1);
+      __threadfence();
+      vs->bar_release = phase_id;
+    }
+  }
+  if (threadIdx.x == 0)
+  {
+    while (vs->bar_release < phase_id) {}
+    __threadfence();
+    ps->done = vs->done;
+    ps->first = (vs->iter == 0);
+    ps->beta = vs->beta;
+    ps->alpha = vs->abs_new / (float)vs->pq; // Eigen: alpha = absNew / p.dot(tmp)
+  }
+  consumer_sync(NW * 32);
+}
+
+template <int NW, int RPW>
+__global__ void __launch_bounds__((NW + 1) * 32)
+k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float* __restrict__ r,
+           float* __restrict__ p0, float* __restrict__ p1, int ld, int tiles_x, int n_tiles,
+           int stages, int stage_bytes, const CgCoef coef, CgScalars* __restrict__ s,
+           double* __restrict__ partials, const __grid_constant__ ShardArgs sh,
+           const __grid_constant__ SolvePush push)
+{
+  constexpr int TH = NW * RPW;
+  using Sd = DirStage<TH>;
+  using Su = UpdStage<TH>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full[kMaxStages], empty[kMaxStages];
+  __shared__ float4 lut[8];
+  __shared__ PhaseState ps;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  volatile CgScalars* vs = s;
+
+  load_lut(lut, coef);
+  if (threadIdx.x == 0)
+  {
+    for (int k = 0; k < stages; ++k)
+    {
+      mbar_init(&full[k], 1);
+      mbar_init(&empty[k], NW);
+    }
+    fence_barrier_init();
+    ps.done = vs->done;
+    ps.first = (vs->iter == 0);
+    ps.beta = vs->beta;
+    ps.alpha = 0.0f;
+  }
+  __syncthreads();
+  unsigned phase_id = 0;
+  int st = 0, round = 0; // ring position: advances identically in the producer and every consumer warp
+
+  if (warp == NW)
+  {
+    // ---- producer: one elected lane
+    if (lane != 0) return;
+    int cur = 0;
+    bool done = vs->done != 0;
+    bool first = vs->iter == 0;
+    while (!done)
+    {
+      {
+        TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
+        {
+          if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
+          const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
+          unsigned char* base = smem + st * stage_bytes;
+          mbar_expect_tx(&full[st], first ? Sd::kTx - Sd::kF32 : Sd::kTx);
+          tma_load_2d(base + Sd::oR, &maps.halo_r, c0 - 4, j0 - 1, &full[st]);
+          if (!first) tma_load_2d(base + Sd::oP, &maps.halo_p[cur], c0 - 4, j0 - 1, &full[st]);
+          tma_load_2d(base + Sd::oC, &maps.code, c0 - 16, j0 - 1, &full[st]);
+          if (++st == stages) { st = 0; ++round; }
+        }
+      }
+      ++phase_id;
+      while (vs->bar_release < phase_id) {}
+      __threadfence();
+      fence_proxy_async_all();
+      if (vs->done) break; // a peer timed out
+      {
+        TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
+        {
+          if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
+          const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
+          unsigned char* base = smem + st * stage_bytes;
+          mbar_expect_tx(&full[st], Su::kTx);
+          tma_load_2d(base + Su::oP, &maps.halo_p[cur ^ 1], c0 - 4, j0 - 1, &full[st]);
+          tma_load_2d(base + Su::oX, &maps.inner_x, c0, j0, &full[st]);
+          tma_load_2d(base + Su::oR, &maps.inner_r, c0, j0, &full[st]);
+          tma_load_2d(base + Su::oC, &maps.code, c0 - 16, j0 - 1, &full[st]);
+          if (++st == stages) { st = 0; ++round; }
+        }
+      }
+      ++phase_id;
+      while (vs->bar_release < phase_id) {}
+      __threadfence();
+      fence_proxy_async_all();
+      done = vs->done != 0;
+      first = false;
+      cur ^= 1;
+    }
+    return;
+  }
+
+  // ---- consumers
+  const float inv5 = coef.invdiag[4], diag5 = coef.diag[4], off = coef.off;
+  const int r0 = (int)warp * RPW;
+  const int fo = r0 * kHaloW + 4 + (int)lane * 4;
+  const int hfo = r0 * kHaloW + (lane == 31 ? 4 + kTileW : 3);
+  const int hco = r0 * kCodeW + (lane == 31 ? 16 + kTileW : 15);
+  const int co = r0 * kCodeW + 16 + (int)lane * 4;
+  const int io = r0 * kTileW + (int)lane * 4;
+  const bool edge = (lane == 0 || lane == 31);
+  int cur = 0;
+  while (!ps.done)
+  {
+    // ================= phase A: direction + p.Ap =================
+    {
+      const bool first = ps.first != 0;
+      const float beta = first ? 0.0f : ps.beta;
+      float* __restrict__ p_new = cur ? p0 : p1;
+      float* push_lo = push.p_lo[cur ^ 1];
+      float* push_hi = push.p_hi[cur ^ 1];
+      double acc[1] = {0.0};
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
+      {
+        const unsigned char* base = smem + st * stage_bytes;
+        const float* sr = reinterpret_cast<const float*>(base + Sd::oR);
+        const float* sp = reinterpret_cast<const float*>(base + Sd::oP);
+        const unsigned char* sc = base + Sd::oC;
+        mbar_wait(&full[st], round & 1);
+        float4 pn[RPW + 2];
+        uint32_t cd[RPW + 2];
+        float he[RPW + 2];
+#pragma unroll
+        for (int k = 0; k < RPW + 2; ++k)
+        {
+          cd[k] = *reinterpret_cast<const uint32_t*>(sc + co + k * kCodeW);
+          const float4 r4 = *reinterpret_cast<const float4*>(sr + fo + k * kHaloW);
+          float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!first) p4 = *reinterpret_cast<const float4*>(sp + fo + k * kHaloW);
+          pn[k] = direction4(r4, p4, cd[k], lut, inv5, beta);
+          he[k] = 0.0f;
+          if (edge && k >= 1 && k <= RPW)
+          {
+            const float inv = lut[sc[hco + k * kCodeW]].x;
+            const float hp = first ? 0.0f : sp[hfo + k * kHaloW];
+            he[k] = fmaf(beta, hp, inv * sr[hfo + k * kHaloW]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (++st == stages) { st = 0; ++round; }
+        const int ci = t.tx * kTileW + (int)lane * 4;
+        const int jb = sh.row_lo + t.ty * TH + r0;
+#pragma unroll
+        for (int k = 1; k <= RPW; ++k)
+        {
+          float w = __shfl_up_sync(0xffffffffu, pn[k].w, 1);
+          float e = __shfl_down_sync(0xffffffffu, pn[k].x, 1);
+          if (lane == 0) w = he[k];
+          if (lane == 31) e = he[k];
+          const float4 q = apply_a4(pn[k], w, e, pn[k - 1], pn[k + 1], cd[k], lut, diag5, off);
+          const int j = jb + k - 1;
+          if (j < sh.row_hi && ci < ld)
+          {
+            acc[0] += (double)dot4(pn[k], q);
+            *reinterpret_cast<float4*>(p_new + (size_t)j * ld + ci) = pn[k];
+            if (j == sh.row_lo && push_lo) *reinterpret_cast<float4*>(push_lo + ci) = pn[k];
+            if (j == sh.row_hi - 1 && push_hi) *reinterpret_cast<float4*>(push_hi + ci) = pn[k];
+          }
+        }
+      }
+      ++phase_id;
+      grid_reduce<NW, 1, 0>(acc, s, partials, phase_id, sh, &ps);
+      if (ps.done) break; // only a communication failure ends the solve here
+    }
+    // ================= phase B: update + |r|^2, r.z =================
+    {
+      const float alpha = ps.alpha, nalpha = -alpha;
+      double acc[2] = {0.0, 0.0};
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
+      {
+        const unsigned char* base = smem + st * stage_bytes;
+        const float* sp = reinterpret_cast<const float*>(base + Su::oP);
+        const float* sx = reinterpret_cast<const float*>(base + Su::oX);
+        const float* sr = reinterpret_cast<const float*>(base + Su::oR);
+        const unsigned char* sc = base + Su::oC;
+        mbar_wait(&full[st], round & 1);
+        float4 pc[RPW + 2], xo[RPW], ro[RPW];
+        uint32_t cd[RPW];
+        float he[RPW];
+#pragma unroll
+        for (int k = 0; k < RPW + 2; ++k)
+          pc[k] = *reinterpret_cast<const float4*>(sp + fo + k * kHaloW);
+#pragma unroll
+        for (int k = 0; k < RPW; ++k)
+        {
+          cd[k] = *reinterpret_cast<const uint32_t*>(sc + co + (k + 1) * kCodeW);
+          xo[k] = *reinterpret_cast<const float4*>(sx + io + k * kTileW);
+          ro[k] = *reinterpret_cast<const float4*>(sr + io + k * kTileW);
+          he[k] = edge ? sp[hfo + (k + 1) * kHaloW] : 0.0f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (++st == stages) { st = 0; ++round; }
+        const int ci = t.tx * kTileW + (int)lane * 4;
+        const int jb = sh.row_lo + t.ty * TH + r0;
+#pragma unroll
+        for (int k = 0; k < RPW; ++k)
+        {
+          const float4 p4 = pc[k + 1];
+          float w = __shfl_up_sync(0xffffffffu, p4.w, 1);
+          float e = __shfl_down_sync(0xffffffffu, p4.x, 1);
+          if (lane == 0) w = he[k];
+          if (lane == 31) e = he[k];
+          const uint32_t c4 = cd[k];
+          const int j = jb + k;
+          if (c4 != 0 && j < sh.row_hi)
+          {
+            const float4 q = apply_a4(p4, w, e, pc[k], pc[k + 2], c4, lut, diag5, off);
+            float4 xn, rn;
+            xn.x = fmaf(alpha, p4.x, xo[k].x); rn.x = fmaf(nalpha, q.x, ro[k].x);
+            xn.y = fmaf(alpha, p4.y, xo[k].y); rn.y = fmaf(nalpha, q.y, ro[k].y);
+            xn.z = fmaf(alpha, p4.z, xo[k].z); rn.z = fmaf(nalpha, q.z, ro[k].z);
+            xn.w = fmaf(alpha, p4.w, xo[k].w); rn.w = fmaf(nalpha, q.w, ro[k].w);
+            const size_t o = (size_t)j * ld + ci;
+            *reinterpret_cast<float4*>(x + o) = xn;
+            *reinterpret_cast<float4*>(r + o) = rn;
+            if (j == sh.row_lo && push.r_lo) *reinterpret_cast<float4*>(push.r_lo + ci) = rn;
+            if (j == sh.row_hi - 1 && push.r_hi) *reinterpret_cast<float4*>(push.r_hi + ci) = rn;
+            float4 z;
+            if (c4 == kInterior4) z = make_float4(inv5 * rn.x, inv5 * rn.y, inv5 * rn.z, inv5 * rn.w);
+            else
+              z = make_float4(lut[c4 & 0xff].x * rn.x, lut[(c4 >> 8) & 0xff].x * rn.y,
+                              lut[(c4 >> 16) & 0xff].x * rn.z, lut[c4 >> 24].x * rn.w);
+            acc[0] += (double)dot4(rn, rn);
+            acc[1] += (double)dot4(rn, z);
+          }
+        }
+      }
+      ++phase_id;
+      grid_reduce<NW, 2, 1>(acc, s, partials, phase_id, sh, &ps);
+    }
+    cur ^= 1;
   }
 }
 
@@ -906,6 +1320,34 @@ int configure_kernels(fsb_ctx* c, int64_t n_tiles)
   return FSB_OK;
 }
 
+template <int RPW>
+int configure_fused(fsb_ctx* c, int64_t n_tiles)
+{
+  constexpr int TH = kNW * RPW;
+  const int threads = (kNW + 1) * 32;
+  c->cg_fused_stage_bytes = std::max(DirStage<TH>::kBytes, UpdStage<TH>::kBytes);
+  const int budget = (227 * 1024 - 2 * 2048) / 2; // two resident CTAs per SM
+  int stages = std::max(2, std::min(kMaxStages, budget / c->cg_fused_stage_bytes));
+  if (const char* e = getenv("FSB_CG_STAGES"))
+  {
+    const int v = atoi(e);
+    if (v >= 2 && v <= kMaxStages) stages = v;
+  }
+  const int smem = stages * c->cg_fused_stage_bytes;
+  if (smem > 227 * 1024 - 2048)
+    return fsb_fail(c, FSB_ERR_INVALID, "CG ring of %d stages does not fit shared memory", stages);
+  auto kf = k_cg_solve<kNW, RPW>;
+  FSB_CUDA(c, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int occ = 1;
+  FSB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, threads, smem));
+  int cap = 4;
+  if (const char* e = getenv("FSB_CG_CTAS_PER_SM")) cap = std::max(1, atoi(e));
+  occ = std::max(1, std::min(occ, cap));
+  c->cg_fused_stages = stages;
+  c->cg_grid_fused = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count * occ);
+  return FSB_OK;
+}
+
 int configure_cg(fsb_ctx* c)
 {
   if (c->cg_tile_rows != 0) return FSB_OK;
@@ -920,6 +1362,19 @@ int configure_cg(fsb_ctx* c)
   if (th == 32) FSB_TRY(configure_kernels<4>(c, n_tiles));
   else if (th == 16) FSB_TRY(configure_kernels<2>(c, n_tiles));
   else FSB_TRY(configure_kernels<1>(c, n_tiles));
+  if (th == 32) FSB_TRY(configure_fused<4>(c, n_tiles));
+  else if (th == 16) FSB_TRY(configure_fused<2>(c, n_tiles));
+  else FSB_TRY(configure_fused<1>(c, n_tiles));
+  {
+    // the fused kernel needs every CTA resident at once: cooperative launch
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+    // FSB_CG_MODE=fused selects the persistent single-kernel solve.  Measured on B200 it is
+    // no faster than two launches per iteration (its grid barrier costs what a kernel boundary
+    // costs, profiles/r01e), so the default stays the two-kernel graph.
+    const char* mode = getenv("FSB_CG_MODE");
+    c->cg_fused = coop != 0 && mode && mode[0] == 'f';
+  }
 
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -934,6 +1389,16 @@ int configure_cg(fsb_ctx* c)
   FSB_TRY(make_map(c, encode, &inner_x, c->cg_x, true, kTileW, th));
   FSB_TRY(make_map(c, encode, &inner_r, c->cg_r, true, kTileW, th));
   FSB_TRY(make_map(c, encode, &code, c->cg_code, false, kCodeW, th + 2));
+  {
+    SolveMaps* m = reinterpret_cast<SolveMaps*>(c->cg_maps_fused);
+    memset(m, 0, sizeof(SolveMaps));
+    m->halo_r = halo_r;
+    m->halo_p[0] = halo_p[0];
+    m->halo_p[1] = halo_p[1];
+    m->inner_x = inner_x;
+    m->inner_r = inner_r;
+    m->code = code;
+  }
   for (int cur = 0; cur < 2; ++cur)
   {
     CgMaps* d = reinterpret_cast<CgMaps*>(c->cg_maps_dir[cur]);
@@ -973,17 +1438,50 @@ int launch_iteration(fsb_ctx* c, const CgCoef& coef, int cur)
                              c->cg_stages_dir * DirStage<kNW * RPW>::kBytes, c->stream>>>(         \
       md, c->cg_p[cur ^ 1], c->ld, tiles_x, n_tiles, c->cg_stages_dir, coef, c->scal, c->partials, \
       sh, p_lo, p_hi);                                                                             \
-  if (sh.world > 1) k_cg_combine<0><<<1, 32, 0, c->stream>>>(sh, c->scal);                         \
   k_cg_update<kNW, RPW><<<c->cg_grid_upd, (kNW + 1) * 32,                                          \
                           c->cg_stages_upd * UpdStage<kNW * RPW>::kBytes, c->stream>>>(            \
       mu, c->cg_x, c->cg_r, c->ld, tiles_x, n_tiles, c->cg_stages_upd, coef, c->scal, c->partials, \
-      sh, r_lo, r_hi);                                                                             \
-  if (sh.world > 1) k_cg_combine<1><<<1, 32, 0, c->stream>>>(sh, c->scal)
+      sh, r_lo, r_hi)
   if (th == 32) { FSB_CG_LAUNCH(4); }
   else if (th == 16) { FSB_CG_LAUNCH(2); }
   else { FSB_CG_LAUNCH(1); }
 #undef FSB_CG_LAUNCH
   FSB_CUDA(c, cudaGetLastError());
+  return FSB_OK;
+}
+
+// the whole solve as one cooperative launch (k_cg_solve)
+int launch_fused(fsb_ctx* c, const CgCoef& coef)
+{
+  const int th = c->cg_tile_rows;
+  int tiles_x = fsb_div_up(c->ld, kTileW);
+  const ShardArgs& sh = c->shard;
+  int n_tiles = tiles_x * fsb_div_up(sh.row_hi - sh.row_lo, th);
+  const SolveMaps& maps = *reinterpret_cast<const SolveMaps*>(c->cg_maps_fused);
+  const bool south = sh.world > 1 && sh.rank > 0, north = sh.world > 1 && sh.rank < sh.world - 1;
+  const size_t lo_off = (size_t)sh.row_lo * c->ld, hi_off = (size_t)(sh.row_hi - 1) * c->ld;
+  SolvePush push;
+  for (int k = 0; k < 2; ++k)
+  {
+    push.p_lo[k] = south ? c->peer_p[k][sh.rank - 1] + lo_off : nullptr;
+    push.p_hi[k] = north ? c->peer_p[k][sh.rank + 1] + hi_off : nullptr;
+  }
+  push.r_lo = south ? c->peer_r[sh.rank - 1] + lo_off : nullptr;
+  push.r_hi = north ? c->peer_r[sh.rank + 1] + hi_off : nullptr;
+  int ld = c->ld, stages = c->cg_fused_stages, stage_bytes = c->cg_fused_stage_bytes;
+  CgCoef cf = coef;
+  void* args[] = {(void*)&maps, &c->cg_x, &c->cg_r, &c->cg_p[0], &c->cg_p[1], &ld, &tiles_x, &n_tiles,
+                  &stages, &stage_bytes, &cf, &c->scal, &c->partials, (void*)&sh, &push};
+  const dim3 grid(c->cg_grid_fused), block((kNW + 1) * 32);
+  const size_t smem = (size_t)stages * stage_bytes;
+  cudaError_t e;
+  if (th == 32) e = cudaLaunchCooperativeKernel((void*)k_cg_solve<kNW, 4>, grid, block, args, smem, c->stream);
+  else if (th == 16) e = cudaLaunchCooperativeKernel((void*)k_cg_solve<kNW, 2>, grid, block, args, smem, c->stream);
+  else e = cudaLaunchCooperativeKernel((void*)k_cg_solve<kNW, 1>, grid, block, args, smem, c->stream);
+  if (e != cudaSuccess)
+    return fsb_fail(c, FSB_ERR_CUDA, "cooperative launch of the CG solve failed: %s",
+                    cudaGetErrorString(e));
+  c->launches += 1;
   return FSB_OK;
 }
 
@@ -1026,7 +1524,7 @@ int launch_chunk(fsb_ctx* c, const CgCoef& coef)
   {
     for (int k = 0; k < kCheckEvery; ++k) FSB_TRY(launch_iteration(c, coef, k & 1));
   }
-  c->launches += (c->shard.world > 1 ? 4 : 2) * kCheckEvery;
+  c->launches += 2 * kCheckEvery;
   return FSB_OK;
 }
 
@@ -1050,7 +1548,8 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
   const int64_t total = (int64_t)c->ld * c->ny;
   const int build_blocks = (int)std::min<int64_t>(fsb_div_up(total, 256), c->sm_count * 8);
   FSB_TRY(configure_cg(c));
-  const int need = std::max(3 * build_blocks, std::max(c->cg_grid_dir, 2 * c->cg_grid_upd));
+  const int need = std::max(std::max(3 * build_blocks, 2 * c->cg_grid_fused),
+                            std::max(c->cg_grid_dir, 2 * c->cg_grid_upd));
   if (need > c->partials_cap)
   {
     if (c->partials) cudaFree(c->partials);
@@ -1073,7 +1572,16 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
   // waits for the poll.  Launches after convergence return immediately.
   fsb_prof_begin(c, FSB_PROF_CG);
   CgScalars fin = c->scal_h[0];
-  if (!fin.done)
+  if (!fin.done && c->cg_fused)
+  {
+    // one persistent kernel runs the loop to completion; no polling
+    FSB_TRY(launch_fused(c, coef));
+    FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[0], c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
+                                c->stream));
+    FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    fin = c->scal_h[0];
+  }
+  else if (!fin.done)
   {
     FSB_TRY(ensure_cg_graph(c, coef));
     const int max_chunks = fsb_div_up(std::max(fin.max_iters, 1), kCheckEvery);

@@ -39,6 +39,9 @@ struct CgScalars
   // and a flag raised when a peer did not answer in time
   unsigned long long seq[4];
   int comm_error;
+  // software grid barrier of the persistent solve kernel: arrivals so far / last released phase
+  unsigned int bar_count;
+  unsigned int bar_release;
 };
 
 // ---------------------------------------------------------------------------
@@ -130,6 +133,9 @@ struct fsb_ctx
   // TMA descriptors of the two iteration kernels for both ping-pong phases (CgMaps in fsb_cg.cu)
   alignas(64) unsigned char cg_maps_dir[2][5 * sizeof(CUtensorMap)];
   alignas(64) unsigned char cg_maps_upd[2][5 * sizeof(CUtensorMap)];
+  alignas(64) unsigned char cg_maps_fused[6 * sizeof(CUtensorMap)]; // SolveMaps
+  bool cg_fused = false; // persistent cooperative solve kernel in use
+  int cg_grid_fused = 0, cg_fused_stages = 0, cg_fused_stage_bytes = 0;
   int max_iters = 100;
   float tol = 1.1920929e-7f;
   int iters = 0;
@@ -206,6 +212,7 @@ int fsb_k_save_previous(fsb_ctx* c);
 int fsb_k_update_diff(fsb_ctx* c);
 int fsb_k_add_acceleration(fsb_ctx* c, float ax, float ay, float dt);
 int fsb_k_enforce_dirichlet(fsb_ctx* c);
+int fsb_k_prev_gravity_dirichlet(fsb_ctx* c, float ax, float ay, float dt, int save_prev);
 int fsb_k_extend_velocity(fsb_ctx* c, int n_iter);
 int fsb_k_advect_velocity_sl(fsb_ctx* c, float dt);
 // particle stages: fsb_particles.cu
