@@ -253,6 +253,16 @@ __device__ __forceinline__ void fence_barrier_init()
 {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// programmatic dependent launch: let the next kernel of the stream be scheduled early / wait
+// for the previous kernel's memory before touching anything it wrote
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ void consumer_sync(int n_threads) // named barrier 1: consumer warps only
 {
   asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
@@ -542,16 +552,14 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
                const __grid_constant__ ShardArgs sh, float* __restrict__ push_lo,
                float* __restrict__ push_hi)
 {
-  if (s->done) return;
   constexpr int TH = NW * RPW;
   using St = DirStage<TH>;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full[kMaxStages], empty[kMaxStages];
   __shared__ float4 lut[8];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool first = (s->iter == 0);
-  const float beta = first ? 0.0f : s->beta;
 
+  // set-up that does not depend on the previous kernel overlaps its tail (PDL)
   load_lut(lut, coef);
   if (threadIdx.x == 0)
   {
@@ -563,6 +571,11 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+  if (s->done) return;
+  const bool first = (s->iter == 0);
+  const float beta = first ? 0.0f : s->beta;
 
   if (warp == NW)
   {
@@ -688,15 +701,12 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
             const __grid_constant__ ShardArgs sh, float* __restrict__ push_lo,
             float* __restrict__ push_hi)
 {
-  if (s->done) return;
   constexpr int TH = NW * RPW;
   using St = UpdStage<TH>;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full[kMaxStages], empty[kMaxStages];
   __shared__ float4 lut[8];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float alpha = s->abs_new / (float)s->pq; // Eigen: alpha = absNew / p.dot(tmp)
-  const float nalpha = -alpha;
 
   load_lut(lut, coef);
   if (threadIdx.x == 0)
@@ -709,6 +719,11 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+  if (s->done) return;
+  const float alpha = s->abs_new / (float)s->pq; // Eigen: alpha = absNew / p.dot(tmp)
+  const float nalpha = -alpha;
 
   if (warp == NW)
   {
@@ -1374,6 +1389,8 @@ int configure_cg(fsb_ctx* c)
     // costs, profiles/r01e), so the default stays the two-kernel graph.
     const char* mode = getenv("FSB_CG_MODE");
     c->cg_fused = coop != 0 && mode && mode[0] == 'f';
+    const char* pdl = getenv("FSB_CG_PDL"); // profiling knob: 0 disables dependent launch
+    c->cg_pdl = !(pdl && pdl[0] == '0');
   }
 
   void* fn = nullptr;
@@ -1433,20 +1450,33 @@ int launch_iteration(fsb_ctx* c, const CgCoef& coef, int cur)
   float* p_hi = north ? c->peer_p[cur ^ 1][sh.rank + 1] + hi_off : nullptr;
   float* r_lo = south ? c->peer_r[sh.rank - 1] + lo_off : nullptr;
   float* r_hi = north ? c->peer_r[sh.rank + 1] + hi_off : nullptr;
+  // both kernels allow programmatic dependent launch: the next kernel's CTAs are scheduled and
+  // run their set-up while this kernel's reduction tail finishes (griddepcontrol in the kernels)
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = c->cg_pdl ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3((kNW + 1) * 32);
+  cfg.stream = c->stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  float* p_new = c->cg_p[cur ^ 1];
+  cudaError_t e1, e2;
 #define FSB_CG_LAUNCH(RPW)                                                                         \
-  k_cg_direction<kNW, RPW><<<c->cg_grid_dir, (kNW + 1) * 32,                                       \
-                             c->cg_stages_dir * DirStage<kNW * RPW>::kBytes, c->stream>>>(         \
-      md, c->cg_p[cur ^ 1], c->ld, tiles_x, n_tiles, c->cg_stages_dir, coef, c->scal, c->partials, \
-      sh, p_lo, p_hi);                                                                             \
-  k_cg_update<kNW, RPW><<<c->cg_grid_upd, (kNW + 1) * 32,                                          \
-                          c->cg_stages_upd * UpdStage<kNW * RPW>::kBytes, c->stream>>>(            \
-      mu, c->cg_x, c->cg_r, c->ld, tiles_x, n_tiles, c->cg_stages_upd, coef, c->scal, c->partials, \
-      sh, r_lo, r_hi)
+  cfg.gridDim = dim3(c->cg_grid_dir);                                                              \
+  cfg.dynamicSmemBytes = (size_t)c->cg_stages_dir * DirStage<kNW * RPW>::kBytes;                   \
+  e1 = cudaLaunchKernelEx(&cfg, k_cg_direction<kNW, RPW>, md, p_new, c->ld, tiles_x, n_tiles,      \
+                          c->cg_stages_dir, coef, c->scal, c->partials, sh, p_lo, p_hi);           \
+  cfg.gridDim = dim3(c->cg_grid_upd);                                                              \
+  cfg.dynamicSmemBytes = (size_t)c->cg_stages_upd * UpdStage<kNW * RPW>::kBytes;                   \
+  e2 = cudaLaunchKernelEx(&cfg, k_cg_update<kNW, RPW>, mu, c->cg_x, c->cg_r, c->ld, tiles_x,       \
+                          n_tiles, c->cg_stages_upd, coef, c->scal, c->partials, sh, r_lo, r_hi)
   if (th == 32) { FSB_CG_LAUNCH(4); }
   else if (th == 16) { FSB_CG_LAUNCH(2); }
   else { FSB_CG_LAUNCH(1); }
 #undef FSB_CG_LAUNCH
-  FSB_CUDA(c, cudaGetLastError());
+  FSB_CUDA(c, e1);
+  FSB_CUDA(c, e2);
   return FSB_OK;
 }
 
