@@ -435,6 +435,57 @@ __device__ __forceinline__ bool mail_collect(const ShardArgs& sh, int type, unsi
   return true;
 }
 
+// The same exchange done by a whole warp (all 32 lanes call it with v0, v1 already broadcast):
+// lane q posts into rank q's mailbox and polls this rank's slot q, so the NVLink stores and the
+// polls of all peers are in flight together; the entries are then added in rank order through
+// shuffles, which keeps the totals bit-identical on every rank.
+__device__ __forceinline__ bool mail_allreduce_warp(const ShardArgs& sh, int type,
+                                                    unsigned long long seq, double* v0, double* v1)
+{
+  const int lane = threadIdx.x & 31;
+  const unsigned long long tag = seq & 0xffffffffull;
+  double a = 0.0, b = 0.0;
+  bool ok = true;
+  if (lane < sh.world)
+  {
+    const unsigned long long b0 = (unsigned long long)__double_as_longlong(*v0);
+    const unsigned long long b1 = (unsigned long long)__double_as_longlong(*v1);
+    volatile unsigned long long* out =
+        reinterpret_cast<volatile unsigned long long*>(sh.mail[lane] + type * kMaxRanks + sh.rank);
+    out[0] = mail_word((unsigned int)b0, seq);
+    out[1] = mail_word((unsigned int)(b0 >> 32), seq);
+    out[2] = mail_word((unsigned int)b1, seq);
+    out[3] = mail_word((unsigned int)(b1 >> 32), seq);
+    volatile unsigned long long* w =
+        reinterpret_cast<volatile unsigned long long*>(sh.mail[sh.rank] + type * kMaxRanks + lane);
+    const unsigned long long t0 = global_ns();
+    unsigned long long w0, w1, w2, w3;
+    for (;;)
+    {
+      w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3];
+      if ((w0 >> 32) == tag && (w1 >> 32) == tag && (w2 >> 32) == tag && (w3 >> 32) == tag) break;
+      if (global_ns() - t0 > kMailTimeoutNs)
+      {
+        ok = false;
+        break;
+      }
+    }
+    a = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    b = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  __threadfence_system(); // acquire: the peers' boundary rows were stored before their entries
+  double s0 = 0.0, s1 = 0.0;
+  for (int q = 0; q < sh.world; ++q)
+  {
+    s0 += __shfl_sync(0xffffffffu, a, q);
+    s1 += __shfl_sync(0xffffffffu, b, q);
+  }
+  *v0 = s0;
+  *v1 = s1;
+  return ok;
+}
+
 // end-of-solve barrier (TYPE 2): one thread waits for every rank's entry
 template <int TYPE>
 __global__ void k_cg_combine(const ShardArgs sh, CgScalars* __restrict__ s)
@@ -668,24 +719,30 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
     }
   }
 
-  double tot[1];
-  if (fold_consumers<NW, 1>(acc, &s->ticket[1], partials, tot, pushed) && threadIdx.x == 0)
+  double tot[1] = {0.0};
+  if (fold_consumers<NW, 1>(acc, &s->ticket[1], partials, tot, pushed) && warp == 0)
   {
-    double pq = tot[0], unused = 0.0;
+    // last CTA, warp 0: (sharded) exchange the slab sums with all ranks, then publish p.Ap
+    double pq = __shfl_sync(0xffffffffu, tot[0], 0), unused = 0.0;
+    bool ok = true;
+    unsigned long long seq = 0;
     if (sh.world > 1)
     {
-      __threadfence_system(); // every CTA's check-in (and its peer rows) precedes the entry
-      // the last CTA of every rank publishes its slab's sum to all ranks and collects theirs
-      const unsigned long long seq = s->seq[0] + 1;
-      mail_post(sh, 0, pq, 0.0, seq);
-      if (!mail_collect(sh, 0, seq, &pq, &unused))
+      seq = s->seq[0] + 1;
+      if (lane == 0) __threadfence_system(); // every CTA's check-in (and its peer rows) precede the entry
+      __syncwarp();
+      ok = mail_allreduce_warp(sh, 0, seq, &pq, &unused);
+    }
+    if (lane == 0)
+    {
+      if (sh.world > 1) s->seq[0] = seq;
+      if (!ok)
       {
         s->comm_error = 1;
         s->done = 1;
       }
-      s->seq[0] = seq;
+      s->pq = pq;
     }
-    s->pq = pq;
   }
 }
 
@@ -824,24 +881,28 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
     }
   }
 
-  double tot[2];
-  if (fold_consumers<NW, 2>(acc, &s->ticket[2], partials, tot, pushed) && threadIdx.x == 0)
+  double tot[2] = {0.0, 0.0};
+  if (fold_consumers<NW, 2>(acc, &s->ticket[2], partials, tot, pushed) && warp == 0)
   {
-    double tr2 = tot[0], trz = tot[1];
+    double tr2 = __shfl_sync(0xffffffffu, tot[0], 0), trz = __shfl_sync(0xffffffffu, tot[1], 0);
     bool ok = true;
+    unsigned long long seq = 0;
     if (sh.world > 1)
     {
-      __threadfence_system();
-      const unsigned long long seq = s->seq[1] + 1;
-      mail_post(sh, 1, tr2, trz, seq);
-      ok = mail_collect(sh, 1, seq, &tr2, &trz);
-      s->seq[1] = seq;
+      seq = s->seq[1] + 1;
+      if (lane == 0) __threadfence_system();
+      __syncwarp();
+      ok = mail_allreduce_warp(sh, 1, seq, &tr2, &trz);
     }
-    if (ok) finalize_update(s, tr2, trz);
-    else
+    if (lane == 0)
     {
-      s->comm_error = 1;
-      s->done = 1;
+      if (sh.world > 1) s->seq[1] = seq;
+      if (ok) finalize_update(s, tr2, trz);
+      else
+      {
+        s->comm_error = 1;
+        s->done = 1;
+      }
     }
   }
 }

