@@ -280,26 +280,46 @@ __device__ __forceinline__ void load_lut(float4* lut, const CgCoef& coef)
   }
 }
 
-// walk of the CTA's tile list (tile = blockIdx.x, += gridDim.x) without a division per tile
+// walk of the CTA's tile list (tiles blockIdx.x, + gridDim.x, ...) without a division per tile.
+// `reverse` walks the SAME list from its last tile down: consecutive sweeps over the grid then
+// meet at the rows the previous sweep touched last, which are the ones still in the L2.
 struct TileWalk
 {
-  int tx, ty, step_x, step_y, tiles_x;
-  __device__ __forceinline__ TileWalk(int first_tile, int stride, int tiles_x_)
+  int tx, ty, step_x, step_y, tiles_x, count;
+  bool rev;
+  __device__ __forceinline__ TileWalk(int first_tile, int stride, int tiles_x_, int n_tiles,
+                                      bool reverse = false)
   {
     tiles_x = tiles_x_;
-    tx = first_tile % tiles_x;
-    ty = first_tile / tiles_x;
+    rev = reverse;
+    count = first_tile < n_tiles ? (n_tiles - 1 - first_tile) / stride + 1 : 0;
+    const int start = reverse ? first_tile + (count - 1) * stride : first_tile;
+    tx = start % tiles_x;
+    ty = start / tiles_x;
     step_x = stride % tiles_x;
     step_y = stride / tiles_x;
   }
   __device__ __forceinline__ void next()
   {
-    tx += step_x;
-    ty += step_y;
-    if (tx >= tiles_x)
+    if (!rev)
     {
-      tx -= tiles_x;
-      ++ty;
+      tx += step_x;
+      ty += step_y;
+      if (tx >= tiles_x)
+      {
+        tx -= tiles_x;
+        ++ty;
+      }
+    }
+    else
+    {
+      tx -= step_x;
+      ty -= step_y;
+      if (tx < 0)
+      {
+        tx += tiles_x;
+        --ty;
+      }
     }
   }
 };
@@ -408,6 +428,43 @@ __device__ __forceinline__ unsigned long long global_ns()
 // A peer that stays silent for kMailTimeoutNs raises comm_error and ends the solve instead of
 // hanging the GPU.
 constexpr unsigned long long kMailTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+// Watchdog of the persistent kernel's spin loops: a wait that outlives every legitimate cause
+// (the mailbox time-out included) traps, so a protocol bug ends the launch with an error instead
+// of occupying the GPU forever.
+constexpr unsigned long long kHangNs = 45ull * 1000ull * 1000ull * 1000ull;
+struct SpinGuard
+{
+  unsigned int n = 0;
+  unsigned long long t0 = 0;
+  __device__ __forceinline__ void tick()
+  {
+    if ((++n & 4095u) == 0)
+    {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kHangNs) __trap();
+    }
+  }
+};
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity)
+{
+  SpinGuard g;
+  while (!mbar_try(bar, parity)) g.tick();
+}
 
 __device__ __forceinline__ bool mail_collect(const ShardArgs& sh, int type, unsigned long long seq,
                                              double* v0, double* v1)
@@ -601,7 +658,7 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
                int tiles_x, int n_tiles, int stages, const CgCoef coef,
                CgScalars* __restrict__ s, double* __restrict__ partials,
                const __grid_constant__ ShardArgs sh, float* __restrict__ push_lo,
-               float* __restrict__ push_hi)
+               float* __restrict__ push_hi, int reverse)
 {
   constexpr int TH = NW * RPW;
   using St = DirStage<TH>;
@@ -633,9 +690,9 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
     // ---- producer
     if (lane == 0)
     {
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, reverse != 0);
       int st = 0, round = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
+      for (int tk = 0; tk < t.count; ++tk, t.next())
       {
         if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
         const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
@@ -661,11 +718,11 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
   const int hco = r0 * kCodeW + (lane == 31 ? 16 + kTileW : 15);
   const bool edge = (lane == 0 || lane == 31);
   double acc[1] = {0.0};
-  TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+  TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, reverse != 0);
   int st = 0, round = 0;
   bool pushed = false; // CTA-uniform: one of this CTA's tiles holds a slab boundary row with a peer
   const int last_ty = n_tiles / tiles_x - 1;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
+  for (int tk = 0; tk < t.count; ++tk, t.next())
   {
     const unsigned char* base = smem + st * St::kBytes;
     const float* sr = reinterpret_cast<const float*>(base + St::oR);
@@ -756,7 +813,7 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
             int ld, int tiles_x, int n_tiles, int stages, const CgCoef coef,
             CgScalars* __restrict__ s, double* __restrict__ partials,
             const __grid_constant__ ShardArgs sh, float* __restrict__ push_lo,
-            float* __restrict__ push_hi)
+            float* __restrict__ push_hi, int reverse)
 {
   constexpr int TH = NW * RPW;
   using St = UpdStage<TH>;
@@ -786,9 +843,9 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
   {
     if (lane == 0)
     {
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, reverse != 0);
       int st = 0, round = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
+      for (int tk = 0; tk < t.count; ++tk, t.next())
       {
         if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
         const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
@@ -812,11 +869,11 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
   const int hfo = r0 * kHaloW + (lane == 31 ? 4 + kTileW : 3);
   const bool edge = (lane == 0 || lane == 31);
   double acc[2] = {0.0, 0.0};
-  TileWalk t(blockIdx.x, gridDim.x, tiles_x);
+  TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, reverse != 0);
   int st = 0, round = 0;
   bool pushed = false;
   const int last_ty = n_tiles / tiles_x - 1;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
+  for (int tk = 0; tk < t.count; ++tk, t.next())
   {
     const unsigned char* base = smem + st * St::kBytes;
     const float* sp = reinterpret_cast<const float*>(base + St::oP);
@@ -908,17 +965,26 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
 }
 
 // ------------------------------------------------ persistent fused solve --
-// The whole CG loop as ONE cooperative kernel: every CTA stays resident, runs the
-// direction phase and the update phase of every iteration over its tile list
-// (same TMA ring, same per-tile code as the two kernels above) and meets the
-// other CTAs at a software grid barrier after each phase.  The barrier carries
-// the reduction: every CTA stores its partial sums, the LAST CTA to arrive folds
-// them in index order, (sharded: exchanges the slab sums with the peer GPUs
-// through the mailboxes,) updates the device scalars and releases the others.
-// This removes two kernel boundaries (launch gap + pipeline prologue + last-CTA
-// tail, ~6 us each) per iteration, which is what bounds small grids and the
-// multi-GPU slabs; it also needs no host polling: the kernel returns when the
-// solve is done.
+// The whole CG loop as ONE cooperative kernel: every CTA stays resident and runs the
+// direction phase and the update phase of every iteration over its tile list (same TMA
+// ring, same per-tile arithmetic as the two kernels above), with a software grid barrier
+// after each phase that carries the reduction.
+//
+// Barrier = reduction, with no serial hop through a "last" CTA:
+//   * a CTA stores its partial sums, fences, and adds 1 to a monotone arrival counter;
+//   * single GPU: warp 0 of EVERY CTA spins on the counter, then folds all the partials
+//     itself in a fixed order (strided per lane + xor butterfly: fp addition commutes, so
+//     all lanes and all CTAs get the same bits) and advances ITS OWN copy of the CG scalars
+//     (alpha, beta, iteration count, done) in shared memory -- nothing is broadcast;
+//   * sharded: only CTA 0 waits for the counter and folds; its warp posts the slab sum into
+//     every rank's mailbox (lane q -> rank q, NVLink stores in flight together) and warp 0 of
+//     every CTA of every rank polls its OWN rank's mailbox (local HBM) for the `world` tagged
+//     entries and adds them in rank order -> bit-identical scalars everywhere.  A rank's entry
+//     implies all of its CTAs arrived (and fenced their peer-row stores at system scope).
+//   * the producer thread meanwhile has already issued the next phase's loads that do not
+//     depend on the barrier (phase A: p_old, code; phase B: x, r, code -- written by this same
+//     CTA or before the previous barrier) for a full ring of tiles; only the one dependent
+//     array (A: r halo, B: p_new halo) is requested after the release.
 struct SolveMaps
 {
   CUtensorMap halo_r, halo_p[2], inner_x, inner_r, code;
@@ -933,23 +999,48 @@ __device__ __forceinline__ void fence_proxy_async_all()
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 
-struct PhaseState // broadcast of the device scalars after a barrier
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
-  int done, first;
-  float beta, alpha;
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1,
+                                                 uint64_t* bar, uint64_t policy)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void st_f4_hint(float* ptr, const float4 v, uint64_t policy)
+{
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
+               : "memory");
+}
+
+// per-CTA copy of the CG scalars: every CTA derives the same values from the same totals
+struct SolveState
+{
+  double pq, r2, rz;
+  unsigned long long seq[2];
+  float abs_new, abs_old, beta, alpha, thr;
+  int iter, done, max_iters, comm_error;
+  volatile unsigned int released; // last phase whose reduction this CTA has completed
 };
 
 // Barrier + reduction for the NW consumer warps of every CTA (see above).  TYPE 0: p.Ap,
-// TYPE 1: (|r|^2, r.z).  Returns with `ps` filled from the released scalars.
+// TYPE 1: (|r|^2, r.z).  `partials` is this TYPE's own region (N * gridDim.x doubles): a region
+// is rewritten two barriers later, after every reader has arrived at the barrier in between.
 template <int NW, int N, int TYPE>
 __device__ __forceinline__ void grid_reduce(double (&acc)[N], CgScalars* s,
                                             double* __restrict__ partials, unsigned phase_id,
-                                            const ShardArgs& sh, PhaseState* ps)
+                                            const ShardArgs& sh, SolveState* ss, bool pushed)
 {
   __shared__ double s_part[N][32];
-  __shared__ bool s_last;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  volatile CgScalars* vs = s;
 #pragma unroll
   for (int n = 0; n < N; ++n)
   {
@@ -960,83 +1051,149 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[N], CgScalars* s,
   consumer_sync(NW * 32);
   if (warp == 0)
   {
-    // the CTA's global stores (p / x / r rows, peer rows) must be visible to the TMA loads of
-    // the next phase on every SM (and GPU): one thread fences after the CTA barrier
-    if (lane == 0)
-    {
-      fence_proxy_async_all();
-      if (sh.world > 1) __threadfence_system();
-    }
+    const int G = (int)gridDim.x;
+    double tot[N];
 #pragma unroll
     for (int n = 0; n < N; ++n)
     {
       double v = (lane < NW) ? s_part[n][lane] : 0.0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) partials[n * gridDim.x + blockIdx.x] = v;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      tot[n] = v;
     }
     if (lane == 0)
     {
+#pragma unroll
+      for (int n = 0; n < N; ++n) partials[n * G + blockIdx.x] = tot[n];
+      // the CTA's global stores (p / x / r rows, peer rows) must be visible to the TMA loads of
+      // the next phase on every SM (and GPU) before the arrival is
+      fence_proxy_async_all();
+      if (pushed) __threadfence_system();
+      else __threadfence();
+      atomicAdd(&s->bar_count, 1u);
+    }
+    __syncwarp();
+    if (sh.world == 1 || blockIdx.x == 0)
+    {
+      const volatile unsigned int* cnt = &s->bar_count;
+      const unsigned int target = phase_id * (unsigned int)G;
+      {
+        SpinGuard g;
+        while (*cnt < target) g.tick();
+      }
       __threadfence();
-      s_last = (atomicAdd(&s->bar_count, 1u) == phase_id * gridDim.x - 1);
-    }
-  }
-  consumer_sync(NW * 32);
-  if (s_last)
-  {
-    __threadfence();
-    const volatile double* part = partials;
-    double tot[N];
-#pragma unroll
-    for (int n = 0; n < N; ++n)
-    {
-      double v = 0.0;
-      for (int k = threadIdx.x; k < (int)gridDim.x; k += NW * 32) v += part[n * gridDim.x + k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) s_part[n][warp] = v;
-    }
-    consumer_sync(NW * 32);
-    if (threadIdx.x == 0)
-    {
+      const volatile double* part = partials;
 #pragma unroll
       for (int n = 0; n < N; ++n)
       {
-        double t = 0.0;
-        for (int k = 0; k < NW; ++k) t += s_part[n][k];
-        tot[n] = t;
+        double v = 0.0;
+        for (int k = (int)lane; k < G; k += 32) v += part[n * G + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        tot[n] = v;
       }
-      double v0 = tot[0], v1 = (N > 1) ? tot[N - 1] : 0.0;
-      bool ok = true;
-      if (sh.world > 1)
+    }
+    bool ok = true;
+    const unsigned long long seq = ss->seq[TYPE] + 1;
+    if (sh.world > 1)
+    {
+      const unsigned long long tag = seq & 0xffffffffull;
+      if (blockIdx.x == 0)
       {
-        const unsigned long long seq = s->seq[TYPE] + 1;
-        mail_post(sh, TYPE, v0, v1, seq);
-        ok = mail_collect(sh, TYPE, seq, &v0, &v1);
-        s->seq[TYPE] = seq;
+        // every local CTA's arrival (and its peer rows, fenced at system scope) precedes the entry
+        __threadfence_system();
+        if ((int)lane < sh.world)
+        {
+          const unsigned long long b0 = (unsigned long long)__double_as_longlong(tot[0]);
+          const unsigned long long b1 = (unsigned long long)__double_as_longlong(tot[N - 1]);
+          volatile unsigned long long* out = reinterpret_cast<volatile unsigned long long*>(
+              sh.mail[lane] + TYPE * kMaxRanks + sh.rank);
+          out[0] = mail_word((unsigned int)b0, seq);
+          out[1] = mail_word((unsigned int)(b0 >> 32), seq);
+          out[2] = mail_word((unsigned int)b1, seq);
+          out[3] = mail_word((unsigned int)(b1 >> 32), seq);
+        }
       }
+      double a = 0.0, b = 0.0;
+      if ((int)lane < sh.world)
+      {
+        volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(
+            sh.mail[sh.rank] + TYPE * kMaxRanks + lane);
+        const unsigned long long t0 = global_ns();
+        unsigned long long w0, w1, w2, w3;
+        unsigned int spins = 0;
+        for (;;)
+        {
+          w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3];
+          if ((w0 >> 32) == tag && (w1 >> 32) == tag && (w2 >> 32) == tag && (w3 >> 32) == tag) break;
+          if ((++spins & 1023u) == 0 && global_ns() - t0 > kMailTimeoutNs)
+          {
+            ok = false;
+            break;
+          }
+        }
+        a = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+        b = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
+      }
+      ok = __all_sync(0xffffffffu, ok);
+      __threadfence_system(); // acquire: the peers' boundary rows were stored before their entries
+      double s0 = 0.0, s1 = 0.0;
+      for (int q = 0; q < sh.world; ++q) // rank order: identical totals on every rank
+      {
+        s0 += __shfl_sync(0xffffffffu, a, q);
+        s1 += __shfl_sync(0xffffffffu, b, q);
+      }
+      tot[0] = s0;
+      if (N > 1) tot[N - 1] = s1;
+    }
+    if (lane == 0)
+    {
+      ss->seq[TYPE] = seq;
       if (!ok)
       {
-        s->comm_error = 1;
-        s->done = 1;
+        ss->comm_error = 1;
+        ss->done = 1;
       }
-      else if (TYPE == 0) s->pq = v0;
-      else finalize_update(s, v0, v1);
-      __threadfence();
-      vs->bar_release = phase_id;
+      else if (TYPE == 0)
+      {
+        ss->pq = tot[0];
+        ss->alpha = ss->abs_new / (float)tot[0]; // Eigen: alpha = absNew / p.dot(tmp)
+      }
+      else
+      {
+        // finalize_update on the CTA's own copy
+        ss->r2 = tot[0];
+        ss->rz = tot[N - 1];
+        if ((float)tot[0] < ss->thr) ss->done = 1; // converged: Eigen breaks before i++
+        else
+        {
+          ss->abs_old = ss->abs_new;
+          ss->abs_new = (float)tot[N - 1];
+          ss->beta = ss->abs_new / ss->abs_old;
+          ss->iter = ss->iter + 1;
+          if (ss->iter >= ss->max_iters) ss->done = 1;
+        }
+      }
+      __threadfence_block();
+      ss->released = phase_id;
     }
-  }
-  if (threadIdx.x == 0)
-  {
-    while (vs->bar_release < phase_id) {}
-    __threadfence();
-    ps->done = vs->done;
-    ps->first = (vs->iter == 0);
-    ps->beta = vs->beta;
-    ps->alpha = vs->abs_new / (float)vs->pq; // Eigen: alpha = absNew / p.dot(tmp)
   }
   consumer_sync(NW * 32);
 }
+
+// ring slot bookkeeping shared by the producer and the consumers
+struct RingPos
+{
+  int st, round;
+  __device__ __forceinline__ void advance(int stages)
+  {
+    if (++st == stages)
+    {
+      st = 0;
+      ++round;
+    }
+  }
+};
 
 template <int NW, int RPW>
 __global__ void __launch_bounds__((NW + 1) * 32)
@@ -1044,7 +1201,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
            float* __restrict__ p0, float* __restrict__ p1, int ld, int tiles_x, int n_tiles,
            int stages, int stage_bytes, const CgCoef coef, CgScalars* __restrict__ s,
            double* __restrict__ partials, const __grid_constant__ ShardArgs sh,
-           const __grid_constant__ SolvePush push)
+           const __grid_constant__ SolvePush push, int flags)
 {
   constexpr int TH = NW * RPW;
   using Sd = DirStage<TH>;
@@ -1052,9 +1209,13 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full[kMaxStages], empty[kMaxStages];
   __shared__ float4 lut[8];
-  __shared__ PhaseState ps;
+  __shared__ SolveState ss;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  volatile CgScalars* vs = s;
+  const bool serp = (flags & 1) != 0;     // phase B walks the tile list backwards
+  const bool xhint = (flags & 2) != 0;    // x is pure streaming: evict-first loads and stores
+  const bool prefetch = (flags & 4) != 0; // barrier-independent loads issued before the barrier
+  double* part_a = partials;              // phase A region: gridDim.x doubles
+  double* part_b = partials + gridDim.x;  // phase B region: 2 * gridDim.x doubles
 
   load_lut(lut, coef);
   if (threadIdx.x == 0)
@@ -1065,70 +1226,119 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       mbar_init(&empty[k], NW);
     }
     fence_barrier_init();
-    ps.done = vs->done;
-    ps.first = (vs->iter == 0);
-    ps.beta = vs->beta;
-    ps.alpha = 0.0f;
+    volatile CgScalars* vs = s;
+    ss.pq = 0.0; ss.r2 = vs->r2; ss.rz = vs->rz;
+    ss.seq[0] = vs->seq[0]; ss.seq[1] = vs->seq[1];
+    ss.abs_new = vs->abs_new; ss.abs_old = vs->abs_old; ss.beta = vs->beta; ss.alpha = 0.0f;
+    ss.thr = vs->thr;
+    ss.iter = vs->iter; ss.done = vs->done; ss.max_iters = vs->max_iters; ss.comm_error = 0;
+    ss.released = 0;
   }
   __syncthreads();
   unsigned phase_id = 0;
-  int st = 0, round = 0; // ring position: advances identically in the producer and every consumer warp
 
   if (warp == NW)
   {
     // ---- producer: one elected lane
     if (lane != 0) return;
+    const uint64_t pol_x = l2_policy_evict_first();
+    RingPos rp = {0, 0};  // next slot to allocate
+    RingPos pre = {0, 0}; // first slot of the tiles whose independent loads are already out
+    int npre = 0;
     int cur = 0;
-    bool done = vs->done != 0;
-    bool first = vs->iter == 0;
-    while (!done)
+    bool first = ss.iter == 0;
+    int kind = 0; // 0: phase A (direction), 1: phase B (update)
+    if (ss.done) return;
+    // part: 1 = loads that do not depend on the barrier, 2 = the dependent one, 3 = both
+    auto issue = [&](int knd, int part, bool frst, int cr, int slot, int c0, int j0) {
+      unsigned char* base = smem + slot * stage_bytes;
+      if (knd == 0)
+      {
+        if (part & 1)
+        {
+          mbar_expect_tx(&full[slot], frst ? Sd::kTx - Sd::kF32 : Sd::kTx);
+          if (!frst) tma_load_2d(base + Sd::oP, &maps.halo_p[cr], c0 - 4, j0 - 1, &full[slot]);
+          tma_load_2d(base + Sd::oC, &maps.code, c0 - 16, j0 - 1, &full[slot]);
+        }
+        if (part & 2) tma_load_2d(base + Sd::oR, &maps.halo_r, c0 - 4, j0 - 1, &full[slot]);
+      }
+      else
+      {
+        if (part & 1)
+        {
+          mbar_expect_tx(&full[slot], Su::kTx);
+          if (xhint) tma_load_2d_hint(base + Su::oX, &maps.inner_x, c0, j0, &full[slot], pol_x);
+          else tma_load_2d(base + Su::oX, &maps.inner_x, c0, j0, &full[slot]);
+          tma_load_2d(base + Su::oR, &maps.inner_r, c0, j0, &full[slot]);
+          tma_load_2d(base + Su::oC, &maps.code, c0 - 16, j0 - 1, &full[slot]);
+        }
+        if (part & 2) tma_load_2d(base + Su::oP, &maps.halo_p[cr ^ 1], c0 - 4, j0 - 1, &full[slot]);
+      }
+    };
+    for (;;)
     {
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, serp && kind == 1);
+      // 1. the dependent load of the tiles that were started before the barrier
+      RingPos q = pre;
+      int k = 0;
+      for (; k < npre; ++k, t.next())
       {
-        TileWalk t(blockIdx.x, gridDim.x, tiles_x);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
+        issue(kind, 2, first, cur, q.st, t.tx * kTileW, sh.row_lo + t.ty * TH);
+        q.advance(stages);
+      }
+      // 2. the rest of this phase's tiles
+      for (; k < t.count; ++k, t.next())
+      {
+        if (rp.round > 0) mbar_wait_guarded(&empty[rp.st], (rp.round - 1) & 1);
+        issue(kind, 3, first, cur, rp.st, t.tx * kTileW, sh.row_lo + t.ty * TH);
+        rp.advance(stages);
+      }
+      // 3. start the next phase's tiles: everything that does not depend on this phase's
+      //    reduction or on other CTAs' stores of this phase
+      const int nkind = kind ^ 1;
+      const int ncur = kind == 1 ? cur ^ 1 : cur;
+      npre = 0;
+      pre = rp;
+      if (prefetch)
+      {
+        TileWalk tn(blockIdx.x, gridDim.x, tiles_x, n_tiles, serp && nkind == 1);
+        const int want = min(stages, tn.count);
+        for (; npre < want; ++npre, tn.next())
         {
-          if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
-          const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
-          unsigned char* base = smem + st * stage_bytes;
-          mbar_expect_tx(&full[st], first ? Sd::kTx - Sd::kF32 : Sd::kTx);
-          tma_load_2d(base + Sd::oR, &maps.halo_r, c0 - 4, j0 - 1, &full[st]);
-          if (!first) tma_load_2d(base + Sd::oP, &maps.halo_p[cur], c0 - 4, j0 - 1, &full[st]);
-          tma_load_2d(base + Sd::oC, &maps.code, c0 - 16, j0 - 1, &full[st]);
-          if (++st == stages) { st = 0; ++round; }
+          if (rp.round > 0) mbar_wait_guarded(&empty[rp.st], (rp.round - 1) & 1);
+          issue(nkind, 1, false, ncur, rp.st, tn.tx * kTileW, sh.row_lo + tn.ty * TH);
+          rp.advance(stages);
         }
       }
+      // 4. the barrier
       ++phase_id;
-      while (vs->bar_release < phase_id) {}
-      __threadfence();
-      fence_proxy_async_all();
-      if (vs->done) break; // a peer timed out
       {
-        TileWalk t(blockIdx.x, gridDim.x, tiles_x);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
-        {
-          if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
-          const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
-          unsigned char* base = smem + st * stage_bytes;
-          mbar_expect_tx(&full[st], Su::kTx);
-          tma_load_2d(base + Su::oP, &maps.halo_p[cur ^ 1], c0 - 4, j0 - 1, &full[st]);
-          tma_load_2d(base + Su::oX, &maps.inner_x, c0, j0, &full[st]);
-          tma_load_2d(base + Su::oR, &maps.inner_r, c0, j0, &full[st]);
-          tma_load_2d(base + Su::oC, &maps.code, c0 - 16, j0 - 1, &full[st]);
-          if (++st == stages) { st = 0; ++round; }
-        }
+        SpinGuard g;
+        while (ss.released < phase_id) g.tick();
       }
-      ++phase_id;
-      while (vs->bar_release < phase_id) {}
-      __threadfence();
       fence_proxy_async_all();
-      done = vs->done != 0;
+      const bool done = ss.done != 0;
+      kind = nkind;
+      cur = ncur;
       first = false;
-      cur ^= 1;
+      if (done)
+      {
+        // nobody will consume the started tiles: complete them before the CTA may exit
+        TileWalk tn(blockIdx.x, gridDim.x, tiles_x, n_tiles, serp && kind == 1);
+        RingPos w = pre;
+        for (int m = 0; m < npre; ++m, tn.next())
+        {
+          issue(kind, 2, false, cur, w.st, tn.tx * kTileW, sh.row_lo + tn.ty * TH);
+          mbar_wait_guarded(&full[w.st], w.round & 1);
+          w.advance(stages);
+        }
+        return;
+      }
     }
-    return;
   }
 
   // ---- consumers
+  const uint64_t pol_x = l2_policy_evict_first();
   const float inv5 = coef.invdiag[4], diag5 = coef.diag[4], off = coef.off;
   const int r0 = (int)warp * RPW;
   const int fo = r0 * kHaloW + 4 + (int)lane * 4;
@@ -1137,25 +1347,29 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
   const int co = r0 * kCodeW + 16 + (int)lane * 4;
   const int io = r0 * kTileW + (int)lane * 4;
   const bool edge = (lane == 0 || lane == 31);
+  const int last_ty = n_tiles / tiles_x - 1;
+  RingPos rp = {0, 0};
   int cur = 0;
-  while (!ps.done)
+  while (!ss.done)
   {
     // ================= phase A: direction + p.Ap =================
     {
-      const bool first = ps.first != 0;
-      const float beta = first ? 0.0f : ps.beta;
+      const bool first = ss.iter == 0;
+      const float beta = first ? 0.0f : ss.beta;
       float* __restrict__ p_new = cur ? p0 : p1;
       float* push_lo = push.p_lo[cur ^ 1];
       float* push_hi = push.p_hi[cur ^ 1];
       double acc[1] = {0.0};
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x);
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
+      bool pushed = false;
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, false);
+      for (int tk = 0; tk < t.count; ++tk, t.next())
       {
-        const unsigned char* base = smem + st * stage_bytes;
+        const unsigned char* base = smem + rp.st * stage_bytes;
         const float* sr = reinterpret_cast<const float*>(base + Sd::oR);
         const float* sp = reinterpret_cast<const float*>(base + Sd::oP);
         const unsigned char* sc = base + Sd::oC;
-        mbar_wait(&full[st], round & 1);
+        pushed |= (push_lo && t.ty == 0) || (push_hi && t.ty == last_ty);
+        mbar_wait_guarded(&full[rp.st], rp.round & 1);
         float4 pn[RPW + 2];
         uint32_t cd[RPW + 2];
         float he[RPW + 2];
@@ -1176,8 +1390,8 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
-        if (++st == stages) { st = 0; ++round; }
+        if (lane == 0) mbar_arrive(&empty[rp.st]);
+        rp.advance(stages);
         const int ci = t.tx * kTileW + (int)lane * 4;
         const int jb = sh.row_lo + t.ty * TH + r0;
 #pragma unroll
@@ -1199,22 +1413,24 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
         }
       }
       ++phase_id;
-      grid_reduce<NW, 1, 0>(acc, s, partials, phase_id, sh, &ps);
-      if (ps.done) break; // only a communication failure ends the solve here
+      grid_reduce<NW, 1, 0>(acc, s, part_a, phase_id, sh, &ss, pushed);
+      if (ss.done) break; // only a communication failure ends the solve here
     }
     // ================= phase B: update + |r|^2, r.z =================
     {
-      const float alpha = ps.alpha, nalpha = -alpha;
+      const float alpha = ss.alpha, nalpha = -alpha;
       double acc[2] = {0.0, 0.0};
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x);
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, t.next())
+      bool pushed = false;
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, serp);
+      for (int tk = 0; tk < t.count; ++tk, t.next())
       {
-        const unsigned char* base = smem + st * stage_bytes;
+        const unsigned char* base = smem + rp.st * stage_bytes;
         const float* sp = reinterpret_cast<const float*>(base + Su::oP);
         const float* sx = reinterpret_cast<const float*>(base + Su::oX);
         const float* sr = reinterpret_cast<const float*>(base + Su::oR);
         const unsigned char* sc = base + Su::oC;
-        mbar_wait(&full[st], round & 1);
+        pushed |= (push.r_lo && t.ty == 0) || (push.r_hi && t.ty == last_ty);
+        mbar_wait_guarded(&full[rp.st], rp.round & 1);
         float4 pc[RPW + 2], xo[RPW], ro[RPW];
         uint32_t cd[RPW];
         float he[RPW];
@@ -1230,8 +1446,8 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
           he[k] = edge ? sp[hfo + (k + 1) * kHaloW] : 0.0f;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
-        if (++st == stages) { st = 0; ++round; }
+        if (lane == 0) mbar_arrive(&empty[rp.st]);
+        rp.advance(stages);
         const int ci = t.tx * kTileW + (int)lane * 4;
         const int jb = sh.row_lo + t.ty * TH + r0;
 #pragma unroll
@@ -1253,7 +1469,8 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
             xn.z = fmaf(alpha, p4.z, xo[k].z); rn.z = fmaf(nalpha, q.z, ro[k].z);
             xn.w = fmaf(alpha, p4.w, xo[k].w); rn.w = fmaf(nalpha, q.w, ro[k].w);
             const size_t o = (size_t)j * ld + ci;
-            *reinterpret_cast<float4*>(x + o) = xn;
+            if (xhint) st_f4_hint(x + o, xn, pol_x);
+            else *reinterpret_cast<float4*>(x + o) = xn;
             *reinterpret_cast<float4*>(r + o) = rn;
             if (j == sh.row_lo && push.r_lo) *reinterpret_cast<float4*>(push.r_lo + ci) = rn;
             if (j == sh.row_hi - 1 && push.r_hi) *reinterpret_cast<float4*>(push.r_hi + ci) = rn;
@@ -1268,9 +1485,19 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
         }
       }
       ++phase_id;
-      grid_reduce<NW, 2, 1>(acc, s, partials, phase_id, sh, &ps);
+      grid_reduce<NW, 2, 1>(acc, s, part_b, phase_id, sh, &ss, pushed);
     }
     cur ^= 1;
+  }
+  // every CTA holds the same final scalars; CTA 0 publishes them for the host
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    s->pq = ss.pq; s->r2 = ss.r2; s->rz = ss.rz;
+    s->abs_new = ss.abs_new; s->abs_old = ss.abs_old; s->beta = ss.beta;
+    s->iter = ss.iter;
+    s->done = ss.done;
+    s->seq[0] = ss.seq[0]; s->seq[1] = ss.seq[1];
+    if (ss.comm_error) s->comm_error = 1;
   }
 }
 
@@ -1452,6 +1679,14 @@ int configure_cg(fsb_ctx* c)
     c->cg_fused = coop != 0 && mode && mode[0] == 'f';
     const char* pdl = getenv("FSB_CG_PDL"); // profiling knob: 0 disables dependent launch
     c->cg_pdl = !(pdl && pdl[0] == '0');
+    // bit 0: serpentine sweeps (the update walks the tile list backwards), bit 1: x loads / stores
+    // carry an L2 evict-first hint, bit 2: the fused kernel issues barrier-independent loads early
+    auto knob = [](const char* name, int dflt) {
+      const char* e = getenv(name);
+      return e ? atoi(e) != 0 : dflt != 0;
+    };
+    c->cg_flags = (knob("FSB_CG_SERP", 1) ? 1 : 0) | (knob("FSB_CG_XHINT", 0) ? 2 : 0) |
+                  (knob("FSB_CG_PREFETCH", 1) ? 4 : 0);
   }
 
   void* fn = nullptr;
@@ -1527,11 +1762,12 @@ int launch_iteration(fsb_ctx* c, const CgCoef& coef, int cur)
   cfg.gridDim = dim3(c->cg_grid_dir);                                                              \
   cfg.dynamicSmemBytes = (size_t)c->cg_stages_dir * DirStage<kNW * RPW>::kBytes;                   \
   e1 = cudaLaunchKernelEx(&cfg, k_cg_direction<kNW, RPW>, md, p_new, c->ld, tiles_x, n_tiles,      \
-                          c->cg_stages_dir, coef, c->scal, c->partials, sh, p_lo, p_hi);           \
+                          c->cg_stages_dir, coef, c->scal, c->partials, sh, p_lo, p_hi, 0);        \
   cfg.gridDim = dim3(c->cg_grid_upd);                                                              \
   cfg.dynamicSmemBytes = (size_t)c->cg_stages_upd * UpdStage<kNW * RPW>::kBytes;                   \
   e2 = cudaLaunchKernelEx(&cfg, k_cg_update<kNW, RPW>, mu, c->cg_x, c->cg_r, c->ld, tiles_x,       \
-                          n_tiles, c->cg_stages_upd, coef, c->scal, c->partials, sh, r_lo, r_hi)
+                          n_tiles, c->cg_stages_upd, coef, c->scal, c->partials, sh, r_lo, r_hi,   \
+                          c->cg_flags & 1)
   if (th == 32) { FSB_CG_LAUNCH(4); }
   else if (th == 16) { FSB_CG_LAUNCH(2); }
   else { FSB_CG_LAUNCH(1); }
@@ -1561,8 +1797,9 @@ int launch_fused(fsb_ctx* c, const CgCoef& coef)
   push.r_hi = north ? c->peer_r[sh.rank + 1] + hi_off : nullptr;
   int ld = c->ld, stages = c->cg_fused_stages, stage_bytes = c->cg_fused_stage_bytes;
   CgCoef cf = coef;
+  int flags = c->cg_flags;
   void* args[] = {(void*)&maps, &c->cg_x, &c->cg_r, &c->cg_p[0], &c->cg_p[1], &ld, &tiles_x, &n_tiles,
-                  &stages, &stage_bytes, &cf, &c->scal, &c->partials, (void*)&sh, &push};
+                  &stages, &stage_bytes, &cf, &c->scal, &c->partials, (void*)&sh, &push, &flags};
   const dim3 grid(c->cg_grid_fused), block((kNW + 1) * 32);
   const size_t smem = (size_t)stages * stage_bytes;
   cudaError_t e;
@@ -1639,7 +1876,7 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
   const int64_t total = (int64_t)c->ld * c->ny;
   const int build_blocks = (int)std::min<int64_t>(fsb_div_up(total, 256), c->sm_count * 8);
   FSB_TRY(configure_cg(c));
-  const int need = std::max(std::max(3 * build_blocks, 2 * c->cg_grid_fused),
+  const int need = std::max(std::max(3 * build_blocks, 3 * c->cg_grid_fused),
                             std::max(c->cg_grid_dir, 2 * c->cg_grid_upd));
   if (need > c->partials_cap)
   {

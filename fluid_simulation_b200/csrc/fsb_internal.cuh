@@ -136,6 +136,7 @@ struct fsb_ctx
   alignas(64) unsigned char cg_maps_fused[6 * sizeof(CUtensorMap)]; // SolveMaps
   bool cg_fused = false; // persistent cooperative solve kernel in use
   bool cg_pdl = true;    // programmatic dependent launch between the iteration kernels
+  int cg_flags = 0;      // tuning bits of the iteration kernels, see configure_cg
   int cg_grid_fused = 0, cg_fused_stages = 0, cg_fused_stage_bytes = 0;
   int max_iters = 100;
   float tol = 1.1920929e-7f;
