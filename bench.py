@@ -406,6 +406,19 @@ def main():
     alg_bytes = ALG_BYTES_CG_PER_CELL * n * n / world
     achieved = alg_bytes / (it_ms * 1e-3) / 1e9 if iters_total else 0.0
     stages = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
+    # every stage against the HBM roofline: algorithmic bytes of SURVEY.md 8(d) (C cells, P
+    # particles; the cell sort is overhead and has no algorithmic bytes) / CUDA-event time
+    C, P = float(n * n), float(n_part)
+    alg = {"classify": 8 * P + C, "p2g": 16 * P + 8 * C, "extend": 17 * C, "rhs": 13 * C,
+           "grid_pre+patch": (17 + 21) * C if wl["kind"] not in ("cg", "sl") else 21 * C + 17 * C,
+           "g2p": 32 * P + 17 * C, "advect_sl": 17 * C, "advect_part": 16 * P + 8 * C}
+    stage_roofline = {}
+    for name, nbytes in alg.items():
+        t_ms = sum(stages.get(k, 0.0) for k in name.split("+"))
+        if t_ms > 0:
+            gbs = nbytes / (t_ms * 1e-3) / 1e9
+            stage_roofline[name] = {"ms": round(t_ms, 4), "alg_gb": round(nbytes / 1e9, 4),
+                                    "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 3)}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, world)),
                 "traffic_source": NCU_TRAFFIC_SOURCE if (args.workload, world) in NCU_TRAFFIC else None,
@@ -441,6 +454,7 @@ def main():
         "cg_iters_per_s": iters_total / (cg_ms * 1e-3) if cg_ms else None,
         "cg_relres": relres,
         "stage_ms_per_step": stages,
+        "stage_roofline": stage_roofline,
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "e2e": e2e,

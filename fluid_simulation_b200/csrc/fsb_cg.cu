@@ -1672,11 +1672,10 @@ int configure_cg(fsb_ctx* c)
     // the fused kernel needs every CTA resident at once: cooperative launch
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
-    // FSB_CG_MODE=fused selects the persistent single-kernel solve.  Measured on B200 it is
-    // no faster than two launches per iteration (its grid barrier costs what a kernel boundary
-    // costs, profiles/r01e), so the default stays the two-kernel graph.
+    // Default: the persistent single-kernel solve (k_cg_solve) -- fastest at every size measured
+    // (profiles/r01g).  FSB_CG_MODE=graph selects two launches per iteration in a CUDA graph.
     const char* mode = getenv("FSB_CG_MODE");
-    c->cg_fused = coop != 0 && mode && mode[0] == 'f';
+    c->cg_fused = coop != 0 && !(mode && mode[0] == 'g');
     const char* pdl = getenv("FSB_CG_PDL"); // profiling knob: 0 disables dependent launch
     c->cg_pdl = !(pdl && pdl[0] == '0');
     // bit 0: serpentine sweeps (the update walks the tile list backwards), bit 1: x loads / stores

@@ -244,6 +244,57 @@ def test_pressure_solve(capi, checkers, nx, ny):
                 assert np.array_equal(g.get_grid(wb), fields[wf])  # swapped
 
 
+CG_MODES = [
+    dict(FSB_CG_MODE="graph", FSB_CG_SERP="0"),
+    dict(FSB_CG_MODE="graph", FSB_CG_SERP="1"),
+    dict(FSB_CG_MODE="fused", FSB_CG_SERP="0", FSB_CG_PREFETCH="0"),
+    dict(FSB_CG_MODE="fused", FSB_CG_SERP="1", FSB_CG_PREFETCH="1"),
+    dict(FSB_CG_MODE="fused", FSB_CG_SERP="1", FSB_CG_PREFETCH="1", FSB_CG_XHINT="1"),
+    dict(FSB_CG_MODE="fused", FSB_CG_SERP="1", FSB_CG_PREFETCH="1", FSB_CG_TILE_ROWS="16"),
+    dict(FSB_CG_MODE="fused", FSB_CG_SERP="1", FSB_CG_PREFETCH="1", FSB_CG_STAGES="2"),
+]
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 64), (130, 67), (700, 300)])
+def test_pressure_solve_launch_modes(capi, port, monkeypatch, nx, ny):
+    """Every launch mode of the CG (two kernels per iteration in a CUDA graph / one persistent
+    cooperative kernel; serpentine sweeps; early loads; L2 hints; tile shapes) runs the same
+    iteration: same stopping rule, iteration count within 2 %, pressure within the solver
+    tolerance of the CPU port, and converged to the requested residual."""
+    rng = np.random.default_rng(21)
+    lab = scenes.random_labels(nx, ny, rng)
+    fu, fv = scenes.random_field(nx, ny, rng), scenes.random_field(nx, ny, rng)
+    tol = 1e-6
+    c = make_pair(capi, port, nx, ny)[1]
+    c.set_cell_types(lab); c.set_grid(U_FRONT, fu); c.set_grid(V_FRONT, fv)
+    c.set_cg(20000, tol)
+    c.pressure_solve(0.01, 0.01)
+    ic, _ = c.cg_info()
+    pc = c.get_pressure().astype(np.float64)
+    for env in CG_MODES:
+        for k in ("FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH", "FSB_CG_XHINT", "FSB_CG_TILE_ROWS",
+                  "FSB_CG_STAGES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g = make_pair(capi, port, nx, ny)[0]
+        for rep in range(2):  # the second solve reuses the configured context
+            g.set_cell_types(lab); g.set_grid(U_FRONT, fu); g.set_grid(V_FRONT, fv)
+            g.set_cg(20000, tol)
+            g.pressure_solve(0.01, 0.01)
+            ig, eg = g.cg_info()
+            assert eg < tol, (env, eg)
+            assert abs(ig - ic) <= max(2, 0.02 * ic), (env, ig, ic)
+            rel = np.linalg.norm(g.get_pressure().astype(np.float64) - pc) / np.linalg.norm(pc)
+            assert rel < 2e-3, (env, rel)
+        # capped solve: the iteration count is exactly the cap
+        g.set_cell_types(lab); g.set_grid(U_FRONT, fu); g.set_grid(V_FRONT, fv)
+        g.set_cg(7, tol)
+        g.pressure_solve(0.01, 0.01)
+        assert g.cg_info()[0] == 7, (env, g.cg_info())
+        g.close()
+
+
 def test_pressure_patch_exact_given_same_pressure(capi, port):
     """With zero divergence-free input (rhs == 0) the solve returns x = 0 in 0 iterations and
     the patch copies front to back on liquid-touching faces: bit-exact on both sides."""
