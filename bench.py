@@ -15,9 +15,10 @@ This is the configuration BASELINE.json's north_star quotes its single-GPU targe
 value   cell-updates/s = size_x*size_y*steps / device time, state resident in HBM
 e2e     same metric through the C ABI with HOST buffers: every step uploads the particle set
         from pinned host memory, runs fsb_step, and downloads the particle set again
-roofline  the CG iteration (k_cg_dir_spmv + k_cg_update), which is >95 % of the step:
-        algorithmic bytes = 45 B x cells per iteration / CUDA-event time of the
-        CG loop on the library's stream / iterations, against MEASURED_PEAKS.json hbm_gbs
+roofline  the CG iteration (one direction + one update sweep of the persistent k_cg_solve kernel),
+        which is >99 % of the step: algorithmic bytes = 45 B x cells per iteration
+        / (CUDA-event time of the CG loop on the library's stream / iterations), against
+        MEASURED_PEAKS.json hbm_gbs.  stage_roofline gives the same figure for every other stage.
 cpu_baseline  the reference's own sources (oracle/_ref) or the C restatement (oracle port) on one
         host core, bounded sample (see `sample`), reported only
 
@@ -38,10 +39,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 ALG_BYTES_CG_PER_CELL = 45.0  # bytes per cell per CG iteration
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_cg_direction + k_cg_update pair, from the
-# committed ncu --set full capture (bytes per iteration)
-NCU_TRAFFIC = {("picflip4096", 1): 491.7e6}
-NCU_TRAFFIC_SOURCE = "profiles/r01d_cg_ncu_full.md"
+# dram__bytes_read.sum + dram__bytes_write.sum of the persistent k_cg_solve launch / its iterations, from
+# the committed ncu --set full capture (bytes per CG iteration, 4096^2)
+NCU_TRAFFIC = {("picflip4096", 1): 469.6e6, ("cg4096", 1): 469.6e6}
+NCU_TRAFFIC_SOURCE = "profiles/r01g_cg_solve_ncu_full.md"
 
 WORKLOADS = {
     # name: (n, step kind, pic_ratio, cg tol, cg cap, particles per cell side)
@@ -400,6 +401,7 @@ def main():
         return 0
 
     peak, peak_src = measured_peak_gbs()
+    cg_mode = "graph" if os.environ.get("FSB_CG_MODE", "")[:1] == "g" else "persistent"
     cg_ms, _ = prof["cg"]
     it_ms = cg_ms / max(iters_total, 1)
     # per GPU: each rank sweeps 1/world of the rows per iteration
@@ -422,10 +424,14 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, world)),
                 "traffic_source": NCU_TRAFFIC_SOURCE if (args.workload, world) in NCU_TRAFFIC else None,
-                "kernel": "CG iteration = k_cg_direction + k_cg_update (2 launches"
-                          + (" + 2 one-warp mailbox combines" if world > 1 else "") + "), per GPU",
-                "algorithmic_bytes_per_launch_pair": alg_bytes,
-                "design_bytes_per_launch_pair": 34.0 * n * n / world,
+                "kernel": ("k_cg_solve (persistent cooperative kernel, the whole solve is ONE launch): "
+                           "figures are per CG iteration = one direction sweep + one update sweep"
+                           if cg_mode != "graph" else
+                           "CG iteration = k_cg_direction + k_cg_update (2 launches in a CUDA graph)")
+                          + (", per GPU, slab halos + dot products over peer memory" if world > 1 else ""),
+                "algorithmic_bytes_per_iteration": alg_bytes,
+                "design_bytes_per_iteration": 34.0 * n * n / world,
+                "iterations_per_launch": (iters_total / args.steps) if cg_mode != "graph" else 0.5,
                 "avg_iteration_us": it_ms * 1e3, "peak_source": peak_src,
                 "cg_share_of_step": cg_ms / ms if ms else None}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
