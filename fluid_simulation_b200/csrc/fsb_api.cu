@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -234,6 +235,7 @@ int fsb_create(fsb_ctx** out, int size_x, int size_y, float length_x, float leng
   c->pic_ratio = pic_ratio;
   c->grav_x = 0.0f;
   c->grav_y = (float)-9.82; // src/FluidSolver.cpp:232
+  if (const char* e = getenv("FSB_STAGE_KERNELS")) c->stage_v1 = (strcmp(e, "v1") == 0);
   memset(c->prof_ms, 0, sizeof c->prof_ms);
   memset(c->prof_calls, 0, sizeof c->prof_calls);
 
@@ -633,22 +635,41 @@ int fsb_step(fsb_ctx* c, int kind, float dt)
     FSB_TRY(flush_diff(c));
     FSB_TRY(fsb_k_classify(c));
     FSB_TRY(fsb_k_advect_velocity_sl(c, dt));
-    FSB_TRY(fsb_k_add_acceleration(c, gx, gy, dt));
-    FSB_TRY(fsb_k_enforce_dirichlet(c));
-    FSB_TRY(fsb_k_pressure_solve(c, c->density, dt));
-    FSB_TRY(fsb_k_enforce_dirichlet(c));
+    if (c->stage_v1)
+    {
+      FSB_TRY(fsb_k_add_acceleration(c, gx, gy, dt));
+      FSB_TRY(fsb_k_enforce_dirichlet(c));
+      FSB_TRY(fsb_k_pressure_solve(c, c->density, dt));
+      FSB_TRY(fsb_k_enforce_dirichlet(c));
+    }
+    else
+    {
+      // gravity + walls in one pass; the walls after the projection ride on the velocity patch
+      FSB_TRY(fsb_k_prev_gravity_dirichlet(c, gx, gy, dt, 0));
+      FSB_TRY(fsb_k_pressure_solve(c, c->density, dt, true));
+    }
     FSB_TRY(fsb_k_advect_particles_grid(c, dt));
     return FSB_OK;
   }
   // src/FluidSolver.cpp:136-251
   if (kind == FSB_STEP_PIC) FSB_TRY(flush_diff(c));
-  FSB_TRY(fsb_k_classify(c));
+  if (c->stage_v1 || c->sort_valid || c->n == 0) FSB_TRY(fsb_k_classify(c));
+  else
+  {
+    // classification rides on the cell sort's counting pass: the particle set is read once
+    FSB_TRY(fsb_k_classify_reset(c));
+    FSB_TRY(fsb_k_sort_particles(c, true));
+  }
   FSB_TRY(fsb_k_p2g(c));
   // updatePreviousVelocityBuffer + addExternalAcceleration + enforceDirichlet in one pass
   FSB_TRY(fsb_k_prev_gravity_dirichlet(c, gx, gy, dt, kind != FSB_STEP_PIC));
   FSB_TRY(fsb_k_extend_velocity(c, 2));
-  FSB_TRY(fsb_k_pressure_solve(c, c->density, dt));
-  FSB_TRY(fsb_k_enforce_dirichlet(c));
+  if (c->stage_v1)
+  {
+    FSB_TRY(fsb_k_pressure_solve(c, c->density, dt));
+    FSB_TRY(fsb_k_enforce_dirichlet(c));
+  }
+  else FSB_TRY(fsb_k_pressure_solve(c, c->density, dt, true));
   if (kind == FSB_STEP_PIC)
   {
     FSB_TRY(fsb_k_g2p_advect(c, FSB_G2P_PIC, 0.0f, dt, 0));

@@ -26,11 +26,14 @@
 // converging iteration.
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
 #include "fsb_device.cuh"
 #include "fsb_internal.cuh"
+#define FSB_VEC_WANT_CG
+#include "fsb_vec_kernels.cuh"
 
 namespace {
 
@@ -60,6 +63,34 @@ __device__ __forceinline__ double fold_partials(const volatile double* part, int
 }
 
 // --------------------------------------------------------- system set-up --
+// first dot products -> device scalars (thread 0 of the last block of the build kernel)
+__device__ __forceinline__ void cg_init_scalars(CgScalars* __restrict__ s, double tb2, double tbz,
+                                                double tn, float tol, int max_iters)
+{
+  const float rhs2 = (float)tb2;
+  s->rhs2 = tb2;
+  s->r2 = tb2;
+  s->rz = tbz;
+  s->pq = 0.0;
+  s->n_liquid = (int)tn;
+  s->tol = tol;
+  s->max_iters = max_iters < 0 ? 2 * (int)tn : max_iters;
+  // Eigen: threshold = max(tol*tol*rhsNorm2, FLT_MIN)
+  float thr = tol * tol * rhs2;
+  if (thr < FLT_MIN) thr = FLT_MIN;
+  s->thr = thr;
+  s->abs_new = (float)tbz;
+  s->abs_old = 1.0f;
+  s->beta = 0.0f;
+  s->iter = 0;
+  // rhsNorm2 == 0 -> x = 0, 0 iterations; |r|^2 < threshold -> 0 iterations;
+  // maxIters == 0 -> the while loop never runs
+  s->done = (rhs2 == 0.0f || rhs2 < thr || s->max_iters <= 0) ? 1 : 0;
+  s->ticket[0] = 0;
+  s->bar_count = 0;
+  s->bar_release = 0;
+}
+
 // src/FluidSolver.cpp:329-346,368-416: stencil code, right-hand side
 // b = divVelX + divVelY (include/MacGrid.h:98-111) on LIQUID cells, x = 0,
 // r = b, and the first dot products (|b|^2, b.z).
@@ -115,31 +146,49 @@ __global__ void k_cg_build(const float* __restrict__ uf, const float* __restrict
     const double tb2 = fold_partials(partials, gridDim.x);
     const double tbz = fold_partials(partials + gridDim.x, gridDim.x);
     const double tn = fold_partials(partials + 2 * gridDim.x, gridDim.x);
-    if (threadIdx.x == 0)
-    {
-      const float rhs2 = (float)tb2;
-      s->rhs2 = tb2;
-      s->r2 = tb2;
-      s->rz = tbz;
-      s->pq = 0.0;
-      s->n_liquid = (int)tn;
-      s->tol = tol;
-      s->max_iters = max_iters < 0 ? 2 * (int)tn : max_iters;
-      // Eigen: threshold = max(tol*tol*rhsNorm2, FLT_MIN)
-      float thr = tol * tol * rhs2;
-      if (thr < FLT_MIN) thr = FLT_MIN;
-      s->thr = thr;
-      s->abs_new = (float)tbz;
-      s->abs_old = 1.0f;
-      s->beta = 0.0f;
-      s->iter = 0;
-      // rhsNorm2 == 0 -> x = 0, 0 iterations; |r|^2 < threshold -> 0 iterations;
-      // maxIters == 0 -> the while loop never runs
-      s->done = (rhs2 == 0.0f || rhs2 < thr || s->max_iters <= 0) ? 1 : 0;
-      s->ticket[0] = 0;
-      s->bar_count = 0;
-      s->bar_release = 0;
-    }
+    if (threadIdx.x == 0) cg_init_scalars(s, tb2, tbz, tn, tol, max_iters);
+  }
+}
+
+
+// The same set-up with four cells per thread (cg_build_group, fsb_vec_kernels.cuh)
+__global__ void __launch_bounds__(256)
+k_cg_build4(const float* __restrict__ uf, const float* __restrict__ vf,
+            const uint8_t* __restrict__ cell, uint8_t* __restrict__ code, float* __restrict__ x,
+            float* __restrict__ r, const GridDims d, const CgCoef coef, CgScalars* __restrict__ s,
+            double* __restrict__ partials, float tol, int max_iters)
+{
+  const int segs = (d.ld + 1023) / 1024;
+  const int n_work = segs * d.ny;
+  double acc_b2 = 0.0, acc_bz = 0.0, acc_n = 0.0;
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x)
+  {
+    const int j = w / segs;
+    const int i0 = ((w - j * segs) * 256 + threadIdx.x) * 4;
+    if (i0 >= d.ld) continue;
+    const size_t t0 = i0 + (size_t)j * d.ld;
+    uint32_t cd;
+    float4 b;
+    cg_build_group(uf, vf, cell, d, coef.invdiag, i0, j, &cd, &b, &acc_b2, &acc_bz, &acc_n);
+    *reinterpret_cast<uint32_t*>(code + t0) = cd;
+    *reinterpret_cast<float4*>(x + t0) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    *reinterpret_cast<float4*>(r + t0) = b;
+  }
+  const double b2 = block_sum(acc_b2);
+  const double bz = block_sum(acc_bz);
+  const double nn = block_sum(acc_n);
+  if (threadIdx.x == 0)
+  {
+    partials[blockIdx.x] = b2;
+    partials[gridDim.x + blockIdx.x] = bz;
+    partials[2 * gridDim.x + blockIdx.x] = nn;
+  }
+  if (last_block_done(&s->ticket[0], gridDim.x))
+  {
+    const double tb2 = fold_partials(partials, gridDim.x);
+    const double tbz = fold_partials(partials + gridDim.x, gridDim.x);
+    const double tn = fold_partials(partials + 2 * gridDim.x, gridDim.x);
+    if (threadIdx.x == 0) cg_init_scalars(s, tb2, tbz, tn, tol, max_iters);
   }
 }
 
@@ -1005,6 +1054,16 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first()
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+// evict-last on a fraction q/4 of the accesses (q = 1..4); the fraction must be an immediate
+__device__ __forceinline__ uint64_t l2_policy_evict_last(int q)
+{
+  uint64_t pol;
+  if (q >= 4) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else if (q == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.75;" : "=l"(pol));
+  else if (q == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.5;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.25;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1,
                                                  uint64_t* bar, uint64_t policy)
 {
@@ -1214,6 +1273,12 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
   const bool serp = (flags & 1) != 0;     // phase B walks the tile list backwards
   const bool xhint = (flags & 2) != 0;    // x is pure streaming: evict-first loads and stores
   const bool prefetch = (flags & 4) != 0; // barrier-independent loads issued before the barrier
+  // L2 residency: r and the stencil codes are touched by BOTH sweeps of every iteration and are the
+  // only data worth keeping when the vectors do not all fit (4096^2: r 67 MB + code 17 MB of the
+  // 126 MB L2) -> evict-last on a fraction keep/4 of their loads and stores; the old direction is
+  // dead once phase A has read it -> evict-first
+  const bool phint = (flags & 8) != 0;
+  const int keep = (flags >> 4) & 7;
   double* part_a = partials;              // phase A region: gridDim.x doubles
   double* part_b = partials + gridDim.x;  // phase B region: 2 * gridDim.x doubles
 
@@ -1242,6 +1307,14 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
     // ---- producer: one elected lane
     if (lane != 0) return;
     const uint64_t pol_x = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last(keep);
+    // a load with or without an L2 policy
+    auto load = [&](void* dst, const CUtensorMap* map, int c0, int j0, uint64_t* bar, int hint) {
+      if (hint == 1) tma_load_2d_hint(dst, map, c0, j0, bar, pol_x);
+      else if (hint == 2) tma_load_2d_hint(dst, map, c0, j0, bar, pol_keep);
+      else tma_load_2d(dst, map, c0, j0, bar);
+    };
+    const int h_keep = keep ? 2 : 0, h_x = xhint ? 1 : 0, h_pold = phint ? 1 : 0;
     RingPos rp = {0, 0};  // next slot to allocate
     RingPos pre = {0, 0}; // first slot of the tiles whose independent loads are already out
     int npre = 0;
@@ -1257,20 +1330,19 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
         if (part & 1)
         {
           mbar_expect_tx(&full[slot], frst ? Sd::kTx - Sd::kF32 : Sd::kTx);
-          if (!frst) tma_load_2d(base + Sd::oP, &maps.halo_p[cr], c0 - 4, j0 - 1, &full[slot]);
-          tma_load_2d(base + Sd::oC, &maps.code, c0 - 16, j0 - 1, &full[slot]);
+          if (!frst) load(base + Sd::oP, &maps.halo_p[cr], c0 - 4, j0 - 1, &full[slot], h_pold);
+          load(base + Sd::oC, &maps.code, c0 - 16, j0 - 1, &full[slot], h_keep);
         }
-        if (part & 2) tma_load_2d(base + Sd::oR, &maps.halo_r, c0 - 4, j0 - 1, &full[slot]);
+        if (part & 2) load(base + Sd::oR, &maps.halo_r, c0 - 4, j0 - 1, &full[slot], h_keep);
       }
       else
       {
         if (part & 1)
         {
           mbar_expect_tx(&full[slot], Su::kTx);
-          if (xhint) tma_load_2d_hint(base + Su::oX, &maps.inner_x, c0, j0, &full[slot], pol_x);
-          else tma_load_2d(base + Su::oX, &maps.inner_x, c0, j0, &full[slot]);
-          tma_load_2d(base + Su::oR, &maps.inner_r, c0, j0, &full[slot]);
-          tma_load_2d(base + Su::oC, &maps.code, c0 - 16, j0 - 1, &full[slot]);
+          load(base + Su::oX, &maps.inner_x, c0, j0, &full[slot], h_x);
+          load(base + Su::oR, &maps.inner_r, c0, j0, &full[slot], h_keep);
+          load(base + Su::oC, &maps.code, c0 - 16, j0 - 1, &full[slot], h_keep);
         }
         if (part & 2) tma_load_2d(base + Su::oP, &maps.halo_p[cr ^ 1], c0 - 4, j0 - 1, &full[slot]);
       }
@@ -1339,6 +1411,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
 
   // ---- consumers
   const uint64_t pol_x = l2_policy_evict_first();
+  const uint64_t pol_keep = l2_policy_evict_last(keep);
   const float inv5 = coef.invdiag[4], diag5 = coef.diag[4], off = coef.off;
   const int r0 = (int)warp * RPW;
   const int fo = r0 * kHaloW + 4 + (int)lane * 4;
@@ -1471,7 +1544,8 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
             const size_t o = (size_t)j * ld + ci;
             if (xhint) st_f4_hint(x + o, xn, pol_x);
             else *reinterpret_cast<float4*>(x + o) = xn;
-            *reinterpret_cast<float4*>(r + o) = rn;
+            if (keep) st_f4_hint(r + o, rn, pol_keep);
+            else *reinterpret_cast<float4*>(r + o) = rn;
             if (j == sh.row_lo && push.r_lo) *reinterpret_cast<float4*>(push.r_lo + ci) = rn;
             if (j == sh.row_hi - 1 && push.r_hi) *reinterpret_cast<float4*>(push.r_hi + ci) = rn;
             float4 z;
@@ -1527,6 +1601,7 @@ __global__ void k_pressure_patch(const float* __restrict__ uf, const float* __re
   ub[k] = uf[k] - ((dt / density) * ddx) / d.dx;
   vb[k] = vf[k] - ((dt / density) * ddy) / d.dy;
 }
+
 
 } // namespace
 
@@ -1684,8 +1759,15 @@ int configure_cg(fsb_ctx* c)
       const char* e = getenv(name);
       return e ? atoi(e) != 0 : dflt != 0;
     };
+    // bit 3: the old direction is loaded evict-first; bits 4-6: r and the stencil codes are kept
+    // evict-last on a fraction keep/4 of their accesses (FSB_CG_KEEP = 0..4)
+    int keep = 0;
+    if (const char* e = getenv("FSB_CG_KEEP")) keep = std::max(0, std::min(4, atoi(e)));
+    c->cg_persist_mb = 0;
+    if (const char* e = getenv("FSB_CG_PERSIST_MB")) c->cg_persist_mb = std::max(0, atoi(e));
     c->cg_flags = (knob("FSB_CG_SERP", 1) ? 1 : 0) | (knob("FSB_CG_XHINT", 0) ? 2 : 0) |
-                  (knob("FSB_CG_PREFETCH", 1) ? 4 : 0);
+                  (knob("FSB_CG_PREFETCH", 1) ? 4 : 0) | (knob("FSB_CG_PHINT", 0) ? 8 : 0) |
+                  (keep << 4);
   }
 
   void* fn = nullptr;
@@ -1773,6 +1855,41 @@ int launch_iteration(fsb_ctx* c, const CgCoef& coef, int cur)
 #undef FSB_CG_LAUNCH
   FSB_CUDA(c, e1);
   FSB_CUDA(c, e2);
+  return FSB_OK;
+}
+
+// L2 persistence for the residual: r is touched three times per iteration (read by both sweeps,
+// written by the update), more than any other vector.  FSB_CG_PERSIST_MB > 0 sets that much of the
+// L2 aside (cudaLimitPersistingL2CacheSize) and puts an access-policy window over this rank's rows
+// of r on the context's stream for the duration of the solve.
+int set_l2_window(fsb_ctx* c, bool on)
+{
+  if (c->cg_persist_mb <= 0) return FSB_OK;
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof attr);
+  if (on)
+  {
+    cudaDeviceProp prop;
+    FSB_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    size_t carve = std::min((size_t)c->cg_persist_mb << 20, (size_t)prop.persistingL2CacheMaxSize);
+    if (carve == 0) return FSB_OK;
+    FSB_CUDA(c, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+    const ShardArgs& sh = c->shard;
+    size_t bytes = (size_t)(sh.row_hi - sh.row_lo) * c->ld * sizeof(float);
+    bytes = std::min(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.base_ptr = c->cg_r + (size_t)sh.row_lo * c->ld;
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (getenv("FSB_CG_VERBOSE"))
+      fprintf(stderr, "[fsb] L2 %d MB, persisting max %d MB, window max %d MB; carve %zu MB over %zu MB of r, hit ratio %.3f\n",
+              prop.l2CacheSize >> 20, prop.persistingL2CacheMaxSize >> 20,
+              prop.accessPolicyMaxWindowSize >> 20, carve >> 20, bytes >> 20,
+              attr.accessPolicyWindow.hitRatio);
+  }
+  FSB_CUDA(c, cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  if (!on) cudaCtxResetPersistingL2Cache();
   return FSB_OK;
 }
 
@@ -1865,7 +1982,7 @@ void fsb_cg_reconfigure(fsb_ctx* c)
   c->cg_graph_state = 0;
 }
 
-int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
+int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichlet)
 {
   const GridDims d = make_grid_dims(c->nx, c->ny, c->ld, c->dx, c->dy);
   const CgCoef coef = make_coef(c);
@@ -1884,15 +2001,21 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
     FSB_CUDA(c, cudaMalloc(&c->partials, sizeof(double) * need));
     c->partials_cap = need;
   }
-  k_cg_build<<<build_blocks, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell, c->cg_code,
-                                                  c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
-                                                  c->tol, c->max_iters);
+  if (c->stage_v1)
+    k_cg_build<<<build_blocks, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell, c->cg_code,
+                                                    c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
+                                                    c->tol, c->max_iters);
+  else
+    k_cg_build4<<<build_blocks, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell, c->cg_code,
+                                                     c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
+                                                     c->tol, c->max_iters);
   FSB_LAUNCHED(c);
   FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[0], c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
                               c->stream));
   fsb_prof_end(c, FSB_PROF_RHS);
   FSB_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (c->scal_h[0].n_liquid == 0) return FSB_OK; // :347-350: nothing touched, no swap
+  if (c->scal_h[0].n_liquid == 0) // :347-350: nothing touched, no swap
+    return fuse_dirichlet ? fsb_k_enforce_dirichlet(c) : FSB_OK;
 
   // ---- iterate: chunks of kCheckEvery iterations; the host reads the device
   // scalars of chunk k while chunk k+1 is already queued, so the GPU never
@@ -1902,10 +2025,12 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
   if (!fin.done && c->cg_fused)
   {
     // one persistent kernel runs the loop to completion; no polling
+    FSB_TRY(set_l2_window(c, true));
     FSB_TRY(launch_fused(c, coef));
     FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[0], c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
                                 c->stream));
     FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    FSB_TRY(set_l2_window(c, false));
     fin = c->scal_h[0];
   }
   else if (!fin.done)
@@ -1973,10 +2098,19 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt)
 
   // ---- patch + swap
   fsb_prof_begin(c, FSB_PROF_PATCH);
-  k_pressure_patch<<<dim3(fsb_div_up(c->ld, 256), c->ny), 256, 0, c->stream>>>(
-      fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), c->cg_x, c->cg_code, d, dt, density);
+  const dim3 grid4(fsb_div_up(c->ld, 1024), c->ny);
+  if (c->stage_v1)
+    k_pressure_patch<<<dim3(fsb_div_up(c->ld, 256), c->ny), 256, 0, c->stream>>>(
+        fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), c->cg_x, c->cg_code, d, dt, density);
+  else if (fuse_dirichlet)
+    k_pressure_patch4<true><<<grid4, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c),
+                                                          c->cg_x, c->cell, d, dt, density);
+  else
+    k_pressure_patch4<false><<<grid4, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c),
+                                                           c->cg_x, c->cell, d, dt, density);
   FSB_LAUNCHED(c);
   c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:482
   fsb_prof_end(c, FSB_PROF_PATCH);
+  if (fuse_dirichlet && c->stage_v1) return fsb_k_enforce_dirichlet(c);
   return FSB_OK;
 }

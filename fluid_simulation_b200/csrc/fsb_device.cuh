@@ -199,6 +199,7 @@ __device__ __forceinline__ void advected_position(const float* __restrict__ u,
   *yo = y + ddy;
 }
 
+#ifdef __CUDACC__
 // block-wide sum of doubles; result valid in thread 0.  blockDim.x <= 1024.
 __device__ __forceinline__ double block_sum(double v)
 {
@@ -218,3 +219,138 @@ __device__ __forceinline__ double block_sum(double v)
   }
   return v;
 }
+#endif // __CUDACC__
+
+// ---------------------------------------------------------------------------
+// Label windows for the 4-cells-per-thread grid kernels.
+// A thread owns cells i0 .. i0+3 of row j (i0 a multiple of 4).  A window holds the labels of
+// columns i0-4 .. i0+7 of one row as three little-endian words, with the reference's index
+// clamping (include/MacGrid.h:92-97) already applied: column < 0 reads column 0, column >= nx
+// reads column nx-1, and the row index is clamped by the caller-visible helper below.
+// From a window the kernels derive 12-bit masks: bit (t + 4) describes column i0 + t.
+struct LabWin
+{
+  uint32_t w, c, e;
+};
+
+__device__ __forceinline__ uint32_t set_byte(uint32_t word, int t, uint32_t v)
+{
+  return (word & ~(0xffu << (8 * t))) | (v << (8 * t));
+}
+
+__device__ __forceinline__ LabWin lab_window(const uint8_t* __restrict__ cell, const GridDims& d,
+                                             int i0, int j)
+{
+  const int jc = clampi(j, 0, d.ny - 1);
+  const uint8_t* row = cell + (size_t)jc * d.ld;
+  LabWin L;
+  L.c = *reinterpret_cast<const uint32_t*>(row + i0);
+  L.w = (i0 >= 4) ? *reinterpret_cast<const uint32_t*>(row + i0 - 4) : 0u;
+  L.e = (i0 + 4 < d.ld) ? *reinterpret_cast<const uint32_t*>(row + i0 + 4) : 0u;
+  if (i0 == 0) L.w = (L.c & 0xffu) * 0x01010101u;
+  if (i0 + 8 > d.nx)
+  {
+    const uint32_t last = row[d.nx - 1];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+    {
+      if (i0 + t >= d.nx) L.c = set_byte(L.c, t, last);
+      if (i0 + 4 + t >= d.nx) L.e = set_byte(L.e, t, last);
+    }
+  }
+  return L;
+}
+
+// 4-bit mask of the bytes of `word` equal to `value` (bit t <-> byte t)
+__device__ __forceinline__ uint32_t bytes_equal4(uint32_t word, uint32_t value)
+{
+  const uint32_t eq = __vcmpeq4(word, value * 0x01010101u) & 0x01010101u;
+  return ((eq * 0x01020408u) >> 24) & 0xfu;
+}
+
+// 12-bit mask over a window: bit (t + 4) set when the label of column i0 + t equals `value`
+__device__ __forceinline__ uint32_t window_mask(const LabWin& L, uint32_t value)
+{
+  return bytes_equal4(L.w, value) | (bytes_equal4(L.c, value) << 4) | (bytes_equal4(L.e, value) << 8);
+}
+
+// own columns only (bits 4..7): for rows of which a kernel needs no west / east neighbour
+__device__ __forceinline__ uint32_t center_mask(const uint8_t* __restrict__ cell, const GridDims& d,
+                                                int i0, int j, uint32_t value)
+{
+  const int jc = clampi(j, 0, d.ny - 1);
+  const uint8_t* row = cell + (size_t)jc * d.ld;
+  uint32_t c = *reinterpret_cast<const uint32_t*>(row + i0);
+  if (i0 + 4 > d.nx)
+  {
+    const uint32_t last = row[d.nx - 1];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (i0 + t >= d.nx) c = set_byte(c, t, last);
+  }
+  return bytes_equal4(c, value) << 4;
+}
+
+// same for a plain (unclamped) byte row, e.g. a packed validity mask: columns outside the row read 0
+__device__ __forceinline__ LabWin byte_window(const uint8_t* __restrict__ row, int ld, int i0)
+{
+  LabWin L;
+  L.c = *reinterpret_cast<const uint32_t*>(row + i0);
+  L.w = (i0 >= 4) ? *reinterpret_cast<const uint32_t*>(row + i0 - 4) : 0u;
+  L.e = (i0 + 4 < ld) ? *reinterpret_cast<const uint32_t*>(row + i0 + 4) : 0u;
+  return L;
+}
+// 12-bit mask of the bytes of a window that have bit `bit` set
+__device__ __forceinline__ uint32_t window_bit(const LabWin& L, int bit)
+{
+  auto nib = [bit](uint32_t word) {
+    const uint32_t m = (word >> bit) & 0x01010101u;
+    return ((m * 0x01020408u) >> 24) & 0xfu;
+  };
+  return nib(L.w) | (nib(L.c) << 4) | (nib(L.e) << 8);
+}
+
+constexpr uint32_t kOwnBits = 0xf0u; // window-mask bits of the thread's own four columns
+
+__device__ __forceinline__ float f4_get(const float4& v, int t)
+{
+  return t == 0 ? v.x : (t == 1 ? v.y : (t == 2 ? v.z : v.w));
+}
+__device__ __forceinline__ void f4_set(float4& v, int t, float x)
+{
+  if (t == 0) v.x = x;
+  else if (t == 1) v.y = x;
+  else if (t == 2) v.z = x;
+  else v.w = x;
+}
+// window bits of own columns that exist in the grid (i0 + t < nx)
+__device__ __forceinline__ uint32_t own_columns(const GridDims& d, int i0)
+{
+  const int n = d.nx - i0;
+  return n >= 4 ? kOwnBits : ((0xfu >> (4 - n)) << 4);
+}
+// window bits of own columns that are interior cells (1 <= i <= nx-2), zero when the row is not
+__device__ __forceinline__ uint32_t interior_columns(const GridDims& d, int i0, int j)
+{
+  if (j < 1 || j > d.ny - 2) return 0u;
+  uint32_t m = 0u;
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+    if (i0 + t >= 1 && i0 + t <= d.nx - 2) m |= 1u << (t + 4);
+  return m;
+}
+
+// src/FluidSolver.cpp:297-321 on four faces of each kind per thread
+__device__ __forceinline__ void dirichlet4(float4& u, float4& v, uint32_t sd_c, uint32_t sd_s)
+{
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+  {
+    const bool here = (sd_c >> (t + 4)) & 1u, west = (sd_c >> (t + 3)) & 1u,
+               south = (sd_s >> (t + 4)) & 1u;
+    const float a = f4_get(u, t), b = f4_get(v, t);
+    if ((west && a < 0.0f) || (here && a > 0.0f)) f4_set(u, t, 0.0f);
+    if ((south && b < 0.0f) || (here && b > 0.0f)) f4_set(v, t, 0.0f);
+  }
+}
+

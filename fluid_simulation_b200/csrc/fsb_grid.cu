@@ -3,6 +3,8 @@
 // velocity advection.  One thread per cell, rows padded to `ld`.
 #include "fsb_device.cuh"
 #include "fsb_internal.cuh"
+#define FSB_VEC_WANT_GRID
+#include "fsb_vec_kernels.cuh"
 
 namespace {
 
@@ -18,6 +20,9 @@ __device__ __forceinline__ bool cell_of_thread(const GridDims d, int* i, int* j)
 }
 
 inline dim3 cell_grid(const fsb_ctx* c) { return dim3(fsb_div_up(c->ld, kBlock), c->ny); }
+// one thread per float4 group / per 16 labels
+inline dim3 vec4_grid(const fsb_ctx* c) { return dim3(fsb_div_up(c->ld, 4 * kBlock), c->ny); }
+inline dim3 vec16_grid(const fsb_ctx* c) { return dim3(fsb_div_up(c->ld, 16 * kBlock), c->ny); }
 inline GridDims dims(const fsb_ctx* c) { return make_grid_dims(c->nx, c->ny, c->ld, c->dx, c->dy); }
 
 // src/MacGrid.cpp:32-50 clearCellTypeBuffer + the border reset of
@@ -257,13 +262,31 @@ __global__ void k_advect_velocity_sl(const float* __restrict__ uf, const float* 
   }
 }
 
+
 } // namespace
+
+static int fill_labels(fsb_ctx* c)
+{
+  if (c->stage_v1) k_fill_labels<<<cell_grid(c), kBlock, 0, c->stream>>>(c->cell, dims(c));
+  else k_fill_labels16<<<vec16_grid(c), kBlock, 0, c->stream>>>(c->cell, dims(c));
+  FSB_LAUNCHED(c);
+  return FSB_OK;
+}
+
+// the border / AIR reset only; the LIQUID marks come from the cell sort's counting pass, which
+// reads every particle anyway (fsb_k_sort_particles with mark_labels)
+int fsb_k_classify_reset(fsb_ctx* c)
+{
+  fsb_prof_begin(c, FSB_PROF_CLASSIFY);
+  FSB_TRY(fill_labels(c));
+  fsb_prof_end(c, FSB_PROF_CLASSIFY);
+  return FSB_OK;
+}
 
 int fsb_k_classify(fsb_ctx* c)
 {
   fsb_prof_begin(c, FSB_PROF_CLASSIFY);
-  k_fill_labels<<<cell_grid(c), kBlock, 0, c->stream>>>(c->cell, dims(c));
-  FSB_LAUNCHED(c);
+  FSB_TRY(fill_labels(c));
   if (c->n > 0)
   {
     // lengthX() is recomputed as size * delta in float (include/Grid.h:54-55)
@@ -277,12 +300,7 @@ int fsb_k_classify(fsb_ctx* c)
   return FSB_OK;
 }
 
-int fsb_k_clear_labels(fsb_ctx* c)
-{
-  k_fill_labels<<<cell_grid(c), kBlock, 0, c->stream>>>(c->cell, dims(c));
-  FSB_LAUNCHED(c);
-  return FSB_OK;
-}
+int fsb_k_clear_labels(fsb_ctx* c) { return fill_labels(c); }
 
 int fsb_k_save_previous(fsb_ctx* c)
 {
@@ -325,8 +343,12 @@ int fsb_k_prev_gravity_dirichlet(fsb_ctx* c, float ax, float ay, float dt, int s
 int fsb_k_enforce_dirichlet(fsb_ctx* c)
 {
   fsb_prof_begin(c, FSB_PROF_GRID_PRE);
-  k_enforce_dirichlet<<<cell_grid(c), kBlock, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell,
-                                                              dims(c));
+  if (c->stage_v1)
+    k_enforce_dirichlet<<<cell_grid(c), kBlock, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell,
+                                                                dims(c));
+  else
+    k_enforce_dirichlet4<<<vec4_grid(c), kBlock, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell,
+                                                                 dims(c));
   FSB_LAUNCHED(c);
   fsb_prof_end(c, FSB_PROF_GRID_PRE);
   return FSB_OK;
@@ -335,6 +357,22 @@ int fsb_k_enforce_dirichlet(fsb_ctx* c)
 int fsb_k_extend_velocity(fsb_ctx* c, int n_iter)
 {
   fsb_prof_begin(c, FSB_PROF_EXTEND);
+  if (n_iter == 2 && !c->stage_v1)
+  {
+    // two passes, masks recomputed from the labels (see k_extend2_a); mask_x[0] holds the packed
+    // validity byte between the passes.  The stored mask buffers are scratch of this stage (every
+    // call rebuilds them), so leaving them untouched is not observable.
+    uint8_t* m1 = c->mask_x[0];
+    k_extend2_a<<<vec4_grid(c), kBlock, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c),
+                                                        m1, c->cell, dims(c));
+    FSB_LAUNCHED(c);
+    k_extend2_b<<<vec4_grid(c), kBlock, 0, c->stream>>>(fsb_uf(c), fsb_ub(c), fsb_vb(c), m1, c->cell,
+                                                        dims(c));
+    FSB_LAUNCHED(c);
+    c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:621
+    fsb_prof_end(c, FSB_PROF_EXTEND);
+    return FSB_OK;
+  }
   k_extend_init<<<cell_grid(c), kBlock, 0, c->stream>>>(
       fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), c->mask_x[c->mask_front],
       c->mask_x[c->mask_front ^ 1], c->mask_y[c->mask_front], c->mask_y[c->mask_front ^ 1], c->cell,

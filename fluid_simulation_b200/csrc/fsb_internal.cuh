@@ -137,6 +137,7 @@ struct fsb_ctx
   bool cg_fused = false; // persistent cooperative solve kernel in use
   bool cg_pdl = true;    // programmatic dependent launch between the iteration kernels
   int cg_flags = 0;      // tuning bits of the iteration kernels, see configure_cg
+  int cg_persist_mb = 0; // L2 set-aside for the residual during a solve (0: none)
   int cg_grid_fused = 0, cg_fused_stages = 0, cg_fused_stage_bytes = 0;
   int max_iters = 100;
   float tol = 1.1920929e-7f;
@@ -169,6 +170,9 @@ struct fsb_ctx
   cudaEvent_t timer_ev[2] = {nullptr, nullptr};
   int64_t launches = 0;
   int sm_count = 148;
+  // FSB_STAGE_KERNELS=v1 selects the first-generation one-cell-per-thread stage kernels and the
+  // unfused stage sequence (kept for A/B measurements and as a second implementation in the tests)
+  bool stage_v1 = false;
 
   std::string err_msg;
 };
@@ -209,6 +213,7 @@ void fsb_prof_end(fsb_ctx* ctx, int stage);
 // stage launchers (each returns FSB_OK or an error code) ----------------------
 // grid stages: fsb_grid.cu
 int fsb_k_classify(fsb_ctx* c);
+int fsb_k_classify_reset(fsb_ctx* c);
 int fsb_k_clear_labels(fsb_ctx* c);
 int fsb_k_save_previous(fsb_ctx* c);
 int fsb_k_update_diff(fsb_ctx* c);
@@ -218,7 +223,7 @@ int fsb_k_prev_gravity_dirichlet(fsb_ctx* c, float ax, float ay, float dt, int s
 int fsb_k_extend_velocity(fsb_ctx* c, int n_iter);
 int fsb_k_advect_velocity_sl(fsb_ctx* c, float dt);
 // particle stages: fsb_particles.cu
-int fsb_k_sort_particles(fsb_ctx* c);
+int fsb_k_sort_particles(fsb_ctx* c, bool mark_labels = false);
 int fsb_k_p2g(fsb_ctx* c);
 int fsb_k_g2p(fsb_ctx* c, int mode, float pic_ratio);
 int fsb_k_advect_particles(fsb_ctx* c, float dt, int ensure_outside);
@@ -228,5 +233,5 @@ int fsb_k_unpermute(fsb_ctx* c, float4* dst_dense);
 int fsb_k_emit_source_dev(fsb_ctx* c, int64_t first, const float* xs_dev, const float* ys_dev,
                           int64_t count_x, int64_t count_y, float vel_x, float vel_y);
 // pressure: fsb_cg.cu
-int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt);
+int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichlet = false);
 void fsb_cg_reconfigure(fsb_ctx* c); // drop the CG launch configuration and graph (sharding changed)

@@ -19,9 +19,15 @@ inline GridDims pool_dims(const fsb_ctx* c)
 // Key = the particle's interpolation base cell (int)(pos/delta), index-clamped
 // (formula 3 of SURVEY.md A.4), dense index ci + cj*nx.  Runs of equal keys
 // inside a warp are aggregated so that only the run head touches the counter.
+//
+// MARK: the same pass also performs FluidDomain::classifyCells' marking (src/FluidDomain.cpp:
+// 157-167, the formula of k_mark_liquid: (int)((pos / length) * size), clamped, border skipped),
+// so that a step reads the particle set once for both.
+template <bool MARK>
 __global__ void k_sort_count(const float4* __restrict__ part, int64_t n, const GridDims d,
                              int* __restrict__ count, int* __restrict__ key_out,
-                             int* __restrict__ rank_out)
+                             int* __restrict__ rank_out, uint8_t* __restrict__ cell,
+                             const GridDims gd, const GridDims glen)
 {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
@@ -33,6 +39,13 @@ __global__ void k_sort_count(const float4* __restrict__ part, int64_t n, const G
     const int ci = clampi((int)div_dx(d, p.x), 0, d.nx - 1);
     const int cj = clampi((int)div_dy(d, p.y), 0, d.ny - 1);
     key = ci + cj * d.nx;
+    if (MARK)
+    {
+      const int x = clampi((int)(div_dx(glen, p.x) * (float)gd.nx), 0, gd.nx - 1);
+      const int y = clampi((int)(div_dy(glen, p.y) * (float)gd.ny), 0, gd.ny - 1);
+      if (!(x == 0 || y == 0 || x == gd.nx - 1 || y == gd.ny - 1))
+        cell[x + (size_t)y * gd.ld] = FSB_LIQUID;
+    }
   }
   const int prev = __shfl_up_sync(0xffffffffu, key, 1);
   const bool head = (lane == 0) || (key != prev);
@@ -511,16 +524,25 @@ __global__ void k_emit_source(float4* __restrict__ part, int* __restrict__ orig,
 
 } // namespace
 
-int fsb_k_sort_particles(fsb_ctx* c)
+int fsb_k_sort_particles(fsb_ctx* c, bool mark_labels)
 {
-  if (c->sort_valid) return FSB_OK;
+  if (c->sort_valid) return mark_labels ? fsb_fail(c, FSB_ERR_INVALID, "sort already valid") : FSB_OK;
   const int m = c->nx * c->ny;
   fsb_prof_begin(c, FSB_PROF_SORT);
   FSB_CUDA(c, cudaMemsetAsync(c->cell_count, 0, (size_t)m * sizeof(int), c->stream));
   if (c->n > 0)
   {
-    k_sort_count<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
-        c->part[c->pcur], c->n, pool_dims(c), c->cell_count, c->sort_key, c->sort_rank);
+    // lengthX() is recomputed as size * delta in float (include/Grid.h:54-55)
+    const GridDims len =
+        make_grid_dims(c->nx, c->ny, c->ld, (float)c->nx * c->dx, (float)c->ny * c->dy);
+    if (mark_labels)
+      k_sort_count<true><<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+          c->part[c->pcur], c->n, pool_dims(c), c->cell_count, c->sort_key, c->sort_rank, c->cell,
+          dims(c), len);
+    else
+      k_sort_count<false><<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+          c->part[c->pcur], c->n, pool_dims(c), c->cell_count, c->sort_key, c->sort_rank, c->cell,
+          dims(c), len);
     FSB_LAUNCHED(c);
   }
   const int nb = fsb_div_up(m, kScanTile);

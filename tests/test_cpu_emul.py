@@ -1,0 +1,168 @@
+"""The vectorised stage kernels (fluid_simulation_b200/csrc/fsb_vec_kernels.cuh) compiled for the
+HOST and checked bit for bit against the CPU checkers -- runs without a GPU.
+
+tests/cpu_emul/emul_vec_kernels.cpp compiles the product's kernel source unchanged with the CUDA
+keywords defined away and runs one loop iteration per CUDA thread.  This pins the kernels' label
+bit-mask logic, clamping and per-face arithmetic before any GPU time is spent; the GPU parity
+tests (tests/test_gpu_parity.py) run the same kernels on the device.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import scenes
+from oracle_lib import U_BACK, U_FRONT, V_BACK, V_FRONT
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL_DIR = os.path.join(ROOT, "tests", "cpu_emul")
+SIZES = [(64, 64), (37, 53), (96, 40), (130, 67), (5, 7), (33, 9)]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = os.path.join(EMUL_DIR, "emul_vec_kernels.cpp")
+    out = os.path.join(EMUL_DIR, "libfsbemul.so")
+    csrc = os.path.join(ROOT, "fluid_simulation_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("fsb_vec_kernels.cuh", "fsb_device.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(p) > os.path.getmtime(out) for p in deps):
+        cuda_inc = "/usr/local/cuda/include"
+        if not os.path.isdir(cuda_inc):
+            pytest.skip("CUDA headers not present")
+        subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+                        "-I", cuda_inc, "-I", csrc, "-I", os.path.join(ROOT, "include"),
+                        "-o", out, src], check=True)
+    return ctypes.CDLL(out)
+
+
+def pitched(a, fill=0):
+    ny, nx = a.shape
+    ld = (nx + 31) // 32 * 32
+    p = np.full((ny, ld), fill, dtype=a.dtype)
+    p[:, :nx] = a
+    return p
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def dims(sim, nx, ny):
+    ld = (nx + 31) // 32 * 32
+    return (ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(ld), ctypes.c_float(sim.dx),
+            ctypes.c_float(sim.dy))
+
+
+def make_sim(chk, nx, ny):
+    return chk.sim(nx, ny, 1.0, float(np.float32(ny) / np.float32(nx)), 0.01, 0.05)
+
+
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_fill_labels(emul, port, nx, ny):
+    c = make_sim(port, nx, ny)
+    c.classify_cells()  # no particles: border SOLID, interior AIR
+    cell = np.full((ny, (nx + 31) // 32 * 32), 7, dtype=np.uint8)
+    emul.emul_fill_labels(ptr(cell), *dims(c, nx, ny))
+    assert np.array_equal(cell[:, :nx], c.get_cell_types())
+    assert (cell[:, nx:] == scenes.SOLID).all()  # pad columns
+
+
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_enforce_dirichlet(emul, checkers, nx, ny):
+    rng = np.random.default_rng(21)
+    for chk in checkers:
+        c = make_sim(chk, nx, ny)
+        lab = scenes.random_labels(nx, ny, rng, p_solid=0.15)
+        u, v = scenes.random_field(nx, ny, rng), scenes.random_field(nx, ny, rng)
+        c.set_cell_types(lab); c.set_grid(U_FRONT, u); c.set_grid(V_FRONT, v)
+        c.enforce_dirichlet()
+        pu, pv, pl = pitched(u), pitched(v), pitched(lab, scenes.SOLID)
+        emul.emul_enforce_dirichlet(ptr(pu), ptr(pv), ptr(pl), *dims(c, nx, ny))
+        assert np.array_equal(pu[:, :nx], c.get_grid(U_FRONT))
+        assert np.array_equal(pv[:, :nx], c.get_grid(V_FRONT))
+        assert not pu[:, nx:].any() and not pv[:, nx:].any()
+
+
+@pytest.mark.parametrize("nx,ny", SIZES)
+@pytest.mark.parametrize("p_liquid", [0.5, 0.08])
+def test_extend_velocity_two_sweeps(emul, checkers, nx, ny, p_liquid):
+    rng = np.random.default_rng(22)
+    for chk in checkers:
+        c = make_sim(chk, nx, ny)
+        lab = scenes.random_labels(nx, ny, rng, p_liquid=p_liquid, p_solid=0.05)
+        f = {w: scenes.random_field(nx, ny, rng) for w in (U_FRONT, V_FRONT, U_BACK, V_BACK)}
+        c.set_cell_types(lab)
+        for w, a in f.items():
+            c.set_grid(w, a)
+        c.extend_velocity(2)  # swaps: the extended field is the new FRONT, the zeroed old front the BACK
+        pu, pv = pitched(f[U_FRONT]), pitched(f[V_FRONT])
+        pub, pvb = pitched(f[U_BACK]), pitched(f[V_BACK])
+        pl = pitched(lab, scenes.SOLID)
+        m1 = np.zeros_like(pl)
+        emul.emul_extend2(ptr(pu), ptr(pv), ptr(pub), ptr(pvb), ptr(m1), ptr(pl), *dims(c, nx, ny))
+        assert np.array_equal(pub[:, :nx], c.get_grid(U_FRONT))
+        assert np.array_equal(pvb[:, :nx], c.get_grid(V_FRONT))
+        assert np.array_equal(pu[:, :nx], c.get_grid(U_BACK))  # incl. the :527 typo
+        assert np.array_equal(pv[:, :nx], c.get_grid(V_BACK))
+        assert not pub[:, nx:].any() and not pvb[:, nx:].any()
+
+
+@pytest.mark.parametrize("nx,ny", SIZES)
+@pytest.mark.parametrize("dirichlet", [0, 1])
+def test_pressure_patch(emul, checkers, nx, ny, dirichlet):
+    rng = np.random.default_rng(23)
+    for chk in checkers:
+        c = make_sim(chk, nx, ny)
+        lab = scenes.random_labels(nx, ny, rng, p_solid=0.08)
+        f = {w: scenes.random_field(nx, ny, rng) for w in (U_FRONT, V_FRONT, U_BACK, V_BACK)}
+        c.set_cell_types(lab)
+        for w, a in f.items():
+            c.set_grid(w, a)
+        c.set_cg(7, 1e-6)  # a few iterations: a non-trivial pressure field
+        dt, rho = 0.01, 0.013
+        c.pressure_solve(rho, dt)
+        x = c.get_pressure()
+        if dirichlet:
+            c.enforce_dirichlet()
+        pub, pvb = pitched(f[U_BACK]), pitched(f[V_BACK])
+        emul.emul_pressure_patch(ptr(pitched(f[U_FRONT])), ptr(pitched(f[V_FRONT])), ptr(pub),
+                                 ptr(pvb), ptr(pitched(x)), ptr(pitched(lab, scenes.SOLID)),
+                                 *dims(c, nx, ny), ctypes.c_float(dt), ctypes.c_float(rho),
+                                 ctypes.c_int(dirichlet))
+        if (lab == scenes.LIQUID).any():
+            assert np.array_equal(pub[:, :nx], c.get_grid(U_FRONT))
+            assert np.array_equal(pvb[:, :nx], c.get_grid(V_FRONT))
+        assert not pub[:, nx:].any() and not pvb[:, nx:].any()
+
+
+@pytest.mark.parametrize("nx,ny", SIZES)
+def test_cg_build_group(emul, nx, ny):
+    """Stencil codes and right-hand side against a float32 numpy statement of
+    src/FluidSolver.cpp:368-416 / include/MacGrid.h:98-111."""
+    rng = np.random.default_rng(24)
+    lab = scenes.random_labels(nx, ny, rng, p_solid=0.08)
+    u, v = scenes.random_field(nx, ny, rng), scenes.random_field(nx, ny, rng)
+    dx = np.float32(1.0) / np.float32(nx)
+    dy = np.float32(np.float32(ny) / np.float32(nx)) / np.float32(ny)
+    liq, nonsolid = lab == scenes.LIQUID, lab != scenes.SOLID
+    pad = np.pad(nonsolid, 1, mode="edge")
+    cnt = (pad[1:-1, :-2].astype(int) + pad[1:-1, 2:] + pad[:-2, 1:-1] + pad[2:, 1:-1])
+    code_ref = np.where(liq, 1 + cnt, 0).astype(np.uint8)
+    ue = np.concatenate([u[:, 1:], u[:, -1:]], axis=1)
+    vn = np.concatenate([v[1:, :], v[-1:, :]], axis=0)
+    b_ref = np.where(liq, (ue - u) / dx + (vn - v) / dy, np.float32(0)).astype(np.float32)
+    invdiag = np.array([1.0] + [1.0 / float(np.float32(-n / float(dx) ** 2)) for n in range(1, 5)],
+                       dtype=np.float32)
+    pl = pitched(lab, scenes.SOLID)
+    code, r = np.full_like(pl, 9), np.full(pl.shape, 5.0, dtype=np.float32)
+    sums = np.zeros(3)
+    ld = pl.shape[1]
+    emul.emul_cg_build(ptr(pitched(u)), ptr(pitched(v)), ptr(pl), ptr(code), ptr(r), ptr(invdiag),
+                       ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(ld), ctypes.c_float(dx),
+                       ctypes.c_float(dy), ptr(sums))
+    assert np.array_equal(code[:, :nx], code_ref) and not code[:, nx:].any()
+    assert np.array_equal(r[:, :nx], b_ref) and not r[:, nx:].any()
+    assert sums[2] == liq.sum()
+    assert np.isclose(sums[0], (b_ref.astype(np.float64) ** 2).sum(), rtol=1e-12)

@@ -350,6 +350,35 @@ def test_full_steps_config0(capi, checkers, kind):
             assert abs(int((lg == 0).sum()) - int((lc == 0).sum())) <= 0.02 * (lc == 0).sum() + 2
 
 
+@pytest.mark.parametrize("kind", [STEP_PICFLIP, STEP_FLIP, STEP_PIC, STEP_SL])
+@pytest.mark.parametrize("n", [64, 130])
+def test_stage_kernel_generations_agree_bit_for_bit(capi, monkeypatch, kind, n):
+    """The steps use the vectorised / fused stage kernels (classification riding on the sort's
+    counting pass, two-pass extension, projection patch + walls in one pass, 4-cell set-up);
+    FSB_STAGE_KERNELS=v1 selects the first-generation one-cell-per-thread kernels and the unfused
+    stage sequence.  Both must produce the same bits: labels, all six grids, particles, CG count."""
+    out = []
+    for gen in ("v1", "v2"):
+        monkeypatch.setenv("FSB_STAGE_KERNELS", gen)
+        g = capi.Sim(n, n, 1.0, 1.0, 0.01, 0.05)
+        g.emit_source(*scenes.dam_break_args(n))
+        iters = []
+        for _ in range(4):
+            g.step(kind, 0.01)
+            iters.append(g.cg_info()[0])
+        out.append((g.get_cell_types(), [g.get_grid(w) for w in
+                                         (U_FRONT, V_FRONT, U_BACK, V_BACK, U_PREV, V_PREV)],
+                    g.get_particles(), iters))
+        g.close()
+    monkeypatch.delenv("FSB_STAGE_KERNELS")
+    (l1, g1, p1, i1), (l2, g2, p2, i2) = out
+    assert np.array_equal(l1, l2)
+    assert i1 == i2
+    for a, b in zip(g1, g2):
+        assert np.array_equal(a, b)
+    assert np.array_equal(p1, p2)
+
+
 def test_first_step_stage_by_stage_config0(capi, ref):
     """Buffer-state contract of SURVEY.md A.8 after every stage of the first two PIC/FLIP steps."""
     n = 64

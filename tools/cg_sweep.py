@@ -28,9 +28,37 @@ CONFIGS = [
                                       FSB_CG_XHINT="1")),
     ("fused serp=1 pre=1 1cta/sm", dict(FSB_CG_MODE="fused", FSB_CG_SERP="1", FSB_CG_PREFETCH="1",
                                         FSB_CG_CTAS_PER_SM="1")),
+    # L2 residency hints (r + stencil codes evict-last on keep/4 of the accesses, x and the dead
+    # old direction evict-first)
+    ("fused keep=4", dict(FSB_CG_MODE="fused", FSB_CG_KEEP="4")),                              # 7
+    ("fused keep=4 xhint", dict(FSB_CG_MODE="fused", FSB_CG_KEEP="4", FSB_CG_XHINT="1")),      # 8
+    ("fused keep=4 xhint phint", dict(FSB_CG_MODE="fused", FSB_CG_KEEP="4", FSB_CG_XHINT="1",
+                                      FSB_CG_PHINT="1")),                                      # 9
+    ("fused keep=3 xhint phint", dict(FSB_CG_MODE="fused", FSB_CG_KEEP="3", FSB_CG_XHINT="1",
+                                      FSB_CG_PHINT="1")),                                      # 10
+    ("fused keep=2 xhint phint", dict(FSB_CG_MODE="fused", FSB_CG_KEEP="2", FSB_CG_XHINT="1",
+                                      FSB_CG_PHINT="1")),                                      # 11
+    ("fused keep=1 xhint phint", dict(FSB_CG_MODE="fused", FSB_CG_KEEP="1", FSB_CG_XHINT="1",
+                                      FSB_CG_PHINT="1")),                                      # 12
+    ("fused xhint phint", dict(FSB_CG_MODE="fused", FSB_CG_XHINT="1", FSB_CG_PHINT="1")),      # 13
+    ("fused keep=4 xhint phint rows=8", dict(FSB_CG_MODE="fused", FSB_CG_KEEP="4", FSB_CG_XHINT="1",
+                                             FSB_CG_PHINT="1", FSB_CG_TILE_ROWS="8")),         # 14
+    ("fused keep=4 xhint phint rows=32", dict(FSB_CG_MODE="fused", FSB_CG_KEEP="4", FSB_CG_XHINT="1",
+                                              FSB_CG_PHINT="1", FSB_CG_TILE_ROWS="32")),       # 15
+    ("fused rows=8", dict(FSB_CG_MODE="fused", FSB_CG_TILE_ROWS="8")),                         # 16
+    ("fused rows=32", dict(FSB_CG_MODE="fused", FSB_CG_TILE_ROWS="32")),                       # 17
+    ("fused stages=2", dict(FSB_CG_MODE="fused", FSB_CG_STAGES="2")),                          # 18
+    ("fused stages=3", dict(FSB_CG_MODE="fused", FSB_CG_STAGES="3")),                          # 19
+    # L2 set-aside + access-policy window over r
+    ("fused persist=32MB", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="32")),                 # 20
+    ("fused persist=64MB", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="64")),                 # 21
+    ("fused persist=96MB", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="96")),                 # 22
+    ("fused persist=64MB xhint phint", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="64",
+                                            FSB_CG_XHINT="1", FSB_CG_PHINT="1")),              # 23
+    ("fused persist=48MB", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="48")),                 # 24
 ]
 KNOBS = ["FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH", "FSB_CG_XHINT", "FSB_CG_CTAS_PER_SM",
-         "FSB_CG_TILE_ROWS", "FSB_CG_STAGES"]
+         "FSB_CG_TILE_ROWS", "FSB_CG_STAGES", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB"]
 
 
 def main():
