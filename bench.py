@@ -411,7 +411,9 @@ def main():
     # every stage against the HBM roofline: algorithmic bytes of SURVEY.md 8(d) (C cells, P
     # particles; the cell sort is overhead and has no algorithmic bytes) / CUDA-event time
     C, P = float(n * n), float(n_part)
-    alg = {"classify": 8 * P + C, "p2g": 16 * P + 8 * C, "extend": 17 * C, "rhs": 13 * C,
+    # classification rides on the cell sort's counting pass (one read of the particle set for both),
+    # so the two are timed together; the sort itself is overhead of the deterministic P2G
+    alg = {"classify+sort": 8 * P + C, "p2g": 16 * P + 8 * C, "extend": 17 * C, "rhs": 13 * C,
            "grid_pre+patch": (17 + 21) * C if wl["kind"] not in ("cg", "sl") else 21 * C + 17 * C,
            "g2p": 32 * P + 17 * C, "advect_sl": 17 * C, "advect_part": 16 * P + 8 * C}
     stage_roofline = {}

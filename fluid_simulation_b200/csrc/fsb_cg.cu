@@ -1765,6 +1765,7 @@ int configure_cg(fsb_ctx* c)
     if (const char* e = getenv("FSB_CG_KEEP")) keep = std::max(0, std::min(4, atoi(e)));
     c->cg_persist_mb = 0;
     if (const char* e = getenv("FSB_CG_PERSIST_MB")) c->cg_persist_mb = std::max(0, atoi(e));
+    c->cg_persist_miss_normal = knob("FSB_CG_PERSIST_MISS_NORMAL", 0);
     c->cg_flags = (knob("FSB_CG_SERP", 1) ? 1 : 0) | (knob("FSB_CG_XHINT", 0) ? 2 : 0) |
                   (knob("FSB_CG_PREFETCH", 1) ? 4 : 0) | (knob("FSB_CG_PHINT", 0) ? 8 : 0) |
                   (keep << 4);
@@ -1881,7 +1882,8 @@ int set_l2_window(fsb_ctx* c, bool on)
     attr.accessPolicyWindow.num_bytes = bytes;
     attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)bytes);
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    attr.accessPolicyWindow.missProp =
+        c->cg_persist_miss_normal ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
     if (getenv("FSB_CG_VERBOSE"))
       fprintf(stderr, "[fsb] L2 %d MB, persisting max %d MB, window max %d MB; carve %zu MB over %zu MB of r, hit ratio %.3f\n",
               prop.l2CacheSize >> 20, prop.persistingL2CacheMaxSize >> 20,
@@ -1889,7 +1891,12 @@ int set_l2_window(fsb_ctx* c, bool on)
               attr.accessPolicyWindow.hitRatio);
   }
   FSB_CUDA(c, cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-  if (!on) cudaCtxResetPersistingL2Cache();
+  if (!on)
+  {
+    // give the set-aside back: it shrinks the L2 every other kernel sees
+    cudaCtxResetPersistingL2Cache();
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+  }
   return FSB_OK;
 }
 

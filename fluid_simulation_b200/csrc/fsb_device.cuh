@@ -46,6 +46,21 @@ __device__ __forceinline__ float div_dy(const GridDims& d, float y)
   return (d.pow2 & 2) ? y * d.inv_dy : y / d.dy;
 }
 
+// Compile-time form of the fast path: both deltas are powers of two.  Kernels templated on the
+// dims type lose the per-call run-time test (and the IEEE-division slow path with its branches,
+// which otherwise serialise the tap loads of the interpolation), same bits.
+struct GridDimsP2 : GridDims
+{
+};
+__host__ inline GridDimsP2 as_pow2(const GridDims& d)
+{
+  GridDimsP2 p;
+  static_cast<GridDims&>(p) = d;
+  return p;
+}
+__device__ __forceinline__ float div_dx(const GridDimsP2& d, float x) { return x * d.inv_dx; }
+__device__ __forceinline__ float div_dy(const GridDimsP2& d, float y) { return y * d.inv_dy; }
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi)
 {
   // include/MathDefinitions.h:16-19 clamps through float; for |v| < 2^24 and
@@ -56,8 +71,9 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi)
 // include/Grid.h:117-144  Grid<T>::valueInterpolated.
 // Truncating index, fraction taken BEFORE the index clamp, i+1 from the
 // clamped i, x interpolated first, then y.
-__device__ __forceinline__ float grid_interp(const float* __restrict__ g, const GridDims d,
-                                             float x, float y)
+template <class D>
+__device__ __forceinline__ float grid_interp(const float* __restrict__ g, const D d, float x,
+                                             float y)
 {
   const float xd = div_dx(d, x);
   const float yd = div_dy(d, y);
@@ -69,10 +85,12 @@ __device__ __forceinline__ float grid_interp(const float* __restrict__ g, const 
   j = clampi(j, 0, d.ny - 1);
   const int i1 = clampi(i + 1, 0, d.nx - 1);
   const int j1 = clampi(j + 1, 0, d.ny - 1);
-  const float v00 = __ldg(g + i + (size_t)j * d.ld);
-  const float v10 = __ldg(g + i1 + (size_t)j * d.ld);
-  const float v01 = __ldg(g + i + (size_t)j1 * d.ld);
-  const float v11 = __ldg(g + i1 + (size_t)j1 * d.ld);
+  // 32-bit element offsets (ld * ny < 2^30, fsb_create): one IMAD.WIDE per tap address
+  const int r0 = j * d.ld, r1 = j1 * d.ld;
+  const float v00 = __ldg(g + (r0 + i));
+  const float v10 = __ldg(g + (r0 + i1));
+  const float v01 = __ldg(g + (r1 + i));
+  const float v11 = __ldg(g + (r1 + i1));
   const float v0 = (1.0f - fi) * v00 + fi * v10;
   const float v1 = (1.0f - fi) * v01 + fi * v11;
   return (1.0f - fj) * v0 + fj * v1;
@@ -80,9 +98,10 @@ __device__ __forceinline__ float grid_interp(const float* __restrict__ g, const 
 
 // Same, on the difference of two grids taken tap by tap: identical to
 // interpolating MacGrid's diff buffer (src/MacGrid.cpp:64-67).
+template <class D>
 __device__ __forceinline__ float grid_interp_diff(const float* __restrict__ a,
-                                                  const float* __restrict__ b, const GridDims d,
-                                                  float x, float y)
+                                                  const float* __restrict__ b, const D d, float x,
+                                                  float y)
 {
   const float xd = div_dx(d, x);
   const float yd = div_dy(d, y);
@@ -94,8 +113,8 @@ __device__ __forceinline__ float grid_interp_diff(const float* __restrict__ a,
   j = clampi(j, 0, d.ny - 1);
   const int i1 = clampi(i + 1, 0, d.nx - 1);
   const int j1 = clampi(j + 1, 0, d.ny - 1);
-  const size_t k00 = i + (size_t)j * d.ld, k10 = i1 + (size_t)j * d.ld;
-  const size_t k01 = i + (size_t)j1 * d.ld, k11 = i1 + (size_t)j1 * d.ld;
+  const int r0 = j * d.ld, r1 = j1 * d.ld;
+  const int k00 = r0 + i, k10 = r0 + i1, k01 = r1 + i, k11 = r1 + i1;
   const float v00 = __ldg(a + k00) - __ldg(b + k00);
   const float v10 = __ldg(a + k10) - __ldg(b + k10);
   const float v01 = __ldg(a + k01) - __ldg(b + k01);
@@ -108,9 +127,10 @@ __device__ __forceinline__ float grid_interp_diff(const float* __restrict__ a,
 // Both of the above at the same point with one set of index arithmetic and one load per tap of
 // `a` (the PIC/FLIP blend needs the front value and the front-minus-previous value at the same
 // position): bit-identical to calling grid_interp and grid_interp_diff separately.
+template <class D>
 __device__ __forceinline__ void grid_interp_pair(const float* __restrict__ a,
-                                                 const float* __restrict__ b, const GridDims d,
-                                                 float x, float y, float* va, float* vdiff)
+                                                 const float* __restrict__ b, const D d, float x,
+                                                 float y, float* va, float* vdiff)
 {
   const float xd = div_dx(d, x);
   const float yd = div_dy(d, y);
@@ -122,8 +142,8 @@ __device__ __forceinline__ void grid_interp_pair(const float* __restrict__ a,
   j = clampi(j, 0, d.ny - 1);
   const int i1 = clampi(i + 1, 0, d.nx - 1);
   const int j1 = clampi(j + 1, 0, d.ny - 1);
-  const size_t k00 = i + (size_t)j * d.ld, k10 = i1 + (size_t)j * d.ld;
-  const size_t k01 = i + (size_t)j1 * d.ld, k11 = i1 + (size_t)j1 * d.ld;
+  const int r0 = j * d.ld, r1 = j1 * d.ld;
+  const int k00 = r0 + i, k10 = r0 + i1, k01 = r1 + i, k11 = r1 + i1;
   const float a00 = __ldg(a + k00), a10 = __ldg(a + k10), a01 = __ldg(a + k01), a11 = __ldg(a + k11);
   const float d00 = a00 - __ldg(b + k00), d10 = a10 - __ldg(b + k10);
   const float d01 = a01 - __ldg(b + k01), d11 = a11 - __ldg(b + k11);
@@ -144,13 +164,15 @@ __device__ __forceinline__ void grid_interp_pair(const float* __restrict__ a,
 // The reference forms the half-cell shift in double (`_DELTA_Y * 0.5`) and
 // rounds once; 0.5*d is exact and the fp32 subtraction rounds the same exact
 // difference, so fp32 gives the same bits (probe A).
-__device__ __forceinline__ float vel_x_interp(const float* __restrict__ u, const GridDims d,
-                                              float x, float y)
+template <class D>
+__device__ __forceinline__ float vel_x_interp(const float* __restrict__ u, const D d, float x,
+                                              float y)
 {
   return grid_interp(u, d, x, y - d.dy * 0.5f);
 }
-__device__ __forceinline__ float vel_y_interp(const float* __restrict__ v, const GridDims d,
-                                              float x, float y)
+template <class D>
+__device__ __forceinline__ float vel_y_interp(const float* __restrict__ v, const D d, float x,
+                                              float y)
 {
   return grid_interp(v, d, x - d.dx * 0.5f, y);
 }
@@ -161,13 +183,14 @@ __device__ __forceinline__ int cell_type(const uint8_t* __restrict__ cell, const
   // include/MacGrid.h:92-97: index-clamped
   i = clampi(i, 0, d.nx - 1);
   j = clampi(j, 0, d.ny - 1);
-  return cell[i + (size_t)j * d.ld];
+  return cell[j * d.ld + i];
 }
 
 // src/FluidSolver.cpp:793-814 + include/OdeSolver.h:78-86,102-113 with the
 // Vec2 operators of include/FluidSolver.h:119-141.  `h` is +dt or -dt.
+template <class D>
 __device__ __forceinline__ void advected_position(const float* __restrict__ u,
-                                                  const float* __restrict__ v, const GridDims d,
+                                                  const float* __restrict__ v, const D d,
                                                   int integrator, float x, float y, float h,
                                                   float* xo, float* yo)
 {

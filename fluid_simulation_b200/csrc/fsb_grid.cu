@@ -209,8 +209,9 @@ __global__ void k_extend_sweep(float* __restrict__ ub, float* __restrict__ vb,
 
 // include/Grid.h:152-184 as a scatter with float atomics (order of the sums
 // differs from the reference's face order: within 1e-5 of the field maximum).
-__device__ __forceinline__ void grid_splat_atomic(float* __restrict__ g, const GridDims d, float x,
-                                                  float y, float value)
+template <class D>
+__device__ __forceinline__ void grid_splat_atomic(float* __restrict__ g, const D d, float x, float y,
+                                                  float value)
 {
   const float xd = div_dx(d, x);
   const float yd = div_dy(d, y);
@@ -234,9 +235,10 @@ __device__ __forceinline__ void grid_splat_atomic(float* __restrict__ g, const G
 
 // src/FluidSolver.cpp:721-771: forward splat of each liquid-adjacent face value
 // to its back-traced position, into the zeroed BACK buffer; no swap.
+template <class D>
 __global__ void k_advect_velocity_sl(const float* __restrict__ uf, const float* __restrict__ vf,
                                      float* __restrict__ ub, float* __restrict__ vb,
-                                     const uint8_t* __restrict__ cell, const GridDims d, float dt,
+                                     const uint8_t* __restrict__ cell, const D d, float dt,
                                      int integrator)
 {
   int i, j;
@@ -363,11 +365,12 @@ int fsb_k_extend_velocity(fsb_ctx* c, int n_iter)
     // validity byte between the passes.  The stored mask buffers are scratch of this stage (every
     // call rebuilds them), so leaving them untouched is not observable.
     uint8_t* m1 = c->mask_x[0];
-    k_extend2_a<<<vec4_grid(c), kBlock, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c),
-                                                        m1, c->cell, dims(c));
+    const dim3 grid(fsb_div_up(c->ld, 4 * kBlock), fsb_div_up(c->ny, kExtendRows));
+    k_extend2_a<<<grid, kBlock, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), m1,
+                                                c->cell, dims(c));
     FSB_LAUNCHED(c);
-    k_extend2_b<<<vec4_grid(c), kBlock, 0, c->stream>>>(fsb_uf(c), fsb_ub(c), fsb_vb(c), m1, c->cell,
-                                                        dims(c));
+    k_extend2_b<<<grid, kBlock, 0, c->stream>>>(fsb_uf(c), fsb_ub(c), fsb_vb(c), m1, c->cell,
+                                                dims(c));
     FSB_LAUNCHED(c);
     c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:621
     fsb_prof_end(c, FSB_PROF_EXTEND);
@@ -397,8 +400,13 @@ int fsb_k_advect_velocity_sl(fsb_ctx* c, float dt)
   fsb_prof_begin(c, FSB_PROF_ADVECT_SL);
   FSB_CUDA(c, cudaMemsetAsync(fsb_ub(c), 0, bytes, c->stream));
   FSB_CUDA(c, cudaMemsetAsync(fsb_vb(c), 0, bytes, c->stream));
-  k_advect_velocity_sl<<<cell_grid(c), kBlock, 0, c->stream>>>(
-      fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), c->cell, dims(c), dt, c->integrator);
+  const GridDims d = dims(c);
+  if (d.pow2 == 3)
+    k_advect_velocity_sl<GridDimsP2><<<cell_grid(c), kBlock, 0, c->stream>>>(
+        fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), c->cell, as_pow2(d), dt, c->integrator);
+  else
+    k_advect_velocity_sl<GridDims><<<cell_grid(c), kBlock, 0, c->stream>>>(
+        fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), c->cell, d, dt, c->integrator);
   FSB_LAUNCHED(c);
   fsb_prof_end(c, FSB_PROF_ADVECT_SL);
   return FSB_OK;

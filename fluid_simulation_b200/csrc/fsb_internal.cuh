@@ -138,6 +138,7 @@ struct fsb_ctx
   bool cg_pdl = true;    // programmatic dependent launch between the iteration kernels
   int cg_flags = 0;      // tuning bits of the iteration kernels, see configure_cg
   int cg_persist_mb = 0; // L2 set-aside for the residual during a solve (0: none)
+  bool cg_persist_miss_normal = false;
   int cg_grid_fused = 0, cg_fused_stages = 0, cg_fused_stage_bytes = 0;
   int max_iters = 100;
   float tol = 1.1920929e-7f;

@@ -23,11 +23,11 @@ inline GridDims pool_dims(const fsb_ctx* c)
 // MARK: the same pass also performs FluidDomain::classifyCells' marking (src/FluidDomain.cpp:
 // 157-167, the formula of k_mark_liquid: (int)((pos / length) * size), clamped, border skipped),
 // so that a step reads the particle set once for both.
-template <bool MARK>
-__global__ void k_sort_count(const float4* __restrict__ part, int64_t n, const GridDims d,
+template <bool MARK, class D>
+__global__ void k_sort_count(const float4* __restrict__ part, int64_t n, const D d,
                              int* __restrict__ count, int* __restrict__ key_out,
                              int* __restrict__ rank_out, uint8_t* __restrict__ cell,
-                             const GridDims gd, const GridDims glen)
+                             const GridDims gd, const D glen)
 {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
@@ -178,9 +178,22 @@ __global__ void k_scan_apply(const int* __restrict__ count, int m,
 __global__ void k_sort_place(const int* __restrict__ key, const int* __restrict__ rank, int64_t n,
                              const int* __restrict__ start, int* __restrict__ idx)
 {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // four particles per thread: the four dependent start[] look-ups are in flight together
+  const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (k >= n) return;
-  idx[start[key[k]] + rank[k]] = (int)k;
+  if (k + 4 <= n)
+  {
+    const int4 ky = *reinterpret_cast<const int4*>(key + k);
+    const int4 rk = *reinterpret_cast<const int4*>(rank + k);
+    const int s0 = __ldg(start + ky.x), s1 = __ldg(start + ky.y), s2 = __ldg(start + ky.z),
+              s3 = __ldg(start + ky.w);
+    idx[s0 + rk.x] = (int)k;
+    idx[s1 + rk.y] = (int)k + 1;
+    idx[s2 + rk.z] = (int)k + 2;
+    idx[s3 + rk.w] = (int)k + 3;
+    return;
+  }
+  for (int64_t q = k; q < n; ++q) idx[start[key[q]] + rank[q]] = (int)q;
 }
 
 // Make the order inside each cell canonical (ascending source position), which
@@ -191,6 +204,38 @@ __global__ void k_sort_canon(const int* __restrict__ start, int m, int* __restri
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= m) return;
   const int a = start[c], b = start[c + 1];
+  const int n = b - a;
+  if (n <= 1) return;
+  if (n <= 8)
+  {
+    // the common case: all entries loaded at once (independent loads), a fixed 19-exchange
+    // sorting network in registers, and a write-back only where the order changed
+    int v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = (t < n) ? idx[a + t] : 0x7fffffff;
+    int w[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) w[t] = v[t];
+#define FSB_CX(p, q)                  \
+  {                                   \
+    const int lo = min(w[p], w[q]);   \
+    const int hi = max(w[p], w[q]);   \
+    w[p] = lo;                        \
+    w[q] = hi;                        \
+  }
+    FSB_CX(0, 1) FSB_CX(2, 3) FSB_CX(4, 5) FSB_CX(6, 7)
+    FSB_CX(0, 2) FSB_CX(1, 3) FSB_CX(4, 6) FSB_CX(5, 7)
+    FSB_CX(1, 2) FSB_CX(5, 6) FSB_CX(0, 4) FSB_CX(3, 7)
+    FSB_CX(1, 5) FSB_CX(2, 6)
+    FSB_CX(1, 4) FSB_CX(3, 6)
+    FSB_CX(2, 4) FSB_CX(3, 5)
+    FSB_CX(3, 4)
+#undef FSB_CX
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (t < n && w[t] != v[t]) idx[a + t] = w[t];
+    return;
+  }
   for (int s = a + 1; s < b; ++s)
   {
     const int v = idx[s];
@@ -269,8 +314,9 @@ __device__ __forceinline__ void p2g_add_v(P2gAcc& a, int di, int dj, float val, 
       }
 }
 
-__device__ __forceinline__ void p2g_particle(P2gAcc& a, const float4 p, const GridDims& d, int ci,
-                                             int c, float half_dx, float half_dy)
+template <class D>
+__device__ __forceinline__ void p2g_particle(P2gAcc& a, const float4 p, const D& d, int ci, int c,
+                                             float half_dx, float half_dy)
 {
   // ---- u: splat (vel_x, 1) at (px, py - dy/2)
   {
@@ -336,9 +382,10 @@ __device__ __forceinline__ void p2g_particle(P2gAcc& a, const float4 p, const Gr
   }
 }
 
+template <class D>
 __global__ void __launch_bounds__(256)
 k_p2g_stream(const float4* __restrict__ part, const int* __restrict__ cell_start,
-             float* __restrict__ ub, float* __restrict__ vb, const GridDims d, float half_dx,
+             float* __restrict__ ub, float* __restrict__ vb, const D d, float half_dx,
              float half_dy, int strips_x, int n_warps)
 {
   const int warp_id = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -486,10 +533,65 @@ __global__ void k_g2p_advect(float4* __restrict__ part, int64_t n, const float* 
   part[k] = p;
 }
 
+// The transfer of the fused steps as straight-line code: mode and the delta fast path are
+// compile-time, the (front - previous) difference is taken per tap (src/MacGrid.cpp:64-67), and
+// all sixteen taps are independent loads the compiler can issue back to back.  Per particle the
+// arithmetic is that of k_g2p_advect<true, true> with diff_is_prev (bit-identical).
+template <int MODE, class D>
+__global__ void __launch_bounds__(256)
+k_g2p_step(float4* __restrict__ part, int64_t n, const float* __restrict__ uf,
+           const float* __restrict__ vf, const float* __restrict__ up, const float* __restrict__ vp,
+           const uint8_t* __restrict__ cell, const D d, float pic_ratio, float dt, int ensure_outside)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  float4 p = part[k];
+  float nvx, nvy;
+  if (MODE == FSB_G2P_PIC)
+  {
+    nvx = vel_x_interp(uf, d, p.x, p.y);
+    nvy = vel_y_interp(vf, d, p.x, p.y);
+  }
+  else if (MODE == FSB_G2P_FLIP)
+  {
+    nvx = p.z + grid_interp_diff(uf, up, d, p.x, p.y - d.dy * 0.5f);
+    nvy = p.w + grid_interp_diff(vf, vp, d, p.x - d.dx * 0.5f, p.y);
+  }
+  else
+  {
+    float pic_x, pic_y, dvx, dvy;
+    grid_interp_pair(uf, up, d, p.x, p.y - d.dy * 0.5f, &pic_x, &dvx);
+    grid_interp_pair(vf, vp, d, p.x - d.dx * 0.5f, p.y, &pic_y, &dvy);
+    const float flip_x = p.z + dvx;
+    const float flip_y = p.w + dvy;
+    nvx = pic_x * pic_ratio + flip_x * (1.0f - pic_ratio);
+    nvy = pic_y * pic_ratio + flip_y * (1.0f - pic_ratio);
+  }
+  p.z = nvx;
+  p.w = nvy;
+  // include/MarkerParticleSet.h:37-41
+  p.x += p.z * dt;
+  p.y += p.w * dt;
+  if (ensure_outside)
+  {
+    // src/MarkerParticleSet.cpp:55-60: the roll-back is a second advect(-dt)
+    const int x = (int)div_dx(d, p.x);
+    const int y = (int)div_dy(d, p.y);
+    if (cell_type(cell, d, x, y) == FSB_SOLID)
+    {
+      const float mdt = -dt;
+      p.x += p.z * mdt;
+      p.y += p.w * mdt;
+    }
+  }
+  part[k] = p;
+}
+
 // src/FluidSolver.cpp:774-791
+template <class D>
 __global__ void k_advect_particles_grid(float4* __restrict__ part, int64_t n,
                                         const float* __restrict__ uf, const float* __restrict__ vf,
-                                        const GridDims d, float dt, int integrator)
+                                        const D d, float dt, int integrator)
 {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -535,14 +637,18 @@ int fsb_k_sort_particles(fsb_ctx* c, bool mark_labels)
     // lengthX() is recomputed as size * delta in float (include/Grid.h:54-55)
     const GridDims len =
         make_grid_dims(c->nx, c->ny, c->ld, (float)c->nx * c->dx, (float)c->ny * c->dy);
-    if (mark_labels)
-      k_sort_count<true><<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
-          c->part[c->pcur], c->n, pool_dims(c), c->cell_count, c->sort_key, c->sort_rank, c->cell,
-          dims(c), len);
-    else
-      k_sort_count<false><<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
-          c->part[c->pcur], c->n, pool_dims(c), c->cell_count, c->sort_key, c->sort_rank, c->cell,
-          dims(c), len);
+    const GridDims pd = pool_dims(c);
+    const dim3 grid(fsb_div_up(c->n, kBlock));
+#define FSB_COUNT(MARK, D, pd_, len_)                                                              \
+  k_sort_count<MARK, D><<<grid, kBlock, 0, c->stream>>>(c->part[c->pcur], c->n, pd_, c->cell_count, \
+                                                        c->sort_key, c->sort_rank, c->cell, dims(c), \
+                                                        len_)
+    const bool p2 = pd.pow2 == 3 && (!mark_labels || len.pow2 == 3);
+    if (p2 && mark_labels) FSB_COUNT(true, GridDimsP2, as_pow2(pd), as_pow2(len));
+    else if (p2) FSB_COUNT(false, GridDimsP2, as_pow2(pd), as_pow2(len));
+    else if (mark_labels) FSB_COUNT(true, GridDims, pd, len);
+    else FSB_COUNT(false, GridDims, pd, len);
+#undef FSB_COUNT
     FSB_LAUNCHED(c);
   }
   const int nb = fsb_div_up(m, kScanTile);
@@ -554,7 +660,7 @@ int fsb_k_sort_particles(fsb_ctx* c, bool mark_labels)
   FSB_LAUNCHED(c);
   if (c->n > 0)
   {
-    k_sort_place<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+    k_sort_place<<<fsb_div_up(fsb_div_up(c->n, 4), kBlock), kBlock, 0, c->stream>>>(
         c->sort_key, c->sort_rank, c->n, c->cell_start, c->sort_idx);
     FSB_LAUNCHED(c);
     k_sort_canon<<<fsb_div_up(m, kBlock), kBlock, 0, c->stream>>>(c->cell_start, m, c->sort_idx);
@@ -577,9 +683,14 @@ int fsb_k_p2g(fsb_ctx* c)
   const GridDims d = pool_dims(c);
   const int strips_x = fsb_div_up(c->nx, kP2gCols);
   const int64_t n_warps = (int64_t)strips_x * fsb_div_up(c->ny, kP2gRows);
-  k_p2g_stream<<<fsb_div_up(n_warps * 32, 256), 256, 0, c->stream>>>(
-      c->part[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), d, 0.5f * c->dx, 0.5f * c->dy,
-      strips_x, (int)n_warps);
+  if (d.pow2 == 3)
+    k_p2g_stream<GridDimsP2><<<fsb_div_up(n_warps * 32, 256), 256, 0, c->stream>>>(
+        c->part[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), as_pow2(d), 0.5f * c->dx,
+        0.5f * c->dy, strips_x, (int)n_warps);
+  else
+    k_p2g_stream<GridDims><<<fsb_div_up(n_warps * 32, 256), 256, 0, c->stream>>>(
+        c->part[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), d, 0.5f * c->dx, 0.5f * c->dy,
+        strips_x, (int)n_warps);
   FSB_LAUNCHED(c);
   c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:918
   fsb_prof_end(c, FSB_PROF_P2G);
@@ -617,9 +728,24 @@ int fsb_k_g2p_advect(fsb_ctx* c, int mode, float pic_ratio, float dt, int ensure
 {
   if (c->n == 0) return FSB_OK;
   fsb_prof_begin(c, FSB_PROF_G2P);
-  k_g2p_advect<true, true><<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
-      c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c), c->u_prev, c->v_prev, 1, c->cell, dims(c), mode,
-      pic_ratio, dt, ensure_outside);
+  const GridDims d = dims(c);
+  const dim3 grid(fsb_div_up(c->n, kBlock));
+  if (c->stage_v1)
+    k_g2p_advect<true, true><<<grid, kBlock, 0, c->stream>>>(
+        c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c), c->u_prev, c->v_prev, 1, c->cell, d, mode,
+        pic_ratio, dt, ensure_outside);
+  else
+  {
+#define FSB_G2P(MODE, D, d_)                                                                        \
+  k_g2p_step<MODE, D><<<grid, kBlock, 0, c->stream>>>(c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c),  \
+                                                      c->u_prev, c->v_prev, c->cell, d_, pic_ratio,  \
+                                                      dt, ensure_outside)
+    const bool p2 = d.pow2 == 3;
+    if (mode == FSB_G2P_PIC) { if (p2) FSB_G2P(FSB_G2P_PIC, GridDimsP2, as_pow2(d)); else FSB_G2P(FSB_G2P_PIC, GridDims, d); }
+    else if (mode == FSB_G2P_FLIP) { if (p2) FSB_G2P(FSB_G2P_FLIP, GridDimsP2, as_pow2(d)); else FSB_G2P(FSB_G2P_FLIP, GridDims, d); }
+    else { if (p2) FSB_G2P(FSB_G2P_PICFLIP, GridDimsP2, as_pow2(d)); else FSB_G2P(FSB_G2P_PICFLIP, GridDims, d); }
+#undef FSB_G2P
+  }
   FSB_LAUNCHED(c);
   c->sort_valid = false;
   fsb_prof_end(c, FSB_PROF_G2P);
@@ -630,8 +756,13 @@ int fsb_k_advect_particles_grid(fsb_ctx* c, float dt)
 {
   if (c->n == 0) return FSB_OK;
   fsb_prof_begin(c, FSB_PROF_ADVECT_PART);
-  k_advect_particles_grid<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
-      c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c), dims(c), dt, c->integrator);
+  const GridDims d = dims(c);
+  if (d.pow2 == 3)
+    k_advect_particles_grid<GridDimsP2><<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+        c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c), as_pow2(d), dt, c->integrator);
+  else
+    k_advect_particles_grid<GridDims><<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+        c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c), d, dt, c->integrator);
   FSB_LAUNCHED(c);
   c->sort_valid = false;
   fsb_prof_end(c, FSB_PROF_ADVECT_PART);

@@ -97,14 +97,15 @@ __device__ __forceinline__ void extend_faces(float4& out, uint32_t& valid_c, uin
   }
 }
 
-__global__ void __launch_bounds__(256)
-k_extend2_a(const float* __restrict__ uf, const float* __restrict__ vf, float* __restrict__ ub,
-            float* __restrict__ vb, uint8_t* __restrict__ m1, const uint8_t* __restrict__ cell,
-            const GridDims d)
+constexpr int kExtendRows = 4; // rows per thread: fewer, fatter CTAs and independent loads in flight
+
+__device__ __forceinline__ void extend2_a_group(const float* __restrict__ uf,
+                                                const float* __restrict__ vf,
+                                                float* __restrict__ ub, float* __restrict__ vb,
+                                                uint8_t* __restrict__ m1,
+                                                const uint8_t* __restrict__ cell, const GridDims& d,
+                                                int i0, int j)
 {
-  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int j = blockIdx.y;
-  if (i0 >= d.nx) return;
   const size_t k = i0 + (size_t)j * d.ld;
   const float4 u4 = *reinterpret_cast<const float4*>(uf + k);
   const float4 v4 = *reinterpret_cast<const float4*>(vf + k);
@@ -167,12 +168,26 @@ k_extend2_a(const float* __restrict__ uf, const float* __restrict__ vf, float* _
 }
 
 __global__ void __launch_bounds__(256)
-k_extend2_b(float* __restrict__ uf, float* __restrict__ ub, float* __restrict__ vb,
-            const uint8_t* __restrict__ m1, const uint8_t* __restrict__ cell, const GridDims d)
+k_extend2_a(const float* __restrict__ uf, const float* __restrict__ vf, float* __restrict__ ub,
+            float* __restrict__ vb, uint8_t* __restrict__ m1, const uint8_t* __restrict__ cell,
+            const GridDims d)
 {
   const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int j = blockIdx.y;
   if (i0 >= d.nx) return;
+#pragma unroll
+  for (int r = 0; r < kExtendRows; ++r)
+  {
+    const int j = blockIdx.y * kExtendRows + r;
+    if (j < d.ny) extend2_a_group(uf, vf, ub, vb, m1, cell, d, i0, j);
+  }
+}
+
+__device__ __forceinline__ void extend2_b_group(float* __restrict__ uf, float* __restrict__ ub,
+                                                float* __restrict__ vb,
+                                                const uint8_t* __restrict__ m1,
+                                                const uint8_t* __restrict__ cell, const GridDims& d,
+                                                int i0, int j)
+{
   const size_t k = i0 + (size_t)j * d.ld;
   // four LIQUID cells: nothing to zero and every face was valid from the start
   if (i0 + 4 <= d.nx && *reinterpret_cast<const uint32_t*>(cell + k) == FSB_LIQUID * 0x01010101u)
@@ -233,6 +248,20 @@ k_extend2_b(float* __restrict__ uf, float* __restrict__ ub, float* __restrict__ 
   }
 }
 
+
+__global__ void __launch_bounds__(256)
+k_extend2_b(float* __restrict__ uf, float* __restrict__ ub, float* __restrict__ vb,
+            const uint8_t* __restrict__ m1, const uint8_t* __restrict__ cell, const GridDims d)
+{
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= d.nx) return;
+#pragma unroll
+  for (int r = 0; r < kExtendRows; ++r)
+  {
+    const int j = blockIdx.y * kExtendRows + r;
+    if (j < d.ny) extend2_b_group(uf, ub, vb, m1, cell, d, i0, j);
+  }
+}
 
 #endif // FSB_VEC_WANT_GRID
 
@@ -323,12 +352,15 @@ __device__ __forceinline__ void cg_build_group(const float* __restrict__ uf,
       const int jn = min(j + 1, d.ny - 1);
       const float4 vn = *reinterpret_cast<const float4*>(vf + i0 + (size_t)jn * d.ld);
       const float ue = uf[min(i0 + 4, d.nx - 1) + (size_t)j * d.ld];
+      // bulk of the liquid: four LIQUID cells without a SOLID neighbour
+      const bool bulk = liq == kOwnBits && ((sd_c & 0x1f8u) | sd_s | sd_n) == 0u;
 #pragma unroll
       for (int t = 0; t < 4; ++t)
       {
         if (!((liq >> (t + 4)) & 1u)) continue;
-        const int n = (int)(((~sd_c >> (t + 3)) & 1u) + ((~sd_c >> (t + 5)) & 1u) +
-                            ((~sd_s >> (t + 4)) & 1u) + ((~sd_n >> (t + 4)) & 1u));
+        const int n = bulk ? 4
+                           : (int)(((~sd_c >> (t + 3)) & 1u) + ((~sd_c >> (t + 5)) & 1u) +
+                                   ((~sd_s >> (t + 4)) & 1u) + ((~sd_n >> (t + 4)) & 1u));
         cd |= (uint32_t)(1 + n) << (8 * t);
         const int ie = min(i0 + t + 1, d.nx - 1) - i0; // east face: inside the group, after it, or clamped
         const float u_e =

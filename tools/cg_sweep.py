@@ -56,9 +56,19 @@ CONFIGS = [
     ("fused persist=64MB xhint phint", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="64",
                                             FSB_CG_XHINT="1", FSB_CG_PHINT="1")),              # 23
     ("fused persist=48MB", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="48")),                 # 24
+    ("fused persist=40MB", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="40")),                 # 25
+    ("fused persist=56MB", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="56")),                 # 26
+    ("fused persist=32MB miss=normal", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="32",
+                                            FSB_CG_PERSIST_MISS_NORMAL="1")),                  # 27
+    ("fused persist=48MB miss=normal", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="48",
+                                            FSB_CG_PERSIST_MISS_NORMAL="1")),                  # 28
+    ("fused persist=64MB miss=normal", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="64",
+                                            FSB_CG_PERSIST_MISS_NORMAL="1")),                  # 29
+    ("fused persist=16MB miss=normal", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="16",
+                                            FSB_CG_PERSIST_MISS_NORMAL="1")),                  # 30
 ]
 KNOBS = ["FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH", "FSB_CG_XHINT", "FSB_CG_CTAS_PER_SM",
-         "FSB_CG_TILE_ROWS", "FSB_CG_STAGES", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB"]
+         "FSB_CG_TILE_ROWS", "FSB_CG_STAGES", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB", "FSB_CG_PERSIST_MISS_NORMAL"]
 
 
 def main():
