@@ -41,8 +41,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 ALG_BYTES_CG_PER_CELL = 45.0  # bytes per cell per CG iteration
 # dram__bytes_read.sum + dram__bytes_write.sum of the persistent k_cg_solve launch / its iterations, from
 # the committed ncu --set full capture (bytes per CG iteration, 4096^2)
-NCU_TRAFFIC = {("picflip4096", 1): 469.6e6, ("cg4096", 1): 469.6e6}
-NCU_TRAFFIC_SOURCE = "profiles/r01g_cg_solve_ncu_full.md"
+NCU_TRAFFIC = {("picflip4096", 1): 417.4e6, ("cg4096", 1): 417.4e6}
+NCU_TRAFFIC_SOURCE = "profiles/r01h_cg_solve_ncu_full.md"
 
 WORKLOADS = {
     # name: (n, step kind, pic_ratio, cg tol, cg cap, particles per cell side)
@@ -432,7 +432,7 @@ def main():
                            "CG iteration = k_cg_direction + k_cg_update (2 launches in a CUDA graph)")
                           + (", per GPU, slab halos + dot products over peer memory" if world > 1 else ""),
                 "algorithmic_bytes_per_iteration": alg_bytes,
-                "design_bytes_per_iteration": 34.0 * n * n / world,
+                "design_bytes_per_iteration": 32.0 * n * n / world,
                 "iterations_per_launch": (iters_total / args.steps) if cg_mode != "graph" else 0.5,
                 "avg_iteration_us": it_ms * 1e3, "peak_source": peak_src,
                 "cg_share_of_step": cg_ms / ms if ms else None}

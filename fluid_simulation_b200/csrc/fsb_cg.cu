@@ -247,6 +247,13 @@ struct UpdStage // k_cg_update: p (with halo), x, r (interior), code (with halo)
   static constexpr int kTx = kHalo + 2 * kInner + kCode;
 };
 
+template <int TH>
+struct UpdStageX : UpdStage<TH> // persistent solve: + the previous direction (deferred x update)
+{
+  static constexpr int oQ = UpdStage<TH>::kBytes;
+  static constexpr int kBytes = align128(oQ + UpdStage<TH>::kInner);
+};
+
 struct CgMaps
 {
   CUtensorMap halo_a; // fp32, box kHaloW x (TH+2)
@@ -1037,6 +1044,7 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
 struct SolveMaps
 {
   CUtensorMap halo_r, halo_p[2], inner_x, inner_r, code;
+  CUtensorMap inner_p[2]; // the deferred x update reads the previous direction without halo
 };
 struct SolvePush // peer rows receiving this rank's slab boundary rows (null: no neighbour)
 {
@@ -1264,11 +1272,17 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
 {
   constexpr int TH = NW * RPW;
   using Sd = DirStage<TH>;
-  using Su = UpdStage<TH>;
+  using Su = UpdStageX<TH>;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full[kMaxStages], empty[kMaxStages];
   __shared__ float4 lut[8];
   __shared__ SolveState ss;
+  // Deferred x update: x is touched only in the update phase of ODD iterations, where
+  // x += alpha_{k-1} p_{k-1} and x += alpha_k p_k are applied back to back (the previous direction
+  // is still intact in the other ping-pong buffer) -- the same two roundings in the same order,
+  // so x is bit-identical, for 12 instead of 16 B per cell and iteration pair.  A solve that ends
+  // on an even iteration applies the pending update in a final sweep.
+  const bool xdefer = (flags & 128) != 0;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool serp = (flags & 1) != 0;     // phase B walks the tile list backwards
   const bool xhint = (flags & 2) != 0;    // x is pure streaming: evict-first loads and stores
@@ -1323,8 +1337,10 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
     int kind = 0; // 0: phase A (direction), 1: phase B (update)
     if (ss.done) return;
     // part: 1 = loads that do not depend on the barrier, 2 = the dependent one, 3 = both
+    int it_p = 0; // iteration the producer is issuing loads for (a solve starts at iteration 0)
     auto issue = [&](int knd, int part, bool frst, int cr, int slot, int c0, int j0) {
       unsigned char* base = smem + slot * stage_bytes;
+      const bool with_x = !xdefer || (it_p & 1);
       if (knd == 0)
       {
         if (part & 1)
@@ -1339,8 +1355,10 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       {
         if (part & 1)
         {
-          mbar_expect_tx(&full[slot], Su::kTx);
-          load(base + Su::oX, &maps.inner_x, c0, j0, &full[slot], h_x);
+          mbar_expect_tx(&full[slot], Su::kTx - (with_x ? 0 : Su::kInner) +
+                                          (with_x && xdefer ? Su::kInner : 0));
+          if (with_x) load(base + Su::oX, &maps.inner_x, c0, j0, &full[slot], h_x);
+          if (with_x && xdefer) load(base + Su::oQ, &maps.inner_p[cr], c0, j0, &full[slot], h_pold);
           load(base + Su::oR, &maps.inner_r, c0, j0, &full[slot], h_keep);
           load(base + Su::oC, &maps.code, c0 - 16, j0 - 1, &full[slot], h_keep);
         }
@@ -1390,6 +1408,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       }
       fence_proxy_async_all();
       const bool done = ss.done != 0;
+      if (kind == 1) ++it_p;
       kind = nkind;
       cur = ncur;
       first = false;
@@ -1423,13 +1442,18 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
   const int last_ty = n_tiles / tiles_x - 1;
   RingPos rp = {0, 0};
   int cur = 0;
+  float alpha_prev = 0.0f;       // alpha of the previous iteration (pending x update)
+  bool pending = false;          // x lacks the update of the last iteration
+  const float* last_p = nullptr; // direction of the last iteration
   while (!ss.done)
   {
+    const bool with_x = !xdefer || (ss.iter & 1);
     // ================= phase A: direction + p.Ap =================
     {
       const bool first = ss.iter == 0;
       const float beta = first ? 0.0f : ss.beta;
       float* __restrict__ p_new = cur ? p0 : p1;
+      last_p = p_new;
       float* push_lo = push.p_lo[cur ^ 1];
       float* push_hi = push.p_hi[cur ^ 1];
       double acc[1] = {0.0};
@@ -1500,6 +1524,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
         const unsigned char* base = smem + rp.st * stage_bytes;
         const float* sp = reinterpret_cast<const float*>(base + Su::oP);
         const float* sx = reinterpret_cast<const float*>(base + Su::oX);
+        const float* sq = reinterpret_cast<const float*>(base + Su::oQ);
         const float* sr = reinterpret_cast<const float*>(base + Su::oR);
         const unsigned char* sc = base + Su::oC;
         pushed |= (push.r_lo && t.ty == 0) || (push.r_hi && t.ty == last_ty);
@@ -1514,7 +1539,20 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
         for (int k = 0; k < RPW; ++k)
         {
           cd[k] = *reinterpret_cast<const uint32_t*>(sc + co + (k + 1) * kCodeW);
-          xo[k] = *reinterpret_cast<const float4*>(sx + io + k * kTileW);
+          xo[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (with_x)
+          {
+            xo[k] = *reinterpret_cast<const float4*>(sx + io + k * kTileW);
+            if (xdefer)
+            {
+              // the pending update of the previous iteration first (same rounding order as before)
+              const float4 pp = *reinterpret_cast<const float4*>(sq + io + k * kTileW);
+              xo[k].x = fmaf(alpha_prev, pp.x, xo[k].x);
+              xo[k].y = fmaf(alpha_prev, pp.y, xo[k].y);
+              xo[k].z = fmaf(alpha_prev, pp.z, xo[k].z);
+              xo[k].w = fmaf(alpha_prev, pp.w, xo[k].w);
+            }
+          }
           ro[k] = *reinterpret_cast<const float4*>(sr + io + k * kTileW);
           he[k] = edge ? sp[hfo + (k + 1) * kHaloW] : 0.0f;
         }
@@ -1542,8 +1580,11 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
             xn.z = fmaf(alpha, p4.z, xo[k].z); rn.z = fmaf(nalpha, q.z, ro[k].z);
             xn.w = fmaf(alpha, p4.w, xo[k].w); rn.w = fmaf(nalpha, q.w, ro[k].w);
             const size_t o = (size_t)j * ld + ci;
-            if (xhint) st_f4_hint(x + o, xn, pol_x);
-            else *reinterpret_cast<float4*>(x + o) = xn;
+            if (with_x)
+            {
+              if (xhint) st_f4_hint(x + o, xn, pol_x);
+              else *reinterpret_cast<float4*>(x + o) = xn;
+            }
             if (keep) st_f4_hint(r + o, rn, pol_keep);
             else *reinterpret_cast<float4*>(r + o) = rn;
             if (j == sh.row_lo && push.r_lo) *reinterpret_cast<float4*>(push.r_lo + ci) = rn;
@@ -1560,8 +1601,38 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       }
       ++phase_id;
       grid_reduce<NW, 2, 1>(acc, s, part_b, phase_id, sh, &ss, pushed);
+      alpha_prev = alpha;
+      pending = !with_x;
     }
     cur ^= 1;
+  }
+  if (pending && !ss.comm_error)
+  {
+    // the solve ended on an even iteration: x += alpha p of that iteration.  Same tile -> thread
+    // mapping as the phases (this thread wrote these p and x elements itself); p is exactly zero
+    // outside LIQUID cells, so masked cells keep x = 0.
+    TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, false);
+    for (int tk = 0; tk < t.count; ++tk, t.next())
+    {
+      const int ci = t.tx * kTileW + (int)lane * 4;
+      const int jb = sh.row_lo + t.ty * TH + r0;
+#pragma unroll
+      for (int k = 0; k < RPW; ++k)
+      {
+        const int j = jb + k;
+        if (j < sh.row_hi && ci < ld)
+        {
+          const size_t o = (size_t)j * ld + ci;
+          const float4 p4 = *reinterpret_cast<const float4*>(last_p + o);
+          float4 x4 = *reinterpret_cast<const float4*>(x + o);
+          x4.x = fmaf(alpha_prev, p4.x, x4.x);
+          x4.y = fmaf(alpha_prev, p4.y, x4.y);
+          x4.z = fmaf(alpha_prev, p4.z, x4.z);
+          x4.w = fmaf(alpha_prev, p4.w, x4.w);
+          *reinterpret_cast<float4*>(x + o) = x4;
+        }
+      }
+    }
   }
   // every CTA holds the same final scalars; CTA 0 publishes them for the host
   if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -1703,7 +1774,7 @@ int configure_fused(fsb_ctx* c, int64_t n_tiles)
 {
   constexpr int TH = kNW * RPW;
   const int threads = (kNW + 1) * 32;
-  c->cg_fused_stage_bytes = std::max(DirStage<TH>::kBytes, UpdStage<TH>::kBytes);
+  c->cg_fused_stage_bytes = std::max(DirStage<TH>::kBytes, UpdStageX<TH>::kBytes);
   const int budget = (227 * 1024 - 2 * 2048) / 2; // two resident CTAs per SM
   int stages = std::max(2, std::min(kMaxStages, budget / c->cg_fused_stage_bytes));
   if (const char* e = getenv("FSB_CG_STAGES"))
@@ -1768,7 +1839,7 @@ int configure_cg(fsb_ctx* c)
     c->cg_persist_miss_normal = knob("FSB_CG_PERSIST_MISS_NORMAL", 0);
     c->cg_flags = (knob("FSB_CG_SERP", 1) ? 1 : 0) | (knob("FSB_CG_XHINT", 0) ? 2 : 0) |
                   (knob("FSB_CG_PREFETCH", 1) ? 4 : 0) | (knob("FSB_CG_PHINT", 0) ? 8 : 0) |
-                  (keep << 4);
+                  (keep << 4) | (knob("FSB_CG_XDEFER", 1) ? 128 : 0);
   }
 
   void* fn = nullptr;
@@ -1777,7 +1848,9 @@ int configure_cg(fsb_ctx* c)
   if (!fn || qres != cudaDriverEntryPointSuccess)
     return fsb_fail(c, FSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
   EncodeTiledFn encode = (EncodeTiledFn)fn;
-  CUtensorMap halo_r, halo_p[2], inner_x, inner_r, code;
+  CUtensorMap halo_r, halo_p[2], inner_x, inner_r, code, inner_p[2];
+  FSB_TRY(make_map(c, encode, &inner_p[0], c->cg_p[0], true, kTileW, th));
+  FSB_TRY(make_map(c, encode, &inner_p[1], c->cg_p[1], true, kTileW, th));
   FSB_TRY(make_map(c, encode, &halo_r, c->cg_r, true, kHaloW, th + 2));
   FSB_TRY(make_map(c, encode, &halo_p[0], c->cg_p[0], true, kHaloW, th + 2));
   FSB_TRY(make_map(c, encode, &halo_p[1], c->cg_p[1], true, kHaloW, th + 2));
@@ -1793,6 +1866,8 @@ int configure_cg(fsb_ctx* c)
     m->inner_x = inner_x;
     m->inner_r = inner_r;
     m->code = code;
+    m->inner_p[0] = inner_p[0];
+    m->inner_p[1] = inner_p[1];
   }
   for (int cur = 0; cur < 2; ++cur)
   {

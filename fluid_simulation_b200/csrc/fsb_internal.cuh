@@ -133,7 +133,7 @@ struct fsb_ctx
   // TMA descriptors of the two iteration kernels for both ping-pong phases (CgMaps in fsb_cg.cu)
   alignas(64) unsigned char cg_maps_dir[2][5 * sizeof(CUtensorMap)];
   alignas(64) unsigned char cg_maps_upd[2][5 * sizeof(CUtensorMap)];
-  alignas(64) unsigned char cg_maps_fused[6 * sizeof(CUtensorMap)]; // SolveMaps
+  alignas(64) unsigned char cg_maps_fused[8 * sizeof(CUtensorMap)]; // SolveMaps
   bool cg_fused = false; // persistent cooperative solve kernel in use
   bool cg_pdl = true;    // programmatic dependent launch between the iteration kernels
   int cg_flags = 0;      // tuning bits of the iteration kernels, see configure_cg

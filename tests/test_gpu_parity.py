@@ -252,7 +252,12 @@ CG_MODES = [
     dict(FSB_CG_MODE="fused", FSB_CG_SERP="1", FSB_CG_PREFETCH="1", FSB_CG_XHINT="1"),
     dict(FSB_CG_MODE="fused", FSB_CG_SERP="1", FSB_CG_PREFETCH="1", FSB_CG_TILE_ROWS="16"),
     dict(FSB_CG_MODE="fused", FSB_CG_SERP="1", FSB_CG_PREFETCH="1", FSB_CG_STAGES="2"),
+    dict(FSB_CG_MODE="fused", FSB_CG_XDEFER="0"),
+    dict(FSB_CG_MODE="fused", FSB_CG_KEEP="1", FSB_CG_XHINT="1", FSB_CG_PHINT="1"),
+    dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="4"),
 ]
+CG_KNOBS = ("FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH", "FSB_CG_XHINT", "FSB_CG_TILE_ROWS",
+            "FSB_CG_STAGES", "FSB_CG_XDEFER", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB")
 
 
 @pytest.mark.parametrize("nx,ny", [(64, 64), (130, 67), (700, 300)])
@@ -272,8 +277,7 @@ def test_pressure_solve_launch_modes(capi, port, monkeypatch, nx, ny):
     ic, _ = c.cg_info()
     pc = c.get_pressure().astype(np.float64)
     for env in CG_MODES:
-        for k in ("FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH", "FSB_CG_XHINT", "FSB_CG_TILE_ROWS",
-                  "FSB_CG_STAGES"):
+        for k in CG_KNOBS:
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -293,6 +297,35 @@ def test_pressure_solve_launch_modes(capi, port, monkeypatch, nx, ny):
         g.pressure_solve(0.01, 0.01)
         assert g.cg_info()[0] == 7, (env, g.cg_info())
         g.close()
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 64), (130, 67), (520, 300)])
+def test_deferred_x_update_is_bit_identical(capi, monkeypatch, nx, ny):
+    """The persistent solve touches x only every other iteration (two updates back to back, same
+    rounding order) and applies a pending update when the solve ends on an even iteration: for
+    every iteration cap -- both parities -- and for a converged solve the pressure field must equal
+    the two-kernels-per-iteration solve, which updates x in every iteration, bit for bit."""
+    rng = np.random.default_rng(31)
+    lab = scenes.random_labels(nx, ny, rng)
+    fu, fv = scenes.random_field(nx, ny, rng), scenes.random_field(nx, ny, rng)
+    out = {}
+    for mode in ("graph", "fused"):
+        for k in CG_KNOBS:
+            monkeypatch.delenv(k, raising=False)
+        monkeypatch.setenv("FSB_CG_MODE", mode)
+        g = capi.Sim(nx, ny, 1.0, float(np.float32(ny) / np.float32(nx)), 0.01, 0.05)
+        res = []
+        for cap in (1, 2, 3, 4, 7, 8, 33, 20000):
+            g.set_cell_types(lab); g.set_grid(U_FRONT, fu); g.set_grid(V_FRONT, fv)
+            g.set_cg(cap, 1e-6)
+            g.pressure_solve(0.01, 0.01)
+            res.append((g.cg_info()[0], g.get_pressure()))
+        out[mode] = res
+        g.close()
+    monkeypatch.delenv("FSB_CG_MODE")
+    for (ia, xa), (ib, xb) in zip(out["graph"], out["fused"]):
+        assert ia == ib
+        assert np.array_equal(xa, xb), (ia, np.abs(xa - xb).max())
 
 
 def test_pressure_patch_exact_given_same_pressure(capi, port):

@@ -66,9 +66,15 @@ CONFIGS = [
                                             FSB_CG_PERSIST_MISS_NORMAL="1")),                  # 29
     ("fused persist=16MB miss=normal", dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="16",
                                             FSB_CG_PERSIST_MISS_NORMAL="1")),                  # 30
+    ("fused xdefer=0", dict(FSB_CG_MODE="fused", FSB_CG_XDEFER="0")),                          # 31
+    ("fused xdefer=0 persist=48MB", dict(FSB_CG_MODE="fused", FSB_CG_XDEFER="0",
+                                         FSB_CG_PERSIST_MB="48")),                             # 32
+    ("fused keep=1 xhint phint", dict(FSB_CG_MODE="fused", FSB_CG_KEEP="1", FSB_CG_XHINT="1",
+                                      FSB_CG_PHINT="1")),                                      # 33
+    ("fused phint", dict(FSB_CG_MODE="fused", FSB_CG_PHINT="1")),                              # 34
 ]
 KNOBS = ["FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH", "FSB_CG_XHINT", "FSB_CG_CTAS_PER_SM",
-         "FSB_CG_TILE_ROWS", "FSB_CG_STAGES", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB", "FSB_CG_PERSIST_MISS_NORMAL"]
+         "FSB_CG_TILE_ROWS", "FSB_CG_STAGES", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB", "FSB_CG_PERSIST_MISS_NORMAL", "FSB_CG_XDEFER"]
 
 
 def main():
