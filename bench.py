@@ -278,6 +278,9 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     dt = float(np.float32(0.01 * 64.0 / n))
@@ -401,7 +404,7 @@ def main():
         return 0
 
     peak, peak_src = measured_peak_gbs()
-    cg_mode = "graph" if os.environ.get("FSB_CG_MODE", "")[:1] == "g" else "persistent"
+    cg_mode = "graph" if sim.cg_launch_mode() == 1 else "persistent"
     cg_ms, _ = prof["cg"]
     it_ms = cg_ms / max(iters_total, 1)
     # per GPU: each rank sweeps 1/world of the rows per iteration

@@ -74,7 +74,11 @@ SIGNATURES = {
     "fsb_advect_particles": (_i, [_p, _f, _i]),
     "fsb_advect_velocity_sl": (_i, [_p, _f]),
     "fsb_advect_particles_grid": (_i, [_p, _f]),
+    "fsb_add_external_force": (_i, [_p, _f, _f, _f]),
+    "fsb_p2g_gather": (_i, [_p]),
     "fsb_step": (_i, [_p, _i, _f]),
+    "fsb_save_state": (_i, [_p, C.c_char_p]),
+    "fsb_load_state": (_i, [_p, C.c_char_p]),
     "fsb_shard_export": (_i, [_p, _p]),
     "fsb_shard_connect": (_i, [_p, _i, _i, _p]),
     "fsb_shard_disconnect": (_i, [_p]),
@@ -82,6 +86,7 @@ SIGNATURES = {
     "fsb_profile_enable": (_i, [_p, _i]),
     "fsb_profile_read": (_i, [_p, _p, _p]),
     "fsb_launch_count": (_l, [_p]),
+    "fsb_cg_launch_mode": (_i, [_p]),
     "fsb_timer_start": (_i, [_p]),
     "fsb_timer_stop": (_i, [_p, C.POINTER(_f)]),
 }
@@ -291,6 +296,24 @@ class Sim:
 
     def launch_count(self):
         return _lib.fsb_launch_count(self.h)
+
+    def cg_launch_mode(self):
+        """0 not configured yet, 1 two kernels per iteration (CUDA graph), 2 persistent kernel."""
+        return _lib.fsb_cg_launch_mode(self.h)
+
+    # routines of the reference's solver that no step calls
+    def add_external_force(self, fx, fy, dt):
+        self._ck(_lib.fsb_add_external_force(self.h, fx, fy, dt))
+
+    def p2g_gather(self):
+        self._ck(_lib.fsb_p2g_gather(self.h))
+
+    # state files
+    def save_state(self, path):
+        self._ck(_lib.fsb_save_state(self.h, os.fsencode(path)))
+
+    def load_state(self, path):
+        self._ck(_lib.fsb_load_state(self.h, os.fsencode(path)))
 
     def timer_start(self):
         self._ck(_lib.fsb_timer_start(self.h))

@@ -1,5 +1,6 @@
 // C ABI of libfsb.so (include/fsb.h): context life cycle, host<->HBM state
 // transfer, stage entry points and the fused step drivers.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -621,6 +622,20 @@ int fsb_advect_particles_grid(fsb_ctx* c, float dt)
   return fsb_k_advect_particles_grid(c, dt);
 }
 
+int fsb_add_external_force(fsb_ctx* c, float fx, float fy, float dt)
+{
+  CHECK_CTX(c);
+  FSB_TRY(flush_diff(c));
+  // :266-271: vel + F / density * dt, i.e. an acceleration of F / density (one fp32 division)
+  return fsb_k_add_acceleration(c, fx / c->density, fy / c->density, dt);
+}
+int fsb_p2g_gather(fsb_ctx* c)
+{
+  CHECK_CTX(c);
+  FSB_TRY(flush_diff(c));
+  return fsb_k_p2g_gather(c);
+}
+
 // -------------------------------------------------------------------- steps
 int fsb_step(fsb_ctx* c, int kind, float dt)
 {
@@ -682,6 +697,115 @@ int fsb_step(fsb_ctx* c, int kind, float dt)
     if (kind == FSB_STEP_FLIP) FSB_TRY(fsb_k_g2p_advect(c, FSB_G2P_FLIP, 0.0f, dt, 0));
     else FSB_TRY(fsb_k_g2p_advect(c, FSB_G2P_PICFLIP, c->pic_ratio, dt, 1));
   }
+  return FSB_OK;
+}
+
+// --------------------------------------------------------------- state files
+namespace {
+struct StateHeader
+{
+  char magic[8];
+  uint32_t version;
+  int32_t nx, ny;
+  float dx, dy, density, pic_ratio, grav_x, grav_y;
+  int32_t integrator, max_iters;
+  float tol, pool_dx, pool_dy;
+  int32_t pool_nx, pool_ny;
+  int64_t n_particles;
+  uint8_t reserved[16];
+};
+static_assert(sizeof(StateHeader) == 96, "state header layout");
+const char kStateMagic[8] = {'F', 'S', 'B', 'S', 'T', 'A', 'T', 'E'};
+} // namespace
+
+int fsb_save_state(fsb_ctx* c, const char* path)
+{
+  CHECK_CTX(c);
+  if (!path) return fsb_fail(c, FSB_ERR_INVALID, "null path");
+  FILE* f = fopen(path, "wb");
+  if (!f) return fsb_fail(c, FSB_ERR_INVALID, "cannot open %s for writing", path);
+  StateHeader hd;
+  memset(&hd, 0, sizeof hd);
+  memcpy(hd.magic, kStateMagic, 8);
+  hd.version = 1;
+  hd.nx = c->nx; hd.ny = c->ny; hd.dx = c->dx; hd.dy = c->dy;
+  hd.density = c->density; hd.pic_ratio = c->pic_ratio; hd.grav_x = c->grav_x; hd.grav_y = c->grav_y;
+  hd.integrator = c->integrator; hd.max_iters = c->max_iters; hd.tol = c->tol;
+  hd.pool_dx = c->pool_dx; hd.pool_dy = c->pool_dy; hd.pool_nx = c->pool_nx; hd.pool_ny = c->pool_ny;
+  hd.n_particles = c->n;
+  const size_t cells = (size_t)c->nx * c->ny;
+  std::vector<float> buf(std::max(cells, (size_t)c->n * 4));
+  int rc = FSB_OK;
+  bool ok = fwrite(&hd, sizeof hd, 1, f) == 1;
+  if (ok)
+  {
+    std::vector<uint8_t> lab(cells);
+    rc = fsb_get_cell_types(c, lab.data());
+    ok = rc == FSB_OK && fwrite(lab.data(), 1, cells, f) == cells;
+  }
+  for (int w = FSB_U_FRONT; ok && w <= FSB_V_DIFF; ++w)
+  {
+    rc = fsb_get_grid(c, w, buf.data());
+    ok = rc == FSB_OK && fwrite(buf.data(), sizeof(float), cells, f) == cells;
+  }
+  if (ok && c->n > 0)
+  {
+    rc = fsb_get_particles(c, buf.data());
+    ok = rc == FSB_OK && fwrite(buf.data(), 4 * sizeof(float), (size_t)c->n, f) == (size_t)c->n;
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (rc != FSB_OK) return rc;
+  if (!ok) return fsb_fail(c, FSB_ERR_INVALID, "short write to %s", path);
+  return FSB_OK;
+}
+
+int fsb_load_state(fsb_ctx* c, const char* path)
+{
+  CHECK_CTX(c);
+  if (!path) return fsb_fail(c, FSB_ERR_INVALID, "null path");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fsb_fail(c, FSB_ERR_INVALID, "cannot open %s", path);
+  StateHeader hd;
+  if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, kStateMagic, 8) != 0 || hd.version != 1)
+  {
+    fclose(f);
+    return fsb_fail(c, FSB_ERR_INVALID, "%s is not a version-1 FSBSTATE file", path);
+  }
+  if (hd.nx != c->nx || hd.ny != c->ny || hd.n_particles < 0)
+  {
+    fclose(f);
+    return fsb_fail(c, FSB_ERR_INVALID, "%s holds a %dx%d domain, the context is %dx%d", path, hd.nx,
+                    hd.ny, c->nx, c->ny);
+  }
+  const size_t cells = (size_t)c->nx * c->ny;
+  std::vector<float> buf(std::max(cells, (size_t)hd.n_particles * 4));
+  std::vector<uint8_t> lab(cells);
+  int rc = FSB_OK;
+  bool ok = fread(lab.data(), 1, cells, f) == cells;
+  if (ok) rc = fsb_set_cell_types(c, lab.data());
+  c->diff_pending = false;
+  for (int w = FSB_U_FRONT; ok && rc == FSB_OK && w <= FSB_V_DIFF; ++w)
+  {
+    ok = fread(buf.data(), sizeof(float), cells, f) == cells;
+    if (ok) rc = fsb_set_grid(c, w, buf.data());
+    // the staging vector is reused: the copy must have left it before the next read
+    if (ok && rc == FSB_OK) rc = fsb_synchronize(c);
+  }
+  if (ok && rc == FSB_OK)
+  {
+    ok = hd.n_particles == 0 ||
+         fread(buf.data(), 4 * sizeof(float), (size_t)hd.n_particles, f) == (size_t)hd.n_particles;
+    if (ok) rc = fsb_set_particles(c, buf.data(), hd.n_particles);
+    if (ok && rc == FSB_OK) rc = fsb_synchronize(c);
+  }
+  fclose(f);
+  if (rc != FSB_OK) return rc;
+  if (!ok) return fsb_fail(c, FSB_ERR_INVALID, "%s is truncated", path);
+  c->dx = hd.dx; c->dy = hd.dy; c->density = hd.density; c->pic_ratio = hd.pic_ratio;
+  c->grav_x = hd.grav_x; c->grav_y = hd.grav_y; c->integrator = hd.integrator;
+  c->max_iters = hd.max_iters; c->tol = hd.tol;
+  c->pool_dx = hd.pool_dx; c->pool_dy = hd.pool_dy; c->pool_nx = hd.pool_nx; c->pool_ny = hd.pool_ny;
+  c->pressure_valid = false;
   return FSB_OK;
 }
 
@@ -820,6 +944,11 @@ int fsb_profile_read(fsb_ctx* c, float* ms, int* calls)
   return FSB_OK;
 }
 int64_t fsb_launch_count(const fsb_ctx* c) { return c ? c->launches : 0; }
+int fsb_cg_launch_mode(const fsb_ctx* c)
+{
+  if (!c || c->cg_tile_rows == 0) return 0;
+  return c->cg_fused ? 2 : 1;
+}
 int fsb_timer_start(fsb_ctx* c)
 {
   CHECK_CTX(c);

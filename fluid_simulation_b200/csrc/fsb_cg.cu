@@ -1822,6 +1822,14 @@ int configure_cg(fsb_ctx* c)
     // (profiles/r01g).  FSB_CG_MODE=graph selects two launches per iteration in a CUDA graph.
     const char* mode = getenv("FSB_CG_MODE");
     c->cg_fused = coop != 0 && !(mode && mode[0] == 'g');
+    // Sharded solves on short slabs are bound by the two cross-GPU reductions per iteration, and the
+    // kernel-boundary form of that handshake (last CTA + one-warp combine) is lighter than the
+    // in-kernel one where every CTA polls the mailbox: measured on 2 B200, 8.4 M cells per rank
+    // 64.8 us (graph) vs 68.5 us (persistent), 33.5 M cells per rank 209.5 vs 194.0 us
+    // (profiles/r01h_2gpu.md).  FSB_CG_MODE=fused / graph overrides.
+    if (!mode && c->shard.world > 1 &&
+        (int64_t)(c->shard.row_hi - c->shard.row_lo) * c->ld < (int64_t)12 * 1000 * 1000)
+      c->cg_fused = false;
     const char* pdl = getenv("FSB_CG_PDL"); // profiling knob: 0 disables dependent launch
     c->cg_pdl = !(pdl && pdl[0] == '0');
     // bit 0: serpentine sweeps (the update walks the tile list backwards), bit 1: x loads / stores

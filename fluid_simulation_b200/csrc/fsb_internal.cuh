@@ -231,6 +231,7 @@ int fsb_k_advect_particles(fsb_ctx* c, float dt, int ensure_outside);
 int fsb_k_g2p_advect(fsb_ctx* c, int mode, float pic_ratio, float dt, int ensure_outside);
 int fsb_k_advect_particles_grid(fsb_ctx* c, float dt);
 int fsb_k_unpermute(fsb_ctx* c, float4* dst_dense);
+int fsb_k_p2g_gather(fsb_ctx* c);
 int fsb_k_emit_source_dev(fsb_ctx* c, int64_t first, const float* xs_dev, const float* ys_dev,
                           int64_t count_x, int64_t count_y, float vel_x, float vel_y);
 // pressure: fsb_cg.cu

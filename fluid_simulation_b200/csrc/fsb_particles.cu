@@ -624,7 +624,86 @@ __global__ void k_emit_source(float4* __restrict__ part, int* __restrict__ orig,
   orig[first + k] = (int)(first + k);
 }
 
+// src/FluidSolver.cpp:816-871 transferVelocityToGridGather.  weight = 1 - (|dx|/deltaX +
+// |dy|/deltaY) >= 1 selects the particles numerically ON the face position (the sum must be
+// <= 2^-25); such a particle lies in the 3x3 sort cells around the face position, so the
+// reference's scan over the whole set becomes a scan of nine cells.  The reference adds the
+// selected particles in particle-set order: they are picked by ascending original index.
+__device__ __forceinline__ void gather_face(const float4* __restrict__ part,
+                                            const int* __restrict__ orig,
+                                            const int* __restrict__ cell_start, const GridDims& pd,
+                                            const GridDims& d, float xf, float yf, bool want_x,
+                                            float* wsum, float* vsum)
+{
+  const int ci = clampi((int)div_dx(pd, xf), 0, pd.nx - 1);
+  const int cj = clampi((int)div_dy(pd, yf), 0, pd.ny - 1);
+  float ws = 0.0f, vs = 0.0f;
+  int last = -1;
+  for (;;)
+  {
+    int best = 0x7fffffff;
+    float bw = 0.0f, bv = 0.0f;
+    for (int jj = max(cj - 1, 0); jj <= min(cj + 1, pd.ny - 1); ++jj)
+      for (int ii = max(ci - 1, 0); ii <= min(ci + 1, pd.nx - 1); ++ii)
+      {
+        const int c0 = ii + jj * pd.nx;
+        for (int k = cell_start[c0]; k < cell_start[c0 + 1]; ++k)
+        {
+          const int o = orig[k];
+          if (o <= last || o >= best) continue;
+          const float4 p = part[k];
+          const float ax = fabsf(p.x - xf);
+          const float ay = fabsf(p.y - yf);
+          const float w = 1.0f - (ax / d.dx + ay / d.dy);
+          if (w >= 1.0f)
+          {
+            best = o;
+            bw = w;
+            bv = want_x ? p.z : p.w;
+          }
+        }
+      }
+    if (best == 0x7fffffff) break;
+    ws += bw;
+    vs += bv;
+    last = best;
+  }
+  *wsum = ws;
+  *vsum = vs;
+}
+
+__global__ void k_p2g_gather(const float4* __restrict__ part, const int* __restrict__ orig,
+                             const int* __restrict__ cell_start, float* __restrict__ ub,
+                             float* __restrict__ vb, const GridDims pd, const GridDims d)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= d.nx || j >= d.ny) return;
+  // :823-826: i * deltaX in float; (j + 0.5) * deltaY in double, rounded to MyFloat
+  const float x_u = (float)i * d.dx;
+  const float y_u = (float)(((double)j + 0.5) * (double)d.dy);
+  const float x_v = (float)(((double)i + 0.5) * (double)d.dx);
+  const float y_v = (float)j * d.dy;
+  float w, v;
+  gather_face(part, orig, cell_start, pd, d, x_u, y_u, true, &w, &v);
+  if (w != 0.0f) ub[i + (size_t)j * d.ld] = v / w;
+  gather_face(part, orig, cell_start, pd, d, x_v, y_v, false, &w, &v);
+  if (w != 0.0f) vb[i + (size_t)j * d.ld] = v / w;
+}
+
 } // namespace
+
+int fsb_k_p2g_gather(fsb_ctx* c)
+{
+  FSB_TRY(fsb_k_sort_particles(c));
+  fsb_prof_begin(c, FSB_PROF_P2G);
+  k_p2g_gather<<<dim3(fsb_div_up(c->nx, kBlock), c->ny), kBlock, 0, c->stream>>>(
+      c->part[c->pcur], c->orig[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), pool_dims(c), dims(c));
+  FSB_LAUNCHED(c);
+  c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:870
+  fsb_prof_end(c, FSB_PROF_P2G);
+  return FSB_OK;
+}
 
 int fsb_k_sort_particles(fsb_ctx* c, bool mark_labels)
 {

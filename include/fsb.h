@@ -159,12 +159,36 @@ int fsb_advect_velocity_sl(fsb_ctx* ctx, float dt);
 /* FluidSolver::advectParticlesWithGrid src/FluidSolver.cpp:774-791 */
 int fsb_advect_particles_grid(fsb_ctx* ctx, float dt);
 
+/* FluidSolver routines that no step* calls (API completeness):
+ * addExternalForce src/FluidSolver.cpp:253-274 -- F / density * dt on the left and bottom faces
+ * of LIQUID cells, with the context's density */
+int fsb_add_external_force(fsb_ctx* ctx, float fx, float fy, float dt);
+/* transferVelocityToGridGather src/FluidSolver.cpp:816-871 -- every face takes the mean velocity
+ * of the particles whose hat weight is >= 1 (particles numerically ON the face position), in
+ * particle-set order; other faces keep the back buffer's value; swap.  The reference scans all
+ * particles per face; the device scans the face's 3x3 cells of the cell-sorted set. */
+int fsb_p2g_gather(fsb_ctx* ctx);
+/* (extendVelocityAvarageing :625-707 is not provided: its two-face writes make every sweep
+ * depend on the scan order) */
+
 /* ---- fused steps: FluidSolver::step* src/FluidSolver.cpp:99-251 ------- */
 
 /* kind = FSB_STEP_*.  Uses the context's density and pic ratio the way the
  * reference reads them from the FluidDomain.  FSB_ERR_INVALID when the
  * reference's validate() (src/FluidSolver.cpp:89-97) would throw. */
 int fsb_step(fsb_ctx* ctx, int kind, float dt);
+
+/* ---- state dump / reload -------------------------- */
+
+/* Everything a step reads, as one little-endian file: a 96-byte header (magic "FSBSTATE",
+ * version, sizes, deltas, density, pic ratio, gravity, integrator, CG cap and tolerance, pool,
+ * particle count), the labels (size_x*size_y bytes), the eight MacGrid buffers in FSB_U_FRONT ..
+ * FSB_V_DIFF order (dense fp32) and the particles in the caller's order (AoS fp32 x 4).  The
+ * reference has no state format (its only output is the PPM frame, src/Renderer.cpp); a run
+ * continued from a reloaded file is bit-identical to the uninterrupted run. */
+int fsb_save_state(fsb_ctx* ctx, const char* path);
+/* The context must have the file's grid size. */
+int fsb_load_state(fsb_ctx* ctx, const char* path);
 
 /* ---- multi-GPU: row-slab sharding of the pressure solve ---------------- */
 
@@ -199,6 +223,9 @@ enum {
 int fsb_profile_enable(fsb_ctx* ctx, int on);
 /* ms[FSB_PROF_COUNT], calls[FSB_PROF_COUNT]: totals since the last read */
 int fsb_profile_read(fsb_ctx* ctx, float* ms, int* calls);
+/* launch mode of the pressure solve as configured by the last solve: 0 not configured yet,
+ * 1 two kernels per iteration in a CUDA graph, 2 one persistent cooperative kernel */
+int fsb_cg_launch_mode(const fsb_ctx* ctx);
 /* number of kernels this library launched on the context since creation */
 int64_t fsb_launch_count(const fsb_ctx* ctx);
 /* a pair of events around an arbitrary region of this context's stream */

@@ -498,6 +498,71 @@ void fso_extend_velocity(void* h, int n_iter)
   swap_velocity(c);
 }
 
+/* src/FluidSolver.cpp:253-274  addExternalForce: F / density * dt on the left and bottom faces
+ * of LIQUID cells (not called by any step) */
+void fso_add_external_force(void* h, float fx, float fy, float dt)
+{
+  Ctx* c = (Ctx*)h;
+  float *uf = UF(c), *vf = VF(c);
+  for (int j = 0; j < c->ny; ++j)
+    for (int i = 0; i < c->nx; ++i)
+      if (cell_type(c, i, j) == LIQUID)
+      {
+        const size_t k = AT(c, i, j);
+        uf[k] = uf[k] + fx / c->density * dt;
+        vf[k] = vf[k] + fy / c->density * dt;
+      }
+}
+
+/* src/FluidSolver.cpp:816-871  transferVelocityToGridGather: for every face the particles whose
+ * hat weight 1 - (|dx|/deltaX + |dy|/deltaY) is >= 1, i.e. (numerically) ON the face position;
+ * mean of their velocities, written to the back buffer, swap (not called by any step) */
+void fso_p2g_gather(void* h)
+{
+  Ctx* c = (Ctx*)h;
+  float *ub = UB(c), *vb = VB(c);
+  for (int j = 0; j < c->ny; ++j)
+    for (int i = 0; i < c->nx; ++i)
+    {
+      const float x_u = i * c->dx;
+      const float y_u = (float)((j + 0.5) * c->dy);
+      const float x_v = (float)((i + 0.5) * c->dx);
+      const float y_v = j * c->dy;
+      float wx = 0, sx = 0, wy = 0, sy = 0;
+      for (int64_t q = 0; q < c->n; ++q)
+      {
+        const float* p = c->part + 4 * q;
+        float ax = fabsf(p[0] - x_u);
+        float ay = fabsf(p[1] - y_u);
+        const float w_u = 1 - (ax / c->dx + ay / c->dy);
+        if (w_u >= 1)
+        {
+          wx += w_u;
+          sx += p[2];
+        }
+        ax = fabsf(p[0] - x_v);
+        ay = fabsf(p[1] - y_v);
+        const float w_v = 1 - (ax / c->dx + ay / c->dy);
+        if (w_v >= 1)
+        {
+          wy += w_v;
+          sy += p[3];
+        }
+      }
+      if (wx)
+      {
+        sx /= wx;
+        ub[AT(c, i, j)] = sx;
+      }
+      if (wy)
+      {
+        sy /= wy;
+        vb[AT(c, i, j)] = sy;
+      }
+    }
+  swap_velocity(c);
+}
+
 /* Eigen ConjugateGradient<SparseMatrix<float>, Lower, DiagonalPreconditioner>
  * restated matrix-free on the compact liquid numbering, in the same operation
  * order as oracle/eigen_shim/Eigen/IterativeLinearSolvers (column sweep over

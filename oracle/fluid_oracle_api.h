@@ -63,6 +63,11 @@ void FSX(g2p)(void* h, int mode, float pic_ratio);
 void FSX(advect_particles)(void* h, float dt, int ensure_outside);
 void FSX(advect_velocity_sl)(void* h, float dt);
 void FSX(advect_particles_grid)(void* h, float dt);
+/* routines of FluidSolver that no step* calls */
+/* addExternalForce src/FluidSolver.cpp:253-274 (reads the domain's density) */
+void FSX(add_external_force)(void* h, float fx, float fy, float dt);
+/* transferVelocityToGridGather src/FluidSolver.cpp:816-871 */
+void FSX(p2g_gather)(void* h);
 /* returns 0, or 1 when the reference's validate() would throw */
 int FSX(step)(void* h, int kind, float dt);
 

@@ -206,6 +206,15 @@ void fsr_advect_particles_grid(void* h, float dt)
   RefCtx* c = C(h);
   c->solver.advectParticlesWithGrid(c->domain.markerParticleSet(), c->domain.macGrid(), dt);
 }
+void fsr_add_external_force(void* h, float fx, float fy, float dt)
+{
+  C(h)->solver.addExternalForce(C(h)->domain, fx, fy, dt);
+}
+void fsr_p2g_gather(void* h)
+{
+  C(h)->solver.transferVelocityToGridGather(C(h)->domain.markerParticleSet(),
+                                            C(h)->domain.macGrid());
+}
 int fsr_step(void* h, int kind, float dt)
 {
   RefCtx* c = C(h);

@@ -57,6 +57,36 @@ def stage_vectors(ref):
     np.savez_compressed(os.path.join(HERE, "stages_24x20.npz"), **out)
 
 
+def uncalled_vectors(ref):
+    """addExternalForce and transferVelocityToGridGather (no step calls them): a separate file so
+    that stages_24x20.npz stays byte-identical to its first commit."""
+    nx, ny = 24, 20
+    rng = np.random.default_rng(20240612)
+    lab = scenes.random_labels(nx, ny, rng, p_liquid=0.45, p_solid=0.04)
+    s = ref.sim(nx, ny, 1.0, float(np.float32(ny) / np.float32(nx)), 0.013, 0.05)
+    fields = {w: scenes.random_field(nx, ny, rng) for w in range(4)}
+    parts = scenes.particles_in_liquid(lab, s.dx, rng, 3)
+    dx, dy = np.float32(s.dx), np.float32(s.dy)
+    k = 0  # particles exactly ON face positions: the only ones the gather transfer selects
+    for (i, j) in [(3, 4), (5, 5), (5, 5), (7, 2), (10, 10), (0, 3), (nx - 1, 5), (12, ny - 1)]:
+        parts[k, 0] = np.float32(i) * dx; parts[k, 1] = np.float32((j + 0.5) * np.float64(dy)); k += 1
+        parts[k, 0] = np.float32((i + 0.5) * np.float64(dx)); parts[k, 1] = np.float32(j) * dy; k += 1
+    out = {"nx": nx, "ny": ny, "labels": lab, "particles": parts, "density": np.float32(0.013)}
+    for w, f in fields.items():
+        out[f"in_grid{w}"] = f
+    s.set_cell_types(lab)
+    for w, f in fields.items():
+        s.set_grid(w, f)
+    s.set_particles(parts)
+    s.add_external_force(0.3, -1.7, 0.01)
+    for w in range(4):
+        out[f"force_grid{w}"] = s.get_grid(w)
+    s.p2g_gather()
+    for w in range(4):
+        out[f"gather_grid{w}"] = s.get_grid(w)
+    np.savez_compressed(os.path.join(HERE, "uncalled_24x20.npz"), **out)
+
+
 def config0_trace(ref):
     """examples/simple.cpp scene: 64 x 64, one source, dt = 0.01, stepPICFLIP."""
     n = 64
@@ -86,7 +116,9 @@ def config0_trace(ref):
 if __name__ == "__main__":
     assert ol.available("fsr"), "build oracle/_ref first: make -C oracle ref"
     ref = ol.OracleLib("fsr")
-    stage_vectors(ref)
-    config0_trace(ref)
+    if "--only-uncalled" not in sys.argv:
+        stage_vectors(ref)
+        config0_trace(ref)
+    uncalled_vectors(ref)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

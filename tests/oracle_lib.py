@@ -57,6 +57,8 @@ _SIGS = {
     "advect_velocity_sl": (None, [_p, _f]),
     "advect_particles_grid": (None, [_p, _f]),
     "step": (_i, [_p, _i, _f]),
+    "add_external_force": (None, [_p, _f, _f, _f]),
+    "p2g_gather": (None, [_p]),
 }
 
 
@@ -190,6 +192,12 @@ class OracleSim:
 
     def advect_particles_grid(self, dt):
         self.L._advect_particles_grid(self.h, dt)
+
+    def add_external_force(self, fx, fy, dt):
+        self.L._add_external_force(self.h, fx, fy, dt)
+
+    def p2g_gather(self):
+        self.L._p2g_gather(self.h)
 
     def step(self, kind, dt):
         rc = self.L._step(self.h, kind, dt)

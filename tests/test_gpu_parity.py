@@ -447,6 +447,62 @@ def test_first_step_stage_by_stage_config0(capi, ref):
             assert e <= 5e-3, (step, name, e)
 
 
+@pytest.mark.parametrize("nx,ny", SIZES[:3])
+def test_uncalled_solver_routines_bit_exact(capi, checkers, nx, ny):
+    """addExternalForce (src/FluidSolver.cpp:253-274) and transferVelocityToGridGather (:816-871):
+    not called by any step, provided for API completeness, bit-exact against the reference."""
+    rng = np.random.default_rng(41)
+    for chk in checkers:
+        g, c = make_pair(capi, chk, nx, ny, density=0.013)
+        lab, fields, parts = load_state((g, c), rng, nx, ny, per_cell=3)
+        dx, dy = np.float32(g.dx), np.float32(g.dy)
+        parts = parts.copy()
+        k = 0  # particles exactly ON face positions (the only ones the gather transfer selects)
+        for (i, j) in [(3, 4), (5, 5), (5, 5), (7, 2), (10, 10), (0, 3), (nx - 1, 5), (nx // 2, ny - 1)]:
+            parts[k, 0] = np.float32(i) * dx; parts[k, 1] = np.float32((j + 0.5) * np.float64(dy)); k += 1
+            parts[k, 0] = np.float32((i + 0.5) * np.float64(dx)); parts[k, 1] = np.float32(j) * dy; k += 1
+        for s in (g, c):
+            s.set_particles(parts)
+            s.add_external_force(0.3, -1.7, 0.01)
+        assert_grids_equal(g, c)
+        before = g.get_grid(U_BACK)
+        for s in (g, c):
+            s.p2g_gather()
+        assert_grids_equal(g, c)
+        assert (g.get_grid(U_FRONT) != before).sum() >= 5  # the planted particles were found
+        assert np.array_equal(g.get_particles(), c.get_particles())
+
+
+def test_state_file_round_trip_continues_bit_identically(capi, tmp_path):
+    """fsb_save_state / fsb_load_state: a run continued from a reloaded file equals the
+    uninterrupted run bit for bit (labels, grids, particles in the caller's order)."""
+    n = 96
+    a = capi.Sim(n, n, 1.0, 1.0, 0.01, 0.05)
+    a.emit_source(*scenes.dam_break_args(n))
+    for _ in range(3):
+        a.step(STEP_PICFLIP, 0.01)
+    path = str(tmp_path / "state.fsb")
+    a.save_state(path)
+    b = capi.Sim(n, n, 1.0, 1.0, 0.5, 0.9)  # different parameters: the file must overwrite them
+    b.load_state(path)
+    assert np.array_equal(a.get_cell_types(), b.get_cell_types())
+    assert np.array_equal(a.get_particles(), b.get_particles())
+    for w in (U_FRONT, V_FRONT, U_BACK, V_BACK, U_PREV, V_PREV, U_DIFF, V_DIFF):
+        assert np.array_equal(a.get_grid(w), b.get_grid(w)), w
+    for _ in range(3):
+        a.step(STEP_PICFLIP, 0.01)
+        b.step(STEP_PICFLIP, 0.01)
+    assert a.cg_info() == b.cg_info()
+    assert np.array_equal(a.get_cell_types(), b.get_cell_types())
+    assert np.array_equal(a.get_particles(), b.get_particles())
+    for w in (U_FRONT, V_FRONT, U_BACK, V_BACK, U_PREV, V_PREV):
+        assert np.array_equal(a.get_grid(w), b.get_grid(w)), w
+    with pytest.raises(RuntimeError):
+        capi.Sim(64, 64).load_state(path)  # wrong grid size
+    with pytest.raises(RuntimeError):
+        b.load_state(str(tmp_path / "missing.fsb"))
+
+
 def test_particle_order_is_the_callers(capi):
     rng = np.random.default_rng(13)
     g = capi.Sim(64, 64)

@@ -143,6 +143,25 @@ def test_port_equals_compiled_reference_random_stages(port, ref, nx, ny):
         assert np.array_equal(a.get_pressure(), b.get_pressure())
 
 
+def test_port_matches_golden_uncalled_routines(checkers):
+    """addExternalForce / transferVelocityToGridGather against vectors from the reference's code."""
+    z = np.load(os.path.join(GOLD, "uncalled_24x20.npz"))
+    nx, ny = int(z["nx"]), int(z["ny"])
+    for chk in checkers:
+        s = chk.sim(nx, ny, 1.0, float(np.float32(ny) / np.float32(nx)), float(z["density"]), 0.05)
+        s.set_cell_types(z["labels"])
+        for w in range(4):
+            s.set_grid(w, z[f"in_grid{w}"])
+        s.set_particles(z["particles"])
+        s.add_external_force(0.3, -1.7, 0.01)
+        for w in range(4):
+            assert np.array_equal(s.get_grid(w), z[f"force_grid{w}"]), ("force", w)
+        s.p2g_gather()
+        for w in range(4):
+            assert np.array_equal(s.get_grid(w), z[f"gather_grid{w}"]), ("gather", w)
+        assert (z["gather_grid0"] != z["force_grid2"]).sum() >= 5  # planted particles were selected
+
+
 def test_validate_rejects_non_square_cells(port):
     s = port.sim(32, 16, 1.0, 1.0)  # dx = 1/32, dy = 1/16 (src/FluidSolver.cpp:56-65,89-97)
     with pytest.raises(RuntimeError):
