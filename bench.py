@@ -50,6 +50,14 @@ WORKLOADS = {
     "picflip2048": dict(n=2048, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
     "picflip1024": dict(n=1024, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
     "sl1024": dict(n=1024, kind="sl", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
+    # BASELINE.json configs[4]: 16384^2 full PIC/FLIP step.  1.0e9 particles: the tank is filled on
+    # the device by fsb_emit_source (the reference's FluidSource lattice, src/FluidDomain.cpp:34-50,
+    # at delta/2 spacing starting a quarter cell in: 4 particles per cell at the stratum centres,
+    # at rest), there is no host copy of the set and no e2e leg
+    "picflip16384": dict(n=16384, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2,
+                         emit=True),
+    "picflip8192e": dict(n=8192, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2,
+                         emit=True),
     "picflip256": dict(n=256, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
     # BASELINE.json configs[3]: pressure Poisson CG only, tank labels, swirl + gravity velocities
     "cg8192": dict(n=8192, kind="cg", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=0),
@@ -247,7 +255,8 @@ def main():
         cfg_name = (f"{n}^2 pressure Poisson solve only (tank labels, swirl + gravity field), "
                     f"Jacobi-PCG to {wl['tol']:g} relative residual")
     else:
-        cfg_name = (f"{n}^2 {wl['kind']} full step, tank scene {wl['per_side']**2} particles/cell, "
+        cfg_name = (f"{n}^2 {wl['kind']} full step, tank scene {wl['per_side']**2} particles/cell"
+                    f"{' (device-emitted lattice, at rest)' if wl.get('emit') else ''}, "
                     f"pic_ratio {wl['pic_ratio']}, CG to {wl['tol']:g} relative residual")
 
     if args.impl == "reference":
@@ -296,6 +305,13 @@ def main():
         n_part = 0
         del u0, v0
         log("fields ready")
+    elif wl.get("emit"):
+        d = 1.0 / n
+        n_part = sim.emit_source(1.25 * d, 1.0 - d, 1.25 * d, 15.0 / 16.0, 1.25 * d, 1.25 * d, 0.0, 0.0)
+        host = None
+        args.no_e2e = True
+        kind = step_kind(capi, wl["kind"])
+        log(f"scene emitted on the device: {n_part} particles")
     else:
         parts = tank_particles(n, wl["per_side"])
         n_part = parts.shape[0]
@@ -456,7 +472,8 @@ def main():
         "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg_name, "particles": int(n_part), "dt": dt,
-                   "l2": "inputs larger than L2 (1.0 GB particles, 64 MB per grid)"
+                   "l2": (f"inputs larger than L2 ({n_part * 16 / 1e9:.1f} GB particles, "
+                          f"{n * n * 4 / 1e6:.0f} MB per grid)")
                    if n >= 4096 else "working set may fit L2: latency-bound, see DESIGN.md",
                    "parallelism": (f"CG sharded over {world} row slabs (peer-memory halo stores + mailbox "
                                    f"reductions over NVLink), other stages replicated")

@@ -750,8 +750,20 @@ int fsb_save_state(fsb_ctx* c, const char* path)
   }
   if (ok && c->n > 0)
   {
-    rc = fsb_get_particles(c, buf.data());
-    ok = rc == FSB_OK && fwrite(buf.data(), 4 * sizeof(float), (size_t)c->n, f) == (size_t)c->n;
+    // the device order (cell-sorted by the last step) and the map back to the caller's indices:
+    // the in-cell order of the next sort -- and with it every P2G rounding -- depends on the order
+    // the sort starts from, so only the exact arrays give a bit-identical continuation
+    FSB_CUDA(c, cudaMemcpyAsync(buf.data(), c->part[c->pcur], sizeof(float4) * c->n,
+                                cudaMemcpyDeviceToHost, c->stream));
+    FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    ok = fwrite(buf.data(), 4 * sizeof(float), (size_t)c->n, f) == (size_t)c->n;
+    if (ok)
+    {
+      FSB_CUDA(c, cudaMemcpyAsync(buf.data(), c->orig[c->pcur], sizeof(int) * c->n,
+                                  cudaMemcpyDeviceToHost, c->stream));
+      FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+      ok = fwrite(buf.data(), sizeof(int), (size_t)c->n, f) == (size_t)c->n;
+    }
   }
   ok = (fclose(f) == 0) && ok;
   if (rc != FSB_OK) return rc;
@@ -793,10 +805,41 @@ int fsb_load_state(fsb_ctx* c, const char* path)
   }
   if (ok && rc == FSB_OK)
   {
-    ok = hd.n_particles == 0 ||
-         fread(buf.data(), 4 * sizeof(float), (size_t)hd.n_particles, f) == (size_t)hd.n_particles;
-    if (ok) rc = fsb_set_particles(c, buf.data(), hd.n_particles);
-    if (ok && rc == FSB_OK) rc = fsb_synchronize(c);
+    const int64_t np = hd.n_particles;
+    c->n = 0;
+    c->sort_valid = false;
+    if (np > 0)
+    {
+      rc = ensure_particle_capacity(c, np);
+      ok = rc == FSB_OK && fread(buf.data(), 4 * sizeof(float), (size_t)np, f) == (size_t)np;
+      if (ok)
+      {
+        FSB_CUDA(c, cudaMemcpyAsync(c->part[c->pcur], buf.data(), sizeof(float4) * np,
+                                    cudaMemcpyHostToDevice, c->stream));
+        FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+        ok = fread(buf.data(), sizeof(int), (size_t)np, f) == (size_t)np;
+      }
+      if (ok)
+      {
+        // the map must be a permutation of 0 .. n-1 (it indexes the caller-order buffer on read-back)
+        const int* o = reinterpret_cast<const int*>(buf.data());
+        std::vector<uint8_t> seen((size_t)np, 0);
+        for (int64_t k = 0; k < np && ok; ++k)
+        {
+          ok = o[k] >= 0 && o[k] < np && !seen[(size_t)o[k]];
+          if (ok) seen[(size_t)o[k]] = 1;
+        }
+        if (!ok)
+        {
+          fclose(f);
+          return fsb_fail(c, FSB_ERR_INVALID, "%s: the particle index map is not a permutation", path);
+        }
+        FSB_CUDA(c, cudaMemcpyAsync(c->orig[c->pcur], buf.data(), sizeof(int) * np,
+                                    cudaMemcpyHostToDevice, c->stream));
+        FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->n = np;
+      }
+    }
   }
   fclose(f);
   if (rc != FSB_OK) return rc;

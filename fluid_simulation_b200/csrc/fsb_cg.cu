@@ -9,21 +9,20 @@
 // zero on non-liquid cells, sum_{LIQUID nbrs} p equals the plain 4-neighbour
 // sum, so the operator needs no neighbour bits.
 //
-// One CG iteration = two kernels (Eigen's statement order is kept):
-//   k_cg_direction : p = z + beta p (z = invdiag r; p = z on the first pass) on a
-//                    tile and its halo, q = A p in registers, partial p.q
-//                    -> 9 B read + 4 B written per cell (q is never stored)
-//   k_cg_update    : alpha = absNew / p.q; q = A p recomputed from the staged
-//                    p tile; x += alpha p; r -= alpha q; partial |r|^2, r.z
-//                    -> 13 B read + 8 B written per cell
-// 34 B of HBM traffic per cell and iteration against the 45 B of the textbook
-// formulation.  The last block to finish each kernel folds the
-// per-block partials in a fixed order (deterministic) and advances the
-// device-resident scalars, so there is no host round trip inside the loop;
-// the loop is a CUDA graph of kCheckEvery iterations and the host polls
-// `done` one chunk behind the GPU.  Once `done` is set every later launch
-// returns immediately, so x and the iteration count are exactly those of the
-// converging iteration.
+// One CG iteration = two sweeps (Eigen's statement order is kept):
+//   direction : p = z + beta p (z = invdiag r; p = z on the first pass) on a tile and its halo,
+//               q = A p in registers, partial p.q        -> 9 B read + 4 B written per cell
+//   update    : alpha = absNew / p.q; q = A p recomputed from the staged p tile (q is never
+//               stored); r -= alpha q; partial |r|^2, r.z; x += alpha p -- in the persistent
+//               kernel only on odd iterations, two updates back to back (bit-identical x)
+//                                                        -> 9 + 4 B (+ 12 B every other iteration)
+// 32 B of HBM traffic per cell and iteration against the 45 B of the textbook formulation
+// (SURVEY.md 8d).  Launch modes: k_cg_solve, one persistent cooperative kernel for the whole solve
+// with a software grid barrier that carries the reductions (default), or k_cg_direction +
+// k_cg_update per iteration in a CUDA graph of kCheckEvery iterations with the host polling `done`
+// one chunk behind the GPU.  Partials are folded in a fixed order (deterministic); once `done` is
+// set nothing is modified any more, so x and the iteration count are exactly those of the
+// converging iteration.  DESIGN.md section 5.
 #include <cfloat>
 #include <cmath>
 #include <cstdio>

@@ -183,9 +183,12 @@ int fsb_step(fsb_ctx* ctx, int kind, float dt);
 /* Everything a step reads, as one little-endian file: a 96-byte header (magic "FSBSTATE",
  * version, sizes, deltas, density, pic ratio, gravity, integrator, CG cap and tolerance, pool,
  * particle count), the labels (size_x*size_y bytes), the eight MacGrid buffers in FSB_U_FRONT ..
- * FSB_V_DIFF order (dense fp32) and the particles in the caller's order (AoS fp32 x 4).  The
- * reference has no state format (its only output is the PPM frame, src/Renderer.cpp); a run
- * continued from a reloaded file is bit-identical to the uninterrupted run. */
+ * FSB_V_DIFF order (dense fp32), the particles in the DEVICE's order (AoS fp32 x 4; cell-sorted
+ * by the last step) and the int32 map from that order to the caller's indices (particle k of the
+ * file is the caller's particle map[k]).  The device order is kept because the in-cell order of
+ * the next sort, and with it every P2G rounding, depends on the order the sort starts from: a
+ * run continued from a reloaded file is bit-identical to the uninterrupted run.  The reference
+ * has no state format (its only output is the PPM frame, src/Renderer.cpp). */
 int fsb_save_state(fsb_ctx* ctx, const char* path);
 /* The context must have the file's grid size. */
 int fsb_load_state(fsb_ctx* ctx, const char* path);
