@@ -389,6 +389,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         barrier()
+        e2e_iters = 0
         t0 = time.perf_counter()
         for _ in range(args.steps):
             if cg_only:
@@ -400,6 +401,7 @@ def main():
                 sim.set_particles_ptr(host.data_ptr(), n_part)
                 sim.step(kind, dt)
                 sim.get_particles_ptr(host.data_ptr())
+            e2e_iters += sim.cg_info()[0]
         barrier()
         t1 = time.perf_counter()
         et = t1 - t0
@@ -410,7 +412,9 @@ def main():
         h2d = 2 * n * n * 4 if cg_only else n_part * 16
         d2h = n * n * 4 if cg_only else n_part * 16
         e2e = {"value": n * n * args.steps / et, "unit": "cell-updates/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               # the e2e steps continue the same simulation: later steps, other iteration counts
+               "cg_iters_per_step": e2e_iters / args.steps}
 
     if world > 1:
         sim.shard_disconnect()

@@ -151,10 +151,11 @@ __global__ void k_cg_build(const float* __restrict__ uf, const float* __restrict
 
 
 // The same set-up with four cells per thread (cg_build_group, fsb_vec_kernels.cuh)
+template <class D>
 __global__ void __launch_bounds__(256)
 k_cg_build4(const float* __restrict__ uf, const float* __restrict__ vf,
             const uint8_t* __restrict__ cell, uint8_t* __restrict__ code, float* __restrict__ x,
-            float* __restrict__ r, const GridDims d, const CgCoef coef, CgScalars* __restrict__ s,
+            float* __restrict__ r, const D d, const CgCoef coef, CgScalars* __restrict__ s,
             double* __restrict__ partials, float tol, int max_iters)
 {
   const int segs = (d.ld + 1023) / 1024;
@@ -2094,10 +2095,14 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     k_cg_build<<<build_blocks, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell, c->cg_code,
                                                     c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
                                                     c->tol, c->max_iters);
+  else if (d.pow2 == 3)
+    k_cg_build4<GridDimsP2><<<build_blocks, 256, 0, c->stream>>>(
+        fsb_uf(c), fsb_vf(c), c->cell, c->cg_code, c->cg_x, c->cg_r, as_pow2(d), coef, c->scal,
+        c->partials, c->tol, c->max_iters);
   else
-    k_cg_build4<<<build_blocks, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell, c->cg_code,
-                                                     c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
-                                                     c->tol, c->max_iters);
+    k_cg_build4<GridDims><<<build_blocks, 256, 0, c->stream>>>(
+        fsb_uf(c), fsb_vf(c), c->cell, c->cg_code, c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
+        c->tol, c->max_iters);
   FSB_LAUNCHED(c);
   FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[0], c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
                               c->stream));
@@ -2191,12 +2196,15 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
   if (c->stage_v1)
     k_pressure_patch<<<dim3(fsb_div_up(c->ld, 256), c->ny), 256, 0, c->stream>>>(
         fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), c->cg_x, c->cg_code, d, dt, density);
-  else if (fuse_dirichlet)
-    k_pressure_patch4<true><<<grid4, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c),
-                                                          c->cg_x, c->cell, d, dt, density);
   else
-    k_pressure_patch4<false><<<grid4, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c),
-                                                           c->cg_x, c->cell, d, dt, density);
+  {
+#define FSB_PATCH(DIR, D, d_)                                                                       \
+  k_pressure_patch4<DIR, D><<<grid4, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), \
+                                                          c->cg_x, c->cell, d_, dt, density)
+    if (d.pow2 == 3) { if (fuse_dirichlet) FSB_PATCH(true, GridDimsP2, as_pow2(d)); else FSB_PATCH(false, GridDimsP2, as_pow2(d)); }
+    else { if (fuse_dirichlet) FSB_PATCH(true, GridDims, d); else FSB_PATCH(false, GridDims, d); }
+#undef FSB_PATCH
+  }
   FSB_LAUNCHED(c);
   c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:482
   fsb_prof_end(c, FSB_PROF_PATCH);

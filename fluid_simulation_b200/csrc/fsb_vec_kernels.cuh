@@ -271,11 +271,11 @@ k_extend2_b(float* __restrict__ uf, float* __restrict__ ub, float* __restrict__ 
 // it acts on the patched value where the face was patched and on the stale back-buffer value
 // elsewhere, exactly what the separate pass sees after the swap.  LIQUID <=> code != 0 (the
 // labels have not changed since k_cg_build), so the labels are the only mask read.
-template <bool DIRICHLET>
+template <bool DIRICHLET, class D>
 __global__ void __launch_bounds__(256)
 k_pressure_patch4(const float* __restrict__ uf, const float* __restrict__ vf, float* __restrict__ ub,
                   float* __restrict__ vb, const float* __restrict__ x,
-                  const uint8_t* __restrict__ cell, const GridDims d, float dt, float density)
+                  const uint8_t* __restrict__ cell, const D d, float dt, float density)
 {
   const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int j = blockIdx.y;
@@ -314,8 +314,9 @@ k_pressure_patch4(const float* __restrict__ uf, const float* __restrict__ vf, fl
       const float ps = ls ? f4_get(xs, t) + 0.0f : 0.0f;
       const float ddx = pc - pw;
       const float ddy = pc - ps;
-      f4_set(ou, t, f4_get(u4, t) - ((dt / density) * ddx) / d.dx);
-      f4_set(ov, t, f4_get(v4, t) - ((dt / density) * ddy) / d.dy);
+      // x / delta through div_dx / div_dy: one multiplication when delta is a power of two
+      f4_set(ou, t, f4_get(u4, t) - div_dx(d, (dt / density) * ddx));
+      f4_set(ov, t, f4_get(v4, t) - div_dy(d, (dt / density) * ddy));
     }
   }
   if (DIRICHLET && walls != 0u) dirichlet4(ou, ov, sd_c, sd_s);
@@ -327,9 +328,10 @@ k_pressure_patch4(const float* __restrict__ uf, const float* __restrict__ vf, fl
 // One float4 group of the pressure system set-up (src/FluidSolver.cpp:329-346,368-416; the
 // arithmetic of k_cg_build): stencil codes, b = divergence on LIQUID cells, and the group's
 // contributions to |b|^2, b.z and the liquid count.  `invdiag` = Eigen's Jacobi preconditioner.
+template <class D>
 __device__ __forceinline__ void cg_build_group(const float* __restrict__ uf,
                                                const float* __restrict__ vf,
-                                               const uint8_t* __restrict__ cell, const GridDims& d,
+                                               const uint8_t* __restrict__ cell, const D& d,
                                                const float* invdiag, int i0, int j, uint32_t* code4,
                                                float4* b4, double* acc_b2, double* acc_bz,
                                                double* acc_n)
@@ -365,7 +367,7 @@ __device__ __forceinline__ void cg_build_group(const float* __restrict__ uf,
         const int ie = min(i0 + t + 1, d.nx - 1) - i0; // east face: inside the group, after it, or clamped
         const float u_e =
             (ie >= 4) ? ue : ((ie == t + 1 && t < 3) ? f4_get(u4, t + 1) : f4_get(u4, t));
-        const float bb = (u_e - f4_get(u4, t)) / d.dx + (f4_get(vn, t) - f4_get(v4, t)) / d.dy;
+        const float bb = div_dx(d, u_e - f4_get(u4, t)) + div_dy(d, f4_get(vn, t) - f4_get(v4, t));
         f4_set(b, t, bb);
         const float z = invdiag[n] * bb;
         *acc_b2 += (double)bb * (double)bb;

@@ -101,12 +101,23 @@ void emul_pressure_patch(const float* uf, const float* vf, float* ub, float* vb,
                          float density, int dirichlet)
 {
   const GridDims d = make_grid_dims(nx, ny, ld, dx, dy);
-  if (dirichlet)
+  // the library picks the compile-time power-of-two form exactly like this
+  if (d.pow2 == 3)
+  {
+    const GridDimsP2 p = as_pow2(d);
+    if (dirichlet)
+      launch(div_up(ld, 1024), ny, 256,
+             [&] { k_pressure_patch4<true, GridDimsP2>(uf, vf, ub, vb, x, cell, p, dt, density); });
+    else
+      launch(div_up(ld, 1024), ny, 256,
+             [&] { k_pressure_patch4<false, GridDimsP2>(uf, vf, ub, vb, x, cell, p, dt, density); });
+  }
+  else if (dirichlet)
     launch(div_up(ld, 1024), ny, 256,
-           [&] { k_pressure_patch4<true>(uf, vf, ub, vb, x, cell, d, dt, density); });
+           [&] { k_pressure_patch4<true, GridDims>(uf, vf, ub, vb, x, cell, d, dt, density); });
   else
     launch(div_up(ld, 1024), ny, 256,
-           [&] { k_pressure_patch4<false>(uf, vf, ub, vb, x, cell, d, dt, density); });
+           [&] { k_pressure_patch4<false, GridDims>(uf, vf, ub, vb, x, cell, d, dt, density); });
 }
 
 // pressure system set-up; sums[3] = |b|^2, b.z, liquid count
@@ -120,7 +131,10 @@ void emul_cg_build(const float* uf, const float* vf, const uint8_t* cell, uint8_
     {
       uint32_t cd;
       float4 b;
-      cg_build_group(uf, vf, cell, d, invdiag5, i0, j, &cd, &b, &sums[0], &sums[1], &sums[2]);
+      if (d.pow2 == 3)
+        cg_build_group(uf, vf, cell, as_pow2(d), invdiag5, i0, j, &cd, &b, &sums[0], &sums[1], &sums[2]);
+      else
+        cg_build_group(uf, vf, cell, d, invdiag5, i0, j, &cd, &b, &sums[0], &sums[1], &sums[2]);
       std::memcpy(code + i0 + (size_t)j * ld, &cd, 4);
       std::memcpy(r + i0 + (size_t)j * ld, &b, 16);
     }
