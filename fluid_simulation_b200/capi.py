@@ -77,6 +77,8 @@ SIGNATURES = {
     "fsb_add_external_force": (_i, [_p, _f, _f, _f]),
     "fsb_p2g_gather": (_i, [_p]),
     "fsb_step": (_i, [_p, _i, _f]),
+    "fsb_render_rgb": (_i, [_p, _i, _i, _f, _f, _f, _f, _p]),
+    "fsb_write_ppm": (_i, [_p, C.c_char_p, _i, _i, _f, _f, _f, _f]),
     "fsb_save_state": (_i, [_p, C.c_char_p]),
     "fsb_load_state": (_i, [_p, C.c_char_p]),
     "fsb_shard_export": (_i, [_p, _p]),
@@ -307,6 +309,16 @@ class Sim:
 
     def p2g_gather(self):
         self._ck(_lib.fsb_p2g_gather(self.h))
+
+    # frames
+    def render_rgb(self, width, height, area=(0.0, 1.0, 0.0, 1.0)):
+        a = np.zeros((height, width, 3), dtype=np.uint8)
+        self._ck(_lib.fsb_render_rgb(self.h, width, height, *[float(v) for v in area], _ptr(a)))
+        return a
+
+    def write_ppm(self, path, width, height, area=(0.0, 1.0, 0.0, 1.0)):
+        self._ck(_lib.fsb_write_ppm(self.h, os.fsencode(path), width, height,
+                                    *[float(v) for v in area]))
 
     # state files
     def save_state(self, path):

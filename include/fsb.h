@@ -193,6 +193,20 @@ int fsb_save_state(fsb_ctx* ctx, const char* path);
 /* The context must have the file's grid size. */
 int fsb_load_state(fsb_ctx* ctx, const char* path);
 
+/* ---- frames -------------------------------------- */
+
+/* The frame examples/simple.cpp:73-82 draws with the reference's software renderer --
+ * Renderer::clearCanvas + renderGridCellsToCanvas + renderParticlesToCanvas (src/Renderer.cpp:
+ * 14-56,141-162, src/Canvas.cpp:62-92) and the byte conversion of writeCanvasToPpm (:217-248) --
+ * rasterised on the device from the state in HBM: width*height*3 bytes, row j of the canvas at
+ * offset j*width*3, byte-identical to the reference's PPM payload.  (x_min..y_max) is the
+ * world-space area of Renderer's constructor. */
+int fsb_render_rgb(fsb_ctx* ctx, int width, int height, float x_min, float x_max, float y_min,
+                   float y_max, uint8_t* rgb);
+/* Renderer::writeCanvasToPpm of that frame: "P6\n<w> <h>\n255\n" + the bytes */
+int fsb_write_ppm(fsb_ctx* ctx, const char* path, int width, int height, float x_min, float x_max,
+                  float y_min, float y_max);
+
 /* ---- multi-GPU: row-slab sharding of the pressure solve ---------------- */
 
 /* One process per GPU, each holding the same domain (every stage except the CG

@@ -563,6 +563,62 @@ void fso_p2g_gather(void* h)
   swap_velocity(c);
 }
 
+/* examples/simple.cpp:73-82 frame: src/Renderer.cpp clearCanvas (:14-17), renderGridCellsToCanvas
+ * (:19-56), renderParticlesToCanvas (:141-162) with src/Canvas.cpp fillRectangle / drawPoint
+ * (:62-92), and the float -> byte conversion of writeCanvasToPpm (:217-248). */
+typedef struct { float r, g, b; } Rgb;
+static void canvas_fill_rect(Rgb* px, int W, int H, int x0, int x1, int y0, int y1, Rgb line, Rgb fill)
+{
+  x0 = (int)CLAMPf((float)x0, 0, (float)(W - 1));
+  x1 = (int)CLAMPf((float)x1, 0, (float)(W - 1));
+  y0 = (int)CLAMPf((float)y0, 0, (float)(H - 1));
+  y1 = (int)CLAMPf((float)y1, 0, (float)(H - 1));
+  for (int j = y0; j <= y1; ++j)
+    for (int i = x0; i <= x1; ++i)
+      px[i + (size_t)j * W] = (i == x0 || i == x1 || j == y0 || j == y1) ? line : fill;
+}
+void fso_render_rgb(void* h, int W, int H, float x_min, float x_max, float y_min, float y_max,
+                    uint8_t* rgb)
+{
+  Ctx* c = (Ctx*)h;
+  Rgb* px = (Rgb*)malloc(sizeof(Rgb) * (size_t)W * H);
+  const Rgb white = {1, 1, 1};
+  for (size_t k = 0; k < (size_t)W * H; ++k) px[k] = white;
+  const float scale_x = W / (x_max - x_min);
+  const float scale_y = H / (y_max - y_min);
+  const float translate_x = (float)(0.5 * (x_min * W));
+  const float translate_y = (float)(0.5 * (y_min * H));
+  const float cell_x = c->dx * scale_x;
+  const float cell_y = c->dy * scale_y;
+  for (int j = 0; j < c->ny; ++j)
+    for (int i = 0; i < c->nx; ++i)
+    {
+      const int t = cell_type(c, i, j);
+      Rgb fill;
+      if (t == LIQUID) { fill.r = (float)0.7; fill.g = (float)0.7; fill.b = 1; }
+      else if (t == AIR) { fill = white; }
+      else { fill.r = fill.g = fill.b = (float)0.5; }
+      canvas_fill_rect(px, W, H, (int)(-translate_x + i * cell_x), (int)(-translate_x + (i + 1) * cell_x),
+                       (int)(-translate_y + j * cell_y), (int)(-translate_y + (j + 1) * cell_y), white,
+                       fill);
+    }
+  Rgb blue;
+  blue.r = (float)0.3; blue.g = (float)0.6; blue.b = (float)0.9;
+  for (int64_t q = 0; q < c->n; ++q)
+  {
+    const int pos_x = (int)(-translate_x + scale_x * c->part[4 * q]);
+    const int pos_y = (int)(-translate_y + scale_y * c->part[4 * q + 1]);
+    canvas_fill_rect(px, W, H, pos_x - 3 / 2, pos_x + 3 / 2, pos_y - 3 / 2, pos_y + 3 / 2, blue, blue);
+  }
+  for (size_t k = 0; k < (size_t)W * H; ++k)
+  {
+    rgb[3 * k + 0] = (unsigned char)(CLAMPf(px[k].r, 0, 1) * 255);
+    rgb[3 * k + 1] = (unsigned char)(CLAMPf(px[k].g, 0, 1) * 255);
+    rgb[3 * k + 2] = (unsigned char)(CLAMPf(px[k].b, 0, 1) * 255);
+  }
+  free(px);
+}
+
 /* Eigen ConjugateGradient<SparseMatrix<float>, Lower, DiagonalPreconditioner>
  * restated matrix-free on the compact liquid numbering, in the same operation
  * order as oracle/eigen_shim/Eigen/IterativeLinearSolvers (column sweep over

@@ -68,6 +68,11 @@ void FSX(advect_particles_grid)(void* h, float dt);
 void FSX(add_external_force)(void* h, float fx, float fy, float dt);
 /* transferVelocityToGridGather src/FluidSolver.cpp:816-871 */
 void FSX(p2g_gather)(void* h);
+/* One frame as examples/simple.cpp:73-82 draws it: Renderer::clearCanvas, renderGridCellsToCanvas,
+ * renderParticlesToCanvas (src/Renderer.cpp:14-56,141-162) on a width x height canvas over the
+ * world-space area, converted to bytes like writeCanvasToPpm (:217-248).  rgb: width*height*3. */
+void FSX(render_rgb)(void* h, int width, int height, float x_min, float x_max, float y_min,
+                     float y_max, uint8_t* rgb);
 /* returns 0, or 1 when the reference's validate() would throw */
 int FSX(step)(void* h, int kind, float dt);
 

@@ -8,6 +8,9 @@
 // affects THIS translation unit; the reference translation units are
 // compiled as they are, and GCC lays members out in declaration order
 // regardless of access, so the object layout is the same on both sides.
+#include <unistd.h>
+#include <cstdio>
+#include <cstdlib>
 #include <cassert>
 #include <cmath>
 #include <cstdint>
@@ -25,6 +28,7 @@
 #define protected public
 #include <FluidSolver.h>
 #include <FluidDomain.h>
+#include <Renderer.h>
 #undef private
 #undef protected
 
@@ -214,6 +218,33 @@ void fsr_p2g_gather(void* h)
 {
   C(h)->solver.transferVelocityToGridGather(C(h)->domain.markerParticleSet(),
                                             C(h)->domain.macGrid());
+}
+void fsr_render_rgb(void* h, int width, int height, float x_min, float x_max, float y_min,
+                    float y_max, uint8_t* rgb)
+{
+  // the reference's own frame path, including its PPM writer (read back from a temporary file)
+  RefCtx* c = C(h);
+  Canvas canvas(width, height);
+  Renderer renderer(BBox<MyFloat>{x_min, x_max, y_min, y_max});
+  renderer.clearCanvas(canvas);
+  renderer.renderGridCellsToCanvas(c->domain.macGrid(), canvas);
+  renderer.renderParticlesToCanvas(c->domain.markerParticleSet(), canvas);
+  char path[] = "/tmp/fsr_frame_XXXXXX";
+  const int fd = mkstemp(path);
+  if (fd >= 0) close(fd);
+  renderer.writeCanvasToPpm(path, canvas);
+  FILE* f = fopen(path, "rb");
+  if (f)
+  {
+    int w = 0, hh = 0, mx = 0;
+    if (fscanf(f, "P6\n%d %d\n%d", &w, &hh, &mx) == 3 && w == width && hh == height)
+    {
+      fgetc(f); // the single whitespace after the maxval
+      if (fread(rgb, 1, (size_t)width * height * 3, f) != (size_t)width * height * 3) memset(rgb, 0, 3);
+    }
+    fclose(f);
+  }
+  remove(path);
 }
 int fsr_step(void* h, int kind, float dt)
 {

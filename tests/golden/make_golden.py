@@ -87,6 +87,21 @@ def uncalled_vectors(ref):
     np.savez_compressed(os.path.join(HERE, "uncalled_24x20.npz"), **out)
 
 
+def frame_vectors(ref):
+    """The reference renderer's frame of the initial examples/simple.cpp scene (particles emitted,
+    cells classified; no solver step, so the state is reproducible without the CG)."""
+    n = 64
+    s = ref.sim(n, n, 1.0, 1.0, 0.01, 0.05)
+    s.emit_source(*scenes.dam_break_args(n))
+    s.classify_cells()
+    out = {}
+    for tag, (w, h, area) in {"full": (160, 160, (0, 1, 0, 1)), "zoom": (97, 61, (0.1, 0.6, 0.3, 0.9)),
+                              "wide": (64, 48, (-0.5, 1.5, -0.2, 1.3))}.items():
+        out[f"{tag}_area"] = np.array(area, dtype=np.float32)
+        out[f"{tag}_rgb"] = s.render_rgb(w, h, area)
+    np.savez_compressed(os.path.join(HERE, "frames_config0.npz"), **out)
+
+
 def config0_trace(ref):
     """examples/simple.cpp scene: 64 x 64, one source, dt = 0.01, stepPICFLIP."""
     n = 64
@@ -120,5 +135,6 @@ if __name__ == "__main__":
         stage_vectors(ref)
         config0_trace(ref)
     uncalled_vectors(ref)
+    frame_vectors(ref)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -59,6 +59,7 @@ _SIGS = {
     "step": (_i, [_p, _i, _f]),
     "add_external_force": (None, [_p, _f, _f, _f]),
     "p2g_gather": (None, [_p]),
+    "render_rgb": (None, [_p, _i, _i, _f, _f, _f, _f, _p]),
 }
 
 
@@ -198,6 +199,11 @@ class OracleSim:
 
     def p2g_gather(self):
         self.L._p2g_gather(self.h)
+
+    def render_rgb(self, width, height, area=(0.0, 1.0, 0.0, 1.0)):
+        a = np.zeros((height, width, 3), dtype=np.uint8)
+        self.L._render_rgb(self.h, width, height, *[float(v) for v in area], _ptr(a))
+        return a
 
     def step(self, kind, dt):
         rc = self.L._step(self.h, kind, dt)

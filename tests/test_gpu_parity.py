@@ -473,6 +473,34 @@ def test_uncalled_solver_routines_bit_exact(capi, checkers, nx, ny):
         assert np.array_equal(g.get_particles(), c.get_particles())
 
 
+def test_frames_are_byte_identical_to_the_reference_renderer(capi, checkers, tmp_path):
+    """fsb_render_rgb / fsb_write_ppm against Renderer + Canvas of the reference (compiled into
+    oracle/_ref) and the C restatement: the frame of examples/simple.cpp, full view, odd canvas
+    sizes, a zoomed area and an area larger than the domain (clamped rectangles and points)."""
+    n = 64
+    for chk in checkers:
+        g, c = make_pair(capi, chk, n, n)
+        args = scenes.dam_break_args(n)
+        g.emit_source(*args); c.emit_source(*args)
+        c.classify_cells(); g.classify_cells()
+        for step in range(3):
+            for (w, h, area) in [(400, 400, (0, 1, 0, 1)), (333, 250, (0, 1, 0, 1)),
+                                 (200, 200, (0.2, 0.7, 0.1, 0.9)), (100, 80, (-0.5, 1.5, -0.2, 1.3)),
+                                 (50, 50, (0, 1, 0, 1)), (1, 1, (0, 1, 0, 1))]:
+                a, b = g.render_rgb(w, h, area), c.render_rgb(w, h, area)
+                assert np.array_equal(a, b), (step, w, h, area, int((a != b).sum()))
+            g.step(STEP_PICFLIP, 0.01); c.step(STEP_PICFLIP, 0.01)
+            # keep the two simulations on the same state: frames compare renderers, not solvers
+            g.set_particles(c.get_particles()); g.set_cell_types(c.get_cell_types())
+        path = str(tmp_path / "frame.ppm")
+        g.write_ppm(path, 400, 400)
+        raw = open(path, "rb").read()
+        assert raw.startswith(b"P6\n400 400\n255\n")
+        body = np.frombuffer(raw[len(b"P6\n400 400\n255\n"):], dtype=np.uint8).reshape(400, 400, 3)
+        assert np.array_equal(body, c.render_rgb(400, 400))
+        assert len(np.unique(body.reshape(-1, 3), axis=0)) == 4  # air, liquid, solid, particles
+
+
 def test_state_file_round_trip_continues_bit_identically(capi, tmp_path):
     """fsb_save_state / fsb_load_state: a run continued from a reloaded file equals the
     uninterrupted run bit for bit (labels, grids, particles in the caller's order)."""

@@ -162,6 +162,21 @@ def test_port_matches_golden_uncalled_routines(checkers):
         assert (z["gather_grid0"] != z["force_grid2"]).sum() >= 5  # planted particles were selected
 
 
+def test_port_matches_golden_frames(checkers):
+    """The frame renderer (Renderer + Canvas restated) against frames from the reference's code."""
+    z = np.load(os.path.join(GOLD, "frames_config0.npz"))
+    for chk in checkers:
+        s = chk.sim(64, 64, 1.0, 1.0, 0.01, 0.05)
+        assert s.emit_source(*scenes.dam_break_args(64)) == 7800
+        s.classify_cells()
+        for tag in ("full", "zoom", "wide"):
+            ref_rgb = z[f"{tag}_rgb"]
+            h, w, _ = ref_rgb.shape
+            got = s.render_rgb(w, h, tuple(float(v) for v in z[f"{tag}_area"]))
+            assert np.array_equal(got, ref_rgb), tag
+    assert len(np.unique(z["full_rgb"].reshape(-1, 3), axis=0)) >= 3  # white, solid, particles (+ liquid)
+
+
 def test_validate_rejects_non_square_cells(port):
     s = port.sim(32, 16, 1.0, 1.0)  # dx = 1/32, dy = 1/16 (src/FluidSolver.cpp:56-65,89-97)
     with pytest.raises(RuntimeError):

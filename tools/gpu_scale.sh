@@ -1,7 +1,7 @@
 # strong scaling of the CG-only workload (BASELINE configs[3]) on one 8-GPU box: N = 1, 2, 4, 8
 set -x
 WL=${1:-cg8192}
-for n in 1 2 4 8; do
+for n in ${SCALE_NS:-1 2 4 8}; do
   if [ $n -eq 1 ]; then
     timeout 900 python bench.py --workload $WL --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/scale_${WL}_n$n.json 2> gpurun_out/scale_${WL}_n$n.err
   else
