@@ -237,6 +237,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cg-cap", type=int, default=None, help="override the CG iteration cap (debug)")
+    ap.add_argument("--precond", default="jacobi", choices=["jacobi", "mg"],
+                    help="jacobi: the reference's preconditioner (headline); mg: the opt-in multigrid "
+                         "V-cycle (same system and stopping rule, not the reference's algorithm)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -299,6 +302,8 @@ def main():
     dt = float(np.float32(0.01 * 64.0 / n))
     sim = capi.Sim(n, n, 1.0, 1.0, dt, wl["pic_ratio"], device=local_rank)
     sim.set_cg(wl["cap"], wl["tol"])
+    if args.precond == "mg":
+        sim.set_preconditioner(capi.PRECOND_MULTIGRID)
     cg_only = wl["kind"] == "cg"
     if cg_only:
         lab, u0, v0 = tank_fields(n)
@@ -420,7 +425,7 @@ def main():
                # the e2e steps continue the same simulation: later steps, other iteration counts
                "cg_iters_per_step": e2e_iters / args.steps}
 
-    cg_mode = "graph" if sim.cg_launch_mode() == 1 else "persistent"
+    cg_mode = {1: "graph", 3: "multigrid"}.get(sim.cg_launch_mode(), "persistent")
     if world > 1:
         sim.shard_disconnect()
         dist.barrier()
@@ -453,7 +458,10 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, world)),
                 "traffic_source": NCU_TRAFFIC_SOURCE if (args.workload, world) in NCU_TRAFFIC else None,
-                "kernel": ("k_cg_solve (persistent cooperative kernel, the whole solve is ONE launch): "
+                "kernel": ("OPT-IN multigrid-preconditioned CG iteration (one V-cycle + four sweeps; NOT the "
+                           "reference's Jacobi iteration: the 45 B/cell accounting does not apply)"
+                           if cg_mode == "multigrid" else
+                           "k_cg_solve (persistent cooperative kernel, the whole solve is ONE launch): "
                            "figures are per CG iteration = one direction sweep + one update sweep"
                            if cg_mode != "graph" else
                            "CG iteration = k_cg_direction + k_cg_update (2 launches in a CUDA graph)")
@@ -480,6 +488,8 @@ def main():
         "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg_name, "particles": int(n_part), "dt": dt,
+                   "preconditioner": ("multigrid V-cycle (opt-in)" if args.precond == "mg"
+                                      else "Jacobi (the reference's)"),
                    "l2": (f"inputs larger than L2 ({n_part * 16 / 1e9:.1f} GB particles, "
                           f"{n * n * 4 / 1e6:.0f} MB per grid)")
                    if n >= 4096 else "working set may fit L2: latency-bound, see DESIGN.md",

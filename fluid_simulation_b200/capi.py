@@ -45,6 +45,7 @@ SIGNATURES = {
     "fsb_delta_y": (_f, [_p]),
     "fsb_set_cg": (_i, [_p, _i, _f]),
     "fsb_get_cg_info": (_i, [_p, C.POINTER(_i), C.POINTER(_f)]),
+    "fsb_set_preconditioner": (_i, [_p, _i]),
     "fsb_set_pic_ratio": (_i, [_p, _f]),
     "fsb_set_density": (_i, [_p, _f]),
     "fsb_set_integrator": (_i, [_p, _i]),
@@ -99,6 +100,9 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.argtypes = _args
 
 
+PRECOND_JACOBI, PRECOND_MULTIGRID = 0, 1
+
+
 def version():
     return _lib.fsb_version().decode()
 
@@ -137,6 +141,10 @@ class Sim:
             pass
 
     # parameters
+    def set_preconditioner(self, kind):
+        """PRECOND_JACOBI (the reference's, default) or PRECOND_MULTIGRID (opt-in)."""
+        self._ck(_lib.fsb_set_preconditioner(self.h, kind))
+
     def set_cg(self, max_iters, tol):
         self._ck(_lib.fsb_set_cg(self.h, max_iters, tol))
 

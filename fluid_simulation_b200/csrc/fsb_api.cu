@@ -237,6 +237,7 @@ int fsb_create(fsb_ctx** out, int size_x, int size_y, float length_x, float leng
   c->grav_x = 0.0f;
   c->grav_y = (float)-9.82; // src/FluidSolver.cpp:232
   if (const char* e = getenv("FSB_STAGE_KERNELS")) c->stage_v1 = (strcmp(e, "v1") == 0);
+  if (const char* e = getenv("FSB_MG_MAX_ITERS")) c->mg_max_iters = std::max(1, atoi(e));
   memset(c->prof_ms, 0, sizeof c->prof_ms);
   memset(c->prof_calls, 0, sizeof c->prof_calls);
 
@@ -310,6 +311,7 @@ void fsb_destroy(fsb_ctx* c)
   cudaFree(c->sort_key); cudaFree(c->sort_rank); cudaFree(c->sort_idx);
   for (int k = 0; k < c->n_ipc_opened; ++k) cudaIpcCloseMemHandle(c->ipc_opened[k]);
   cudaFree(c->peer_x_dev); cudaFree(c->mail_local);
+  fsb_mg_free(c);
   cudaFree(c->partials); cudaFree(c->scal); cudaFree(c->stage);
   if (c->scal_h) cudaFreeHost(c->scal_h);
   if (c->cg_graph) cudaGraphExecDestroy(c->cg_graph);
@@ -361,6 +363,14 @@ int fsb_get_cg_info(const fsb_ctx* c, int* iterations, float* error)
   if (!c) return FSB_ERR_INVALID;
   if (iterations) *iterations = c->iters;
   if (error) *error = c->err;
+  return FSB_OK;
+}
+int fsb_set_preconditioner(fsb_ctx* c, int kind)
+{
+  CHECK_CTX(c);
+  if (kind != FSB_PRECOND_JACOBI && kind != FSB_PRECOND_MULTIGRID)
+    return fsb_fail(c, FSB_ERR_INVALID, "unknown preconditioner %d", kind);
+  c->precond = kind;
   return FSB_OK;
 }
 int fsb_set_pic_ratio(fsb_ctx* c, float pic_ratio)
@@ -989,7 +999,9 @@ int fsb_profile_read(fsb_ctx* c, float* ms, int* calls)
 int64_t fsb_launch_count(const fsb_ctx* c) { return c ? c->launches : 0; }
 int fsb_cg_launch_mode(const fsb_ctx* c)
 {
-  if (!c || c->cg_tile_rows == 0) return 0;
+  if (!c) return 0;
+  if (c->last_solve_mg) return 3;
+  if (c->cg_tile_rows == 0) return 0;
   return c->cg_fused ? 2 : 1;
 }
 int fsb_timer_start(fsb_ctx* c)

@@ -2091,21 +2091,25 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     FSB_CUDA(c, cudaMalloc(&c->partials, sizeof(double) * need));
     c->partials_cap = need;
   }
-  if (c->stage_v1)
-    k_cg_build<<<build_blocks, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell, c->cg_code,
-                                                    c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
-                                                    c->tol, c->max_iters);
-  else if (d.pow2 == 3)
-    k_cg_build4<GridDimsP2><<<build_blocks, 256, 0, c->stream>>>(
-        fsb_uf(c), fsb_vf(c), c->cell, c->cg_code, c->cg_x, c->cg_r, as_pow2(d), coef, c->scal,
-        c->partials, c->tol, c->max_iters);
-  else
-    k_cg_build4<GridDims><<<build_blocks, 256, 0, c->stream>>>(
-        fsb_uf(c), fsb_vf(c), c->cell, c->cg_code, c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
-        c->tol, c->max_iters);
-  FSB_LAUNCHED(c);
-  FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[0], c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
-                              c->stream));
+  auto build = [&]() -> int {
+    if (c->stage_v1)
+      k_cg_build<<<build_blocks, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell, c->cg_code,
+                                                      c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
+                                                      c->tol, c->max_iters);
+    else if (d.pow2 == 3)
+      k_cg_build4<GridDimsP2><<<build_blocks, 256, 0, c->stream>>>(
+          fsb_uf(c), fsb_vf(c), c->cell, c->cg_code, c->cg_x, c->cg_r, as_pow2(d), coef, c->scal,
+          c->partials, c->tol, c->max_iters);
+    else
+      k_cg_build4<GridDims><<<build_blocks, 256, 0, c->stream>>>(
+          fsb_uf(c), fsb_vf(c), c->cell, c->cg_code, c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
+          c->tol, c->max_iters);
+    FSB_LAUNCHED(c);
+    FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[0], c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
+                                c->stream));
+    return FSB_OK;
+  };
+  FSB_TRY(build());
   fsb_prof_end(c, FSB_PROF_RHS);
   FSB_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->scal_h[0].n_liquid == 0) // :347-350: nothing touched, no swap
@@ -2116,6 +2120,25 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
   // waits for the poll.  Launches after convergence return immediately.
   fsb_prof_begin(c, FSB_PROF_CG);
   CgScalars fin = c->scal_h[0];
+  c->last_solve_mg = false;
+  if (!fin.done && c->precond == FSB_PRECOND_MULTIGRID && c->shard.world == 1)
+  {
+    // opt-in: multigrid-preconditioned CG (fsb_mg.cu); on breakdown the set-up is repeated
+    // (x = 0, r = b, scalars) and the reference's Jacobi-preconditioned iteration runs instead
+    int converged = 0;
+    FSB_TRY(fsb_k_mg_solve(c, &converged));
+    if (converged)
+    {
+      c->last_solve_mg = true;
+      fin.done = 1;
+    }
+    else
+    {
+      FSB_TRY(build());
+      FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+      fin = c->scal_h[0];
+    }
+  }
   if (!fin.done && c->cg_fused)
   {
     // one persistent kernel runs the loop to completion; no polling
@@ -2184,10 +2207,13 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     }
   }
   fsb_prof_end(c, FSB_PROF_CG);
-  c->iters = fin.iter;
-  c->err = (fin.rhs2 == 0.0 || (float)fin.rhs2 == 0.0f)
-               ? 0.0f
-               : std::sqrt((float)fin.r2 / (float)fin.rhs2);
+  if (!c->last_solve_mg)
+  {
+    c->iters = fin.iter;
+    c->err = (fin.rhs2 == 0.0 || (float)fin.rhs2 == 0.0f)
+                 ? 0.0f
+                 : std::sqrt((float)fin.r2 / (float)fin.rhs2);
+  }
   c->pressure_valid = true;
 
   // ---- patch + swap

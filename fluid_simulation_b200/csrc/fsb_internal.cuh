@@ -79,6 +79,8 @@ struct CgCoef
   float invdiag[5]; // Eigen DiagonalPreconditioner: diag != 0 ? 1/diag : 1
 };
 
+struct fsb_mg_state; // multigrid hierarchy of the opt-in preconditioner (fsb_mg.cu)
+
 struct fsb_ctx
 {
   int nx = 0, ny = 0, ld = 0;
@@ -138,6 +140,11 @@ struct fsb_ctx
   bool cg_pdl = true;    // programmatic dependent launch between the iteration kernels
   int cg_flags = 0;      // tuning bits of the iteration kernels, see configure_cg
   int cg_persist_mb = 0; // L2 set-aside for the residual during a solve (0: none)
+  // preconditioner: FSB_PRECOND_JACOBI (the reference's, default) or FSB_PRECOND_MULTIGRID (opt-in)
+  int precond = 0;
+  int mg_max_iters = 200;    // beyond this the multigrid iteration is abandoned for Jacobi
+  bool last_solve_mg = false;
+  fsb_mg_state* mg = nullptr;
   bool cg_persist_miss_normal = false;
   int cg_grid_fused = 0, cg_fused_stages = 0, cg_fused_stage_bytes = 0;
   int max_iters = 100;
@@ -237,3 +244,6 @@ int fsb_k_emit_source_dev(fsb_ctx* c, int64_t first, const float* xs_dev, const 
 // pressure: fsb_cg.cu
 int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichlet = false);
 void fsb_cg_reconfigure(fsb_ctx* c); // drop the CG launch configuration and graph (sharding changed)
+// multigrid-preconditioned CG (fsb_mg.cu)
+int fsb_k_mg_solve(fsb_ctx* c, int* converged);
+void fsb_mg_free(fsb_ctx* c);

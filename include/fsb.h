@@ -57,6 +57,10 @@ enum { FSB_STEP_SEMILAGRANGIAN = 0, FSB_STEP_PIC = 1, FSB_STEP_FLIP = 2, FSB_STE
 /* include/OdeSolver.h: RK3 :102-113 (the reference's hard-wired choice,
  * include/FluidSolver.h:144), EulerExplicit :78-86 */
 enum { FSB_INTEGRATOR_RK3 = 0, FSB_INTEGRATOR_EULER = 1 };
+/* preconditioner of the pressure CG: Eigen's DiagonalPreconditioner as the reference uses it
+ * (include/FluidSolver.h:114), or -- opt-in, not the reference's algorithm -- one geometric
+ * multigrid V-cycle (fluid_simulation_b200/csrc/fsb_mg.cu) */
+enum { FSB_PRECOND_JACOBI = 0, FSB_PRECOND_MULTIGRID = 1 };
 
 /* ---- life cycle ------------------------------------------------------- */
 
@@ -87,6 +91,11 @@ float fsb_delta_y(const fsb_ctx* ctx);
 /* _cg_solver.setMaxIterations / setTolerance (src/FluidSolver.cpp:81).
  * max_iters < 0 means Eigen's default cap (2 * unknowns). */
 int fsb_set_cg(fsb_ctx* ctx, int max_iters, float tol);
+/* Same system, stopping rule and result; the iteration count drops from O(grid size) to a few
+ * tens.  Single-GPU solves only; if the multigrid iteration breaks down
+ * (scattered single-cell obstacles defeat a geometric hierarchy) the solve is repeated with the
+ * Jacobi preconditioner, so the flag never changes what is computed, only how fast. */
+int fsb_set_preconditioner(fsb_ctx* ctx, int kind);
 /* iterations() and error() of the last solve */
 int fsb_get_cg_info(const fsb_ctx* ctx, int* iterations, float* error);
 /* FluidDomain::setPicRatio (src/FluidDomain.cpp:99-102): clamped to [0,1] */
@@ -241,7 +250,8 @@ int fsb_profile_enable(fsb_ctx* ctx, int on);
 /* ms[FSB_PROF_COUNT], calls[FSB_PROF_COUNT]: totals since the last read */
 int fsb_profile_read(fsb_ctx* ctx, float* ms, int* calls);
 /* launch mode of the pressure solve as configured by the last solve: 0 not configured yet,
- * 1 two kernels per iteration in a CUDA graph, 2 one persistent cooperative kernel */
+ * 1 two kernels per iteration in a CUDA graph, 2 one persistent cooperative kernel,
+ * 3 the last solve was a multigrid-preconditioned CG (FSB_PRECOND_MULTIGRID) */
 int fsb_cg_launch_mode(const fsb_ctx* ctx);
 /* number of kernels this library launched on the context since creation */
 int64_t fsb_launch_count(const fsb_ctx* ctx);

@@ -328,6 +328,99 @@ def test_deferred_x_update_is_bit_identical(capi, monkeypatch, nx, ny):
         assert np.array_equal(xa, xb), (ia, np.abs(xa - xb).max())
 
 
+def _solve(capi, nx, ny, lab, fu, fv, precond, tol=1e-6, cap=200000):
+    g = capi.Sim(nx, ny, 1.0, float(np.float32(ny) / np.float32(nx)), 0.01, 0.05)
+    g.set_preconditioner(precond)
+    g.set_cell_types(lab); g.set_grid(U_FRONT, fu); g.set_grid(V_FRONT, fv)
+    g.set_cg(cap, tol)
+    g.pressure_solve(0.01, 0.01)
+    out = (g.cg_info(), g.get_pressure().astype(np.float64), g.get_grid(U_FRONT), g.cg_launch_mode())
+    g.close()
+    return out
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 64), (130, 67), (256, 256), (520, 300)])
+def test_multigrid_preconditioner_same_solution_far_fewer_iterations(capi, nx, ny):
+    """FSB_PRECOND_MULTIGRID (opt-in): same system, same stopping rule, same
+    pressure field within the solver tolerance as the reference's Jacobi-preconditioned CG, in a
+    few tens of iterations instead of hundreds."""
+    rng = np.random.default_rng(51)
+    lab = scenes.random_labels(nx, ny, rng, p_solid=0.02)
+    fu, fv = scenes.random_field(nx, ny, rng), scenes.random_field(nx, ny, rng)
+    (ij, ej), pj, uj, mj = _solve(capi, nx, ny, lab, fu, fv, capi.PRECOND_JACOBI)
+    (im, em), pm, um, mm = _solve(capi, nx, ny, lab, fu, fv, capi.PRECOND_MULTIGRID)
+    assert mj in (1, 2) and mm == 3
+    assert ej < 1e-6 and em < 1e-6
+    assert im <= 60 and im < ij / 3, (im, ij)
+    assert np.linalg.norm(pm - pj) / np.linalg.norm(pj) < 2e-3
+    assert scenes.field_rel_err(um, uj) < 1e-3
+
+
+def test_multigrid_tank_iteration_count_is_grid_independent(capi):
+    import bench
+    its = []
+    for n in (256, 1024):
+        lab, u, v = bench.tank_fields(n)
+        (im, em), _, _, mm = _solve(capi, n, n, lab, u, v, capi.PRECOND_MULTIGRID)
+        assert mm == 3 and em < 1e-6
+        its.append(im)
+    assert its[1] <= its[0] + 15 and its[1] <= 45, its
+
+
+def _no_isolated_liquid(lab):
+    """A LIQUID cell whose four neighbours are SOLID has an all-zero matrix row (an inconsistent
+    system for any solver): turn such cells SOLID."""
+    nons = np.pad(lab != scenes.SOLID, 1, constant_values=False)
+    cnt = nons[1:-1, :-2].astype(int) + nons[1:-1, 2:] + nons[:-2, 1:-1] + nons[2:, 1:-1]
+    out = lab.copy()
+    out[(lab == scenes.LIQUID) & (cnt == 0)] = scenes.SOLID
+    return out
+
+
+def test_multigrid_falls_back_to_jacobi(capi, monkeypatch):
+    """When the multigrid iteration does not converge within its cap (forced here; scattered
+    single-cell obstacles can do it to a geometric hierarchy) the solve is repeated with the
+    reference's Jacobi preconditioner: the very same iterates as a plain Jacobi run."""
+    rng = np.random.default_rng(52)
+    nx = ny = 128
+    lab = _no_isolated_liquid(scenes.random_labels(nx, ny, rng, p_solid=0.03))
+    fu, fv = scenes.random_field(nx, ny, rng), scenes.random_field(nx, ny, rng)
+    (ij, ej), pj, uj, _ = _solve(capi, nx, ny, lab, fu, fv, capi.PRECOND_JACOBI)
+    monkeypatch.setenv("FSB_MG_MAX_ITERS", "2")
+    (im, em), pm, um, mm = _solve(capi, nx, ny, lab, fu, fv, capi.PRECOND_MULTIGRID)
+    monkeypatch.delenv("FSB_MG_MAX_ITERS")
+    assert mm in (1, 2) and ej < 1e-6 and em < 1e-6
+    assert im == ij and np.array_equal(pm, pj) and np.array_equal(um, uj)
+
+
+def test_multigrid_with_many_obstacles_never_returns_a_wrong_answer(capi):
+    rng = np.random.default_rng(53)
+    nx = ny = 128
+    lab = _no_isolated_liquid(scenes.random_labels(nx, ny, rng, p_solid=0.10))
+    fu, fv = scenes.random_field(nx, ny, rng), scenes.random_field(nx, ny, rng)
+    (ij, ej), pj, uj, _ = _solve(capi, nx, ny, lab, fu, fv, capi.PRECOND_JACOBI)
+    (im, em), pm, um, mm = _solve(capi, nx, ny, lab, fu, fv, capi.PRECOND_MULTIGRID)
+    assert ej < 1e-6 and em < 1e-6, (ej, em, mm)
+    assert np.linalg.norm(pm - pj) / np.linalg.norm(pj) < 2e-3
+
+
+def test_multigrid_full_steps_track_the_jacobi_run(capi):
+    n = 64
+    sims = []
+    for pre in (capi.PRECOND_JACOBI, capi.PRECOND_MULTIGRID):
+        g = capi.Sim(n, n, 1.0, 1.0, 0.01, 0.05)
+        g.set_preconditioner(pre)
+        g.set_cg(20000, 1e-6)
+        g.emit_source(*scenes.dam_break_args(n))
+        for _ in range(5):
+            g.step(STEP_PICFLIP, 0.01)
+        sims.append((g.get_particles(), g.get_cell_types(), g.cg_info()[0]))
+        g.close()
+    (pa, la, ia), (pb, lb, ib) = sims
+    assert np.abs(pa[:, :2] - pb[:, :2]).max() < 1e-3
+    assert ib < ia
+
+
 def test_pressure_patch_exact_given_same_pressure(capi, port):
     """With zero divergence-free input (rhs == 0) the solve returns x = 0 in 0 iterations and
     the patch copies front to back on liquid-touching faces: bit-exact on both sides."""
