@@ -178,7 +178,7 @@ int fsb_add_external_force(fsb_ctx* ctx, float fx, float fy, float dt);
  * particles per face; the device scans the face's 3x3 cells of the cell-sorted set. */
 int fsb_p2g_gather(fsb_ctx* ctx);
 /* (extendVelocityAvarageing :625-707 is not provided: its two-face writes make every sweep
- * depend on the scan order, see DESIGN.md section 8.) */
+ * depend on the scan order, see DESIGN.md section 9.) */
 
 /* ---- fused steps: FluidSolver::step* src/FluidSolver.cpp:99-251 ------- */
 
