@@ -43,6 +43,9 @@ public:
   void setTolerance(MyFloat tolerance) { _tolerance = tolerance; }
   int iterations() const { return _last_iterations; }
   MyFloat error() const { return _last_error; }
+  // opt-in geometric-multigrid preconditioner for the pressure CG (same system and stopping rule,
+  // tens of iterations instead of thousands; the default is the reference's diagonal one)
+  void setMultigridPreconditioner(bool on) { _multigrid = on; }
 
 private:
   void step(FluidDomain& fluid_domain, int kind, MyFloat dt)
@@ -53,6 +56,7 @@ private:
     dev->check(fsb_set_pool(dev->get(), _mem_pool.sizeX(), _mem_pool.sizeY(), _mem_pool.deltaX(),
                             _mem_pool.deltaY()));
     dev->check(fsb_set_cg(dev->get(), _max_iterations, _tolerance));
+    dev->check(fsb_set_preconditioner(dev->get(), _multigrid ? FSB_PRECOND_MULTIGRID : FSB_PRECOND_JACOBI));
     fluid_domain.sync_to_device();
     dev->check(fsb_step(dev->get(), kind, dt));
     fluid_domain.device_changed();
@@ -64,6 +68,7 @@ private:
   MyFloat _tolerance;
   int _last_iterations = 0;
   MyFloat _last_error = 0;
+  bool _multigrid = false;
 };
 
 #endif

@@ -624,6 +624,32 @@ def test_state_file_round_trip_continues_bit_identically(capi, tmp_path):
         b.load_state(str(tmp_path / "missing.fsb"))
 
 
+@pytest.mark.parametrize("kind", [STEP_PICFLIP, STEP_SL])
+def test_edge_cases_empty_set_tiny_grid_and_particles_in_wall_cells(capi, port, kind):
+    """No particles at all on the smallest grid the library accepts, and particles everywhere in
+    the domain including the SOLID border cells (the reference itself asserts on particles outside
+    the domain, include/Grid.h:29, so that is outside the contract) -- against the CPU checker."""
+    g, c = make_pair(capi, port, 3, 3)
+    for s in (g, c):
+        s.step(kind, 0.01)
+    assert np.array_equal(g.get_cell_types(), c.get_cell_types())
+    assert_grids_equal(g, c)
+    g, c = make_pair(capi, port, 16, 16)
+    rng = np.random.default_rng(61)
+    parts = rng.uniform(0.001, 0.999, size=(400, 4)).astype(np.float32)
+    f = {w: scenes.random_field(16, 16, rng, 0.1) for w in (U_FRONT, V_FRONT, U_BACK, V_BACK)}
+    for s in (g, c):
+        for w, a in f.items():
+            s.set_grid(w, a)
+        s.set_particles(parts)
+        s.set_cg(400, 1e-6)
+        s.step(kind, 0.002)
+    assert np.array_equal(g.get_cell_types(), c.get_cell_types())
+    assert np.abs(g.get_particles() - c.get_particles()).max() < 1e-4
+    for w in (U_FRONT, V_FRONT):
+        assert scenes.field_rel_err(g.get_grid(w), c.get_grid(w)) < 1e-3
+
+
 def test_particle_order_is_the_callers(capi):
     rng = np.random.default_rng(13)
     g = capi.Sim(64, 64)
