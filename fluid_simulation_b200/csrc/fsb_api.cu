@@ -312,6 +312,7 @@ void fsb_destroy(fsb_ctx* c)
   for (int k = 0; k < c->n_ipc_opened; ++k) cudaIpcCloseMemHandle(c->ipc_opened[k]);
   cudaFree(c->peer_x_dev); cudaFree(c->mail_local);
   fsb_mg_free(c);
+  cudaFree(c->cg_tile_flags); cudaFree(c->cg_tile_list);
   cudaFree(c->partials); cudaFree(c->scal); cudaFree(c->stage);
   if (c->scal_h) cudaFreeHost(c->scal_h);
   if (c->cg_graph) cudaGraphExecDestroy(c->cg_graph);

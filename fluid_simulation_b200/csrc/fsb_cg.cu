@@ -88,6 +88,8 @@ __device__ __forceinline__ void cg_init_scalars(CgScalars* __restrict__ s, doubl
   s->ticket[0] = 0;
   s->bar_count = 0;
   s->bar_release = 0;
+  s->tile_list = nullptr; // set by k_cg_tile_compact when tile skipping is on
+  s->n_active_tiles = 0;
 }
 
 // src/FluidSolver.cpp:329-346,368-416: stencil code, right-hand side
@@ -343,20 +345,49 @@ struct TileWalk
 {
   int tx, ty, step_x, step_y, tiles_x, count;
   bool rev;
-  __device__ __forceinline__ TileWalk(int first_tile, int stride, int tiles_x_, int n_tiles,
-                                      bool reverse = false)
+  // optional list of ACTIVE tiles (packed ty << 16 | tx, ascending tile order): the walk then runs
+  // over list positions instead of tile numbers, so tiles without a LIQUID cell are never visited
+  const int* list;
+  int pos, stride, n_total;
+  __device__ __forceinline__ TileWalk(int first_tile, int stride_, int tiles_x_, int n_tiles,
+                                      bool reverse = false, const int* list_ = nullptr)
   {
     tiles_x = tiles_x_;
     rev = reverse;
-    count = first_tile < n_tiles ? (n_tiles - 1 - first_tile) / stride + 1 : 0;
-    const int start = reverse ? first_tile + (count - 1) * stride : first_tile;
-    tx = start % tiles_x;
-    ty = start / tiles_x;
-    step_x = stride % tiles_x;
-    step_y = stride / tiles_x;
+    list = list_;
+    stride = stride_;
+    n_total = n_tiles;
+    count = first_tile < n_tiles ? (n_tiles - 1 - first_tile) / stride_ + 1 : 0;
+    const int start = reverse ? first_tile + (count - 1) * stride_ : first_tile;
+    pos = start;
+    step_x = stride_ % tiles_x;
+    step_y = stride_ / tiles_x;
+    tx = 0;
+    ty = 0;
+    if (list)
+    {
+      if (count > 0) decode();
+    }
+    else
+    {
+      tx = start % tiles_x;
+      ty = start / tiles_x;
+    }
+  }
+  __device__ __forceinline__ void decode()
+  {
+    const int t = __ldg(list + pos);
+    tx = t & 0xffff;
+    ty = t >> 16;
   }
   __device__ __forceinline__ void next()
   {
+    if (list)
+    {
+      pos += rev ? -stride : stride;
+      if (pos >= 0 && pos < n_total) decode();
+      return;
+    }
     if (!rev)
     {
       tx += step_x;
@@ -379,6 +410,79 @@ struct TileWalk
     }
   }
 };
+
+// ---- active-tile list: tiles whose interior holds at least one LIQUID cell (code != 0).  All CG
+// vectors are exactly zero on the other tiles and stay zero, so the sweeps skip them: in a tank
+// that is the air cap, in a dam-break scene most of the grid.
+__global__ void __launch_bounds__(128)
+k_cg_tile_flags(const uint8_t* __restrict__ code, int ld, int tiles_x, int th, int row_lo, int row_hi,
+                int* __restrict__ flags)
+{
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int col = tx * kTileW + (int)(threadIdx.x & 7) * 16;
+  int any = 0;
+  if (col < ld)
+    for (int r = threadIdx.x >> 3; r < th; r += 16)
+    {
+      const int row = row_lo + ty * th + r;
+      if (row < row_hi)
+      {
+        const uint4 v = *reinterpret_cast<const uint4*>(code + col + (size_t)row * ld);
+        any |= (v.x | v.y | v.z | v.w) != 0u;
+      }
+    }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flags[blockIdx.x] = any ? 1 : 0;
+}
+
+// ordered compaction by one CTA (the list order fixes which CTA sums which tile: deterministic)
+__global__ void __launch_bounds__(1024)
+k_cg_tile_compact(const int* __restrict__ flags, int n_tiles, int tiles_x, int* __restrict__ list,
+                  CgScalars* __restrict__ s)
+{
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < n_tiles; c0 += 1024)
+  {
+    const int t = c0 + (int)threadIdx.x;
+    const int f = (t < n_tiles) ? flags[t] : 0;
+    int incl = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0)
+    {
+      int w = s_warp[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const int v = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += v;
+      }
+      s_warp[lane] = wi - w; // exclusive offset of warp `lane`
+    }
+    __syncthreads();
+    const int base = s_base;
+    const int ex = base + s_warp[wid] + incl - f;
+    if (f) list[ex] = ((t / tiles_x) << 16) | (t % tiles_x);
+    __syncthreads();
+    if (threadIdx.x == 1023) s_base = ex + f;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+  {
+    s->n_active_tiles = s_base;
+    s->tile_list = list;
+  }
+}
 
 // new direction for four cells: z + beta p_old with z = invdiag r
 __device__ __forceinline__ float4 direction4(const float4 r4, const float4 p4, uint32_t c4,
@@ -740,13 +844,15 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
   if (s->done) return;
   const bool first = (s->iter == 0);
   const float beta = first ? 0.0f : s->beta;
+  const int* __restrict__ tile_list = s->tile_list;
+  const int n_walk = tile_list ? s->n_active_tiles : n_tiles;
 
   if (warp == NW)
   {
     // ---- producer
     if (lane == 0)
     {
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, reverse != 0);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list);
       int st = 0, round = 0;
       for (int tk = 0; tk < t.count; ++tk, t.next())
       {
@@ -774,7 +880,7 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
   const int hco = r0 * kCodeW + (lane == 31 ? 16 + kTileW : 15);
   const bool edge = (lane == 0 || lane == 31);
   double acc[1] = {0.0};
-  TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, reverse != 0);
+  TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list);
   int st = 0, round = 0;
   bool pushed = false; // CTA-uniform: one of this CTA's tiles holds a slab boundary row with a peer
   const int last_ty = n_tiles / tiles_x - 1;
@@ -894,12 +1000,14 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
   if (s->done) return;
   const float alpha = s->abs_new / (float)s->pq; // Eigen: alpha = absNew / p.dot(tmp)
   const float nalpha = -alpha;
+  const int* __restrict__ tile_list = s->tile_list;
+  const int n_walk = tile_list ? s->n_active_tiles : n_tiles;
 
   if (warp == NW)
   {
     if (lane == 0)
     {
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, reverse != 0);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list);
       int st = 0, round = 0;
       for (int tk = 0; tk < t.count; ++tk, t.next())
       {
@@ -925,7 +1033,7 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
   const int hfo = r0 * kHaloW + (lane == 31 ? 4 + kTileW : 3);
   const bool edge = (lane == 0 || lane == 31);
   double acc[2] = {0.0, 0.0};
-  TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, reverse != 0);
+  TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list);
   int st = 0, round = 0;
   bool pushed = false;
   const int last_ty = n_tiles / tiles_x - 1;
@@ -1315,6 +1423,8 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
   }
   __syncthreads();
   unsigned phase_id = 0;
+  const int* __restrict__ tile_list = s->tile_list; // fixed for the whole solve
+  const int n_walk = tile_list ? s->n_active_tiles : n_tiles;
 
   if (warp == NW)
   {
@@ -1367,7 +1477,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
     };
     for (;;)
     {
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, serp && kind == 1);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, serp && kind == 1, tile_list);
       // 1. the dependent load of the tiles that were started before the barrier
       RingPos q = pre;
       int k = 0;
@@ -1391,7 +1501,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       pre = rp;
       if (prefetch)
       {
-        TileWalk tn(blockIdx.x, gridDim.x, tiles_x, n_tiles, serp && nkind == 1);
+        TileWalk tn(blockIdx.x, gridDim.x, tiles_x, n_walk, serp && nkind == 1, tile_list);
         const int want = min(stages, tn.count);
         for (; npre < want; ++npre, tn.next())
         {
@@ -1415,7 +1525,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       if (done)
       {
         // nobody will consume the started tiles: complete them before the CTA may exit
-        TileWalk tn(blockIdx.x, gridDim.x, tiles_x, n_tiles, serp && kind == 1);
+        TileWalk tn(blockIdx.x, gridDim.x, tiles_x, n_walk, serp && kind == 1, tile_list);
         RingPos w = pre;
         for (int m = 0; m < npre; ++m, tn.next())
         {
@@ -1458,7 +1568,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       float* push_hi = push.p_hi[cur ^ 1];
       double acc[1] = {0.0};
       bool pushed = false;
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, false);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, false, tile_list);
       for (int tk = 0; tk < t.count; ++tk, t.next())
       {
         const unsigned char* base = smem + rp.st * stage_bytes;
@@ -1518,7 +1628,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       const float alpha = ss.alpha, nalpha = -alpha;
       double acc[2] = {0.0, 0.0};
       bool pushed = false;
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, serp);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, serp, tile_list);
       for (int tk = 0; tk < t.count; ++tk, t.next())
       {
         const unsigned char* base = smem + rp.st * stage_bytes;
@@ -1611,7 +1721,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
     // the solve ended on an even iteration: x += alpha p of that iteration.  Same tile -> thread
     // mapping as the phases (this thread wrote these p and x elements itself); p is exactly zero
     // outside LIQUID cells, so masked cells keep x = 0.
-    TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_tiles, false);
+    TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, false, tile_list);
     for (int tk = 0; tk < t.count; ++tk, t.next())
     {
       const int ci = t.tx * kTileW + (int)lane * 4;
@@ -1845,6 +1955,7 @@ int configure_cg(fsb_ctx* c)
     c->cg_persist_mb = 0;
     if (const char* e = getenv("FSB_CG_PERSIST_MB")) c->cg_persist_mb = std::max(0, atoi(e));
     c->cg_persist_miss_normal = knob("FSB_CG_PERSIST_MISS_NORMAL", 0);
+    c->cg_skip_tiles = knob("FSB_CG_SKIP_TILES", 1);
     c->cg_flags = (knob("FSB_CG_SERP", 1) ? 1 : 0) | (knob("FSB_CG_XHINT", 0) ? 2 : 0) |
                   (knob("FSB_CG_PREFETCH", 1) ? 4 : 0) | (knob("FSB_CG_PHINT", 0) ? 8 : 0) |
                   (keep << 4) | (knob("FSB_CG_XDEFER", 1) ? 128 : 0);
@@ -2105,6 +2216,28 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
           fsb_uf(c), fsb_vf(c), c->cell, c->cg_code, c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
           c->tol, c->max_iters);
     FSB_LAUNCHED(c);
+    if (c->cg_skip_tiles)
+    {
+      // active-tile list of this rank's slab (tiles of the configured height)
+      const int th = c->cg_tile_rows;
+      const int tiles_x = fsb_div_up(c->ld, kTileW);
+      const int n_t = tiles_x * fsb_div_up(c->shard.row_hi - c->shard.row_lo, th);
+      if (n_t > c->cg_tile_cap)
+      {
+        if (c->cg_tile_flags) cudaFree(c->cg_tile_flags);
+        if (c->cg_tile_list) cudaFree(c->cg_tile_list);
+        c->cg_tile_flags = c->cg_tile_list = nullptr;
+        FSB_CUDA(c, cudaMalloc(&c->cg_tile_flags, sizeof(int) * n_t));
+        FSB_CUDA(c, cudaMalloc(&c->cg_tile_list, sizeof(int) * n_t));
+        c->cg_tile_cap = n_t;
+      }
+      k_cg_tile_flags<<<n_t, 128, 0, c->stream>>>(c->cg_code, c->ld, tiles_x, th, c->shard.row_lo,
+                                                  c->shard.row_hi, c->cg_tile_flags);
+      FSB_LAUNCHED(c);
+      k_cg_tile_compact<<<1, 1024, 0, c->stream>>>(c->cg_tile_flags, n_t, tiles_x, c->cg_tile_list,
+                                                   c->scal);
+      FSB_LAUNCHED(c);
+    }
     FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[0], c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
                                 c->stream));
     return FSB_OK;
@@ -2134,6 +2267,11 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     }
     else
     {
+      // the abandoned iteration may have left non-finite values in the direction buffers,
+      // which the sweeps expect to be zero outside the active tiles
+      const size_t bytes = sizeof(float) * (size_t)c->ld * c->ny;
+      FSB_CUDA(c, cudaMemsetAsync(c->cg_p[0], 0, bytes, c->stream));
+      FSB_CUDA(c, cudaMemsetAsync(c->cg_p[1], 0, bytes, c->stream));
       FSB_TRY(build());
       FSB_CUDA(c, cudaStreamSynchronize(c->stream));
       fin = c->scal_h[0];
@@ -2207,6 +2345,15 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     }
   }
   fsb_prof_end(c, FSB_PROF_CG);
+  if (c->cg_skip_tiles)
+  {
+    // skipped tiles rely on the direction buffers being zero there: leave them zero for the next
+    // solve (whose liquid region differs).  Done here, after the end-of-solve barrier of a sharded
+    // run, because a peer may store its first boundary row before this rank starts its next solve.
+    const size_t bytes = sizeof(float) * (size_t)c->ld * c->ny;
+    FSB_CUDA(c, cudaMemsetAsync(c->cg_p[0], 0, bytes, c->stream));
+    FSB_CUDA(c, cudaMemsetAsync(c->cg_p[1], 0, bytes, c->stream));
+  }
   if (!c->last_solve_mg)
   {
     c->iters = fin.iter;

@@ -42,6 +42,9 @@ struct CgScalars
   // software grid barrier of the persistent solve kernel: arrivals so far / last released phase
   unsigned int bar_count;
   unsigned int bar_release;
+  // active-tile list of the solve (tiles with at least one LIQUID cell); null: all tiles
+  const int* tile_list;
+  int n_active_tiles;
 };
 
 // ---------------------------------------------------------------------------
@@ -146,6 +149,10 @@ struct fsb_ctx
   bool last_solve_mg = false;
   fsb_mg_state* mg = nullptr;
   bool cg_persist_miss_normal = false;
+  bool cg_skip_tiles = true; // sweeps visit only tiles that hold a LIQUID cell
+  int* cg_tile_flags = nullptr;
+  int* cg_tile_list = nullptr;
+  int cg_tile_cap = 0;
   int cg_grid_fused = 0, cg_fused_stages = 0, cg_fused_stage_bytes = 0;
   int max_iters = 100;
   float tol = 1.1920929e-7f;

@@ -255,8 +255,10 @@ CG_MODES = [
     dict(FSB_CG_MODE="fused", FSB_CG_XDEFER="0"),
     dict(FSB_CG_MODE="fused", FSB_CG_KEEP="1", FSB_CG_XHINT="1", FSB_CG_PHINT="1"),
     dict(FSB_CG_MODE="fused", FSB_CG_PERSIST_MB="4"),
+    dict(FSB_CG_MODE="fused", FSB_CG_SKIP_TILES="0"),
+    dict(FSB_CG_MODE="graph", FSB_CG_SKIP_TILES="0"),
 ]
-CG_KNOBS = ("FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH", "FSB_CG_XHINT", "FSB_CG_TILE_ROWS",
+CG_KNOBS = ("FSB_CG_SKIP_TILES", "FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH", "FSB_CG_XHINT", "FSB_CG_TILE_ROWS",
             "FSB_CG_STAGES", "FSB_CG_XDEFER", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB")
 
 
@@ -419,6 +421,34 @@ def test_multigrid_full_steps_track_the_jacobi_run(capi):
     (pa, la, ia), (pb, lb, ib) = sims
     assert np.abs(pa[:, :2] - pb[:, :2]).max() < 1e-3
     assert ib < ia
+
+
+@pytest.mark.parametrize("mode", ["fused", "graph"])
+def test_active_tile_list_changes_nothing_but_the_work(capi, monkeypatch, mode):
+    """The CG sweeps visit only tiles that hold a LIQUID cell.  A dam-break scene (two thirds of the
+    grid AIR) stepped several times -- the liquid region moves, tiles become active and inactive --
+    must give the same bits as sweeping every tile."""
+    n = 520  # several tile columns and rows, ragged on both sides
+    out = []
+    for skip in ("1", "0"):
+        for k in CG_KNOBS:
+            monkeypatch.delenv(k, raising=False)
+        monkeypatch.setenv("FSB_CG_MODE", mode)
+        monkeypatch.setenv("FSB_CG_SKIP_TILES", skip)
+        g = capi.Sim(n, n, 1.0, 1.0, 0.01, 0.05)
+        g.set_cg(300, 1e-6)
+        g.emit_source(*scenes.dam_break_args(n))
+        its = []
+        for _ in range(4):
+            g.step(STEP_PICFLIP, 0.004)
+            its.append(g.cg_info())
+        out.append((its, g.get_pressure(), g.get_particles(), g.get_grid(U_FRONT)))
+        g.close()
+    for k in ("FSB_CG_MODE", "FSB_CG_SKIP_TILES"):
+        monkeypatch.delenv(k)
+    assert out[0][0] == out[1][0]
+    for a, b in zip(out[0][1:], out[1][1:]):
+        assert np.array_equal(a, b)
 
 
 def test_pressure_patch_exact_given_same_pressure(capi, port):
