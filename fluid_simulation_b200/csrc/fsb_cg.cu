@@ -2253,6 +2253,10 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
   // waits for the poll.  Launches after convergence return immediately.
   fsb_prof_begin(c, FSB_PROF_CG);
   CgScalars fin = c->scal_h[0];
+  if (getenv("FSB_CG_VERBOSE"))
+    fprintf(stderr, "[fsb] solve: %d liquid cells, active tiles %d (list %s), tile rows %d, mode %s\n",
+            fin.n_liquid, fin.n_active_tiles, fin.tile_list ? "on" : "off", c->cg_tile_rows,
+            c->cg_fused ? "persistent" : "graph");
   c->last_solve_mg = false;
   if (!fin.done && c->precond == FSB_PRECOND_MULTIGRID && c->shard.world == 1)
   {
