@@ -90,6 +90,7 @@ __device__ __forceinline__ void cg_init_scalars(CgScalars* __restrict__ s, doubl
   s->bar_release = 0;
   s->tile_list = nullptr; // set by k_cg_tile_compact when tile skipping is on
   s->n_active_tiles = 0;
+  s->n_prefix_tiles = 0;
 }
 
 // src/FluidSolver.cpp:329-346,368-416: stencil code, right-hand side
@@ -345,21 +346,29 @@ struct TileWalk
 {
   int tx, ty, step_x, step_y, tiles_x, count;
   bool rev;
-  // optional list of ACTIVE tiles (packed ty << 16 | tx, ascending tile order): the walk then runs
-  // over list positions instead of tile numbers, so tiles without a LIQUID cell are never visited
+  // optional list of ACTIVE tiles (packed ty << 16 | tx): the walk then runs over list positions
+  // instead of tile numbers, so tiles without a LIQUID cell are never visited.  The first `prefix`
+  // list entries (a slab's boundary-row tiles in a sharded solve) are visited FIRST in both walk
+  // directions: their rows go to the neighbour GPUs while the rest of the sweep is still running,
+  // so the system-scope fence before the reduction finds the peer stores already acknowledged.
   const int* list;
-  int pos, stride, n_total;
+  int first, stride, n_total, k, n_pre;
   __device__ __forceinline__ TileWalk(int first_tile, int stride_, int tiles_x_, int n_tiles,
-                                      bool reverse = false, const int* list_ = nullptr)
+                                      bool reverse = false, const int* list_ = nullptr,
+                                      int prefix = 0)
   {
     tiles_x = tiles_x_;
     rev = reverse;
     list = list_;
+    first = first_tile;
     stride = stride_;
     n_total = n_tiles;
+    k = 0;
     count = first_tile < n_tiles ? (n_tiles - 1 - first_tile) / stride_ + 1 : 0;
+    // this CTA's list positions below `prefix`
+    n_pre = (list && first_tile < prefix) ? (prefix - 1 - first_tile) / stride_ + 1 : 0;
+    if (n_pre > count) n_pre = count;
     const int start = reverse ? first_tile + (count - 1) * stride_ : first_tile;
-    pos = start;
     step_x = stride_ % tiles_x;
     step_y = stride_ / tiles_x;
     tx = 0;
@@ -374,9 +383,16 @@ struct TileWalk
       ty = start / tiles_x;
     }
   }
+  // list position of the k-th tile of this CTA: prefix entries ascending, then the rest in walk order
+  __device__ __forceinline__ int position() const
+  {
+    if (k < n_pre) return first + k * stride;
+    const int m = k - n_pre; // m-th of the (count - n_pre) non-prefix entries
+    return rev ? first + (count - 1 - m) * stride : first + (n_pre + m) * stride;
+  }
   __device__ __forceinline__ void decode()
   {
-    const int t = __ldg(list + pos);
+    const int t = __ldg(list + position());
     tx = t & 0xffff;
     ty = t >> 16;
   }
@@ -384,8 +400,8 @@ struct TileWalk
   {
     if (list)
     {
-      pos += rev ? -stride : stride;
-      if (pos >= 0 && pos < n_total) decode();
+      ++k;
+      if (k < count) decode();
       return;
     }
     if (!rev)
@@ -435,51 +451,66 @@ k_cg_tile_flags(const uint8_t* __restrict__ code, int ld, int tiles_x, int th, i
   if (threadIdx.x == 0) flags[blockIdx.x] = any ? 1 : 0;
 }
 
-// ordered compaction by one CTA (the list order fixes which CTA sums which tile: deterministic)
+// ordered compaction by one CTA (the list order fixes which CTA sums which tile: deterministic).
+// boundary_first: the active tiles of the slab's first and last tile row go to the front of the
+// list (TileWalk's prefix), then all other active tiles in tile order.
 __global__ void __launch_bounds__(1024)
 k_cg_tile_compact(const int* __restrict__ flags, int n_tiles, int tiles_x, int* __restrict__ list,
-                  CgScalars* __restrict__ s)
+                  CgScalars* __restrict__ s, int boundary_first)
 {
   __shared__ int s_warp[32];
   __shared__ int s_base;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int last_ty = n_tiles / tiles_x - 1;
   if (threadIdx.x == 0) s_base = 0;
   __syncthreads();
-  for (int c0 = 0; c0 < n_tiles; c0 += 1024)
+  int n_prefix = 0;
+  for (int pass = boundary_first ? 0 : 1; pass < 2; ++pass)
   {
-    const int t = c0 + (int)threadIdx.x;
-    const int f = (t < n_tiles) ? flags[t] : 0;
-    int incl = f;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
+    for (int c0 = 0; c0 < n_tiles; c0 += 1024)
     {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    if (wid == 0)
-    {
-      int w = s_warp[lane], wi = w;
+      const int t = c0 + (int)threadIdx.x;
+      int f = (t < n_tiles) ? flags[t] : 0;
+      if (boundary_first && t < n_tiles)
+      {
+        const int ty = t / tiles_x;
+        const bool edge = (ty == 0 || ty == last_ty);
+        if (edge != (pass == 0)) f = 0;
+      }
+      int incl = f;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1)
       {
-        const int v = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= o) wi += v;
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
       }
-      s_warp[lane] = wi - w; // exclusive offset of warp `lane`
+      if (lane == 31) s_warp[wid] = incl;
+      __syncthreads();
+      if (wid == 0)
+      {
+        int w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          const int v = __shfl_up_sync(0xffffffffu, wi, o);
+          if (lane >= o) wi += v;
+        }
+        s_warp[lane] = wi - w; // exclusive offset of warp `lane`
+      }
+      __syncthreads();
+      const int base = s_base;
+      const int ex = base + s_warp[wid] + incl - f;
+      if (f) list[ex] = ((t / tiles_x) << 16) | (t % tiles_x);
+      __syncthreads();
+      if (threadIdx.x == 1023) s_base = ex + f;
+      __syncthreads();
     }
-    __syncthreads();
-    const int base = s_base;
-    const int ex = base + s_warp[wid] + incl - f;
-    if (f) list[ex] = ((t / tiles_x) << 16) | (t % tiles_x);
-    __syncthreads();
-    if (threadIdx.x == 1023) s_base = ex + f;
-    __syncthreads();
+    if (pass == 0) n_prefix = s_base;
   }
   if (threadIdx.x == 0)
   {
     s->n_active_tiles = s_base;
+    s->n_prefix_tiles = n_prefix;
     s->tile_list = list;
   }
 }
@@ -846,13 +877,14 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
   const float beta = first ? 0.0f : s->beta;
   const int* __restrict__ tile_list = s->tile_list;
   const int n_walk = tile_list ? s->n_active_tiles : n_tiles;
+  const int n_prefix = tile_list ? s->n_prefix_tiles : 0;
 
   if (warp == NW)
   {
     // ---- producer
     if (lane == 0)
     {
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list, n_prefix);
       int st = 0, round = 0;
       for (int tk = 0; tk < t.count; ++tk, t.next())
       {
@@ -880,7 +912,7 @@ k_cg_direction(const __grid_constant__ CgMaps maps, float* __restrict__ p_new, i
   const int hco = r0 * kCodeW + (lane == 31 ? 16 + kTileW : 15);
   const bool edge = (lane == 0 || lane == 31);
   double acc[1] = {0.0};
-  TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list);
+  TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list, n_prefix);
   int st = 0, round = 0;
   bool pushed = false; // CTA-uniform: one of this CTA's tiles holds a slab boundary row with a peer
   const int last_ty = n_tiles / tiles_x - 1;
@@ -1002,12 +1034,13 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
   const float nalpha = -alpha;
   const int* __restrict__ tile_list = s->tile_list;
   const int n_walk = tile_list ? s->n_active_tiles : n_tiles;
+  const int n_prefix = tile_list ? s->n_prefix_tiles : 0;
 
   if (warp == NW)
   {
     if (lane == 0)
     {
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list, n_prefix);
       int st = 0, round = 0;
       for (int tk = 0; tk < t.count; ++tk, t.next())
       {
@@ -1033,7 +1066,7 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
   const int hfo = r0 * kHaloW + (lane == 31 ? 4 + kTileW : 3);
   const bool edge = (lane == 0 || lane == 31);
   double acc[2] = {0.0, 0.0};
-  TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list);
+  TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, reverse != 0, tile_list, n_prefix);
   int st = 0, round = 0;
   bool pushed = false;
   const int last_ty = n_tiles / tiles_x - 1;
@@ -1425,6 +1458,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
   unsigned phase_id = 0;
   const int* __restrict__ tile_list = s->tile_list; // fixed for the whole solve
   const int n_walk = tile_list ? s->n_active_tiles : n_tiles;
+  const int n_prefix = tile_list ? s->n_prefix_tiles : 0;
 
   if (warp == NW)
   {
@@ -1477,7 +1511,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
     };
     for (;;)
     {
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, serp && kind == 1, tile_list);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, serp && kind == 1, tile_list, n_prefix);
       // 1. the dependent load of the tiles that were started before the barrier
       RingPos q = pre;
       int k = 0;
@@ -1501,7 +1535,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       pre = rp;
       if (prefetch)
       {
-        TileWalk tn(blockIdx.x, gridDim.x, tiles_x, n_walk, serp && nkind == 1, tile_list);
+        TileWalk tn(blockIdx.x, gridDim.x, tiles_x, n_walk, serp && nkind == 1, tile_list, n_prefix);
         const int want = min(stages, tn.count);
         for (; npre < want; ++npre, tn.next())
         {
@@ -1525,7 +1559,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       if (done)
       {
         // nobody will consume the started tiles: complete them before the CTA may exit
-        TileWalk tn(blockIdx.x, gridDim.x, tiles_x, n_walk, serp && kind == 1, tile_list);
+        TileWalk tn(blockIdx.x, gridDim.x, tiles_x, n_walk, serp && kind == 1, tile_list, n_prefix);
         RingPos w = pre;
         for (int m = 0; m < npre; ++m, tn.next())
         {
@@ -1568,7 +1602,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       float* push_hi = push.p_hi[cur ^ 1];
       double acc[1] = {0.0};
       bool pushed = false;
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, false, tile_list);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, false, tile_list, n_prefix);
       for (int tk = 0; tk < t.count; ++tk, t.next())
       {
         const unsigned char* base = smem + rp.st * stage_bytes;
@@ -1628,7 +1662,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
       const float alpha = ss.alpha, nalpha = -alpha;
       double acc[2] = {0.0, 0.0};
       bool pushed = false;
-      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, serp, tile_list);
+      TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, serp, tile_list, n_prefix);
       for (int tk = 0; tk < t.count; ++tk, t.next())
       {
         const unsigned char* base = smem + rp.st * stage_bytes;
@@ -1721,7 +1755,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
     // the solve ended on an even iteration: x += alpha p of that iteration.  Same tile -> thread
     // mapping as the phases (this thread wrote these p and x elements itself); p is exactly zero
     // outside LIQUID cells, so masked cells keep x = 0.
-    TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, false, tile_list);
+    TileWalk t(blockIdx.x, gridDim.x, tiles_x, n_walk, false, tile_list, n_prefix);
     for (int tk = 0; tk < t.count; ++tk, t.next())
     {
       const int ci = t.tx * kTileW + (int)lane * 4;
@@ -1956,6 +1990,10 @@ int configure_cg(fsb_ctx* c)
     if (const char* e = getenv("FSB_CG_PERSIST_MB")) c->cg_persist_mb = std::max(0, atoi(e));
     c->cg_persist_miss_normal = knob("FSB_CG_PERSIST_MISS_NORMAL", 0);
     c->cg_skip_tiles = knob("FSB_CG_SKIP_TILES", 1);
+    // measured on 2 B200 (profiles/r01i_notes.md): no gain (68.4 vs 68.1 us at 4096^2, 202.2 vs
+    // 201.1 us at 8192^2) -- the system-scope fence after the boundary stores is not what the
+    // sharded iteration waits for; kept as a knob
+    c->cg_edge_first = knob("FSB_CG_EDGE_FIRST", 0);
     c->cg_flags = (knob("FSB_CG_SERP", 1) ? 1 : 0) | (knob("FSB_CG_XHINT", 0) ? 2 : 0) |
                   (knob("FSB_CG_PREFETCH", 1) ? 4 : 0) | (knob("FSB_CG_PHINT", 0) ? 8 : 0) |
                   (keep << 4) | (knob("FSB_CG_XDEFER", 1) ? 128 : 0);
@@ -2235,7 +2273,7 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
                                                   c->shard.row_hi, c->cg_tile_flags);
       FSB_LAUNCHED(c);
       k_cg_tile_compact<<<1, 1024, 0, c->stream>>>(c->cg_tile_flags, n_t, tiles_x, c->cg_tile_list,
-                                                   c->scal);
+                                                   c->scal, (c->shard.world > 1 && c->cg_edge_first) ? 1 : 0);
       FSB_LAUNCHED(c);
     }
     FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[0], c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,

@@ -45,6 +45,7 @@ struct CgScalars
   // active-tile list of the solve (tiles with at least one LIQUID cell); null: all tiles
   const int* tile_list;
   int n_active_tiles;
+  int n_prefix_tiles; // leading list entries that every walk visits first (slab boundary rows)
 };
 
 // ---------------------------------------------------------------------------
@@ -150,6 +151,7 @@ struct fsb_ctx
   fsb_mg_state* mg = nullptr;
   bool cg_persist_miss_normal = false;
   bool cg_skip_tiles = true; // sweeps visit only tiles that hold a LIQUID cell
+  bool cg_edge_first = false; // sharded solves: slab boundary tiles first in every sweep (knob)
   int* cg_tile_flags = nullptr;
   int* cg_tile_list = nullptr;
   int cg_tile_cap = 0;

@@ -72,9 +72,12 @@ CONFIGS = [
     ("fused keep=1 xhint phint", dict(FSB_CG_MODE="fused", FSB_CG_KEEP="1", FSB_CG_XHINT="1",
                                       FSB_CG_PHINT="1")),                                      # 33
     ("fused phint", dict(FSB_CG_MODE="fused", FSB_CG_PHINT="1")),                              # 34
+    # sharded solves: slab boundary tiles first in every sweep (default) vs natural order
+    ("two-kernel edge-first=0", dict(FSB_CG_MODE="graph", FSB_CG_EDGE_FIRST="0")),             # 35
+    ("fused edge-first=0", dict(FSB_CG_MODE="fused", FSB_CG_EDGE_FIRST="0")),                  # 36
 ]
 KNOBS = ["FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH", "FSB_CG_XHINT", "FSB_CG_CTAS_PER_SM",
-         "FSB_CG_TILE_ROWS", "FSB_CG_STAGES", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB", "FSB_CG_PERSIST_MISS_NORMAL", "FSB_CG_XDEFER"]
+         "FSB_CG_TILE_ROWS", "FSB_CG_STAGES", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB", "FSB_CG_PERSIST_MISS_NORMAL", "FSB_CG_XDEFER", "FSB_CG_EDGE_FIRST", "FSB_CG_SKIP_TILES"]
 
 
 def main():
