@@ -86,6 +86,20 @@ SIGNATURES = {
     "fsb_shard_connect": (_i, [_p, _i, _i, _p]),
     "fsb_shard_disconnect": (_i, [_p]),
     "fsb_shard_rows": (_i, [_p, C.POINTER(_i), C.POINTER(_i)]),
+    "fsb_slab_configure": (_i, [_p, _i, _i]),
+    "fsb_slab_rows": (_i, [_p, C.POINTER(_i), C.POINTER(_i)]),
+    "fsb_slab_add": (_i, [_p, _p, _p, _l]),
+    "fsb_slab_sort_out": (_i, [_p, C.POINTER(_l)]),
+    "fsb_slab_take": (_i, [_p, _i, _p, _p]),
+    "fsb_slab_keep_own": (_i, [_p]),
+    "fsb_slab_boundary": (_i, [_p, _i, C.POINTER(_l)]),
+    "fsb_slab_boundary_take": (_i, [_p, _p, _p]),
+    "fsb_slab_get": (_i, [_p, _p, _p]),
+    "fsb_get_rows": (_i, [_p, _i, _i, _i, _p]),
+    "fsb_set_rows": (_i, [_p, _i, _i, _i, _p]),
+    "fsb_slab_step_a": (_i, [_p, _i]),
+    "fsb_slab_step_b": (_i, [_p, _i, _f]),
+    "fsb_slab_step_c": (_i, [_p, _i, _f]),
     "fsb_profile_enable": (_i, [_p, _i]),
     "fsb_profile_read": (_i, [_p, _p, _p]),
     "fsb_launch_count": (_l, [_p]),
@@ -101,6 +115,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 
 PRECOND_JACOBI, PRECOND_MULTIGRID = 0, 1
+ROWS_LABELS = 8
 
 
 def version():
@@ -327,6 +342,64 @@ class Sim:
     def write_ppm(self, path, width, height, area=(0.0, 1.0, 0.0, 1.0)):
         self._ck(_lib.fsb_write_ppm(self.h, os.fsencode(path), width, height,
                                     *[float(v) for v in area]))
+
+    # particle slabs (one rank's view; see sharding.py for the exchanges)
+    def slab_configure(self, rank, world):
+        self._ck(_lib.fsb_slab_configure(self.h, rank, world))
+        lo, hi = _i(), _i()
+        self._ck(_lib.fsb_slab_rows(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def slab_add(self, parts, ids):
+        parts = np.ascontiguousarray(parts, dtype=np.float32).reshape(-1, 4)
+        ids = np.ascontiguousarray(ids, dtype=np.int32).reshape(-1)
+        assert parts.shape[0] == ids.shape[0]
+        self._ck(_lib.fsb_slab_add(self.h, _ptr(parts), _ptr(ids), parts.shape[0]))
+
+    def slab_sort_out(self, world):
+        counts = (_l * world)()
+        self._ck(_lib.fsb_slab_sort_out(self.h, counts))
+        return [int(v) for v in counts]
+
+    def slab_take(self, dest, n):
+        parts, ids = np.empty((n, 4), dtype=np.float32), np.empty(n, dtype=np.int32)
+        self._ck(_lib.fsb_slab_take(self.h, dest, _ptr(parts), _ptr(ids)))
+        return parts, ids
+
+    def slab_keep_own(self):
+        self._ck(_lib.fsb_slab_keep_own(self.h))
+
+    def slab_boundary(self, side):
+        n = _l()
+        self._ck(_lib.fsb_slab_boundary(self.h, side, C.byref(n)))
+        parts, ids = np.empty((n.value, 4), dtype=np.float32), np.empty(n.value, dtype=np.int32)
+        self._ck(_lib.fsb_slab_boundary_take(self.h, _ptr(parts), _ptr(ids)))
+        return parts, ids
+
+    def slab_get(self):
+        n = self.num_particles()
+        parts, ids = np.empty((n, 4), dtype=np.float32), np.empty(n, dtype=np.int32)
+        self._ck(_lib.fsb_slab_get(self.h, _ptr(parts), _ptr(ids)))
+        return parts, ids
+
+    def get_rows(self, which, lo, hi):
+        a = np.empty((hi - lo, self.nx), dtype=np.uint8 if which == ROWS_LABELS else np.float32)
+        self._ck(_lib.fsb_get_rows(self.h, which, lo, hi, _ptr(a)))
+        return a
+
+    def set_rows(self, which, lo, hi, a):
+        a = np.ascontiguousarray(a, dtype=np.uint8 if which == ROWS_LABELS else np.float32)
+        assert a.shape == (hi - lo, self.nx)
+        self._ck(_lib.fsb_set_rows(self.h, which, lo, hi, _ptr(a)))
+
+    def slab_step_a(self, kind):
+        self._ck(_lib.fsb_slab_step_a(self.h, kind))
+
+    def slab_step_b(self, kind, dt):
+        self._ck(_lib.fsb_slab_step_b(self.h, kind, dt))
+
+    def slab_step_c(self, kind, dt):
+        self._ck(_lib.fsb_slab_step_c(self.h, kind, dt))
 
     # state files
     def save_state(self, path):

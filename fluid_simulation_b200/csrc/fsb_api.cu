@@ -312,6 +312,7 @@ void fsb_destroy(fsb_ctx* c)
   for (int k = 0; k < c->n_ipc_opened; ++k) cudaIpcCloseMemHandle(c->ipc_opened[k]);
   cudaFree(c->peer_x_dev); cudaFree(c->mail_local);
   fsb_mg_free(c);
+  cudaFree(c->slab_buf_part); cudaFree(c->slab_buf_orig); cudaFree(c->slab_ctr);
   cudaFree(c->cg_tile_flags); cudaFree(c->cg_tile_list);
   cudaFree(c->partials); cudaFree(c->scal); cudaFree(c->stage);
   if (c->scal_h) cudaFreeHost(c->scal_h);
@@ -709,6 +710,213 @@ int fsb_step(fsb_ctx* c, int kind, float dt)
     else FSB_TRY(fsb_k_g2p_advect(c, FSB_G2P_PICFLIP, c->pic_ratio, dt, 1));
   }
   return FSB_OK;
+}
+
+// ----------------------------------------------------------- particle slabs
+// One process per GPU, full grids on every rank, particles partitioned by row slab with one
+// ghost row from each neighbour.  A step is three device phases with two exchanges in between
+// (the transport -- NCCL in fluid_simulation_b200/sharding.py, plain copies in the in-process
+// tests -- is the caller's):
+//   ghosts in -> fsb_slab_step_a (labels + P2G of the own rows) -> exchange label / u / v rows ->
+//   fsb_slab_step_b (grid passes, pressure solve) -> fsb_slab_step_c (G2P, advection) -> migrate
+int fsb_slab_configure(fsb_ctx* c, int rank, int world)
+{
+  CHECK_CTX(c);
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || c->ny < 4 * world)
+    return fsb_fail(c, FSB_ERR_INVALID, "bad slab arguments (rank %d of %d)", rank, world);
+  c->slab_world = world;
+  c->slab_rank = rank;
+  c->slab_lo = (int)((int64_t)c->ny * rank / world);
+  c->slab_hi = (int)((int64_t)c->ny * (rank + 1) / world);
+  c->slab_grouped = false;
+  if (!c->slab_ctr) FSB_TRY(dev_alloc(c, &c->slab_ctr, (size_t)2 * kMaxRanks));
+  return FSB_OK;
+}
+int fsb_slab_rows(const fsb_ctx* c, int* row_lo, int* row_hi)
+{
+  if (!c) return FSB_ERR_INVALID;
+  if (row_lo) *row_lo = c->slab_world > 1 ? c->slab_lo : 0;
+  if (row_hi) *row_hi = c->slab_world > 1 ? c->slab_hi : c->ny;
+  return FSB_OK;
+}
+// appends particles with their global ids (host or device pointers)
+int fsb_slab_add(fsb_ctx* c, const float* aos4, const int32_t* ids, int64_t n)
+{
+  CHECK_CTX(c);
+  if (n < 0 || (n > 0 && (!aos4 || !ids))) return fsb_fail(c, FSB_ERR_INVALID, "bad particle buffers");
+  if (n == 0) return FSB_OK;
+  FSB_TRY(ensure_particle_capacity(c, c->n + n));
+  FSB_CUDA(c, cudaMemcpyAsync(c->part[c->pcur] + c->n, aos4, sizeof(float4) * n, cudaMemcpyDefault, c->stream));
+  FSB_CUDA(c, cudaMemcpyAsync(c->orig[c->pcur] + c->n, ids, sizeof(int) * n, cudaMemcpyDefault, c->stream));
+  FSB_CUDA(c, cudaStreamSynchronize(c->stream)); // the caller may reuse its buffers
+  c->n += n;
+  c->sort_valid = false;
+  c->slab_grouped = false;
+  return FSB_OK;
+}
+int fsb_slab_sort_out(fsb_ctx* c, int64_t* counts)
+{
+  CHECK_CTX(c);
+  if (!counts) return fsb_fail(c, FSB_ERR_INVALID, "null counts");
+  if (!c->slab_ctr) return fsb_fail(c, FSB_ERR_INVALID, "call fsb_slab_configure first");
+  return fsb_k_slab_sort_out(c, counts);
+}
+int fsb_slab_take(fsb_ctx* c, int dest, float* aos4, int32_t* ids)
+{
+  CHECK_CTX(c);
+  if (!c->slab_grouped || dest < 0 || dest >= c->slab_world)
+    return fsb_fail(c, FSB_ERR_INVALID, "fsb_slab_take without a preceding fsb_slab_sort_out");
+  int64_t off = 0;
+  for (int q = 0; q < dest; ++q) off += c->slab_count[q];
+  const int64_t n = c->slab_count[dest];
+  if (n == 0) return FSB_OK;
+  if (!aos4 || !ids) return fsb_fail(c, FSB_ERR_INVALID, "null buffers");
+  FSB_CUDA(c, cudaMemcpyAsync(aos4, c->part[c->pcur] + off, sizeof(float4) * n, cudaMemcpyDefault, c->stream));
+  FSB_CUDA(c, cudaMemcpyAsync(ids, c->orig[c->pcur] + off, sizeof(int) * n, cudaMemcpyDefault, c->stream));
+  FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FSB_OK;
+}
+int fsb_slab_keep_own(fsb_ctx* c)
+{
+  CHECK_CTX(c);
+  if (!c->slab_grouped) return fsb_fail(c, FSB_ERR_INVALID, "fsb_slab_keep_own without fsb_slab_sort_out");
+  int64_t off = 0;
+  for (int q = 0; q < c->slab_rank; ++q) off += c->slab_count[q];
+  const int64_t n = c->slab_count[c->slab_rank];
+  if (n > 0 && off > 0)
+  {
+    // the other buffer is scratch outside the sort
+    FSB_CUDA(c, cudaMemcpyAsync(c->part[c->pcur ^ 1], c->part[c->pcur] + off, sizeof(float4) * n,
+                                cudaMemcpyDeviceToDevice, c->stream));
+    FSB_CUDA(c, cudaMemcpyAsync(c->orig[c->pcur ^ 1], c->orig[c->pcur] + off, sizeof(int) * n,
+                                cudaMemcpyDeviceToDevice, c->stream));
+    c->pcur ^= 1;
+  }
+  c->n = n;
+  c->sort_valid = false;
+  c->slab_grouped = false;
+  return FSB_OK;
+}
+int fsb_slab_boundary(fsb_ctx* c, int side, int64_t* n)
+{
+  CHECK_CTX(c);
+  if (!n || (side != 0 && side != 1)) return fsb_fail(c, FSB_ERR_INVALID, "bad arguments");
+  if (!c->slab_ctr) return fsb_fail(c, FSB_ERR_INVALID, "call fsb_slab_configure first");
+  FSB_TRY(fsb_k_slab_row_select(c, side == 0 ? c->slab_lo : c->slab_hi - 1, n));
+  c->slab_sel = *n;
+  return FSB_OK;
+}
+int fsb_slab_boundary_take(fsb_ctx* c, float* aos4, int32_t* ids)
+{
+  CHECK_CTX(c);
+  const int64_t n = c->slab_sel;
+  if (n == 0) return FSB_OK;
+  if (!aos4 || !ids) return fsb_fail(c, FSB_ERR_INVALID, "null buffers");
+  FSB_CUDA(c, cudaMemcpyAsync(aos4, c->slab_buf_part, sizeof(float4) * n, cudaMemcpyDefault, c->stream));
+  FSB_CUDA(c, cudaMemcpyAsync(ids, c->slab_buf_orig, sizeof(int) * n, cudaMemcpyDefault, c->stream));
+  FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FSB_OK;
+}
+// this rank's particles with their global ids, in device order
+int fsb_slab_get(fsb_ctx* c, float* aos4, int32_t* ids)
+{
+  CHECK_CTX(c);
+  if (c->n == 0) return FSB_OK;
+  if (!aos4 || !ids) return fsb_fail(c, FSB_ERR_INVALID, "null buffers");
+  FSB_CUDA(c, cudaMemcpyAsync(aos4, c->part[c->pcur], sizeof(float4) * c->n, cudaMemcpyDefault, c->stream));
+  FSB_CUDA(c, cudaMemcpyAsync(ids, c->orig[c->pcur], sizeof(int) * c->n, cudaMemcpyDefault, c->stream));
+  FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FSB_OK;
+}
+// rows [row_lo, row_hi) of a MacGrid buffer (which = FSB_U_FRONT ..) or of the labels
+// (which = FSB_ROWS_LABELS), dense, host or device pointer
+int fsb_get_rows(fsb_ctx* c, int which, int row_lo, int row_hi, void* dst)
+{
+  CHECK_CTX(c);
+  if (row_lo < 0 || row_hi > c->ny || row_lo > row_hi || !dst) return fsb_fail(c, FSB_ERR_INVALID, "bad row range");
+  if (row_lo == row_hi) return FSB_OK;
+  if (which == FSB_ROWS_LABELS)
+  {
+    FSB_CUDA(c, cudaMemcpy2DAsync(dst, c->nx, c->cell + (size_t)row_lo * c->ld, c->ld, c->nx,
+                                  row_hi - row_lo, cudaMemcpyDefault, c->stream));
+  }
+  else
+  {
+    if (which == FSB_U_DIFF || which == FSB_V_DIFF) FSB_TRY(flush_diff(c));
+    float* g = pick_grid(c, which);
+    if (!g) return fsb_fail(c, FSB_ERR_INVALID, "bad grid selector %d", which);
+    FSB_CUDA(c, cudaMemcpy2DAsync(dst, sizeof(float) * c->nx, g + (size_t)row_lo * c->ld,
+                                  sizeof(float) * c->ld, sizeof(float) * c->nx, row_hi - row_lo,
+                                  cudaMemcpyDefault, c->stream));
+  }
+  FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FSB_OK;
+}
+int fsb_set_rows(fsb_ctx* c, int which, int row_lo, int row_hi, const void* src)
+{
+  CHECK_CTX(c);
+  if (row_lo < 0 || row_hi > c->ny || row_lo > row_hi || !src) return fsb_fail(c, FSB_ERR_INVALID, "bad row range");
+  if (row_lo == row_hi) return FSB_OK;
+  if (which == FSB_ROWS_LABELS)
+  {
+    FSB_CUDA(c, cudaMemcpy2DAsync(c->cell + (size_t)row_lo * c->ld, c->ld, src, c->nx, c->nx,
+                                  row_hi - row_lo, cudaMemcpyDefault, c->stream));
+  }
+  else
+  {
+    FSB_TRY(flush_diff(c));
+    float* g = pick_grid(c, which);
+    if (!g) return fsb_fail(c, FSB_ERR_INVALID, "bad grid selector %d", which);
+    FSB_CUDA(c, cudaMemcpy2DAsync(g + (size_t)row_lo * c->ld, sizeof(float) * c->ld, src,
+                                  sizeof(float) * c->nx, sizeof(float) * c->nx, row_hi - row_lo,
+                                  cudaMemcpyDefault, c->stream));
+  }
+  FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return FSB_OK;
+}
+
+// phase A of a PIC / FLIP / PIC-FLIP step: classification from the local particles (own + ghost
+// rows) and P2G of this rank's rows
+int fsb_slab_step_a(fsb_ctx* c, int kind)
+{
+  CHECK_CTX(c);
+  if (kind < FSB_STEP_PIC || kind > FSB_STEP_PICFLIP)
+    return fsb_fail(c, FSB_ERR_INVALID, "slab steps exist for the particle steps only (kind %d)", kind);
+  FSB_TRY(square_cells(c));
+  if (kind == FSB_STEP_PIC) FSB_TRY(flush_diff(c));
+  if (c->stage_v1 || c->sort_valid || c->n == 0) FSB_TRY(fsb_k_classify(c));
+  else
+  {
+    FSB_TRY(fsb_k_classify_reset(c));
+    FSB_TRY(fsb_k_sort_particles(c, true));
+  }
+  return fsb_k_p2g(c);
+}
+// phase B: everything on the grid (identical on every rank once the rows are exchanged; the CG may
+// additionally be sharded with fsb_shard_connect)
+int fsb_slab_step_b(fsb_ctx* c, int kind, float dt)
+{
+  CHECK_CTX(c);
+  if (kind < FSB_STEP_PIC || kind > FSB_STEP_PICFLIP) return fsb_fail(c, FSB_ERR_INVALID, "bad step kind %d", kind);
+  FSB_TRY(fsb_k_prev_gravity_dirichlet(c, c->grav_x, c->grav_y, dt, kind != FSB_STEP_PIC));
+  FSB_TRY(fsb_k_extend_velocity(c, 2));
+  if (c->stage_v1)
+  {
+    FSB_TRY(fsb_k_pressure_solve(c, c->density, dt));
+    return fsb_k_enforce_dirichlet(c);
+  }
+  return fsb_k_pressure_solve(c, c->density, dt, true);
+}
+// phase C: the ghosts are retired, then G2P + blend + advection of this rank's particles
+int fsb_slab_step_c(fsb_ctx* c, int kind, float dt)
+{
+  CHECK_CTX(c);
+  if (kind < FSB_STEP_PIC || kind > FSB_STEP_PICFLIP) return fsb_fail(c, FSB_ERR_INVALID, "bad step kind %d", kind);
+  if (c->slab_world > 1) FSB_TRY(fsb_k_slab_mark_ghosts(c));
+  if (kind == FSB_STEP_PIC) return fsb_k_g2p_advect(c, FSB_G2P_PIC, 0.0f, dt, 0);
+  c->diff_pending = true;
+  if (kind == FSB_STEP_FLIP) return fsb_k_g2p_advect(c, FSB_G2P_FLIP, 0.0f, dt, 0);
+  return fsb_k_g2p_advect(c, FSB_G2P_PICFLIP, c->pic_ratio, dt, 1);
 }
 
 // --------------------------------------------------------------- state files

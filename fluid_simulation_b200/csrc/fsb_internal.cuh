@@ -175,6 +175,16 @@ struct fsb_ctx
   void* ipc_opened[5 * kMaxRanks] = {nullptr};
   int n_ipc_opened = 0;
 
+  // slab-partitioned particles (fsb_slab_*): world == 1: the whole set lives here
+  int slab_world = 1, slab_rank = 0, slab_lo = 0, slab_hi = 0;
+  int64_t slab_count[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // group sizes after fsb_slab_sort_out
+  bool slab_grouped = false;
+  float4* slab_buf_part = nullptr; // boundary-row selection
+  int* slab_buf_orig = nullptr;
+  int64_t slab_buf_cap = 0;
+  int64_t slab_sel = 0;                   // size of the last boundary-row selection
+  unsigned long long* slab_ctr = nullptr; // device counters / cursors (2 * kMaxRanks)
+
   // measurement
   bool profiling = false;
   static constexpr int kProfPool = 512; // event pairs recorded between two drains
@@ -248,6 +258,9 @@ int fsb_k_g2p_advect(fsb_ctx* c, int mode, float pic_ratio, float dt, int ensure
 int fsb_k_advect_particles_grid(fsb_ctx* c, float dt);
 int fsb_k_unpermute(fsb_ctx* c, float4* dst_dense);
 int fsb_k_p2g_gather(fsb_ctx* c);
+int fsb_k_slab_mark_ghosts(fsb_ctx* c);
+int fsb_k_slab_sort_out(fsb_ctx* c, int64_t* counts);
+int fsb_k_slab_row_select(fsb_ctx* c, int row, int64_t* n_out);
 int fsb_k_emit_source_dev(fsb_ctx* c, int64_t first, const float* xs_dev, const float* ys_dev,
                           int64_t count_x, int64_t count_y, float vel_x, float vel_y);
 // pressure: fsb_cg.cu

@@ -1,6 +1,8 @@
 // Particle-side stages: cell-binned stable sort, particle-to-grid transfer as
 // an atomics-free gather over the sorted particles, grid-to-particle transfer
 // fused with the PIC/FLIP blend and the advection, RK3 particle tracing.
+#include <algorithm>
+
 #include "fsb_device.cuh"
 #include "fsb_internal.cuh"
 
@@ -196,10 +198,13 @@ __global__ void k_sort_place(const int* __restrict__ key, const int* __restrict_
   for (int64_t q = k; q < n; ++q) idx[start[key[q]] + rank[q]] = (int)q;
 }
 
-// Make the order inside each cell canonical (ascending source position), which
-// turns the atomic ranking into a STABLE counting sort: the device order, and
-// with it every floating-point sum over a cell's particles, is reproducible.
-__global__ void k_sort_canon(const int* __restrict__ start, int m, int* __restrict__ idx)
+// Make the order inside each cell canonical: ascending ORIGINAL index (the index the caller knows
+// the particle by; the global id in a slab-partitioned run).  This turns the atomic ranking into a
+// deterministic sort whose result does not depend on the order the particles were stored in
+// before: every floating-point sum over a cell's particles is reproducible across runs, across
+// state files and across particle partitions.
+__global__ void k_sort_canon(const int* __restrict__ start, int m, int* __restrict__ idx,
+                             const int* __restrict__ orig)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= m) return;
@@ -208,20 +213,25 @@ __global__ void k_sort_canon(const int* __restrict__ start, int m, int* __restri
   if (n <= 1) return;
   if (n <= 8)
   {
-    // the common case: all entries loaded at once (independent loads), a fixed 19-exchange
-    // sorting network in registers, and a write-back only where the order changed
-    int v[8];
+    // the common case: all entries and their keys loaded at once (independent loads), a fixed
+    // 19-exchange sorting network in registers, and a write-back only where the order changed
+    int v[8], key[8], w[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) v[t] = (t < n) ? idx[a + t] : 0x7fffffff;
-    int w[8];
+    for (int t = 0; t < 8; ++t) v[t] = (t < n) ? idx[a + t] : -1;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) w[t] = v[t];
-#define FSB_CX(p, q)                  \
-  {                                   \
-    const int lo = min(w[p], w[q]);   \
-    const int hi = max(w[p], w[q]);   \
-    w[p] = lo;                        \
-    w[q] = hi;                        \
+    for (int t = 0; t < 8; ++t)
+    {
+      key[t] = (t < n) ? __ldg(orig + v[t]) : 0x7fffffff;
+      w[t] = v[t];
+    }
+#define FSB_CX(p, q)                                  \
+  {                                                   \
+    const bool sw = key[p] > key[q];                  \
+    const int klo = sw ? key[q] : key[p];             \
+    const int khi = sw ? key[p] : key[q];             \
+    const int wlo = sw ? w[q] : w[p];                 \
+    const int whi = sw ? w[p] : w[q];                 \
+    key[p] = klo; key[q] = khi; w[p] = wlo; w[q] = whi; \
   }
     FSB_CX(0, 1) FSB_CX(2, 3) FSB_CX(4, 5) FSB_CX(6, 7)
     FSB_CX(0, 2) FSB_CX(1, 3) FSB_CX(4, 6) FSB_CX(5, 7)
@@ -239,8 +249,9 @@ __global__ void k_sort_canon(const int* __restrict__ start, int m, int* __restri
   for (int s = a + 1; s < b; ++s)
   {
     const int v = idx[s];
+    const int kv = orig[v];
     int t = s - 1;
-    while (t >= a && idx[t] > v)
+    while (t >= a && orig[idx[t]] > kv)
     {
       idx[t + 1] = idx[t];
       --t;
@@ -386,14 +397,16 @@ template <class D>
 __global__ void __launch_bounds__(256)
 k_p2g_stream(const float4* __restrict__ part, const int* __restrict__ cell_start,
              float* __restrict__ ub, float* __restrict__ vb, const D d, float half_dx,
-             float half_dy, int strips_x, int n_warps)
+             float half_dy, int strips_x, int n_warps, int row_lo, int row_hi)
 {
   const int warp_id = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (warp_id >= n_warps) return; // whole warps leave together
   const int lane = threadIdx.x & 31;
   const int ci = (warp_id % strips_x) * kP2gCols - 1 + lane;
-  const int ja = (warp_id / strips_x) * kP2gRows;
-  const int jb = min(ja + kP2gRows, d.ny);
+  // output rows [ja, jb) of this warp; a node's sum is built in the same order whatever row the
+  // chunk starts at (cell rows j-1, j, j+1 in turn), so a row range gives the same bits as a full pass
+  const int ja = row_lo + (warp_id / strips_x) * kP2gRows;
+  const int jb = min(ja + kP2gRows, row_hi);
   const bool col_ok = ci >= 0 && ci < d.nx;
   const bool writer = col_ok && lane >= 1 && lane <= kP2gCols;
 
@@ -691,6 +704,174 @@ __global__ void k_p2g_gather(const float4* __restrict__ part, const int* __restr
   if (w != 0.0f) vb[i + (size_t)j * d.ld] = v / w;
 }
 
+// ------------------------------------------------------------ particle slabs --
+// Slab-partitioned particle sets (one process per GPU, every rank holds the full grids but only
+// the particles of its row slab plus one ghost row of its neighbours').  Ownership is a pure
+// function of the position: the rank whose rows contain the particle's sort-key row.
+__device__ __forceinline__ int slab_row(const GridDims& d, float y)
+{
+  return clampi((int)div_dy(d, y), 0, d.ny - 1);
+}
+__device__ __forceinline__ int slab_owner(int row, int ny, int world)
+{
+  // rows [ny*q/world, ny*(q+1)/world) belong to rank q
+  int q = (int)(((int64_t)row * world) / ny);
+  while (q + 1 < world && row >= (int)(((int64_t)ny * (q + 1)) / world)) ++q;
+  while (q > 0 && row < (int)(((int64_t)ny * q) / world)) --q;
+  return q;
+}
+
+// particles that are not this rank's (ghosts) are marked dead (orig = -1) before the transfer back
+__global__ void k_slab_mark_ghosts(const float4* __restrict__ part, int* __restrict__ orig, int64_t n,
+                                   const GridDims d, int lo, int hi)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int row = slab_row(d, part[k].y);
+  if (row < lo || row >= hi) orig[k] = -1;
+}
+
+// destination rank of every live particle; counts per rank (block histogram + atomics)
+__global__ void k_slab_count(const float4* __restrict__ part, const int* __restrict__ orig, int64_t n,
+                             const GridDims d, int world, int* __restrict__ dest,
+                             unsigned long long* __restrict__ counts)
+{
+  __shared__ unsigned int s_cnt[kMaxRanks];
+  if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n)
+  {
+    int q = -1;
+    if (orig[k] >= 0) q = slab_owner(slab_row(d, part[k].y), d.ny, world);
+    dest[k] = q;
+    if (q >= 0) atomicAdd(&s_cnt[q], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < kMaxRanks && s_cnt[threadIdx.x])
+    atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// scatter into per-destination groups (order inside a group is irrelevant: the cell sort's
+// in-cell order goes by original index)
+__global__ void k_slab_scatter(const float4* __restrict__ part, const int* __restrict__ orig,
+                               const int* __restrict__ dest, int64_t n,
+                               unsigned long long* __restrict__ cursor, float4* __restrict__ part_out,
+                               int* __restrict__ orig_out)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int q = dest[k];
+  if (q < 0) return;
+  const unsigned long long slot = atomicAdd(&cursor[q], 1ull);
+  part_out[slot] = part[k];
+  orig_out[slot] = orig[k];
+}
+
+// owned particles whose row is `row`: count, then compact into a buffer
+__global__ void k_slab_row_select(const float4* __restrict__ part, const int* __restrict__ orig,
+                                  int64_t n, const GridDims d, int row,
+                                  unsigned long long* __restrict__ cursor, float4* __restrict__ part_out,
+                                  int* __restrict__ orig_out)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n || orig[k] < 0) return;
+  if (slab_row(d, part[k].y) != row) return;
+  const unsigned long long slot = atomicAdd(cursor, 1ull);
+  if (part_out)
+  {
+    part_out[slot] = part[k];
+    orig_out[slot] = orig[k];
+  }
+}
+
+} // namespace
+
+int fsb_k_slab_mark_ghosts(fsb_ctx* c)
+{
+  if (c->n == 0) return FSB_OK;
+  k_slab_mark_ghosts<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+      c->part[c->pcur], c->orig[c->pcur], c->n, pool_dims(c), c->slab_lo, c->slab_hi);
+  FSB_LAUNCHED(c);
+  return FSB_OK;
+}
+
+// groups the live particles by owner rank into the other buffer; counts[world] on return
+int fsb_k_slab_sort_out(fsb_ctx* c, int64_t* counts)
+{
+  const int world = c->slab_world;
+  for (int q = 0; q < kMaxRanks; ++q) c->slab_count[q] = 0;
+  if (c->n > 0)
+  {
+    unsigned long long* dev = c->slab_ctr; // 2 * kMaxRanks words
+    unsigned long long host[2 * kMaxRanks];
+    FSB_CUDA(c, cudaMemsetAsync(dev, 0, sizeof(unsigned long long) * 2 * kMaxRanks, c->stream));
+    k_slab_count<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+        c->part[c->pcur], c->orig[c->pcur], c->n, pool_dims(c), world, c->sort_key, dev);
+    FSB_LAUNCHED(c);
+    FSB_CUDA(c, cudaMemcpyAsync(host, dev, sizeof(unsigned long long) * kMaxRanks,
+                                cudaMemcpyDeviceToHost, c->stream));
+    FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    unsigned long long off = 0;
+    for (int q = 0; q < kMaxRanks; ++q)
+    {
+      c->slab_count[q] = (int64_t)host[q];
+      host[kMaxRanks + q] = off; // cursor start of group q
+      off += host[q];
+    }
+    FSB_CUDA(c, cudaMemcpyAsync(dev + kMaxRanks, host + kMaxRanks, sizeof(unsigned long long) * kMaxRanks,
+                                cudaMemcpyHostToDevice, c->stream));
+    k_slab_scatter<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+        c->part[c->pcur], c->orig[c->pcur], c->sort_key, c->n, dev + kMaxRanks, c->part[c->pcur ^ 1],
+        c->orig[c->pcur ^ 1]);
+    FSB_LAUNCHED(c);
+    FSB_CUDA(c, cudaStreamSynchronize(c->stream)); // `host` leaves scope
+    c->pcur ^= 1;
+    c->n = (int64_t)off;
+  }
+  c->sort_valid = false;
+  c->slab_grouped = true;
+  for (int q = 0; q < world; ++q) counts[q] = c->slab_count[q];
+  return FSB_OK;
+}
+
+// selects this rank's particles of one row into slab_buf; *n_out = how many
+int fsb_k_slab_row_select(fsb_ctx* c, int row, int64_t* n_out)
+{
+  *n_out = 0;
+  if (c->n == 0) return FSB_OK;
+  unsigned long long* dev = c->slab_ctr;
+  unsigned long long cnt = 0;
+  const GridDims d = pool_dims(c);
+  FSB_CUDA(c, cudaMemsetAsync(dev, 0, sizeof(unsigned long long), c->stream));
+  k_slab_row_select<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+      c->part[c->pcur], c->orig[c->pcur], c->n, d, row, dev, nullptr, nullptr);
+  FSB_LAUNCHED(c);
+  FSB_CUDA(c, cudaMemcpyAsync(&cnt, dev, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+  FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if ((int64_t)cnt > c->slab_buf_cap)
+  {
+    if (c->slab_buf_part) cudaFree(c->slab_buf_part);
+    if (c->slab_buf_orig) cudaFree(c->slab_buf_orig);
+    c->slab_buf_part = nullptr; c->slab_buf_orig = nullptr;
+    const int64_t cap = std::max<int64_t>(1024, (int64_t)cnt * 2);
+    FSB_CUDA(c, cudaMalloc(&c->slab_buf_part, sizeof(float4) * cap));
+    FSB_CUDA(c, cudaMalloc(&c->slab_buf_orig, sizeof(int) * cap));
+    c->slab_buf_cap = cap;
+  }
+  if (cnt > 0)
+  {
+    FSB_CUDA(c, cudaMemsetAsync(dev, 0, sizeof(unsigned long long), c->stream));
+    k_slab_row_select<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
+        c->part[c->pcur], c->orig[c->pcur], c->n, d, row, dev, c->slab_buf_part, c->slab_buf_orig);
+    FSB_LAUNCHED(c);
+  }
+  *n_out = (int64_t)cnt;
+  return FSB_OK;
+}
+
+namespace {
+
 } // namespace
 
 int fsb_k_p2g_gather(fsb_ctx* c)
@@ -742,7 +923,8 @@ int fsb_k_sort_particles(fsb_ctx* c, bool mark_labels)
     k_sort_place<<<fsb_div_up(fsb_div_up(c->n, 4), kBlock), kBlock, 0, c->stream>>>(
         c->sort_key, c->sort_rank, c->n, c->cell_start, c->sort_idx);
     FSB_LAUNCHED(c);
-    k_sort_canon<<<fsb_div_up(m, kBlock), kBlock, 0, c->stream>>>(c->cell_start, m, c->sort_idx);
+    k_sort_canon<<<fsb_div_up(m, kBlock), kBlock, 0, c->stream>>>(c->cell_start, m, c->sort_idx,
+                                                                  c->orig[c->pcur]);
     FSB_LAUNCHED(c);
     k_sort_gather<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
         c->part[c->pcur], c->orig[c->pcur], c->sort_idx, c->n, c->part[c->pcur ^ 1],
@@ -761,15 +943,17 @@ int fsb_k_p2g(fsb_ctx* c)
   fsb_prof_begin(c, FSB_PROF_P2G);
   const GridDims d = pool_dims(c);
   const int strips_x = fsb_div_up(c->nx, kP2gCols);
-  const int64_t n_warps = (int64_t)strips_x * fsb_div_up(c->ny, kP2gRows);
+  // slab-partitioned particles: only the faces of this rank's rows (the other rows come from their owners)
+  const int row_lo = c->slab_world > 1 ? c->slab_lo : 0, row_hi = c->slab_world > 1 ? c->slab_hi : c->ny;
+  const int64_t n_warps = (int64_t)strips_x * fsb_div_up(row_hi - row_lo, kP2gRows);
   if (d.pow2 == 3)
     k_p2g_stream<GridDimsP2><<<fsb_div_up(n_warps * 32, 256), 256, 0, c->stream>>>(
         c->part[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), as_pow2(d), 0.5f * c->dx,
-        0.5f * c->dy, strips_x, (int)n_warps);
+        0.5f * c->dy, strips_x, (int)n_warps, row_lo, row_hi);
   else
     k_p2g_stream<GridDims><<<fsb_div_up(n_warps * 32, 256), 256, 0, c->stream>>>(
         c->part[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), d, 0.5f * c->dx, 0.5f * c->dy,
-        strips_x, (int)n_warps);
+        strips_x, (int)n_warps, row_lo, row_hi);
   FSB_LAUNCHED(c);
   c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:918
   fsb_prof_end(c, FSB_PROF_P2G);

@@ -236,6 +236,44 @@ int fsb_shard_disconnect(fsb_ctx* ctx);
 /* rows [*row_lo, *row_hi) of the grid this rank iterates on */
 int fsb_shard_rows(const fsb_ctx* ctx, int* row_lo, int* row_hi);
 
+/* ---- multi-GPU: particle slabs --------------------------- */
+
+/* One process per GPU; every rank keeps the full grids, but only the particles whose row (the
+ * P2G sort-key row, src/FluidSolver.cpp:873-919) lies in its slab, plus one ghost row from each
+ * neighbour while a step is in flight.  The canonical in-cell particle order goes by global id, so
+ * a slab-partitioned run produces the SAME BITS as the single-GPU run.  A PIC / FLIP / PIC-FLIP step
+ * is three device phases with two exchanges in between; the transport is the caller's
+ * (fluid_simulation_b200/sharding.py: torch.distributed / NCCL; tests: in-process copies):
+ *
+ *   fsb_slab_boundary(side) + _take  -> send to the neighbour -> fsb_slab_add      (ghost rows)
+ *   fsb_slab_step_a(kind)            labels from the local particles, P2G of the own rows
+ *   fsb_get_rows / fsb_set_rows      all-gather the label, u and v rows of every slab
+ *   fsb_slab_step_b(kind, dt)        gravity, walls, extension, pressure solve (optionally sharded)
+ *   fsb_slab_step_c(kind, dt)        ghosts retired; G2P + blend + advection of the own particles
+ *   fsb_slab_sort_out -> fsb_slab_take(dest) -> send -> fsb_slab_keep_own -> fsb_slab_add (migration)
+ *
+ * Buffers may be host or device pointers (cudaMemcpyDefault).  Particle ids are the caller's
+ * global indices (fsb_set_particles / fsb_emit_source number them 0 .. n-1 identically on all ranks). */
+#define FSB_ROWS_LABELS 8
+int fsb_slab_configure(fsb_ctx* ctx, int rank, int world);
+int fsb_slab_rows(const fsb_ctx* ctx, int* row_lo, int* row_hi);
+int fsb_slab_add(fsb_ctx* ctx, const float* aos4, const int32_t* ids, int64_t n);
+/* groups the live particles by owner rank; counts[world] */
+int fsb_slab_sort_out(fsb_ctx* ctx, int64_t* counts);
+int fsb_slab_take(fsb_ctx* ctx, int dest, float* aos4, int32_t* ids);
+int fsb_slab_keep_own(fsb_ctx* ctx);
+/* own particles of the slab's first (side 0) / last (side 1) row: count, then copy */
+int fsb_slab_boundary(fsb_ctx* ctx, int side, int64_t* n);
+int fsb_slab_boundary_take(fsb_ctx* ctx, float* aos4, int32_t* ids);
+/* this rank's particles and their global ids (fsb_num_particles of them), device order */
+int fsb_slab_get(fsb_ctx* ctx, float* aos4, int32_t* ids);
+/* rows [row_lo, row_hi) of a MacGrid buffer (FSB_U_FRONT ..) or of the labels (FSB_ROWS_LABELS), dense */
+int fsb_get_rows(fsb_ctx* ctx, int which, int row_lo, int row_hi, void* dst);
+int fsb_set_rows(fsb_ctx* ctx, int which, int row_lo, int row_hi, const void* src);
+int fsb_slab_step_a(fsb_ctx* ctx, int kind);
+int fsb_slab_step_b(fsb_ctx* ctx, int kind, float dt);
+int fsb_slab_step_c(fsb_ctx* ctx, int kind, float dt);
+
 /* ---- measurement ------------------------------------------------------ */
 
 /* Per-stage CUDA-event timing on the context's stream.  Enabling it makes

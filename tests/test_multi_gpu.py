@@ -24,3 +24,22 @@ def test_sharded_cg_two_ranks(built):
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert out["ok"] and out["ranks_identical"], out
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("backend", ["gloo", "nccl"])
+def test_particle_slabs_over_torch_distributed(built, backend):
+    """DistSlabs (fluid_simulation_b200/sharding.py): the slab-partitioned PIC/FLIP step over
+    torch.distributed.  gloo: two ranks share GPU 0 (checks the distributed call sequence on a
+    one-GPU box); nccl: one rank per GPU, needs 2 GPUs."""
+    import torch
+    if backend == "nccl" and torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533" if backend == "gloo" else "29534",
+           os.path.join(ROOT, "tests", "multi_gpu_slab_check.py"), "--backend", backend]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=540, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["ok"] and out["all_particles"] > out["own_particles"] > 0, out
