@@ -122,8 +122,12 @@ class LocalSlabs:
 
 
 class DistSlabs:
-    """One rank of a torch.distributed job (NCCL on GPUs: pass device="cuda"; gloo on CPU tensors).
-    Same call sequence as LocalSlabs; buffers travel as torch tensors."""
+    """One rank of a torch.distributed job (gloo on CPU tensors, or NCCL with device="cuda").
+    Same call sequence as LocalSlabs; buffers travel as torch tensors staged through the host.
+    Round-1 status: the gloo transport is verified on a B200 (two ranks sharing one GPU,
+    tests/test_multi_gpu.py); the NCCL transport's first version deadlocked in ungrouped
+    isend / recv pairs, was rewritten with batch_isend_irecv and has NOT been re-run (the round's GPU
+    budget was spent): its test is opt-in (FSB_TEST_NCCL_SLABS=1)."""
 
     def __init__(self, sim, dist=None, device=None):
         import torch
@@ -147,7 +151,29 @@ class DistSlabs:
         table = [torch.empty_like(n_out) for _ in range(self.world)]
         dist.all_gather(table, n_out)  # table[q][d] = what q sends to d (gloo has no all-to-all)
         n_in = [int(table[q][self.rank].item()) for q in range(self.world)]
-        reqs, recv = [], []
+        recv = []
+        if dist.get_backend() == "nccl":
+            # NCCL point-to-point calls must be issued as ONE group: an ungrouped send / recv pair in
+            # opposite directions between two ranks deadlocks (each send kernel waits for the peer's
+            # recv, which is queued behind the peer's own send)
+            ops, bufs = [], []
+            for q in range(self.world):
+                if q != self.rank and outgoing[q] is not None and outgoing[q][1].shape[0]:
+                    ops.append(dist.P2POp(dist.isend, self._t(outgoing[q][0]), q))
+                    ops.append(dist.P2POp(dist.isend, self._t(outgoing[q][1]), q))
+            for q in range(self.world):
+                if q != self.rank and n_in[q]:
+                    p = torch.empty((n_in[q], 4), dtype=torch.float32, device=self.device)
+                    i = torch.empty(n_in[q], dtype=torch.int32, device=self.device)
+                    ops.append(dist.P2POp(dist.irecv, p, q))
+                    ops.append(dist.P2POp(dist.irecv, i, q))
+                    bufs.append((p, i))
+            if ops:
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()
+                torch.cuda.synchronize()
+            return [(p.cpu().numpy(), i.cpu().numpy()) for p, i in bufs]
+        reqs = []
         for q in range(self.world):
             if q != self.rank and outgoing[q] is not None and outgoing[q][1].shape[0]:
                 reqs.append(dist.isend(self._t(outgoing[q][0]), q))

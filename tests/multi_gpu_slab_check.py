@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"])
     ap.add_argument("--grid", dest="n", type=int, default=128)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--shard-cg", action="store_true",
+                    help="additionally shard the pressure CG over the ranks (peer memory; nccl only)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -47,6 +49,8 @@ def main():
         s.emit_source(*src)
     slabs = sharding.DistSlabs(own, dist, device)
     slabs.distribute()
+    if args.shard_cg:
+        sharding.connect(own, dist, device)
     ok, moved = True, 0
     for step in range(args.steps):
         ref.step(capi.STEP_PICFLIP, 0.01)
@@ -60,11 +64,13 @@ def main():
     flag = torch.tensor([1 if ok else 0])
     flag = flag.to(device) if device is not None else flag
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    out = {"world": world, "backend": args.backend, "n": n, "steps": args.steps,
+    out = {"world": world, "backend": args.backend, "n": n, "steps": args.steps, "cg_sharded": bool(args.shard_cg),
            "own_particles": int(own.num_particles()), "all_particles": int(allp.shape[0]),
            "migrated_by_this_rank": int(moved), "ok": bool(flag.item())}
     if rank == 0:
         print(json.dumps(out), flush=True)
+    if args.shard_cg:
+        own.shard_disconnect()
     dist.barrier()
     dist.destroy_process_group()
     return 0 if out["ok"] else 1
