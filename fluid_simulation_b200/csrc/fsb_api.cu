@@ -935,6 +935,14 @@ struct StateHeader
 };
 static_assert(sizeof(StateHeader) == 96, "state header layout");
 const char kStateMagic[8] = {'F', 'S', 'B', 'S', 'T', 'A', 'T', 'E'};
+// closes the file on every exit path (the CUDA error macros return early)
+struct FileCloser
+{
+  FILE* f;
+  explicit FileCloser(FILE* file) : f(file) {}
+  ~FileCloser() { if (f) fclose(f); }
+  int close() { FILE* t = f; f = nullptr; return t ? fclose(t) : 0; }
+};
 } // namespace
 
 int fsb_save_state(fsb_ctx* c, const char* path)
@@ -943,6 +951,7 @@ int fsb_save_state(fsb_ctx* c, const char* path)
   if (!path) return fsb_fail(c, FSB_ERR_INVALID, "null path");
   FILE* f = fopen(path, "wb");
   if (!f) return fsb_fail(c, FSB_ERR_INVALID, "cannot open %s for writing", path);
+  FileCloser guard(f);
   StateHeader hd;
   memset(&hd, 0, sizeof hd);
   memcpy(hd.magic, kStateMagic, 8);
@@ -969,9 +978,9 @@ int fsb_save_state(fsb_ctx* c, const char* path)
   }
   if (ok && c->n > 0)
   {
-    // the device order (cell-sorted by the last step) and the map back to the caller's indices:
-    // the in-cell order of the next sort -- and with it every P2G rounding -- depends on the order
-    // the sort starts from, so only the exact arrays give a bit-identical continuation
+    // the device order (cell-sorted by the last step) and the map back to the caller's indices;
+    // the next cell sort orders each cell by original index, so the continuation is bit-identical
+    // whatever order the set is stored in -- the device order merely saves an un-permute pass
     FSB_CUDA(c, cudaMemcpyAsync(buf.data(), c->part[c->pcur], sizeof(float4) * c->n,
                                 cudaMemcpyDeviceToHost, c->stream));
     FSB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -984,7 +993,7 @@ int fsb_save_state(fsb_ctx* c, const char* path)
       ok = fwrite(buf.data(), sizeof(int), (size_t)c->n, f) == (size_t)c->n;
     }
   }
-  ok = (fclose(f) == 0) && ok;
+  ok = (guard.close() == 0) && ok;
   if (rc != FSB_OK) return rc;
   if (!ok) return fsb_fail(c, FSB_ERR_INVALID, "short write to %s", path);
   return FSB_OK;
@@ -996,15 +1005,12 @@ int fsb_load_state(fsb_ctx* c, const char* path)
   if (!path) return fsb_fail(c, FSB_ERR_INVALID, "null path");
   FILE* f = fopen(path, "rb");
   if (!f) return fsb_fail(c, FSB_ERR_INVALID, "cannot open %s", path);
+  FileCloser guard(f);
   StateHeader hd;
   if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, kStateMagic, 8) != 0 || hd.version != 1)
-  {
-    fclose(f);
     return fsb_fail(c, FSB_ERR_INVALID, "%s is not a version-1 FSBSTATE file", path);
-  }
   if (hd.nx != c->nx || hd.ny != c->ny || hd.n_particles < 0)
   {
-    fclose(f);
     return fsb_fail(c, FSB_ERR_INVALID, "%s holds a %dx%d domain, the context is %dx%d", path, hd.nx,
                     hd.ny, c->nx, c->ny);
   }
@@ -1049,10 +1055,7 @@ int fsb_load_state(fsb_ctx* c, const char* path)
           if (ok) seen[(size_t)o[k]] = 1;
         }
         if (!ok)
-        {
-          fclose(f);
           return fsb_fail(c, FSB_ERR_INVALID, "%s: the particle index map is not a permutation", path);
-        }
         FSB_CUDA(c, cudaMemcpyAsync(c->orig[c->pcur], buf.data(), sizeof(int) * np,
                                     cudaMemcpyHostToDevice, c->stream));
         FSB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1060,7 +1063,7 @@ int fsb_load_state(fsb_ctx* c, const char* path)
       }
     }
   }
-  fclose(f);
+  guard.close();
   if (rc != FSB_OK) return rc;
   if (!ok) return fsb_fail(c, FSB_ERR_INVALID, "%s is truncated", path);
   c->dx = hd.dx; c->dy = hd.dy; c->density = hd.density; c->pic_ratio = hd.pic_ratio;

@@ -194,10 +194,10 @@ int fsb_step(fsb_ctx* ctx, int kind, float dt);
  * particle count), the labels (size_x*size_y bytes), the eight MacGrid buffers in FSB_U_FRONT ..
  * FSB_V_DIFF order (dense fp32), the particles in the DEVICE's order (AoS fp32 x 4; cell-sorted
  * by the last step) and the int32 map from that order to the caller's indices (particle k of the
- * file is the caller's particle map[k]).  The device order is kept because the in-cell order of
- * the next sort, and with it every P2G rounding, depends on the order the sort starts from: a
- * run continued from a reloaded file is bit-identical to the uninterrupted run.  The reference
- * has no state format (its only output is the PPM frame, src/Renderer.cpp). */
+ * file is the caller's particle map[k]).  A run continued from a reloaded file is bit-identical
+ * to the uninterrupted run (the cell sort orders every cell by original index, so the stored
+ * order does not matter).  The reference has no state format (its only output is the PPM frame,
+ * src/Renderer.cpp). */
 int fsb_save_state(fsb_ctx* ctx, const char* path);
 /* The context must have the file's grid size. */
 int fsb_load_state(fsb_ctx* ctx, const char* path);
