@@ -50,6 +50,8 @@ static inline T __ldg(const T* p)
 #define FSB_VEC_WANT_GRID
 #define FSB_VEC_WANT_CG
 #include "fsb_vec_kernels.cuh"
+#include "fsb_mg_kernels.cuh"
+#include <vector>
 
 namespace {
 template <class F>
@@ -138,6 +140,106 @@ void emul_cg_build(const float* uf, const float* vf, const uint8_t* cell, uint8_
       std::memcpy(code + i0 + (size_t)j * ld, &cd, 4);
       std::memcpy(r + i0 + (size_t)j * ld, &b, 16);
     }
+}
+
+// One V-cycle z = V(r) of the multigrid preconditioner, the launch sequence of mg_vcycle() in
+// fsb_mg.cu (2 + 2 damped-Jacobi sweeps, restriction, 40 sweeps on the coarsest level, prolongation)
+// on host arrays.  lab / code0 / r are pitched (ld = nx rounded up to 32); z receives the result.
+// Returns the number of levels.
+int emul_mg_vcycle(const uint8_t* lab0, const uint8_t* code0, const float* r0, int nx0, int ny0,
+                   float inv_h2_0, float* z)
+{
+  struct Lv
+  {
+    int nx, ny, ld;
+    float inv_h2;
+    std::vector<uint8_t> lab, code;
+    std::vector<float> x[2], b, r;
+  };
+  std::vector<Lv> lv;
+  int nx = nx0, ny = ny0;
+  float inv_h2 = inv_h2_0;
+  for (int l = 0; l < 16; ++l)
+  {
+    Lv L;
+    L.nx = nx; L.ny = ny; L.ld = (nx + 31) / 32 * 32; L.inv_h2 = inv_h2;
+    const size_t cells = (size_t)L.ld * ny;
+    L.lab.assign(cells, FSB_SOLID); L.code.assign(cells, 0);
+    L.x[0].assign(cells, 0.f); L.x[1].assign(cells, 0.f); L.b.assign(cells, 0.f); L.r.assign(cells, 0.f);
+    lv.push_back(std::move(L));
+    if (nx <= 32 && ny <= 32) break;
+    nx = (nx + 1) / 2; ny = (ny + 1) / 2; inv_h2 *= 0.25f;
+  }
+  {
+    Lv& L = lv[0];
+    std::memcpy(L.lab.data(), lab0, L.lab.size());
+    std::memcpy(L.code.data(), code0, L.code.size());
+    std::memcpy(L.b.data(), r0, L.b.size() * sizeof(float));
+  }
+  for (size_t l = 1; l < lv.size(); ++l)
+  {
+    Lv& F = lv[l - 1];
+    Lv& C = lv[l];
+    launch(div_up(C.ld, 256), C.ny, 256, [&] {
+      k_mg_coarsen_labels(F.lab.data(), F.nx, F.ny, F.ld, C.lab.data(), C.nx, C.ny, C.ld);
+    });
+    launch(div_up(C.ld, 256), C.ny, 256, [&] { k_mg_codes(C.lab.data(), C.code.data(), C.nx, C.ny, C.ld); });
+  }
+  auto coef = [](float ih2) {
+    MgCoef k;
+    k.inv_h2 = ih2;
+    k.wdinv[0] = 0.0f;
+    for (int n = 1; n < 5; ++n) k.wdinv[n] = kMgOmega * (-1.0f / ((float)n * ih2));
+    return k;
+  };
+  const int last = (int)lv.size() - 1;
+  std::vector<int> cur(lv.size(), 0);
+  auto smooth_first = [&](Lv& L) {
+    const MgCoef kf = coef(L.inv_h2);
+    launch(div_up(L.ld, 1024), L.ny, 256, [&] {
+      k_mg_smooth<true>(nullptr, L.b.data(), L.code.data(), L.x[0].data(), L.nx, L.ny, L.ld, kf);
+    });
+  };
+  auto smooth = [&](Lv& L, int& c) {
+    const MgCoef kf = coef(L.inv_h2);
+    launch(div_up(L.ld, 1024), L.ny, 256, [&] {
+      k_mg_smooth<false>(L.x[c].data(), L.b.data(), L.code.data(), L.x[c ^ 1].data(), L.nx, L.ny, L.ld, kf);
+    });
+    c ^= 1;
+  };
+  for (int l = 0; l < last; ++l)
+  {
+    Lv& L = lv[l];
+    cur[l] = 0;
+    smooth_first(L);
+    smooth(L, cur[l]); // kMgPre = 2
+    launch(div_up(L.ld, 1024), L.ny, 256, [&] {
+      k_mg_residual(L.x[cur[l]].data(), L.b.data(), L.code.data(), L.r.data(), L.nx, L.ny, L.ld, L.inv_h2);
+    });
+    Lv& C = lv[l + 1];
+    launch(div_up(C.ld, 256), C.ny, 256, [&] {
+      k_mg_restrict(L.r.data(), L.nx, L.ny, L.ld, C.code.data(), C.b.data(), C.nx, C.ny, C.ld);
+    });
+  }
+  {
+    Lv& L = lv[last];
+    cur[last] = 0;
+    smooth_first(L);
+    for (int s = 1; s < 40; ++s) smooth(L, cur[last]); // k_mg_coarse_solve: 40 sweeps from zero
+  }
+  for (int l = last - 1; l >= 0; --l)
+  {
+    Lv& L = lv[l];
+    Lv& C = lv[l + 1];
+    launch(div_up(L.ld, 1024), L.ny, 256, [&] {
+      k_mg_prolong_add(L.x[cur[l]].data(), L.code.data(), L.nx, L.ny, L.ld, C.x[cur[l + 1]].data(), C.nx,
+                       C.ny, C.ld);
+    });
+    smooth(L, cur[l]);
+    smooth(L, cur[l]); // kMgPost = 2
+  }
+  std::memcpy(z, lv[0].x[cur[0]].data(), lv[0].x[cur[0]].size() * sizeof(float));
+  return (int)lv.size();
 }
 
 } // extern "C"

@@ -26,7 +26,8 @@ def emul():
     src = os.path.join(EMUL_DIR, "emul_vec_kernels.cpp")
     out = os.path.join(EMUL_DIR, "libfsbemul.so")
     csrc = os.path.join(ROOT, "fluid_simulation_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("fsb_vec_kernels.cuh", "fsb_device.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("fsb_vec_kernels.cuh", "fsb_device.cuh",
+                                                        "fsb_mg_kernels.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(p) > os.path.getmtime(out) for p in deps):
         cuda_inc = "/usr/local/cuda/include"
         if not os.path.isdir(cuda_inc):
@@ -166,3 +167,37 @@ def test_cg_build_group(emul, nx, ny):
     assert np.array_equal(r[:, :nx], b_ref) and not r[:, nx:].any()
     assert sums[2] == liq.sum()
     assert np.isclose(sums[0], (b_ref.astype(np.float64) ** 2).sum(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("scene,n", [("tank", 64), ("tank", 128), ("blobs", 96), ("blobs", 130)])
+def test_multigrid_vcycle_matches_the_numpy_prototype(emul, scene, n):
+    """One V-cycle of the opt-in multigrid preconditioner -- the level kernels of
+    fsb_mg_kernels.cuh run on the host in the launch order of fsb_mg.cu -- against the independent
+    numpy statement the device code was derived from (tools/studies/mgpcg_prototype.py): coarsening
+    rule, damped-Jacobi sweeps, (1 3 3 1)/8 restriction, 4 R^T prolongation.  Both are fp32 with
+    different summation orders, hence a tolerance."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools", "studies"))
+    import mgpcg_prototype as proto
+    rng = np.random.default_rng(71)
+    if scene == "tank":
+        import bench
+        lab, _, _ = bench.tank_fields(n)
+    else:
+        lab = scenes.random_labels(n, n, rng, p_solid=0.02)
+    dx = np.float32(1.0) / np.float32(n)
+    inv_h2 = np.float32(1.0) / (dx * dx)
+    liq = lab == scenes.LIQUID
+    r = np.where(liq, rng.standard_normal((n, n)), 0.0).astype(np.float32)
+    mg = proto.MG(lab, dx, nmin=32)
+    z_ref = mg.vcycle(r)
+    code = np.where(liq, 1 + proto.make_level(lab)["cnt"], 0).astype(np.uint8)
+    pl, pc, pr = pitched(lab, scenes.SOLID), pitched(code), pitched(r)
+    z = np.zeros_like(pr)
+    emul.emul_mg_vcycle.restype = ctypes.c_int
+    levels = emul.emul_mg_vcycle(ptr(pl), ptr(pc), ptr(pr), ctypes.c_int(n), ctypes.c_int(n),
+                                 ctypes.c_float(inv_h2), ptr(z))
+    assert levels == len(mg.levels)
+    assert not z[:, n:].any() and not z[:, :n][~liq].any()
+    err = np.abs(z[:, :n].astype(np.float64) - z_ref).max() / np.abs(z_ref).max()
+    assert err < 2e-5, err
