@@ -238,6 +238,7 @@ int fsb_create(fsb_ctx** out, int size_x, int size_y, float length_x, float leng
   c->grav_y = (float)-9.82; // src/FluidSolver.cpp:232
   if (const char* e = getenv("FSB_STAGE_KERNELS")) c->stage_v1 = (strcmp(e, "v1") == 0);
   if (const char* e = getenv("FSB_MG_MAX_ITERS")) c->mg_max_iters = std::max(1, atoi(e));
+  if (const char* e = getenv("FSB_MG_SWEEPS")) c->mg_sweeps = std::max(1, std::min(8, atoi(e)));
   memset(c->prof_ms, 0, sizeof c->prof_ms);
   memset(c->prof_calls, 0, sizeof c->prof_calls);
 

@@ -147,6 +147,7 @@ struct fsb_ctx
   // preconditioner: FSB_PRECOND_JACOBI (the reference's, default) or FSB_PRECOND_MULTIGRID (opt-in)
   int precond = 0;
   int mg_max_iters = 200;    // beyond this the multigrid iteration is abandoned for Jacobi
+  int mg_sweeps = 3;         // damped-Jacobi pre- and post-sweeps per level (equal: symmetric V-cycle)
   bool last_solve_mg = false;
   fsb_mg_state* mg = nullptr;
   bool cg_persist_miss_normal = false;

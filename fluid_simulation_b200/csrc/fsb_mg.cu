@@ -10,7 +10,8 @@
 //     is AIR, else LIQUID if any child is LIQUID, else SOLID; the 5-point operator is re-discretised
 //     on the coarse labels with h -> 2h (same matrix-free form as the fine operator: no stored
 //     matrix on any level);
-//   * smoother: damped Jacobi (omega = 2/3), 2 pre- and 2 post-sweeps; restriction = tensor product
+//   * smoother: damped Jacobi (omega = 2/3), 3 pre- and 3 post-sweeps (FSB_MG_SWEEPS; the numpy study
+//     tools/studies/mgpcg_prototype.py needs 36 iterations at 2048^2 with 2 + 2 and 23 with 3 + 3); restriction = tensor product
 //     of (1 3 3 1)/8, prolongation = 4 x its transpose (cell-centred bilinear); the coarsest level is
 //     solved by 40 Jacobi sweeps inside one CTA's shared memory.  Equal pre/post sweeps and
 //     P = 4 R^T keep the V-cycle symmetric, as CG requires.
@@ -35,7 +36,7 @@ constexpr int kMgMaxLevels = 16;
 // coarsened on to 8 x 8 -- the "any AIR child -> AIR" rule misplaces the free surface by up to one
 // coarse cell per level, so very coarse levels add little
 constexpr int kMgStop = 32;
-constexpr int kMgPre = 2, kMgPost = 2, kMgCoarseSweeps = 40;
+constexpr int kMgCoarseSweeps = 40;
 
 struct MgLevel
 {
@@ -320,7 +321,7 @@ int mg_vcycle(fsb_ctx* c, int* cur_out)
     cur[l] = 0;
     k_mg_smooth<true><<<grid4(L), 256, 0, c->stream>>>(nullptr, L.b, L.code, L.x[0], L.nx, L.ny, L.ld, kf);
     FSB_LAUNCHED(c);
-    for (int s = 1; s < kMgPre; ++s)
+    for (int s = 1; s < c->mg_sweeps; ++s)
     {
       k_mg_smooth<false><<<grid4(L), 256, 0, c->stream>>>(L.x[cur[l]], L.b, L.code, L.x[cur[l] ^ 1], L.nx, L.ny, L.ld, kf);
       FSB_LAUNCHED(c);
@@ -347,7 +348,7 @@ int mg_vcycle(fsb_ctx* c, int* cur_out)
     k_mg_prolong_add<<<grid4(L), 256, 0, c->stream>>>(L.x[cur[l]], L.code, L.nx, L.ny, L.ld,
                                                       C.x[cur[l + 1]], C.nx, C.ny, C.ld);
     FSB_LAUNCHED(c);
-    for (int s = 0; s < kMgPost; ++s)
+    for (int s = 0; s < c->mg_sweeps; ++s)
     {
       k_mg_smooth<false><<<grid4(L), 256, 0, c->stream>>>(L.x[cur[l]], L.b, L.code, L.x[cur[l] ^ 1], L.nx, L.ny, L.ld, kf);
       FSB_LAUNCHED(c);

@@ -143,11 +143,11 @@ void emul_cg_build(const float* uf, const float* vf, const uint8_t* cell, uint8_
 }
 
 // One V-cycle z = V(r) of the multigrid preconditioner, the launch sequence of mg_vcycle() in
-// fsb_mg.cu (2 + 2 damped-Jacobi sweeps, restriction, 40 sweeps on the coarsest level, prolongation)
+// fsb_mg.cu (`sweeps` + `sweeps` damped-Jacobi sweeps, restriction, 40 sweeps on the coarsest level, prolongation)
 // on host arrays.  lab / code0 / r are pitched (ld = nx rounded up to 32); z receives the result.
 // Returns the number of levels.
 int emul_mg_vcycle(const uint8_t* lab0, const uint8_t* code0, const float* r0, int nx0, int ny0,
-                   float inv_h2_0, float* z)
+                   float inv_h2_0, float* z, int sweeps)
 {
   struct Lv
   {
@@ -212,7 +212,7 @@ int emul_mg_vcycle(const uint8_t* lab0, const uint8_t* code0, const float* r0, i
     Lv& L = lv[l];
     cur[l] = 0;
     smooth_first(L);
-    smooth(L, cur[l]); // kMgPre = 2
+    for (int s = 1; s < sweeps; ++s) smooth(L, cur[l]); // pre-smoothing
     launch(div_up(L.ld, 1024), L.ny, 256, [&] {
       k_mg_residual(L.x[cur[l]].data(), L.b.data(), L.code.data(), L.r.data(), L.nx, L.ny, L.ld, L.inv_h2);
     });
@@ -235,8 +235,7 @@ int emul_mg_vcycle(const uint8_t* lab0, const uint8_t* code0, const float* r0, i
       k_mg_prolong_add(L.x[cur[l]].data(), L.code.data(), L.nx, L.ny, L.ld, C.x[cur[l + 1]].data(), C.nx,
                        C.ny, C.ld);
     });
-    smooth(L, cur[l]);
-    smooth(L, cur[l]); // kMgPost = 2
+    for (int s = 0; s < sweeps; ++s) smooth(L, cur[l]); // post-smoothing
   }
   std::memcpy(z, lv[0].x[cur[0]].data(), lv[0].x[cur[0]].size() * sizeof(float));
   return (int)lv.size();

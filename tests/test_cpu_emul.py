@@ -169,8 +169,9 @@ def test_cg_build_group(emul, nx, ny):
     assert np.isclose(sums[0], (b_ref.astype(np.float64) ** 2).sum(), rtol=1e-12)
 
 
+@pytest.mark.parametrize("sweeps", [2, 3])
 @pytest.mark.parametrize("scene,n", [("tank", 64), ("tank", 128), ("blobs", 96), ("blobs", 130)])
-def test_multigrid_vcycle_matches_the_numpy_prototype(emul, scene, n):
+def test_multigrid_vcycle_matches_the_numpy_prototype(emul, scene, n, sweeps):
     """One V-cycle of the opt-in multigrid preconditioner -- the level kernels of
     fsb_mg_kernels.cuh run on the host in the launch order of fsb_mg.cu -- against the independent
     numpy statement the device code was derived from (tools/studies/mgpcg_prototype.py): coarsening
@@ -189,14 +190,14 @@ def test_multigrid_vcycle_matches_the_numpy_prototype(emul, scene, n):
     inv_h2 = np.float32(1.0) / (dx * dx)
     liq = lab == scenes.LIQUID
     r = np.where(liq, rng.standard_normal((n, n)), 0.0).astype(np.float32)
-    mg = proto.MG(lab, dx, nmin=32)
+    mg = proto.MG(lab, dx, nmin=32, pre=sweeps, post=sweeps)
     z_ref = mg.vcycle(r)
     code = np.where(liq, 1 + proto.make_level(lab)["cnt"], 0).astype(np.uint8)
     pl, pc, pr = pitched(lab, scenes.SOLID), pitched(code), pitched(r)
     z = np.zeros_like(pr)
     emul.emul_mg_vcycle.restype = ctypes.c_int
     levels = emul.emul_mg_vcycle(ptr(pl), ptr(pc), ptr(pr), ctypes.c_int(n), ctypes.c_int(n),
-                                 ctypes.c_float(inv_h2), ptr(z))
+                                 ctypes.c_float(inv_h2), ptr(z), ctypes.c_int(sweeps))
     assert levels == len(mg.levels)
     assert not z[:, n:].any() and not z[:, :n][~liq].any()
     err = np.abs(z[:, :n].astype(np.float64) - z_ref).max() / np.abs(z_ref).max()
