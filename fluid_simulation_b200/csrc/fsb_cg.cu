@@ -432,9 +432,17 @@ struct TileWalk
 // that is the air cap, in a dam-break scene most of the grid.
 __global__ void __launch_bounds__(128)
 k_cg_tile_flags(const uint8_t* __restrict__ code, int ld, int tiles_x, int th, int row_lo, int row_hi,
-                int* __restrict__ flags)
+                int* __restrict__ flags, int keep_edge_rows)
 {
   const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  // sharded solves: the tiles of the slab's first and last tile row stay active whatever they
+  // hold, so that their rows (zeros included) are stored into the neighbours' ghost rows in
+  // every sweep -- the ghost rows are the peers' to write, this rank never clears them
+  if (keep_edge_rows && (ty == 0 || ty == (int)(gridDim.x / tiles_x) - 1))
+  {
+    if (threadIdx.x == 0) flags[blockIdx.x] = 1;
+    return;
+  }
   const int col = tx * kTileW + (int)(threadIdx.x & 7) * 16;
   int any = 0;
   if (col < ld)
@@ -2270,7 +2278,8 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
         c->cg_tile_cap = n_t;
       }
       k_cg_tile_flags<<<n_t, 128, 0, c->stream>>>(c->cg_code, c->ld, tiles_x, th, c->shard.row_lo,
-                                                  c->shard.row_hi, c->cg_tile_flags);
+                                                  c->shard.row_hi, c->cg_tile_flags,
+                                                  c->shard.world > 1 ? 1 : 0);
       FSB_LAUNCHED(c);
       k_cg_tile_compact<<<1, 1024, 0, c->stream>>>(c->cg_tile_flags, n_t, tiles_x, c->cg_tile_list,
                                                    c->scal, (c->shard.world > 1 && c->cg_edge_first) ? 1 : 0);
@@ -2389,12 +2398,15 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
   fsb_prof_end(c, FSB_PROF_CG);
   if (c->cg_skip_tiles)
   {
-    // skipped tiles rely on the direction buffers being zero there: leave them zero for the next
-    // solve (whose liquid region differs).  Done here, after the end-of-solve barrier of a sharded
-    // run, because a peer may store its first boundary row before this rank starts its next solve.
-    const size_t bytes = sizeof(float) * (size_t)c->ld * c->ny;
-    FSB_CUDA(c, cudaMemsetAsync(c->cg_p[0], 0, bytes, c->stream));
-    FSB_CUDA(c, cudaMemsetAsync(c->cg_p[1], 0, bytes, c->stream));
+    // skipped tiles rely on the direction buffers being zero there: leave this rank's OWN rows zero
+    // for the next solve (whose liquid region differs).  The ghost rows next to the slab belong to
+    // the neighbours (their boundary tiles are always active and rewrite them in every sweep), so
+    // they are not touched here: a peer may already be storing into them for its next solve.
+    const int lo = c->shard.world > 1 ? c->shard.row_lo : 0;
+    const int hi = c->shard.world > 1 ? c->shard.row_hi : c->ny;
+    const size_t off = (size_t)lo * c->ld, bytes = sizeof(float) * (size_t)(hi - lo) * c->ld;
+    FSB_CUDA(c, cudaMemsetAsync(c->cg_p[0] + off, 0, bytes, c->stream));
+    FSB_CUDA(c, cudaMemsetAsync(c->cg_p[1] + off, 0, bytes, c->stream));
   }
   if (!c->last_solve_mg)
   {
