@@ -313,6 +313,7 @@ void fsb_destroy(fsb_ctx* c)
   for (int k = 0; k < c->n_ipc_opened; ++k) cudaIpcCloseMemHandle(c->ipc_opened[k]);
   cudaFree(c->peer_x_dev); cudaFree(c->mail_local);
   fsb_mg_free(c);
+  fsb_cg1_free(c);
   cudaFree(c->slab_buf_part); cudaFree(c->slab_buf_orig); cudaFree(c->slab_ctr);
   cudaFree(c->cg_tile_flags); cudaFree(c->cg_tile_list);
   cudaFree(c->partials); cudaFree(c->scal); cudaFree(c->stage);
@@ -1214,6 +1215,7 @@ int fsb_cg_launch_mode(const fsb_ctx* c)
 {
   if (!c) return 0;
   if (c->last_solve_mg) return 3;
+  if (c->last_solve_single) return 4;
   if (c->cg_tile_rows == 0) return 0;
   return c->cg_fused ? 2 : 1;
 }

@@ -1974,6 +1974,7 @@ int configure_cg(fsb_ctx* c)
     // (profiles/r01g).  FSB_CG_MODE=graph selects two launches per iteration in a CUDA graph.
     const char* mode = getenv("FSB_CG_MODE");
     c->cg_fused = coop != 0 && !(mode && mode[0] == 'g');
+    c->cg_single = mode && mode[0] == 's'; // opt-in single-reduction iteration (fsb_cg1.cu)
     // Sharded solves on short slabs are bound by the two cross-GPU reductions per iteration, and the
     // kernel-boundary form of that handshake (last CTA + one-warp combine) is lighter than the
     // in-kernel one where every CTA polls the mailbox: measured on 2 B200, 8.4 M cells per rank
@@ -2328,6 +2329,13 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
       fin = c->scal_h[0];
     }
   }
+  c->last_solve_single = false;
+  if (!fin.done && c->cg_single && c->shard.world == 1)
+  {
+    FSB_TRY(fsb_k_cg1_solve(c));
+    c->last_solve_single = true;
+    fin.done = 1;
+  }
   if (!fin.done && c->cg_fused)
   {
     // one persistent kernel runs the loop to completion; no polling
@@ -2408,7 +2416,7 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     FSB_CUDA(c, cudaMemsetAsync(c->cg_p[0] + off, 0, bytes, c->stream));
     FSB_CUDA(c, cudaMemsetAsync(c->cg_p[1] + off, 0, bytes, c->stream));
   }
-  if (!c->last_solve_mg)
+  if (!c->last_solve_mg && !c->last_solve_single)
   {
     c->iters = fin.iter;
     c->err = (fin.rhs2 == 0.0 || (float)fin.rhs2 == 0.0f)

@@ -83,7 +83,8 @@ struct CgCoef
   float invdiag[5]; // Eigen DiagonalPreconditioner: diag != 0 ? 1/diag : 1
 };
 
-struct fsb_mg_state; // multigrid hierarchy of the opt-in preconditioner (fsb_mg.cu)
+struct fsb_mg_state;  // multigrid hierarchy of the opt-in preconditioner (fsb_mg.cu)
+struct fsb_cg1_state; // extra vectors of the opt-in single-reduction CG (fsb_cg1.cu)
 
 struct fsb_ctx
 {
@@ -150,6 +151,9 @@ struct fsb_ctx
   int mg_sweeps = 3;         // damped-Jacobi pre- and post-sweeps per level (equal: symmetric V-cycle)
   bool last_solve_mg = false;
   fsb_mg_state* mg = nullptr;
+  bool cg_single = false; // FSB_CG_MODE=single: one sweep + one reduction per iteration (fsb_cg1.cu)
+  bool last_solve_single = false;
+  fsb_cg1_state* cg1 = nullptr;
   bool cg_persist_miss_normal = false;
   bool cg_skip_tiles = true; // sweeps visit only tiles that hold a LIQUID cell
   bool cg_edge_first = false; // sharded solves: slab boundary tiles first in every sweep (knob)
@@ -270,3 +274,6 @@ void fsb_cg_reconfigure(fsb_ctx* c); // drop the CG launch configuration and gra
 // multigrid-preconditioned CG (fsb_mg.cu)
 int fsb_k_mg_solve(fsb_ctx* c, int* converged);
 void fsb_mg_free(fsb_ctx* c);
+// single-reduction Jacobi-PCG (fsb_cg1.cu)
+int fsb_k_cg1_solve(fsb_ctx* c);
+void fsb_cg1_free(fsb_ctx* c);

@@ -6,6 +6,7 @@
 // faces whose bit is 1), so a sequential sweep is a valid schedule.  tests/test_cpu_emul.py
 // compares the results with the oracle; nothing here is linked into libfsb.so.
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 
@@ -25,6 +26,7 @@
 #define __restrict__
 #endif
 
+using std::fmaf;
 using std::max;
 using std::min;
 
@@ -51,6 +53,8 @@ static inline T __ldg(const T* p)
 #define FSB_VEC_WANT_CG
 #include "fsb_vec_kernels.cuh"
 #include "fsb_mg_kernels.cuh"
+#include "fsb_cg1_kernels.cuh"
+#include <cmath>
 #include <vector>
 
 namespace {
@@ -239,6 +243,52 @@ int emul_mg_vcycle(const uint8_t* lab0, const uint8_t* code0, const float* r0, i
   }
   std::memcpy(z, lv[0].x[cur[0]].data(), lv[0].x[cur[0]].size() * sizeof(float));
   return (int)lv.size();
+}
+
+// The single-reduction Jacobi-PCG of fsb_cg1.cu on host arrays: the same per-group source
+// (cg1_group) and the same scalar recurrences (cg1_advance), one loop iteration per CUDA thread,
+// partial sums added in group order.  code / b pitched (from emul_cg_build); x receives the
+// solution.  Returns the iteration count (Eigen's convention); *relres = |r| / |b|.
+int emul_cg1_solve(const uint8_t* code, const float* b, int nx, int ny, int ld, float dx, float tol,
+                   int max_iters, float* x, float* relres)
+{
+  const size_t cells = (size_t)ld * ny;
+  std::vector<float> r[2] = {std::vector<float>(b, b + cells), std::vector<float>(cells, 0.f)};
+  std::vector<float> s[2] = {std::vector<float>(cells, 0.f), std::vector<float>(cells, 0.f)};
+  std::vector<float> w[2] = {std::vector<float>(cells, 0.f), std::vector<float>(cells, 0.f)};
+  std::vector<float> p(cells, 0.f);
+  std::memset(x, 0, cells * sizeof(float));
+  Cg1Coef k;
+  const double dx2 = std::pow((double)dx, 2);
+  k.off = (float)(1 / dx2);
+  for (int n = 0; n < 5; ++n)
+  {
+    k.diag[n] = (float)(-n / dx2);
+    k.invdiag[n] = (k.diag[n] != 0.0f) ? 1.0f / k.diag[n] : 1.0f;
+  }
+  Cg1Scalars sc;
+  std::memset(&sc, 0, sizeof sc);
+  double rhs2 = 0.0;
+  for (size_t q = 0; q < cells; ++q) rhs2 += (double)b[q] * (double)b[q];
+  sc.rhs2 = rhs2; sc.r2 = rhs2;
+  float thr = tol * tol * (float)rhs2; // Eigen: max(tol^2 |b|^2, FLT_MIN)
+  if (thr < 1.17549435e-38f) thr = 1.17549435e-38f;
+  sc.thr = thr; sc.max_iters = max_iters; sc.init = 1;
+  if ((float)rhs2 == 0.0f || max_iters <= 0) { *relres = 0.0f; return 0; }
+  int cur = 0;
+  for (long sweep = 0; !sc.done && sweep < 4L * (max_iters + 2) + 64; ++sweep)
+  {
+    const float alpha = sc.init ? 0.0f : sc.alpha, beta = sc.init ? 0.0f : sc.beta;
+    double ag = 0.0, ad = 0.0, ar = 0.0;
+    for (int j = 0; j < ny; ++j)
+      for (int i0 = 0; i0 < ld; i0 += 4)
+        cg1_group(r[cur].data(), s[cur].data(), w[cur].data(), r[cur ^ 1].data(), s[cur ^ 1].data(),
+                  w[cur ^ 1].data(), p.data(), x, code, nx, ny, ld, i0, j, alpha, beta, k, &ag, &ad, &ar);
+    cg1_advance(&sc, ag, ad, ar);
+    cur ^= 1;
+  }
+  *relres = (float)std::sqrt((float)sc.r2 / (float)sc.rhs2);
+  return sc.iter;
 }
 
 } // extern "C"

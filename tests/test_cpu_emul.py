@@ -27,7 +27,7 @@ def emul():
     out = os.path.join(EMUL_DIR, "libfsbemul.so")
     csrc = os.path.join(ROOT, "fluid_simulation_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in ("fsb_vec_kernels.cuh", "fsb_device.cuh",
-                                                        "fsb_mg_kernels.cuh")]
+                                                        "fsb_mg_kernels.cuh", "fsb_cg1_kernels.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(p) > os.path.getmtime(out) for p in deps):
         cuda_inc = "/usr/local/cuda/include"
         if not os.path.isdir(cuda_inc):
@@ -202,3 +202,48 @@ def test_multigrid_vcycle_matches_the_numpy_prototype(emul, scene, n, sweeps):
     assert not z[:, n:].any() and not z[:, :n][~liq].any()
     err = np.abs(z[:, :n].astype(np.float64) - z_ref).max() / np.abs(z_ref).max()
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 64), (96, 40), (130, 67)])
+def test_single_reduction_cg_matches_the_reference_iteration(emul, port, nx, ny):
+    """The opt-in single-reduction Jacobi-PCG (fsb_cg1_kernels.cuh: one sweep and one reduction
+    point per iteration) run on the host from the device source: same stopping rule, the iteration
+    count of the reference's two-reduction iteration (CPU checker) within 2 %, pressure within the
+    solver tolerance."""
+    rng = np.random.default_rng(81)
+    lab = scenes.random_labels(nx, ny, rng, p_solid=0.03)
+    u, v = scenes.random_field(nx, ny, rng), scenes.random_field(nx, ny, rng)
+    c = make_sim(port, nx, ny)
+    c.set_cell_types(lab); c.set_grid(U_FRONT, u); c.set_grid(V_FRONT, v)
+    tol = 1e-6
+    c.set_cg(20000, tol)
+    c.pressure_solve(0.01, 0.01)
+    it_ref, err_ref = c.cg_info()
+    p_ref = c.get_pressure().astype(np.float64)
+    # set-up through the emulated build (codes + right-hand side), then the emulated solve
+    dx = np.float32(c.dx)
+    invdiag = np.array([1.0] + [1.0 / float(np.float32(-n / float(dx) ** 2)) for n in range(1, 5)],
+                       dtype=np.float32)
+    pl = pitched(lab, scenes.SOLID)
+    ld = pl.shape[1]
+    code, b = np.zeros_like(pl), np.zeros(pl.shape, dtype=np.float32)
+    sums = np.zeros(3)
+    emul.emul_cg_build(ptr(pitched(u)), ptr(pitched(v)), ptr(pl), ptr(code), ptr(b), ptr(invdiag),
+                       ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(ld), ctypes.c_float(c.dx),
+                       ctypes.c_float(c.dy), ptr(sums))
+    x = np.zeros(pl.shape, dtype=np.float32)
+    relres = ctypes.c_float(0)
+    emul.emul_cg1_solve.restype = ctypes.c_int
+    its = emul.emul_cg1_solve(ptr(code), ptr(b), ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(ld),
+                              ctypes.c_float(c.dx), ctypes.c_float(tol), ctypes.c_int(20000), ptr(x),
+                              ctypes.byref(relres))
+    assert relres.value < tol and err_ref < tol
+    assert abs(its - it_ref) <= max(2, 0.02 * it_ref), (its, it_ref)
+    assert not x[:, nx:].any() and not x[:, :nx][lab != scenes.LIQUID].any()
+    rel = np.linalg.norm(x[:, :nx].astype(np.float64) - p_ref) / np.linalg.norm(p_ref)
+    assert rel < 2e-3, rel
+    # a capped solve stops exactly at the cap
+    its = emul.emul_cg1_solve(ptr(code), ptr(b), ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(ld),
+                              ctypes.c_float(c.dx), ctypes.c_float(tol), ctypes.c_int(7), ptr(x),
+                              ctypes.byref(relres))
+    assert its == 7
