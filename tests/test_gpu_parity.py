@@ -451,6 +451,36 @@ def test_active_tile_list_changes_nothing_but_the_work(capi, monkeypatch, mode):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("nx,ny", [(64, 64), (130, 67), (700, 300)])
+def test_single_reduction_mode_experimental(capi, port, monkeypatch, nx, ny):
+    """FSB_CG_MODE=single (fsb_cg1.cu): verified on the CPU through the host emulation of its source;
+    its first GPU run is left to a round with GPU time -- opt-in so that an experimental mode cannot
+    turn the suite red."""
+    import os
+    if os.environ.get("FSB_TEST_EXPERIMENTAL") != "1":
+        pytest.skip("experimental launch mode: set FSB_TEST_EXPERIMENTAL=1")
+    rng = np.random.default_rng(21)
+    lab = scenes.random_labels(nx, ny, rng)
+    fu, fv = scenes.random_field(nx, ny, rng), scenes.random_field(nx, ny, rng)
+    out = {}
+    for mode in ("fused", "single"):
+        for k in CG_KNOBS:
+            monkeypatch.delenv(k, raising=False)
+        monkeypatch.setenv("FSB_CG_MODE", mode)
+        g = capi.Sim(nx, ny, 1.0, float(np.float32(ny) / np.float32(nx)), 0.01, 0.05)
+        g.set_cell_types(lab); g.set_grid(U_FRONT, fu); g.set_grid(V_FRONT, fv)
+        g.set_cg(20000, 1e-6)
+        g.pressure_solve(0.01, 0.01)
+        out[mode] = (g.cg_info(), g.get_pressure().astype(np.float64), g.cg_launch_mode())
+        g.close()
+    monkeypatch.delenv("FSB_CG_MODE")
+    (ia, ea), pa, ma = out["fused"]
+    (ib, eb), pb, mb = out["single"]
+    assert mb == 4 and ea < 1e-6 and eb < 1e-6
+    assert abs(ia - ib) <= max(2, 0.02 * ia)
+    assert np.linalg.norm(pa - pb) / np.linalg.norm(pa) < 2e-3
+
+
 def test_pressure_patch_exact_given_same_pressure(capi, port):
     """With zero divergence-free input (rhs == 0) the solve returns x = 0 in 0 iterations and
     the patch copies front to back on liquid-touching faces: bit-exact on both sides."""
