@@ -1,0 +1,141 @@
+"""Golden vectors at the BASELINE.json configuration sizes, from the reference's OWN code.
+
+Like make_golden.py this drives oracle/_ref/libfsref.so (the reference's sources compiled
+unchanged from /root/reference against oracle/eigen_shim), so it only runs in the build
+container; the outputs are committed and the GPU tests read them.
+
+    python tests/golden/make_golden_big.py config0     # ~2 s   examples/simple.cpp scene, 100 steps
+    python tests/golden/make_golden_big.py config1     # ~2 min 1024^2 semi-Lagrangian dam-break, 3 steps
+    python tests/golden/make_golden_big.py config2     # ~35 min 4096^2 PIC/FLIP tank, one step, CG to 1e-6
+    python tests/golden/make_golden_big.py cg8192c     # ~5 min 8192^2 tank pressure solve, 40 iterations
+
+The CG inside is the restated Eigen loop of the shim (dots accumulated in double, see
+oracle/eigen_shim/Eigen/IterativeLinearSolvers): iteration counts quoted from these files are
+those of that loop, not of an Eigen binary (Eigen is not on this machine).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+import oracle_lib as ol  # noqa: E402
+import scenes  # noqa: E402
+
+
+def config0(ref):
+    """examples/simple.cpp:46-72 -- 64 x 64, one source, dt 0.01, 100 x stepPICFLIP."""
+    n = 64
+    s = ref.sim(n, n, 1.0, 1.0, 0.01, 0.05)
+    assert s.emit_source(*scenes.dam_break_args(n)) == 7800
+    out = {"liquid": [], "cg": [], "mean": [], "labels": []}
+    for step in range(100):
+        s.step(ol.STEP_PICFLIP, 0.01)
+        lab = s.get_cell_types()
+        p = s.get_particles()
+        out["liquid"].append(int((lab == 0).sum()))
+        out["cg"].append(s.cg_info())
+        out["mean"].append(p.astype(np.float64).mean(axis=0))
+        out["labels"].append(np.packbits(lab == 0))
+        if step in (9, 49, 99):
+            out[f"particles_step{step}"] = p.copy()
+    np.savez_compressed(os.path.join(HERE, "config0_100steps.npz"),
+                        liquid=np.array(out["liquid"]), cg=np.array(out["cg"], dtype=np.float64),
+                        mean=np.array(out["mean"]), labels=np.array(out["labels"]),
+                        **{k: v for k, v in out.items() if k.startswith("particles")})
+
+
+def config1(ref):
+    """BASELINE.json configs[1]: 1024^2 semi-Lagrangian dam-break (src/FluidSolver.cpp:99-134),
+    CG run to 1e-6 as in bench.py.  The source box is simple.cpp's, scaled; dt = 0.01 * 64 / n."""
+    n = 1024
+    dt = float(np.float32(0.01 * 64.0 / n))
+    s = ref.sim(n, n, 1.0, 1.0, dt, 0.02)
+    s.set_cg(400000, 1e-6)
+    cnt = s.emit_source(*scenes.dam_break_args(n))
+    out = {"n": n, "dt": dt, "particles0_count": cnt}
+    for step in range(3):
+        t0 = time.time()
+        s.step(ol.STEP_SL, dt)
+        lab = s.get_cell_types()
+        p = s.get_particles()
+        out[f"labels_step{step}"] = np.packbits(lab == 0)
+        out[f"particles_step{step}"] = p[::97].copy()
+        out[f"cg_step{step}"] = np.array(s.cg_info(), dtype=np.float64)
+        out[f"pressure_step{step}"] = s.get_pressure()[::8, ::8].copy()
+        out[f"u_step{step}"] = s.get_grid(ol.U_FRONT)[::8, ::8].copy()
+        out[f"v_step{step}"] = s.get_grid(ol.V_FRONT)[::8, ::8].copy()
+        out[f"uback_step{step}"] = s.get_grid(ol.U_BACK)[::8, ::8].copy()
+        out[f"vback_step{step}"] = s.get_grid(ol.V_BACK)[::8, ::8].copy()
+        out[f"mean_step{step}"] = p.astype(np.float64).mean(axis=0)
+        print("config1 step", step, s.cg_info(), f"{time.time() - t0:.1f}s", flush=True)
+    np.savez_compressed(os.path.join(HERE, "config1_sl1024.npz"), **out)
+
+
+def config2(ref):
+    """BASELINE.json configs[2]: 4096^2 PIC/FLIP (pic_ratio 0.02), bench.py's tank scene (seed 1234),
+    ONE stepPICFLIP with the CG run to 1e-6 (src/FluidSolver.cpp:211-251)."""
+    n = 4096
+    dt = float(np.float32(0.01 * 64.0 / n))
+    s = ref.sim(n, n, 1.0, 1.0, dt, 0.02)
+    s.set_cg(400000, 1e-6)
+    parts = scenes.tank_particles(n, np.random.default_rng(1234), 2)
+    s.set_particles(parts)
+    out = {"n": n, "dt": dt, "n_particles": parts.shape[0]}
+    del parts
+    t0 = time.time()
+    s.step(ol.STEP_PICFLIP, dt)
+    out["seconds"] = time.time() - t0
+    lab = s.get_cell_types()
+    p = s.get_particles()
+    pr = s.get_pressure()
+    out["labels"] = np.packbits(lab == 0)
+    out["liquid"] = int((lab == 0).sum())
+    out["cg"] = np.array(s.cg_info(), dtype=np.float64)
+    out["pressure_ds16"] = pr[::16, ::16].copy()
+    out["pressure_l2"] = float(np.sqrt((pr.astype(np.float64) ** 2).sum()))
+    out["pressure_max"] = float(np.abs(pr).max())
+    out["u_ds16"] = s.get_grid(ol.U_FRONT)[::16, ::16].copy()
+    out["v_ds16"] = s.get_grid(ol.V_FRONT)[::16, ::16].copy()
+    out["particles_ds"] = p[::4099].copy()
+    out["mean"] = p.astype(np.float64).mean(axis=0)
+    print("config2", s.cg_info(), f"{out['seconds']:.0f}s", flush=True)
+    np.savez_compressed(os.path.join(HERE, "config2_picflip4096.npz"), **out)
+
+
+def cg8192c(ref):
+    """BASELINE.json configs[3] sample: the 8192^2 tank pressure system of bench.py (`tank_fields`),
+    the first 40 iterations of the restated Eigen loop: iterate x_40 (down-sampled) and the
+    relative residual -- pins the GPU iteration at this size without a 10-hour CPU solve."""
+    import bench
+    n = 8192
+    dt = float(np.float32(0.01 * 64.0 / n))
+    lab, u0, v0 = bench.tank_fields(n)
+    s = ref.sim(n, n, 1.0, 1.0, dt, 0.02)
+    s.set_cell_types(lab)
+    out = {"n": n, "dt": dt}
+    for cap in (1, 40):
+        s.set_grid(ol.U_FRONT, u0); s.set_grid(ol.V_FRONT, v0)
+        s.set_cg(cap, 1e-6)
+        t0 = time.time()
+        s.pressure_solve(dt, dt)
+        out[f"cg_cap{cap}"] = np.array(s.cg_info(), dtype=np.float64)
+        pr = s.get_pressure()
+        out[f"pressure_cap{cap}_ds32"] = pr[::32, ::32].copy()
+        out[f"pressure_cap{cap}_l2"] = float(np.sqrt((pr.astype(np.float64) ** 2).sum()))
+        print("cg8192 cap", cap, s.cg_info(), f"{time.time() - t0:.0f}s", flush=True)
+    np.savez_compressed(os.path.join(HERE, "cg8192_capped.npz"), **out)
+
+
+if __name__ == "__main__":
+    assert ol.available("fsr"), "build oracle/_ref first: make -C oracle ref"
+    ref = ol.OracleLib("fsr")
+    jobs = {"config0": config0, "config1": config1, "config2": config2, "cg8192c": cg8192c}
+    for name in sys.argv[1:]:
+        t0 = time.time()
+        jobs[name](ref)
+        print(name, f"done in {time.time() - t0:.0f}s", flush=True)

@@ -35,13 +35,14 @@ def cg_single_reduction(L,b,h2,dinv,tol=1e-6,maxit=200000):
         beta=f32(gnew/gamma); gamma=gnew
         alpha=f32(gamma/(delta-float(beta)*gamma/float(alpha)))
     return x,it,np.sqrt(r2/rhs2)
-for n in (256,512,1024):
-    lab,u,v=tank(n); dx=f32(1)/f32(n); b=rhs_from(lab,u,v,dx); L=make_level(lab); h2=f32(1)/(dx*dx)
-    dinv=np.where(L['cnt']>0,f32(-1)/(np.maximum(L['cnt'],1)*h2),f32(0)).astype(f32)
-    t=time.time(); xa,ia,ea=jacobi_pcg(L,b,h2,dinv); ta=time.time()-t
-    t=time.time(); xb,ib,eb=cg_single_reduction(L,b,h2,dinv); tb=time.time()-t
-    # true residuals
-    ra=np.linalg.norm((b-applyA(L,xa,h2)).astype(np.float64))/np.linalg.norm(b.astype(np.float64))
-    rb=np.linalg.norm((b-applyA(L,xb,h2)).astype(np.float64))/np.linalg.norm(b.astype(np.float64))
-    print(n,"standard iters",ia,"relres",float(ea),"true",ra,"| single-reduction iters",ib,"relres",float(eb),"true",rb,
-          "| rel diff",np.linalg.norm(xa.astype(np.float64)-xb)/np.linalg.norm(xa.astype(np.float64)),flush=True)
+if __name__=="__main__":
+  for n in (256,512,1024):
+      lab,u,v=tank(n); dx=f32(1)/f32(n); b=rhs_from(lab,u,v,dx); L=make_level(lab); h2=f32(1)/(dx*dx)
+      dinv=np.where(L['cnt']>0,f32(-1)/(np.maximum(L['cnt'],1)*h2),f32(0)).astype(f32)
+      t=time.time(); xa,ia,ea=jacobi_pcg(L,b,h2,dinv); ta=time.time()-t
+      t=time.time(); xb,ib,eb=cg_single_reduction(L,b,h2,dinv); tb=time.time()-t
+      # true residuals
+      ra=np.linalg.norm((b-applyA(L,xa,h2)).astype(np.float64))/np.linalg.norm(b.astype(np.float64))
+      rb=np.linalg.norm((b-applyA(L,xb,h2)).astype(np.float64))/np.linalg.norm(b.astype(np.float64))
+      print(n,"standard iters",ia,"relres",float(ea),"true",ra,"| single-reduction iters",ib,"relres",float(eb),"true",rb,
+            "| rel diff",np.linalg.norm(xa.astype(np.float64)-xb)/np.linalg.norm(xa.astype(np.float64)),flush=True)
