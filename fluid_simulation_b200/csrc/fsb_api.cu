@@ -269,6 +269,7 @@ int fsb_create(fsb_ctx** out, int size_x, int size_y, float length_x, float leng
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cell, cells);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cg_x, cells);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cg_r, cells);
+  if (rc == FSB_OK) rc = dev_alloc(c, &c->cg_r2, cells);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cg_p[0], cells);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cg_p[1], cells);
   if (rc == FSB_OK) rc = dev_alloc(c, &c->cg_code, cells);
@@ -307,13 +308,12 @@ void fsb_destroy(fsb_ctx* c)
     cudaFree(c->part[k]); cudaFree(c->orig[k]);
   }
   cudaFree(c->u_prev); cudaFree(c->v_prev); cudaFree(c->u_diff); cudaFree(c->v_diff);
-  cudaFree(c->cell); cudaFree(c->cg_x); cudaFree(c->cg_r); cudaFree(c->cg_p[0]); cudaFree(c->cg_p[1]);
+  cudaFree(c->cell); cudaFree(c->cg_x); cudaFree(c->cg_r); cudaFree(c->cg_r2); cudaFree(c->cg_p[0]); cudaFree(c->cg_p[1]);
   cudaFree(c->cg_code); cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->scan_block);
   cudaFree(c->sort_key); cudaFree(c->sort_rank); cudaFree(c->sort_idx);
   for (int k = 0; k < c->n_ipc_opened; ++k) cudaIpcCloseMemHandle(c->ipc_opened[k]);
   cudaFree(c->peer_x_dev); cudaFree(c->mail_local);
   fsb_mg_free(c);
-  fsb_cg1_free(c);
   cudaFree(c->slab_buf_part); cudaFree(c->slab_buf_orig); cudaFree(c->slab_ctr);
   cudaFree(c->cg_tile_flags); cudaFree(c->cg_tile_list);
   cudaFree(c->partials); cudaFree(c->scal); cudaFree(c->stage);
@@ -1082,10 +1082,10 @@ struct ShardBlob
 {
   uint32_t magic;
   int nx, ny, ld;
-  cudaIpcMemHandle_t h[5]; // r, p[0], p[1], x, mailbox
+  cudaIpcMemHandle_t h[6]; // r, p[0], p[1], r2, x, mailbox
 };
 static_assert(sizeof(ShardBlob) <= FSB_SHARD_BLOB_BYTES, "blob too large");
-constexpr uint32_t kBlobMagic = 0x46534231u; // "FSB1"
+constexpr uint32_t kBlobMagic = 0x46534232u; // "FSB2"
 } // namespace
 
 int fsb_shard_export(fsb_ctx* c, void* blob)
@@ -1101,8 +1101,8 @@ int fsb_shard_export(fsb_ctx* c, void* blob)
   memset(&b, 0, sizeof b);
   b.magic = kBlobMagic;
   b.nx = c->nx; b.ny = c->ny; b.ld = c->ld;
-  void* ptrs[5] = {c->cg_r, c->cg_p[0], c->cg_p[1], c->cg_x, c->mail_local};
-  for (int k = 0; k < 5; ++k) FSB_CUDA(c, cudaIpcGetMemHandle(&b.h[k], ptrs[k]));
+  void* ptrs[6] = {c->cg_r, c->cg_p[0], c->cg_p[1], c->cg_r2, c->cg_x, c->mail_local};
+  for (int k = 0; k < 6; ++k) FSB_CUDA(c, cudaIpcGetMemHandle(&b.h[k], ptrs[k]));
   memset(blob, 0, FSB_SHARD_BLOB_BYTES);
   memcpy(blob, &b, sizeof b);
   return FSB_OK;
@@ -1118,7 +1118,7 @@ int fsb_shard_disconnect(fsb_ctx* c)
   c->peer_x_dev = nullptr;
   for (int q = 0; q < kMaxRanks; ++q)
   {
-    c->peer_r[q] = c->peer_p[0][q] = c->peer_p[1][q] = c->peer_x[q] = nullptr;
+    c->peer_r[q] = c->peer_r2[q] = c->peer_p[0][q] = c->peer_p[1][q] = c->peer_x[q] = nullptr;
     c->shard.mail[q] = nullptr;
   }
   c->shard.world = 1;
@@ -1150,11 +1150,11 @@ int fsb_shard_connect(fsb_ctx* c, int rank, int world, const void* all_blobs)
     memcpy(&b, base + (size_t)q * FSB_SHARD_BLOB_BYTES, sizeof b);
     if (b.magic != kBlobMagic || b.nx != c->nx || b.ny != c->ny || b.ld != c->ld)
       return fsb_fail(c, FSB_ERR_INVALID, "rank %d exported a different domain", q);
-    void* opened[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const bool neighbour = (q == rank - 1 || q == rank + 1);
-    for (int k = 0; k < 5; ++k)
+    for (int k = 0; k < 6; ++k)
     {
-      if (k < 3 && !neighbour) continue; // r and p are only needed from the adjacent slabs
+      if (k < 4 && !neighbour) continue; // r and p are only needed from the adjacent slabs
       cudaError_t e = cudaIpcOpenMemHandle(&opened[k], b.h[k], cudaIpcMemLazyEnablePeerAccess);
       if (e != cudaSuccess)
         return fsb_fail(c, FSB_ERR_COMM, "cudaIpcOpenMemHandle(rank %d, buffer %d): %s", q, k,
@@ -1164,8 +1164,9 @@ int fsb_shard_connect(fsb_ctx* c, int rank, int world, const void* all_blobs)
     c->peer_r[q] = (float*)opened[0];
     c->peer_p[0][q] = (float*)opened[1];
     c->peer_p[1][q] = (float*)opened[2];
-    c->peer_x[q] = (float*)opened[3];
-    c->shard.mail[q] = (MailSlot*)opened[4];
+    c->peer_r2[q] = (float*)opened[3];
+    c->peer_x[q] = (float*)opened[4];
+    c->shard.mail[q] = (MailSlot*)opened[5];
     peers_x[n_peers++] = c->peer_x[q];
   }
   FSB_TRY(dev_alloc(c, &c->peer_x_dev, (size_t)kMaxRanks, 0));
@@ -1215,8 +1216,8 @@ int fsb_cg_launch_mode(const fsb_ctx* c)
 {
   if (!c) return 0;
   if (c->last_solve_mg) return 3;
-  if (c->last_solve_single) return 4;
   if (c->cg_tile_rows == 0) return 0;
+  if (c->last_solve_one) return 4;
   return c->cg_fused ? 2 : 1;
 }
 int fsb_timer_start(fsb_ctx* c)

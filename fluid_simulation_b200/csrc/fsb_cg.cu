@@ -33,6 +33,7 @@
 #include "fsb_internal.cuh"
 #define FSB_VEC_WANT_CG
 #include "fsb_vec_kernels.cuh"
+#include "fsb_cg_frame.cuh"
 
 namespace {
 
@@ -195,40 +196,6 @@ k_cg_build4(const float* __restrict__ uf, const float* __restrict__ vf,
   }
 }
 
-// ------------------------------------------------------------ tile frame --
-// Both iteration kernels are TMA-fed, warp-specialised, persistent kernels:
-//   * CTA = NW consumer warps + 1 producer warp; tiles of kTileW = 128 columns
-//     x TH = NW * RPW rows.  Consumer warp w owns the RPW consecutive tile rows
-//     w*RPW ..; lane l owns columns 4l..4l+3 (one 16-byte shared-memory access).
-//   * the producer's elected lane walks the CTA's tile list and issues
-//     cp.async.bulk.tensor (TMA) box loads into a STAGES-deep shared-memory
-//     ring, completion on full[stage] (mbarrier, expect_tx); a consumer warp
-//     releases a stage (arrive on empty[stage]) as soon as it has pulled what it
-//     needs into registers.  Boxes include the one-cell halo (fp32: 136 x (TH+2)
-//     starting at (c0-4, j0-1); code bytes: 160 x (TH+2) starting at (c0-16,
-//     j0-1)); TMA zero-fills everything outside the grid, so there is no bounds
-//     logic on the load side, and (STAGES-1) tiles of loads stay in flight per
-//     CTA regardless of what the consumer warps are doing.
-//   * consumers never write shared memory and never synchronise with each
-//     other inside the tile loop: k_cg_direction re-computes the new direction
-//     on the two halo rows and two halo columns of a warp's row block from the
-//     staged r / p_old / code instead of exchanging it between warps.
-//   * coefficients: a float4 group whose four cells are all liquid with four
-//     non-SOLID neighbours (code word 0x05050505, the bulk of any scene) uses
-//     register constants; other groups read a shared-memory table of float4
-//     {inverse diagonal, diagonal, off-diagonal, 0} indexed by the stencil code
-//     (code 0 -> zeros, so masked cells come out exactly 0 without branches).
-//     (An indexed kernel-parameter array compiles to indexed LDC on the XU
-//     pipe: measured 78 % XU-bound, profiles/r01b.)
-//   * arithmetic uses explicit FMA: the CG is held to the solver tolerance and
-//     comparable iteration counts, not to Eigen's rounding.
-constexpr int kTileW = 128;
-constexpr int kHaloW = kTileW + 8;  // fp32 halo box width: columns c0-4 .. c0+131
-constexpr int kCodeW = kTileW + 32; // code halo box width: columns c0-16 .. c0+143
-constexpr uint32_t kInterior4 = 0x05050505u;
-constexpr int kMaxStages = 8;
-
-__host__ __device__ constexpr int align128(int x) { return (x + 127) / 128 * 128; }
 
 template <int TH>
 struct DirStage // k_cg_direction: r, p_old (both with halo), code (with halo)
@@ -266,166 +233,8 @@ struct CgMaps
   CUtensorMap code;    // u8,   box kCodeW x (TH+2)
 };
 
-// ---- PTX wrappers: mbarrier + TMA (sm_90+ forms, SASS: SYNCS / UTMALDG)
-__device__ __forceinline__ uint32_t smem_u32(const void* p)
-{
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
-                                            uint64_t* bar)
-{
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init()
-{
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-// programmatic dependent launch: let the next kernel of the stream be scheduled early / wait
-// for the previous kernel's memory before touching anything it wrote
-__device__ __forceinline__ void pdl_launch_dependents()
-{
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-__device__ __forceinline__ void pdl_wait()
-{
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-__device__ __forceinline__ void consumer_sync(int n_threads) // named barrier 1: consumer warps only
-{
-  asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
-}
 
-// coefficient table: [code] -> {inv diag, diag, off, 0}; code 0 (not liquid) -> zeros
-__device__ __forceinline__ void load_lut(float4* lut, const CgCoef& coef)
-{
-  if (threadIdx.x < 8)
-  {
-    const int t = threadIdx.x;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t >= 1 && t <= 5) v = make_float4(coef.invdiag[t - 1], coef.diag[t - 1], coef.off, 0.f);
-    lut[t] = v;
-  }
-}
 
-// walk of the CTA's tile list (tiles blockIdx.x, + gridDim.x, ...) without a division per tile.
-// `reverse` walks the SAME list from its last tile down: consecutive sweeps over the grid then
-// meet at the rows the previous sweep touched last, which are the ones still in the L2.
-struct TileWalk
-{
-  int tx, ty, step_x, step_y, tiles_x, count;
-  bool rev;
-  // optional list of ACTIVE tiles (packed ty << 16 | tx): the walk then runs over list positions
-  // instead of tile numbers, so tiles without a LIQUID cell are never visited.  The first `prefix`
-  // list entries (a slab's boundary-row tiles in a sharded solve) are visited FIRST in both walk
-  // directions: their rows go to the neighbour GPUs while the rest of the sweep is still running,
-  // so the system-scope fence before the reduction finds the peer stores already acknowledged.
-  const int* list;
-  int first, stride, n_total, k, n_pre;
-  __device__ __forceinline__ TileWalk(int first_tile, int stride_, int tiles_x_, int n_tiles,
-                                      bool reverse = false, const int* list_ = nullptr,
-                                      int prefix = 0)
-  {
-    tiles_x = tiles_x_;
-    rev = reverse;
-    list = list_;
-    first = first_tile;
-    stride = stride_;
-    n_total = n_tiles;
-    k = 0;
-    count = first_tile < n_tiles ? (n_tiles - 1 - first_tile) / stride_ + 1 : 0;
-    // this CTA's list positions below `prefix`
-    n_pre = (list && first_tile < prefix) ? (prefix - 1 - first_tile) / stride_ + 1 : 0;
-    if (n_pre > count) n_pre = count;
-    const int start = reverse ? first_tile + (count - 1) * stride_ : first_tile;
-    step_x = stride_ % tiles_x;
-    step_y = stride_ / tiles_x;
-    tx = 0;
-    ty = 0;
-    if (list)
-    {
-      if (count > 0) decode();
-    }
-    else
-    {
-      tx = start % tiles_x;
-      ty = start / tiles_x;
-    }
-  }
-  // list position of the k-th tile of this CTA: prefix entries ascending, then the rest in walk order
-  __device__ __forceinline__ int position() const
-  {
-    if (k < n_pre) return first + k * stride;
-    const int m = k - n_pre; // m-th of the (count - n_pre) non-prefix entries
-    return rev ? first + (count - 1 - m) * stride : first + (n_pre + m) * stride;
-  }
-  __device__ __forceinline__ void decode()
-  {
-    const int t = __ldg(list + position());
-    tx = t & 0xffff;
-    ty = t >> 16;
-  }
-  __device__ __forceinline__ void next()
-  {
-    if (list)
-    {
-      ++k;
-      if (k < count) decode();
-      return;
-    }
-    if (!rev)
-    {
-      tx += step_x;
-      ty += step_y;
-      if (tx >= tiles_x)
-      {
-        tx -= tiles_x;
-        ++ty;
-      }
-    }
-    else
-    {
-      tx -= step_x;
-      ty -= step_y;
-      if (tx < 0)
-      {
-        tx += tiles_x;
-        --ty;
-      }
-    }
-  }
-};
 
 // ---- active-tile list: tiles whose interior holds at least one LIQUID cell (code != 0).  All CG
 // vectors are exactly zero on the other tiles and stay zero, so the sweeps skip them: in a tank
@@ -438,7 +247,8 @@ k_cg_tile_flags(const uint8_t* __restrict__ code, int ld, int tiles_x, int th, i
   // sharded solves: the tiles of the slab's first and last tile row stay active whatever they
   // hold, so that their rows (zeros included) are stored into the neighbours' ghost rows in
   // every sweep -- the ghost rows are the peers' to write, this rank never clears them
-  if (keep_edge_rows && (ty == 0 || ty == (int)(gridDim.x / tiles_x) - 1))
+  // (the one-sweep solve sends TWO rows of p per side: every tile holding one of the slab's last two rows)
+  if (keep_edge_rows && (ty == 0 || row_lo + (ty + 1) * th >= row_hi - 1))
   {
     if (threadIdx.x == 0) flags[blockIdx.x] = 1;
     return;
@@ -523,44 +333,6 @@ k_cg_tile_compact(const int* __restrict__ flags, int n_tiles, int tiles_x, int* 
   }
 }
 
-// new direction for four cells: z + beta p_old with z = invdiag r
-__device__ __forceinline__ float4 direction4(const float4 r4, const float4 p4, uint32_t c4,
-                                             const float4* lut, float inv5, float beta)
-{
-  float i0 = inv5, i1 = inv5, i2 = inv5, i3 = inv5;
-  if (c4 != kInterior4)
-  {
-    i0 = lut[c4 & 0xff].x;
-    i1 = lut[(c4 >> 8) & 0xff].x;
-    i2 = lut[(c4 >> 16) & 0xff].x;
-    i3 = lut[c4 >> 24].x;
-  }
-  return make_float4(fmaf(beta, p4.x, i0 * r4.x), fmaf(beta, p4.y, i1 * r4.y),
-                     fmaf(beta, p4.z, i2 * r4.z), fmaf(beta, p4.w, i3 * r4.w));
-}
-
-// q = A p for four cells: centre pc, west / east scalars, south / north float4
-__device__ __forceinline__ float4 apply_a4(const float4 pc, float w, float e, const float4 s4,
-                                           const float4 n4, uint32_t c4, const float4* lut,
-                                           float diag5, float off)
-{
-  const float a0 = (w + pc.y) + (s4.x + n4.x);
-  const float a1 = (pc.x + pc.z) + (s4.y + n4.y);
-  const float a2 = (pc.y + pc.w) + (s4.z + n4.z);
-  const float a3 = (pc.z + e) + (s4.w + n4.w);
-  if (c4 == kInterior4)
-    return make_float4(fmaf(diag5, pc.x, off * a0), fmaf(diag5, pc.y, off * a1),
-                       fmaf(diag5, pc.z, off * a2), fmaf(diag5, pc.w, off * a3));
-  const float4 k0 = lut[c4 & 0xff], k1 = lut[(c4 >> 8) & 0xff], k2 = lut[(c4 >> 16) & 0xff],
-               k3 = lut[c4 >> 24];
-  return make_float4(fmaf(k0.y, pc.x, k0.z * a0), fmaf(k1.y, pc.y, k1.z * a1),
-                     fmaf(k2.y, pc.z, k2.z * a2), fmaf(k3.y, pc.w, k3.z * a3));
-}
-
-__device__ __forceinline__ float dot4(const float4 a, const float4 b)
-{
-  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
-}
 
 // ---- scalar updates shared by the single-GPU last-CTA path and the combine kernels
 __device__ __forceinline__ void finalize_update(CgScalars* s, double tr2, double trz)
@@ -581,15 +353,6 @@ __device__ __forceinline__ void finalize_update(CgScalars* s, double tr2, double
   }
 }
 
-// ---- peer-memory mailbox (row-slab sharding, see fsb_internal.cuh)
-// Every 8-byte word of a slot is self-validating: 32 bits of payload + the low 32 bits of the
-// sequence number.  8-byte stores are single transactions, so the reader needs no flag that is
-// ordered after the payload and the writer needs no fence between them (a system-scope fence
-// costs an NVLink round trip).  One double = two words.
-__device__ __forceinline__ unsigned long long mail_word(unsigned int payload, unsigned long long seq)
-{
-  return (unsigned long long)payload | (seq << 32);
-}
 
 // Called by ONE thread after the values are final (and after a system-scope fence if peer rows
 // were stored by this kernel): write them into every rank's mailbox.
@@ -617,53 +380,6 @@ __device__ __forceinline__ unsigned long long global_ns();
 __device__ __forceinline__ bool mail_collect(const ShardArgs& sh, int type, unsigned long long seq,
                                              double* v0, double* v1);
 
-__device__ __forceinline__ unsigned long long global_ns()
-{
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-// A peer that stays silent for kMailTimeoutNs raises comm_error and ends the solve instead of
-// hanging the GPU.
-constexpr unsigned long long kMailTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
-// Watchdog of the persistent kernel's spin loops: a wait that outlives every legitimate cause
-// (the mailbox time-out included) traps, so a protocol bug ends the launch with an error instead
-// of occupying the GPU forever.
-constexpr unsigned long long kHangNs = 45ull * 1000ull * 1000ull * 1000ull;
-struct SpinGuard
-{
-  unsigned int n = 0;
-  unsigned long long t0 = 0;
-  __device__ __forceinline__ void tick()
-  {
-    if ((++n & 4095u) == 0)
-    {
-      const unsigned long long now = global_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > kHangNs) __trap();
-    }
-  }
-};
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
-{
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity)
-{
-  SpinGuard g;
-  while (!mbar_try(bar, parity)) g.tick();
-}
 
 __device__ __forceinline__ bool mail_collect(const ShardArgs& sh, int type, unsigned long long seq,
                                              double* v0, double* v1)
@@ -1200,42 +916,6 @@ struct SolvePush // peer rows receiving this rank's slab boundary rows (null: no
   float *p_lo[2], *p_hi[2], *r_lo, *r_hi;
 };
 
-__device__ __forceinline__ void fence_proxy_async_all()
-{
-  asm volatile("fence.proxy.async;" ::: "memory");
-}
-
-__device__ __forceinline__ uint64_t l2_policy_evict_first()
-{
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-// evict-last on a fraction q/4 of the accesses (q = 1..4); the fraction must be an immediate
-__device__ __forceinline__ uint64_t l2_policy_evict_last(int q)
-{
-  uint64_t pol;
-  if (q >= 4) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  else if (q == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.75;" : "=l"(pol));
-  else if (q == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.5;" : "=l"(pol));
-  else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.25;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1,
-                                                 uint64_t* bar, uint64_t policy)
-{
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void st_f4_hint(float* ptr, const float4 v, uint64_t policy)
-{
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x),
-               "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
-               : "memory");
-}
 
 // per-CTA copy of the CG scalars: every CTA derives the same values from the same totals
 struct SolveState
@@ -1397,19 +1077,6 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[N], CgScalars* s,
   consumer_sync(NW * 32);
 }
 
-// ring slot bookkeeping shared by the producer and the consumers
-struct RingPos
-{
-  int st, round;
-  __device__ __forceinline__ void advance(int stages)
-  {
-    if (++st == stages)
-    {
-      st = 0;
-      ++round;
-    }
-  }
-};
 
 template <int NW, int RPW>
 __global__ void __launch_bounds__((NW + 1) * 32)
@@ -1843,9 +1510,6 @@ CgCoef make_coef(const fsb_ctx* c)
   return coef;
 }
 
-// Kernel shapes: 8 consumer warps x RPW rows.  RPW = 2 (16-row tiles) when that still
-// gives every SM several tiles, else RPW = 1 (8-row tiles, small grids).
-constexpr int kNW = 8;
 
 
 int pick_tile_rows(const fsb_ctx* c)
@@ -1861,29 +1525,6 @@ int pick_tile_rows(const fsb_ctx* c)
   return 8;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// 2-D tiled tensor map over a pitched grid; out-of-range box elements read as zero
-int make_map(fsb_ctx* c, EncodeTiledFn encode, CUtensorMap* map, void* base, bool is_f32,
-             int box_w, int box_h)
-{
-  const cuuint64_t esz = is_f32 ? 4 : 1;
-  const cuuint64_t gdim[2] = {(cuuint64_t)c->ld, (cuuint64_t)c->ny};
-  const cuuint64_t gstride[1] = {(cuuint64_t)c->ld * esz};
-  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
-  const cuuint32_t estride[2] = {1, 1};
-  const CUresult r = encode(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8,
-                            2, base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fsb_fail(c, FSB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d box", (int)r,
-                    box_w, box_h);
-  return FSB_OK;
-}
 
 template <int RPW>
 int configure_kernels(fsb_ctx* c, int64_t n_tiles)
@@ -1972,15 +1613,18 @@ int configure_cg(fsb_ctx* c)
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
     // Default: the persistent single-kernel solve (k_cg_solve) -- fastest at every size measured
     // (profiles/r01g).  FSB_CG_MODE=graph selects two launches per iteration in a CUDA graph.
+    // Default: the one-sweep solve (fsb_cg_one.cu: one sweep and one reduction point per iteration,
+    // 23 B per cell).  FSB_CG_MODE=fused selects the two-sweep persistent kernel of this file
+    // (Eigen's two reduction points, 32 B per cell), FSB_CG_MODE=graph its two-kernel form.
     const char* mode = getenv("FSB_CG_MODE");
     c->cg_fused = coop != 0 && !(mode && mode[0] == 'g');
-    c->cg_single = mode && mode[0] == 's'; // opt-in single-reduction iteration (fsb_cg1.cu)
+    c->cg_one = coop != 0 && (!mode || mode[0] == 'o');
     // Sharded solves on short slabs are bound by the two cross-GPU reductions per iteration, and the
     // kernel-boundary form of that handshake (last CTA + one-warp combine) is lighter than the
     // in-kernel one where every CTA polls the mailbox: measured on 2 B200, 8.4 M cells per rank
     // 64.8 us (graph) vs 68.5 us (persistent), 33.5 M cells per rank 209.5 vs 194.0 us
     // (profiles/r01h_2gpu.md).  FSB_CG_MODE=fused / graph overrides.
-    if (!mode && c->shard.world > 1 &&
+    if (!mode && !c->cg_one && c->shard.world > 1 &&
         (int64_t)(c->shard.row_hi - c->shard.row_lo) * c->ld < (int64_t)12 * 1000 * 1000)
       c->cg_fused = false;
     const char* pdl = getenv("FSB_CG_PDL"); // profiling knob: 0 disables dependent launch
@@ -2225,6 +1869,7 @@ int launch_chunk(fsb_ctx* c, const CgCoef& coef)
 void fsb_cg_reconfigure(fsb_ctx* c)
 {
   c->cg_tile_rows = 0;
+  c->cg_one_th = 0;
   if (c->cg_graph) cudaGraphExecDestroy(c->cg_graph);
   c->cg_graph = nullptr;
   c->cg_graph_state = 0;
@@ -2240,8 +1885,9 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
   const int64_t total = (int64_t)c->ld * c->ny;
   const int build_blocks = (int)std::min<int64_t>(fsb_div_up(total, 256), c->sm_count * 8);
   FSB_TRY(configure_cg(c));
-  const int need = std::max(std::max(3 * build_blocks, 3 * c->cg_grid_fused),
-                            std::max(c->cg_grid_dir, 2 * c->cg_grid_upd));
+  const int need = std::max(std::max(std::max(3 * build_blocks, 3 * c->cg_grid_fused),
+                                     std::max(c->cg_grid_dir, 2 * c->cg_grid_upd)),
+                            fsb_cg_one_partials(c));
   if (need > c->partials_cap)
   {
     if (c->partials) cudaFree(c->partials);
@@ -2304,7 +1950,7 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
   if (getenv("FSB_CG_VERBOSE"))
     fprintf(stderr, "[fsb] solve: %d liquid cells, active tiles %d (list %s), tile rows %d, mode %s\n",
             fin.n_liquid, fin.n_active_tiles, fin.tile_list ? "on" : "off", c->cg_tile_rows,
-            c->cg_fused ? "persistent" : "graph");
+            c->cg_one ? "one-sweep" : c->cg_fused ? "persistent" : "graph");
   c->last_solve_mg = false;
   if (!fin.done && c->precond == FSB_PRECOND_MULTIGRID && c->shard.world == 1)
   {
@@ -2329,14 +1975,18 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
       fin = c->scal_h[0];
     }
   }
-  c->last_solve_single = false;
-  if (!fin.done && c->cg_single && c->shard.world == 1)
+  c->last_solve_one = false;
+  if (!fin.done && c->cg_one)
   {
-    FSB_TRY(fsb_k_cg1_solve(c));
-    c->last_solve_single = true;
-    fin.done = 1;
+    // one persistent kernel, one sweep per iteration
+    FSB_TRY(fsb_k_cg_one_solve(c, coef));
+    FSB_CUDA(c, cudaMemcpyAsync(&c->scal_h[0], c->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost,
+                                c->stream));
+    FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    fin = c->scal_h[0];
+    c->last_solve_one = true;
   }
-  if (!fin.done && c->cg_fused)
+  else if (!fin.done && c->cg_fused)
   {
     // one persistent kernel runs the loop to completion; no polling
     FSB_TRY(set_l2_window(c, true));
@@ -2404,7 +2054,7 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     }
   }
   fsb_prof_end(c, FSB_PROF_CG);
-  if (c->cg_skip_tiles)
+  if (c->cg_skip_tiles && !c->cg_one)
   {
     // skipped tiles rely on the direction buffers being zero there: leave this rank's OWN rows zero
     // for the next solve (whose liquid region differs).  The ghost rows next to the slab belong to
@@ -2416,7 +2066,7 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     FSB_CUDA(c, cudaMemsetAsync(c->cg_p[0] + off, 0, bytes, c->stream));
     FSB_CUDA(c, cudaMemsetAsync(c->cg_p[1] + off, 0, bytes, c->stream));
   }
-  if (!c->last_solve_mg && !c->last_solve_single)
+  if (!c->last_solve_mg)
   {
     c->iters = fin.iter;
     c->err = (fin.rhs2 == 0.0 || (float)fin.rhs2 == 0.0f)

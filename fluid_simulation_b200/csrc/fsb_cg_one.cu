@@ -1,0 +1,649 @@
+// One-sweep Jacobi-preconditioned CG: the default solve of the pressure projection
+// (src/FluidSolver.cpp:418-426, Eigen's ConjugateGradient as restated in SURVEY.md Appendix B).
+//
+// Eigen's iteration has two reduction points (p.Ap before the update, r.z after it), which forces
+// two sweeps over the grid and two grid-wide (multi-GPU: cross-GPU) synchronisations per
+// iteration.  This kernel runs the SAME iteration -- same alpha, same x / r / p updates in the
+// same statement order, same stopping test on the exact |r|^2 -- with ONE sweep and ONE
+// reduction point per iteration, and no extra vectors:
+//
+//   sweep k  (knows alpha_k, beta_k; reads p_k with a two-cell halo, r_k with a one-cell halo)
+//     on the tile and its one-cell halo:  q_k = A p_k,  r_{k+1} = r_k - alpha_k q_k,
+//                                         z_{k+1} = D^-1 r_{k+1},  p_{k+1} = z_{k+1} + beta_k p_k
+//     on the tile:                        q_{k+1} = A p_{k+1}   (registers only)
+//                                         x += alpha_k p_k      (odd k: two pending updates at once)
+//     partial sums over the tile:  p_{k+1}.q_{k+1},  r_{k+1}.z_{k+1},  |r_{k+1}|^2,
+//                                  z_{k+1}.q_{k+1},  q_{k+1}.D^-1 q_{k+1}
+//   reduction point:  stop if |r_{k+1}|^2 < threshold (Eigen's test, on the exact norm);
+//                     alpha_{k+1} = r_{k+1}.z_{k+1} / p_{k+1}.q_{k+1}            (as Eigen)
+//                     beta_{k+1}  = (r_{k+2}.z_{k+2}) / (r_{k+1}.z_{k+1})  with the numerator from
+//                                   the identity  r'.z' = r.z - 2 alpha z.q + alpha^2 q.D^-1 q
+//                                   (r' = r - alpha q), evaluated in double from the exact dot
+//                                   products of the vectors of THIS sweep.
+// The identity is exact algebra on the vectors actually stored; the only difference to Eigen's
+// beta is that r' enters before its fp32 rounding (relative 1e-7, the size of beta's own
+// rounding).  Nothing is carried by recurrence from one iteration to the next: every alpha comes
+// from exact dot products, so there is no drift.  numpy fp32 study: identical iteration counts
+// (910 / 1714 at 256^2 / 512^2 to 1e-6, 529 / 1007 at 128^2 / 256^2 to FLT_EPSILON) and pressure
+// within 2e-6 of the two-reduction iteration (tools/studies/cg_one_sweep_study.py).
+//
+// HBM traffic per cell and iteration: r 4 + p 4 + code 1 in, r 4 + p 4 out, x (4 + 4 + 4) / 2
+// (deferred: x is touched on odd iterations only) = 23 B, against 32 B for the two-sweep kernel
+// of fsb_cg.cu and 45 B for the textbook formulation.  r and p are double-buffered
+// (neighbouring tiles still read the old halo while a tile is being written).
+//
+// Frame: as k_cg_solve (fsb_cg_frame.cuh) -- one persistent cooperative kernel for the whole
+// solve, 8 consumer warps + 1 TMA producer warp per CTA, 2 CTAs per SM, mbarrier ring; the
+// grid barrier carries the reduction and every CTA derives the scalars itself.  Sharded solves:
+// a slab's two boundary rows of p and one of r are stored straight into the neighbours' ghost
+// rows (NVLink), and the five sums cross the GPUs through ONE mailbox round per iteration.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "fsb_cg_frame.cuh"
+#include "fsb_cg_one_scalars.h"
+
+namespace {
+
+template <int TH>
+struct OneStage // p_old (two-cell halo), r_old (one-cell halo), code (one-cell halo)
+{
+  static constexpr int kP = kHaloW * (TH + 4) * 4; // rows j0-2 .. j0+TH+1
+  static constexpr int kR = kHaloW * (TH + 2) * 4; // rows j0-1 .. j0+TH
+  static constexpr int kCode = kCodeW * (TH + 2);
+  static constexpr int oP = 0, oR = align128(kP), oC = oR + align128(kR);
+  static constexpr int kBytes = align128(oC + kCode);
+  static constexpr int kTx = kP + kR + kCode;
+};
+
+struct OneMaps
+{
+  CUtensorMap halo_p[2]; // fp32, box kHaloW x (TH+4)
+  CUtensorMap halo_r[2]; // fp32, box kHaloW x (TH+2)
+  CUtensorMap code;      // u8,   box kCodeW x (TH+2)
+};
+static_assert(sizeof(OneMaps) <= sizeof(((fsb_ctx*)nullptr)->cg_maps_one), "cg_maps_one too small");
+
+// peers' copies of the direction / residual buffers (whole arrays; null: no neighbour that side)
+struct OnePeers
+{
+  float *p_lo[2], *p_hi[2], *r_lo[2], *r_hi[2];
+};
+
+constexpr int kNSums = 5; // p.q, r.z, |r|^2, z.q, q.D^-1 q
+
+__device__ __forceinline__ void st_mail2(unsigned long long* p, unsigned long long a, unsigned long long b)
+{
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_mail2(const unsigned long long* p, unsigned long long& a,
+                                         unsigned long long& b)
+{
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
+// Barrier + reduction of the kNSums sums for the NW consumer warps of every CTA, then the scalar
+// step of the iteration on the CTA's own copy.  Single GPU: warp 0 of EVERY CTA waits for the
+// arrival counter and folds all partials itself in a fixed order (identical bits everywhere, no
+// broadcast hop).  Sharded: CTA 0 folds the slab's partials and posts them into every rank's
+// mailbox (lane q -> rank q); warp 0 of every CTA polls its own rank's mailbox and adds the
+// `world` entries in rank order.
+template <int NW>
+__device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
+                                           double* __restrict__ partials, unsigned phase_id,
+                                           const ShardArgs& sh, OneState* ss, bool pushed)
+{
+  __shared__ double s_part[kNSums][NW];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int n = 0; n < kNSums; ++n)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_down_sync(0xffffffffu, acc[n], o);
+    if (lane == 0) s_part[n][warp] = acc[n];
+  }
+  consumer_sync(NW * 32);
+  if (warp == 0)
+  {
+    const int G = (int)gridDim.x;
+    double tot[kNSums];
+#pragma unroll
+    for (int n = 0; n < kNSums; ++n)
+    {
+      double v = (lane < NW) ? s_part[n][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      tot[n] = v;
+    }
+    if (lane == 0)
+    {
+#pragma unroll
+      for (int n = 0; n < kNSums; ++n) partials[n * G + blockIdx.x] = tot[n];
+      // the CTA's global stores (p / r / x rows, peer rows) must be visible to the TMA loads of the
+      // next sweep on every SM (and GPU) before the arrival is
+      fence_proxy_async_all();
+      if (pushed) __threadfence_system();
+      else __threadfence();
+      atomicAdd(&s->bar_count, 1u);
+    }
+    __syncwarp();
+    if (sh.world == 1 || blockIdx.x == 0)
+    {
+      const volatile unsigned int* cnt = &s->bar_count;
+      const unsigned int target = phase_id * (unsigned int)G;
+      {
+        SpinGuard g;
+        while (*cnt < target) g.tick();
+      }
+      __threadfence();
+      const volatile double* part = partials;
+#pragma unroll
+      for (int n = 0; n < kNSums; ++n)
+      {
+        double v = 0.0;
+        for (int k = (int)lane; k < G; k += 32) v += part[n * G + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        tot[n] = v;
+      }
+    }
+    bool ok = true;
+    const unsigned long long seq = ss->seq + 1;
+    if (sh.world > 1)
+    {
+      const unsigned long long tag = seq & 0xffffffffull;
+      if (blockIdx.x == 0)
+      {
+        // every local CTA's arrival (and its peer rows, fenced at system scope) precedes the entry
+        __threadfence_system();
+        if ((int)lane < sh.world)
+        {
+          unsigned long long* out = reinterpret_cast<unsigned long long*>(sh.mail[lane]) +
+                                    kOneMailWord + sh.rank * kOneMailStride;
+#pragma unroll
+          for (int n = 0; n < kNSums; ++n)
+          {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(tot[n]);
+            st_mail2(out + 2 * n, mail_word((unsigned int)b, seq), mail_word((unsigned int)(b >> 32), seq));
+          }
+        }
+      }
+      double v[kNSums];
+#pragma unroll
+      for (int n = 0; n < kNSums; ++n) v[n] = 0.0;
+      if ((int)lane < sh.world)
+      {
+        const unsigned long long* in = reinterpret_cast<const unsigned long long*>(sh.mail[sh.rank]) +
+                                       kOneMailWord + lane * kOneMailStride;
+        const unsigned long long t0 = global_ns();
+        unsigned int spins = 0;
+#pragma unroll
+        for (int n = 0; n < kNSums; ++n)
+        {
+          unsigned long long w0, w1;
+          for (;;)
+          {
+            ld_mail2(in + 2 * n, w0, w1);
+            if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+            if ((++spins & 1023u) == 0 && global_ns() - t0 > kMailTimeoutNs)
+            {
+              ok = false;
+              break;
+            }
+          }
+          v[n] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+        }
+      }
+      ok = __all_sync(0xffffffffu, ok);
+      __threadfence_system(); // acquire: the peers' boundary rows were stored before their entries
+#pragma unroll
+      for (int n = 0; n < kNSums; ++n)
+      {
+        double t = 0.0;
+        for (int q = 0; q < sh.world; ++q) t += __shfl_sync(0xffffffffu, v[n], q); // rank order
+        tot[n] = t;
+      }
+    }
+    if (lane == 0)
+    {
+      ss->seq = seq;
+      if (!ok)
+      {
+        ss->comm_error = 1;
+        ss->done = 1;
+      }
+      else
+      {
+        one_advance(ss, tot[0], tot[1], tot[2], tot[3], tot[4]);
+      }
+      __threadfence_block();
+      ss->released = phase_id;
+    }
+  }
+  consumer_sync(NW * 32);
+}
+
+template <int NW, int RPW>
+__global__ void __launch_bounds__((NW + 1) * 32, 2)
+k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* __restrict__ r_a,
+            float* __restrict__ r_b, float* __restrict__ p_a, float* __restrict__ p_b, int ld,
+            int tiles_x, int n_tiles, int stages, const CgCoef coef, CgScalars* __restrict__ s,
+            double* __restrict__ partials, const __grid_constant__ ShardArgs sh,
+            const __grid_constant__ OnePeers peers, int flags)
+{
+  constexpr int TH = NW * RPW;
+  using St = OneStage<TH>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full[kMaxStages], empty[kMaxStages];
+  __shared__ float4 lut[8];
+  __shared__ OneState ss;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool serp = (flags & 1) != 0; // consecutive sweeps walk the tile list in opposite directions
+  const bool xdefer = (flags & 128) != 0;
+
+  load_lut(lut, coef);
+  if (threadIdx.x == 0)
+  {
+    for (int k = 0; k < stages; ++k)
+    {
+      mbar_init(&full[k], 1);
+      mbar_init(&empty[k], NW);
+    }
+    fence_barrier_init();
+    volatile CgScalars* vs = s;
+    ss.rz = vs->rz; ss.r2 = vs->r2;
+    ss.alpha = 0.0f; ss.beta = 0.0f; ss.thr = vs->thr;
+    ss.iter = vs->iter; ss.done = vs->done; ss.max_iters = vs->max_iters; ss.comm_error = 0;
+    ss.sweep = -1;
+    ss.seq = vs->seq[3];
+    ss.released = 0;
+  }
+  __syncthreads();
+  const int* __restrict__ tile_list = s->tile_list; // fixed for the whole solve
+  const int n_walk = tile_list ? s->n_active_tiles : n_tiles;
+  const int n_prefix = tile_list ? s->n_prefix_tiles : 0;
+  const int G = (int)gridDim.x;
+
+  if (warp == NW)
+  {
+    // ---- producer: one elected lane feeds the ring, sweep after sweep
+    if (lane != 0 || ss.done) return;
+    RingPos rp = {0, 0};
+    int cur = 0, sweep = -1;
+    unsigned phase_id = 0;
+    for (;;)
+    {
+      TileWalk t(blockIdx.x, G, tiles_x, n_walk, serp && (sweep & 1) == 0, tile_list, n_prefix);
+      for (int k = 0; k < t.count; ++k, t.next())
+      {
+        if (rp.round > 0) mbar_wait_guarded(&empty[rp.st], (rp.round - 1) & 1);
+        unsigned char* base = smem + rp.st * St::kBytes;
+        const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
+        mbar_expect_tx(&full[rp.st], St::kTx);
+        tma_load_2d(base + St::oP, &maps.halo_p[cur], c0 - 4, j0 - 2, &full[rp.st]);
+        tma_load_2d(base + St::oR, &maps.halo_r[cur], c0 - 4, j0 - 1, &full[rp.st]);
+        tma_load_2d(base + St::oC, &maps.code, c0 - 16, j0 - 1, &full[rp.st]);
+        rp.advance(stages);
+      }
+      ++phase_id;
+      {
+        SpinGuard g;
+        while (ss.released < phase_id) g.tick();
+      }
+      fence_proxy_async_all();
+      if (ss.done) return;
+      cur ^= 1;
+      ++sweep;
+    }
+  }
+
+  // ---- consumers
+  const float inv5 = coef.invdiag[4], diag5 = coef.diag[4], off = coef.off;
+  const int r0 = (int)warp * RPW; // first own tile row
+  // stage-relative offsets of this lane (floats / bytes): P box row r0 + i, R / code box row r0 + m
+  const int fo = r0 * kHaloW + 4 + (int)lane * 4;
+  const int co = r0 * kCodeW + 16 + (int)lane * 4;
+  // lanes 0 / 31 also own the west / east halo column: P / R box columns 3 (and 2 beyond it) for
+  // lane 0, 132 (and 133) for lane 31
+  const bool edge = (lane == 0 || lane == 31);
+  const bool west = (lane == 0);
+  const int hfo = r0 * kHaloW + (west ? 3 : 4 + kTileW);     // the halo column itself
+  const int hff = r0 * kHaloW + (west ? 2 : 4 + kTileW + 1); // the column beyond it
+  const int hco = r0 * kCodeW + (west ? 15 : 16 + kTileW);
+  const bool sharded = sh.world > 1;
+  RingPos rp = {0, 0};
+  int cur = 0, sweep = -1;
+  unsigned phase_id = 0;
+  float alpha_prev = 0.0f;       // alpha of the previous iteration (pending x update)
+  bool pending = false;          // x lacks the update of the last iteration
+  const float* last_p = nullptr; // direction of the last iteration
+  while (!ss.done)
+  {
+    const float alpha = ss.alpha, beta = ss.beta, nalpha = -alpha;
+    const bool iter_sweep = sweep >= 0;
+    const bool with_x = iter_sweep && (!xdefer || (sweep & 1));
+    const bool two_x = with_x && xdefer; // the previous iteration's update is still pending
+    const float* __restrict__ p_old = cur ? p_b : p_a;
+    float* __restrict__ p_new = cur ? p_a : p_b;
+    float* __restrict__ r_new = cur ? r_a : r_b;
+    float* const pp_lo = peers.p_lo[cur ^ 1];
+    float* const pp_hi = peers.p_hi[cur ^ 1];
+    float* const pr_lo = peers.r_lo[cur ^ 1];
+    float* const pr_hi = peers.r_hi[cur ^ 1];
+    double acc[kNSums];
+#pragma unroll
+    for (int n = 0; n < kNSums; ++n) acc[n] = 0.0;
+    bool pushed = false;
+    TileWalk t(blockIdx.x, G, tiles_x, n_walk, serp && (sweep & 1) == 0, tile_list, n_prefix);
+    for (int tk = 0; tk < t.count; ++tk, t.next())
+    {
+      const unsigned char* base = smem + rp.st * St::kBytes;
+      const float* sp = reinterpret_cast<const float*>(base + St::oP);
+      const float* sr = reinterpret_cast<const float*>(base + St::oR);
+      const unsigned char* sc = base + St::oC;
+      const int ci = t.tx * kTileW + (int)lane * 4;
+      const int j0 = sh.row_lo + t.ty * TH;
+      const int jb = j0 + r0;
+      // a tile holding one of the slab's two first / last rows stores into peer memory
+      pushed |= sharded && (t.ty == 0 || j0 + TH >= sh.row_hi - 1);
+
+      // x and the previous direction do not pass through the ring: they are read and written by
+      // this thread only, so the loads are simply issued before the wait for the tile
+      float4 xv[RPW], pv[RPW];
+#pragma unroll
+      for (int k = 0; k < RPW; ++k)
+      {
+        xv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int j = jb + k;
+        if (with_x && j < sh.row_hi && ci < ld)
+        {
+          const size_t o = (size_t)j * ld + ci;
+          xv[k] = *reinterpret_cast<const float4*>(x + o);
+          if (two_x) pv[k] = *reinterpret_cast<const float4*>(p_new + o); // p_{k-1}, overwritten below
+        }
+      }
+      mbar_wait_guarded(&full[rp.st], rp.round & 1);
+
+      float4 pk[RPW + 4], rk[RPW + 2];
+      uint32_t cd[RPW + 2];
+      float hpc[RPW + 2]; // lanes 0 / 31: p_old of the halo-column cell, rows of the stage-1 block
+      float he[RPW];      // lanes 0 / 31: NEW direction of the halo-column cell of the own rows
+#pragma unroll
+      for (int i = 0; i < RPW + 4; ++i) pk[i] = *reinterpret_cast<const float4*>(sp + fo + i * kHaloW);
+#pragma unroll
+      for (int m = 0; m < RPW + 2; ++m)
+      {
+        rk[m] = *reinterpret_cast<const float4*>(sr + fo + m * kHaloW);
+        cd[m] = *reinterpret_cast<const uint32_t*>(sc + co + m * kCodeW);
+        hpc[m] = edge ? sp[hfo + (m + 1) * kHaloW] : 0.0f;
+      }
+      // the update of iteration k for the halo-column cell of the own rows (lanes 0 / 31), with the
+      // same association of the sums as apply_a4 / direction4, so that it equals bit for bit what
+      // the owner of that cell stores:  q = A p, r' = r - alpha q, p' = D^-1 r' + beta p
+#pragma unroll
+      for (int k = 0; k < RPW; ++k)
+      {
+        he[k] = 0.0f;
+        if (edge)
+        {
+          const int m = k + 1;
+          const float far = sp[hff + (m + 1) * kHaloW];
+          const float pc = hpc[m];
+          const float pw = west ? far : pk[m + 1].w;
+          const float pe = west ? pk[m + 1].x : far;
+          const float4 kf = lut[sc[hco + m * kCodeW]];
+          const float q = fmaf(kf.y, pc, kf.z * ((pw + pe) + (hpc[m - 1] + hpc[m + 1])));
+          const float rr = fmaf(nalpha, q, sr[hfo + m * kHaloW]);
+          he[k] = fmaf(beta, pc, kf.x * rr);
+        }
+      }
+      // x += alpha p (odd iterations: the pending update of the previous iteration first, the same
+      // rounding order as one update per iteration)
+      if (with_x)
+      {
+#pragma unroll
+        for (int k = 0; k < RPW; ++k)
+        {
+          const int j = jb + k;
+          if (j < sh.row_hi && ci < ld)
+          {
+            float4 xn = xv[k];
+            if (two_x) xn = fma4(alpha_prev, pv[k], xn);
+            xn = fma4(alpha, pk[k + 2], xn);
+            *reinterpret_cast<float4*>(x + (size_t)j * ld + ci) = xn;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[rp.st]); // everything is in registers
+      rp.advance(stages);
+
+      // ---- the update of iteration k on the warp's rows and one row above / below:
+      //      q = A p, r' = r - alpha q, p' = D^-1 r' + beta p     (stage-1 row m = grid row jb - 1 + m)
+      float4 rn[RPW + 2], pn[RPW + 2];
+#pragma unroll
+      for (int m = 0; m < RPW + 2; ++m)
+      {
+        const float4 pc = pk[m + 1];
+        float w = __shfl_up_sync(0xffffffffu, pc.w, 1);
+        float e = __shfl_down_sync(0xffffffffu, pc.x, 1);
+        if (edge) // lane 0: west neighbour, lane 31: east neighbour = the halo-column cell
+        {
+          if (west) w = hpc[m];
+          else e = hpc[m];
+        }
+        const float4 q = apply_a4(pc, w, e, pk[m], pk[m + 2], cd[m], lut, diag5, off);
+        rn[m] = fma4(nalpha, q, rk[m]);
+        pn[m] = direction4(rn[m], pc, cd[m], lut, inv5, beta);
+      }
+
+      // ---- q' = A p' on the own rows, the five sums, the stores
+#pragma unroll
+      for (int k = 0; k < RPW; ++k)
+      {
+        const int m = k + 1;
+        float w = __shfl_up_sync(0xffffffffu, pn[m].w, 1);
+        float e = __shfl_down_sync(0xffffffffu, pn[m].x, 1);
+        if (lane == 0) w = he[k];
+        if (lane == 31) e = he[k];
+        const uint32_t c4 = cd[m];
+        const float4 q2 = apply_a4(pn[m], w, e, pn[m - 1], pn[m + 1], c4, lut, diag5, off);
+        const int j = jb + k;
+        if (j < sh.row_hi && ci < ld)
+        {
+          const size_t o = (size_t)j * ld + ci;
+          *reinterpret_cast<float4*>(p_new + o) = pn[m];
+          *reinterpret_cast<float4*>(r_new + o) = rn[m];
+          if (sharded)
+          {
+            // the slab's first / last two rows of p and first / last row of r also go straight
+            // into the neighbours' ghost rows (NVLink stores)
+            if (pp_lo && j <= sh.row_lo + 1) *reinterpret_cast<float4*>(pp_lo + o) = pn[m];
+            if (pp_hi && j >= sh.row_hi - 2) *reinterpret_cast<float4*>(pp_hi + o) = pn[m];
+            if (pr_lo && j == sh.row_lo) *reinterpret_cast<float4*>(pr_lo + o) = rn[m];
+            if (pr_hi && j == sh.row_hi - 1) *reinterpret_cast<float4*>(pr_hi + o) = rn[m];
+          }
+          float4 iv = make_float4(inv5, inv5, inv5, inv5);
+          if (c4 != kInterior4)
+            iv = make_float4(lut[c4 & 0xff].x, lut[(c4 >> 8) & 0xff].x, lut[(c4 >> 16) & 0xff].x,
+                             lut[c4 >> 24].x);
+          const float4 z = make_float4(iv.x * rn[m].x, iv.y * rn[m].y, iv.z * rn[m].z, iv.w * rn[m].w);
+          const float4 mq = make_float4(iv.x * q2.x, iv.y * q2.y, iv.z * q2.z, iv.w * q2.w);
+          acc[0] += (double)dot4(pn[m], q2);
+          acc[1] += (double)dot4(rn[m], z);
+          acc[2] += (double)dot4(rn[m], rn[m]);
+          acc[3] += (double)dot4(z, q2);
+          acc[4] += (double)dot4(q2, mq);
+        }
+      }
+    }
+    ++phase_id;
+    one_reduce<NW>(acc, s, partials + (phase_id & 1u) * (kNSums * G), phase_id, sh, &ss, pushed);
+    if (iter_sweep)
+    {
+      alpha_prev = alpha;
+      pending = !with_x;
+      last_p = p_old;
+    }
+    cur ^= 1;
+    ++sweep;
+  }
+  if (pending && !ss.comm_error)
+  {
+    // the solve ended on an iteration whose x update was deferred: x += alpha p of that iteration.
+    // Same tile -> thread mapping as the sweeps; p is exactly zero outside LIQUID cells.
+    TileWalk t(blockIdx.x, G, tiles_x, n_walk, false, tile_list, n_prefix);
+    for (int tk = 0; tk < t.count; ++tk, t.next())
+    {
+      const int ci = t.tx * kTileW + (int)lane * 4;
+      const int jb = sh.row_lo + t.ty * TH + r0;
+#pragma unroll
+      for (int k = 0; k < RPW; ++k)
+      {
+        const int j = jb + k;
+        if (j < sh.row_hi && ci < ld)
+        {
+          const size_t o = (size_t)j * ld + ci;
+          const float4 p4 = *reinterpret_cast<const float4*>(last_p + o);
+          const float4 x4 = *reinterpret_cast<const float4*>(x + o);
+          *reinterpret_cast<float4*>(x + o) = fma4(alpha_prev, p4, x4);
+        }
+      }
+    }
+  }
+  // every CTA holds the same final scalars; CTA 0 publishes them for the host
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    s->r2 = ss.r2;
+    s->rz = ss.rz;
+    s->iter = ss.iter;
+    s->done = ss.done;
+    s->seq[3] = ss.seq;
+    if (ss.comm_error) s->comm_error = 1;
+  }
+}
+
+template <int RPW>
+int configure_one_shape(fsb_ctx* c, int64_t n_tiles)
+{
+  constexpr int TH = kNW * RPW;
+  const int threads = (kNW + 1) * 32;
+  const int budget = (227 * 1024 - 2 * 2048) / 2; // two resident CTAs per SM
+  int stages = std::max(2, std::min(kMaxStages, budget / OneStage<TH>::kBytes));
+  if (const char* e = getenv("FSB_CG_STAGES")) // tuning knob for profiling runs
+  {
+    const int v = atoi(e);
+    if (v >= 2 && v <= kMaxStages) stages = v;
+  }
+  const int smem = stages * OneStage<TH>::kBytes;
+  if (smem > 227 * 1024 - 2048)
+    return fsb_fail(c, FSB_ERR_INVALID, "CG ring of %d stages does not fit shared memory", stages);
+  auto kf = k_cg_solve1<kNW, RPW>;
+  FSB_CUDA(c, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int occ = 1;
+  FSB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, threads, smem));
+  int cap = 2;
+  if (const char* e = getenv("FSB_CG_CTAS_PER_SM")) cap = std::max(1, atoi(e));
+  occ = std::max(1, std::min(occ, cap));
+  c->cg_one_stages = stages;
+  c->cg_one_grid = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count * occ);
+  return FSB_OK;
+}
+
+int configure_one(fsb_ctx* c)
+{
+  const int th = c->cg_tile_rows; // chosen by configure_cg (the active-tile list uses it too)
+  if (c->cg_one_th == th) return FSB_OK;
+  const int64_t n_tiles = (int64_t)fsb_div_up(c->ld, kTileW) *
+                          fsb_div_up(c->shard.row_hi - c->shard.row_lo, th);
+  if (th == 32) FSB_TRY(configure_one_shape<4>(c, n_tiles));
+  else if (th == 16) FSB_TRY(configure_one_shape<2>(c, n_tiles));
+  else FSB_TRY(configure_one_shape<1>(c, n_tiles));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  FSB_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess)
+    return fsb_fail(c, FSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+  EncodeTiledFn encode = (EncodeTiledFn)fn;
+  OneMaps* m = reinterpret_cast<OneMaps*>(c->cg_maps_one);
+  memset(m, 0, sizeof(OneMaps));
+  FSB_TRY(make_map(c, encode, &m->halo_p[0], c->cg_p[0], true, kHaloW, th + 4));
+  FSB_TRY(make_map(c, encode, &m->halo_p[1], c->cg_p[1], true, kHaloW, th + 4));
+  FSB_TRY(make_map(c, encode, &m->halo_r[0], c->cg_r, true, kHaloW, th + 2));
+  FSB_TRY(make_map(c, encode, &m->halo_r[1], c->cg_r2, true, kHaloW, th + 2));
+  FSB_TRY(make_map(c, encode, &m->code, c->cg_code, false, kCodeW, th + 2));
+  c->cg_one_th = th;
+  return FSB_OK;
+}
+
+} // namespace
+
+int fsb_cg_one_partials(const fsb_ctx* c) { return 2 * kNSums * std::max(c->cg_one_grid, c->sm_count * 2); }
+
+// Called after the set-up (k_cg_build*: x = 0, r = b, stencil codes, |b|^2 and the threshold in
+// the CG scalars, the active-tile list) with the solve not yet finished.
+int fsb_k_cg_one_solve(fsb_ctx* c, const CgCoef& coef)
+{
+  FSB_TRY(configure_one(c));
+  const int th = c->cg_tile_rows;
+  const ShardArgs& sh = c->shard;
+  int tiles_x = fsb_div_up(c->ld, kTileW);
+  int n_tiles = tiles_x * fsb_div_up(sh.row_hi - sh.row_lo, th);
+  const int need = 2 * kNSums * c->cg_one_grid;
+  if (need > c->partials_cap)
+    return fsb_fail(c, FSB_ERR_INVALID, "partials buffer too small for the one-sweep solve");
+  {
+    // The sweeps rely on both direction buffers and the second residual buffer being exactly zero
+    // wherever no LIQUID cell is (skipped tiles, masked cells) and on p = 0 before the first
+    // iteration: clear this rank's OWN rows of them.  The neighbours' ghost rows of the buffers
+    // the set-up sweep WRITES (p[1], r2) belong to the peers, which may already be storing into
+    // them; those of p[0] are read by the set-up sweep as "p = 0" and no peer writes them before
+    // this rank has finished that sweep, so they are cleared here as well.
+    const int lo = sh.world > 1 ? sh.row_lo : 0;
+    const int hi = sh.world > 1 ? sh.row_hi : c->ny;
+    const size_t off = (size_t)lo * c->ld, bytes = sizeof(float) * (size_t)(hi - lo) * c->ld;
+    const int glo = std::max(0, lo - 2), ghi = std::min(c->ny, hi + 2);
+    FSB_CUDA(c, cudaMemsetAsync(c->cg_p[0] + (size_t)glo * c->ld, 0,
+                                sizeof(float) * (size_t)(ghi - glo) * c->ld, c->stream));
+    FSB_CUDA(c, cudaMemsetAsync(c->cg_p[1] + off, 0, bytes, c->stream));
+    FSB_CUDA(c, cudaMemsetAsync(c->cg_r2 + off, 0, bytes, c->stream));
+  }
+  const OneMaps& maps = *reinterpret_cast<const OneMaps*>(c->cg_maps_one);
+  OnePeers peers;
+  const bool south = sh.world > 1 && sh.rank > 0, north = sh.world > 1 && sh.rank < sh.world - 1;
+  for (int k = 0; k < 2; ++k)
+  {
+    peers.p_lo[k] = south ? c->peer_p[k][sh.rank - 1] : nullptr;
+    peers.p_hi[k] = north ? c->peer_p[k][sh.rank + 1] : nullptr;
+  }
+  peers.r_lo[0] = south ? c->peer_r[sh.rank - 1] : nullptr;
+  peers.r_hi[0] = north ? c->peer_r[sh.rank + 1] : nullptr;
+  peers.r_lo[1] = south ? c->peer_r2[sh.rank - 1] : nullptr;
+  peers.r_hi[1] = north ? c->peer_r2[sh.rank + 1] : nullptr;
+  int ld = c->ld, stages = c->cg_one_stages;
+  CgCoef cf = coef;
+  int flags = c->cg_flags;
+  void* args[] = {(void*)&maps, &c->cg_x, &c->cg_r, &c->cg_r2, &c->cg_p[0], &c->cg_p[1], &ld, &tiles_x,
+                  &n_tiles, &stages, &cf, &c->scal, &c->partials, (void*)&sh, &peers, &flags};
+  const dim3 grid(c->cg_one_grid), block((kNW + 1) * 32);
+  cudaError_t e;
+  if (th == 32)
+    e = cudaLaunchCooperativeKernel((void*)k_cg_solve1<kNW, 4>, grid, block, args,
+                                    (size_t)stages * OneStage<32>::kBytes, c->stream);
+  else if (th == 16)
+    e = cudaLaunchCooperativeKernel((void*)k_cg_solve1<kNW, 2>, grid, block, args,
+                                    (size_t)stages * OneStage<16>::kBytes, c->stream);
+  else
+    e = cudaLaunchCooperativeKernel((void*)k_cg_solve1<kNW, 1>, grid, block, args,
+                                    (size_t)stages * OneStage<8>::kBytes, c->stream);
+  if (e != cudaSuccess)
+    return fsb_fail(c, FSB_ERR_CUDA, "cooperative launch of the one-sweep CG solve failed: %s",
+                    cudaGetErrorString(e));
+  c->launches += 1;
+  return FSB_OK;
+}

@@ -60,7 +60,11 @@ struct CgScalars
 //   combine kernel waits for all `world` entries and adds them in rank order, so
 //   all ranks derive bit-identical alpha / beta / `done`.  No NCCL call in the loop.
 constexpr int kMaxRanks = 8;
-constexpr int kMailTypes = 4; // 0: p.Ap, 1: (|r|^2, r.z), 2: end-of-solve barrier
+constexpr int kMailTypes = 8; // 0: p.Ap, 1: (|r|^2, r.z), 2: end-of-solve barrier; 4-7: one-sweep solve
+// the one-sweep solve (fsb_cg_one.cu) posts five doubles per reduction: rank q's entry is the 16
+// self-validating words starting at word kOneMailWord + q * kOneMailStride of a mailbox
+constexpr int kOneMailWord = 4 * kMaxRanks * 4;
+constexpr int kOneMailStride = 16;
 
 struct MailSlot
 {
@@ -84,7 +88,6 @@ struct CgCoef
 };
 
 struct fsb_mg_state;  // multigrid hierarchy of the opt-in preconditioner (fsb_mg.cu)
-struct fsb_cg1_state; // extra vectors of the opt-in single-reduction CG (fsb_cg1.cu)
 
 struct fsb_ctx
 {
@@ -127,6 +130,7 @@ struct fsb_ctx
 
   // CG
   float *cg_x = nullptr, *cg_r = nullptr;
+  float* cg_r2 = nullptr; // second residual buffer of the one-sweep solve (r is ping-ponged there)
   float* cg_p[2] = {nullptr, nullptr}; // search direction, ping-pong
   uint8_t* cg_code = nullptr;
   double* partials = nullptr;
@@ -141,6 +145,10 @@ struct fsb_ctx
   alignas(64) unsigned char cg_maps_dir[2][5 * sizeof(CUtensorMap)];
   alignas(64) unsigned char cg_maps_upd[2][5 * sizeof(CUtensorMap)];
   alignas(64) unsigned char cg_maps_fused[8 * sizeof(CUtensorMap)]; // SolveMaps
+  alignas(64) unsigned char cg_maps_one[5 * sizeof(CUtensorMap)]; // OneMaps (fsb_cg_one.cu)
+  int cg_one_th = 0, cg_one_grid = 0, cg_one_stages = 0;
+  bool cg_one = true;    // one sweep + one reduction per iteration (default; fsb_cg_one.cu)
+  bool last_solve_one = false;
   bool cg_fused = false; // persistent cooperative solve kernel in use
   bool cg_pdl = true;    // programmatic dependent launch between the iteration kernels
   int cg_flags = 0;      // tuning bits of the iteration kernels, see configure_cg
@@ -151,9 +159,6 @@ struct fsb_ctx
   int mg_sweeps = 3;         // damped-Jacobi pre- and post-sweeps per level (equal: symmetric V-cycle)
   bool last_solve_mg = false;
   fsb_mg_state* mg = nullptr;
-  bool cg_single = false; // FSB_CG_MODE=single: one sweep + one reduction per iteration (fsb_cg1.cu)
-  bool last_solve_single = false;
-  fsb_cg1_state* cg1 = nullptr;
   bool cg_persist_miss_normal = false;
   bool cg_skip_tiles = true; // sweeps visit only tiles that hold a LIQUID cell
   bool cg_edge_first = false; // sharded solves: slab boundary tiles first in every sweep (knob)
@@ -174,10 +179,11 @@ struct fsb_ctx
   ShardArgs shard = {1, 0, 0, 0, {nullptr}};
   MailSlot* mail_local = nullptr;
   float* peer_r[kMaxRanks] = {nullptr};
+  float* peer_r2[kMaxRanks] = {nullptr};
   float* peer_p[2][kMaxRanks] = {{nullptr}};
   float* peer_x[kMaxRanks] = {nullptr};
   float** peer_x_dev = nullptr; // device array of the world-1 peer x pointers
-  void* ipc_opened[5 * kMaxRanks] = {nullptr};
+  void* ipc_opened[6 * kMaxRanks] = {nullptr};
   int n_ipc_opened = 0;
 
   // slab-partitioned particles (fsb_slab_*): world == 1: the whole set lives here
@@ -274,6 +280,7 @@ void fsb_cg_reconfigure(fsb_ctx* c); // drop the CG launch configuration and gra
 // multigrid-preconditioned CG (fsb_mg.cu)
 int fsb_k_mg_solve(fsb_ctx* c, int* converged);
 void fsb_mg_free(fsb_ctx* c);
-// single-reduction Jacobi-PCG (fsb_cg1.cu)
-int fsb_k_cg1_solve(fsb_ctx* c);
-void fsb_cg1_free(fsb_ctx* c);
+// one-sweep Jacobi-PCG (fsb_cg_one.cu): the default solve
+int fsb_k_cg_one_solve(fsb_ctx* c, const CgCoef& coef);
+int fsb_cg_one_partials(const fsb_ctx* c);
+

@@ -288,9 +288,10 @@ int fsb_profile_enable(fsb_ctx* ctx, int on);
 /* ms[FSB_PROF_COUNT], calls[FSB_PROF_COUNT]: totals since the last read */
 int fsb_profile_read(fsb_ctx* ctx, float* ms, int* calls);
 /* launch mode of the pressure solve as configured by the last solve: 0 not configured yet,
- * 1 two kernels per iteration in a CUDA graph, 2 one persistent cooperative kernel,
+ * 1 two kernels per iteration in a CUDA graph (FSB_CG_MODE=graph), 2 one persistent cooperative
+ * kernel with two sweeps per iteration (FSB_CG_MODE=fused),
  * 3 the last solve was a multigrid-preconditioned CG (FSB_PRECOND_MULTIGRID),
- * 4 the last solve used the single-reduction iteration (FSB_CG_MODE=single, experimental) */
+ * 4 one persistent cooperative kernel with ONE sweep and one reduction per iteration (default) */
 int fsb_cg_launch_mode(const fsb_ctx* ctx);
 /* number of kernels this library launched on the context since creation */
 int64_t fsb_launch_count(const fsb_ctx* ctx);

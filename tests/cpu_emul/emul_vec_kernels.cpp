@@ -53,7 +53,8 @@ static inline T __ldg(const T* p)
 #define FSB_VEC_WANT_CG
 #include "fsb_vec_kernels.cuh"
 #include "fsb_mg_kernels.cuh"
-#include "fsb_cg1_kernels.cuh"
+#include "fsb_cg_math.cuh"
+#include "fsb_cg_one_scalars.h"
 #include <cmath>
 #include <vector>
 
@@ -245,50 +246,126 @@ int emul_mg_vcycle(const uint8_t* lab0, const uint8_t* code0, const float* r0, i
   return (int)lv.size();
 }
 
-// The single-reduction Jacobi-PCG of fsb_cg1.cu on host arrays: the same per-group source
-// (cg1_group) and the same scalar recurrences (cg1_advance), one loop iteration per CUDA thread,
-// partial sums added in group order.  code / b pitched (from emul_cg_build); x receives the
-// solution.  Returns the iteration count (Eigen's convention); *relres = |r| / |b|.
-int emul_cg1_solve(const uint8_t* code, const float* b, int nx, int ny, int ld, float dx, float tol,
-                   int max_iters, float* x, float* relres)
+// The one-sweep Jacobi-PCG of fsb_cg_one.cu on host arrays: the same per-float4 arithmetic
+// (fsb_cg_math.cuh: apply_a4, direction4, dot4, fma4), the same scalar step (one_advance,
+// fsb_cg_one_scalars.h), the same sweep structure -- every float4 group recomputes the update of
+// iteration k for its four neighbours from the OLD vectors (the kernel's halo recomputation),
+// r and p are ping-ponged, x is updated on odd iterations only (two updates back to back) with a
+// final pass when the solve ends on an even one.  Partial sums are added in group order.
+// code / b pitched (from emul_cg_build); x receives the solution.  Returns the iteration count
+// (Eigen's convention); *relres = |r| / |b|.
+int emul_cg_one_solve(const uint8_t* code, const float* b, int nx, int ny, int ld, float dx, float tol,
+                      int max_iters, float* x, float* relres)
 {
   const size_t cells = (size_t)ld * ny;
   std::vector<float> r[2] = {std::vector<float>(b, b + cells), std::vector<float>(cells, 0.f)};
-  std::vector<float> s[2] = {std::vector<float>(cells, 0.f), std::vector<float>(cells, 0.f)};
-  std::vector<float> w[2] = {std::vector<float>(cells, 0.f), std::vector<float>(cells, 0.f)};
-  std::vector<float> p(cells, 0.f);
+  std::vector<float> p[2] = {std::vector<float>(cells, 0.f), std::vector<float>(cells, 0.f)};
   std::memset(x, 0, cells * sizeof(float));
-  Cg1Coef k;
   const double dx2 = std::pow((double)dx, 2);
-  k.off = (float)(1 / dx2);
+  float4 lut[8];
+  for (int t = 0; t < 8; ++t) lut[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int n = 0; n < 5; ++n)
   {
-    k.diag[n] = (float)(-n / dx2);
-    k.invdiag[n] = (k.diag[n] != 0.0f) ? 1.0f / k.diag[n] : 1.0f;
+    const float diag = (float)(-n / dx2);
+    lut[n + 1] = make_float4(diag != 0.0f ? 1.0f / diag : 1.0f, diag, (float)(1 / dx2), 0.f);
   }
-  Cg1Scalars sc;
-  std::memset(&sc, 0, sizeof sc);
+  const float inv5 = lut[5].x, diag5 = lut[5].y, off = lut[5].z;
   double rhs2 = 0.0;
   for (size_t q = 0; q < cells; ++q) rhs2 += (double)b[q] * (double)b[q];
-  sc.rhs2 = rhs2; sc.r2 = rhs2;
+  OneState ss;
+  std::memset(&ss, 0, sizeof ss);
+  ss.r2 = rhs2;
   float thr = tol * tol * (float)rhs2; // Eigen: max(tol^2 |b|^2, FLT_MIN)
   if (thr < 1.17549435e-38f) thr = 1.17549435e-38f;
-  sc.thr = thr; sc.max_iters = max_iters; sc.init = 1;
-  if ((float)rhs2 == 0.0f || max_iters <= 0) { *relres = 0.0f; return 0; }
+  ss.thr = thr; ss.max_iters = max_iters; ss.sweep = -1;
+  if ((float)rhs2 == 0.0f || (float)rhs2 < thr || max_iters <= 0) { *relres = 0.0f; return 0; }
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto ld4 = [&](const std::vector<float>& v, int i0, int j) -> float4 {
+    if (j < 0 || j >= ny || i0 < 0 || i0 >= ld) return zero4; // TMA zero fill
+    return *reinterpret_cast<const float4*>(&v[i0 + (size_t)j * ld]);
+  };
+  auto ld1 = [&](const std::vector<float>& v, int i, int j) -> float {
+    if (j < 0 || j >= ny || i < 0 || i >= ld) return 0.0f;
+    return v[i + (size_t)j * ld];
+  };
+  auto cd4 = [&](int i0, int j) -> uint32_t {
+    if (j < 0 || j >= ny || i0 < 0 || i0 >= ld) return 0u;
+    return *reinterpret_cast<const uint32_t*>(code + i0 + (size_t)j * ld);
+  };
+  auto cd1 = [&](int i, int j) -> uint32_t {
+    if (j < 0 || j >= ny || i < 0 || i >= ld) return 0u;
+    return code[i + (size_t)j * ld];
+  };
   int cur = 0;
-  for (long sweep = 0; !sc.done && sweep < 4L * (max_iters + 2) + 64; ++sweep)
+  float alpha_prev = 0.0f;
+  bool pending = false;
+  const std::vector<float>* last_p = nullptr;
+  for (int sweep = -1; !ss.done; ++sweep, cur ^= 1)
   {
-    const float alpha = sc.init ? 0.0f : sc.alpha, beta = sc.init ? 0.0f : sc.beta;
-    double ag = 0.0, ad = 0.0, ar = 0.0;
+    const float alpha = ss.alpha, beta = ss.beta, nalpha = -alpha;
+    const std::vector<float>&ro = r[cur], &po = p[cur];
+    std::vector<float>&rnw = r[cur ^ 1], &pnw = p[cur ^ 1];
+    const bool with_x = sweep >= 0 && (sweep & 1);
+    // the update of iteration k for one float4 group, from the old vectors only
+    auto upd4 = [&](int i0, int j, float4* rn, float4* pn) {
+      const float4 pc = ld4(po, i0, j);
+      const uint32_t c4 = cd4(i0, j);
+      const float4 q = apply_a4(pc, ld1(po, i0 - 1, j), ld1(po, i0 + 4, j), ld4(po, i0, j - 1),
+                                ld4(po, i0, j + 1), c4, lut, diag5, off);
+      *rn = fma4(nalpha, q, ld4(ro, i0, j));
+      *pn = direction4(*rn, pc, c4, lut, inv5, beta);
+    };
+    auto upd1 = [&](int i, int j) -> float { // the same for one halo-column cell
+      const float pc = ld1(po, i, j);
+      const float4 kf = lut[cd1(i, j)];
+      const float q = fmaf(kf.y, pc, kf.z * ((ld1(po, i - 1, j) + ld1(po, i + 1, j)) +
+                                             (ld1(po, i, j - 1) + ld1(po, i, j + 1))));
+      const float rr = fmaf(nalpha, q, ld1(ro, i, j));
+      return fmaf(beta, pc, kf.x * rr);
+    };
+    double acc[5] = {0, 0, 0, 0, 0};
     for (int j = 0; j < ny; ++j)
       for (int i0 = 0; i0 < ld; i0 += 4)
-        cg1_group(r[cur].data(), s[cur].data(), w[cur].data(), r[cur ^ 1].data(), s[cur ^ 1].data(),
-                  w[cur ^ 1].data(), p.data(), x, code, nx, ny, ld, i0, j, alpha, beta, k, &ag, &ad, &ar);
-    cg1_advance(&sc, ag, ad, ar);
-    cur ^= 1;
+      {
+        float4 rn, pn, rs, ps, rnn, pnn;
+        upd4(i0, j, &rn, &pn);
+        upd4(i0, j - 1, &rs, &ps);
+        upd4(i0, j + 1, &rnn, &pnn);
+        const uint32_t c4 = cd4(i0, j);
+        const float4 q2 = apply_a4(pn, upd1(i0 - 1, j), upd1(i0 + 4, j), ps, pnn, c4, lut, diag5, off);
+        const size_t o = i0 + (size_t)j * ld;
+        if (with_x)
+        {
+          float4 xn = *reinterpret_cast<float4*>(x + o);
+          xn = fma4(alpha_prev, *reinterpret_cast<const float4*>(&pnw[o]), xn); // p_{k-1}
+          xn = fma4(alpha, ld4(po, i0, j), xn);
+          *reinterpret_cast<float4*>(x + o) = xn;
+        }
+        *reinterpret_cast<float4*>(&pnw[o]) = pn;
+        *reinterpret_cast<float4*>(&rnw[o]) = rn;
+        float4 iv = make_float4(inv5, inv5, inv5, inv5);
+        if (c4 != kInterior4)
+          iv = make_float4(lut[c4 & 0xff].x, lut[(c4 >> 8) & 0xff].x, lut[(c4 >> 16) & 0xff].x, lut[c4 >> 24].x);
+        const float4 z = make_float4(iv.x * rn.x, iv.y * rn.y, iv.z * rn.z, iv.w * rn.w);
+        const float4 mq = make_float4(iv.x * q2.x, iv.y * q2.y, iv.z * q2.z, iv.w * q2.w);
+        acc[0] += (double)dot4(pn, q2);
+        acc[1] += (double)dot4(rn, z);
+        acc[2] += (double)dot4(rn, rn);
+        acc[3] += (double)dot4(z, q2);
+        acc[4] += (double)dot4(q2, mq);
+      }
+    one_advance(&ss, acc[0], acc[1], acc[2], acc[3], acc[4]);
+    if (sweep >= 0)
+    {
+      alpha_prev = alpha;
+      pending = !with_x;
+      last_p = &p[cur];
+    }
   }
-  *relres = (float)std::sqrt((float)sc.r2 / (float)sc.rhs2);
-  return sc.iter;
+  if (pending)
+    for (size_t q = 0; q < cells; ++q) x[q] = fmaf(alpha_prev, (*last_p)[q], x[q]);
+  *relres = (float)std::sqrt((float)ss.r2 / (float)rhs2);
+  return ss.iter;
 }
 
 } // extern "C"

@@ -27,7 +27,8 @@ def emul():
     out = os.path.join(EMUL_DIR, "libfsbemul.so")
     csrc = os.path.join(ROOT, "fluid_simulation_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in ("fsb_vec_kernels.cuh", "fsb_device.cuh",
-                                                        "fsb_mg_kernels.cuh", "fsb_cg1_kernels.cuh")]
+                                                        "fsb_mg_kernels.cuh", "fsb_cg_math.cuh",
+                                                        "fsb_cg_one_scalars.h")]
     if not os.path.exists(out) or any(os.path.getmtime(p) > os.path.getmtime(out) for p in deps):
         cuda_inc = "/usr/local/cuda/include"
         if not os.path.isdir(cuda_inc):
@@ -205,11 +206,11 @@ def test_multigrid_vcycle_matches_the_numpy_prototype(emul, scene, n, sweeps):
 
 
 @pytest.mark.parametrize("nx,ny", [(64, 64), (96, 40), (130, 67)])
-def test_single_reduction_cg_matches_the_reference_iteration(emul, port, nx, ny):
-    """The opt-in single-reduction Jacobi-PCG (fsb_cg1_kernels.cuh: one sweep and one reduction
-    point per iteration) run on the host from the device source: same stopping rule, the iteration
-    count of the reference's two-reduction iteration (CPU checker) within 2 %, pressure within the
-    solver tolerance."""
+def test_one_sweep_cg_matches_the_reference_iteration(emul, port, nx, ny):
+    """The one-sweep Jacobi-PCG (fsb_cg_one.cu: one sweep and one reduction point per iteration, beta
+    from the exact identity for r'.z') run on the host from the device arithmetic (fsb_cg_math.cuh) and
+    scalar step (fsb_cg_one_scalars.h): same stopping rule, the iteration count of the reference's
+    two-reduction iteration (CPU checker) within 2 %, pressure within the solver tolerance."""
     rng = np.random.default_rng(81)
     lab = scenes.random_labels(nx, ny, rng, p_solid=0.03)
     u, v = scenes.random_field(nx, ny, rng), scenes.random_field(nx, ny, rng)
@@ -233,8 +234,8 @@ def test_single_reduction_cg_matches_the_reference_iteration(emul, port, nx, ny)
                        ctypes.c_float(c.dy), ptr(sums))
     x = np.zeros(pl.shape, dtype=np.float32)
     relres = ctypes.c_float(0)
-    emul.emul_cg1_solve.restype = ctypes.c_int
-    its = emul.emul_cg1_solve(ptr(code), ptr(b), ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(ld),
+    emul.emul_cg_one_solve.restype = ctypes.c_int
+    its = emul.emul_cg_one_solve(ptr(code), ptr(b), ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(ld),
                               ctypes.c_float(c.dx), ctypes.c_float(tol), ctypes.c_int(20000), ptr(x),
                               ctypes.byref(relres))
     assert relres.value < tol and err_ref < tol
@@ -243,7 +244,7 @@ def test_single_reduction_cg_matches_the_reference_iteration(emul, port, nx, ny)
     rel = np.linalg.norm(x[:, :nx].astype(np.float64) - p_ref) / np.linalg.norm(p_ref)
     assert rel < 2e-3, rel
     # a capped solve stops exactly at the cap
-    its = emul.emul_cg1_solve(ptr(code), ptr(b), ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(ld),
+    its = emul.emul_cg_one_solve(ptr(code), ptr(b), ctypes.c_int(nx), ctypes.c_int(ny), ctypes.c_int(ld),
                               ctypes.c_float(c.dx), ctypes.c_float(tol), ctypes.c_int(7), ptr(x),
                               ctypes.byref(relres))
     assert its == 7
