@@ -1598,19 +1598,32 @@ int configure_cg(fsb_ctx* c)
     c->shard.row_lo = 0;
     c->shard.row_hi = c->ny;
   }
-  const int th = pick_tile_rows(c);
-  const int64_t n_tiles = (int64_t)fsb_div_up(c->ld, kTileW) *
-                          fsb_div_up(c->shard.row_hi - c->shard.row_lo, th);
-  if (th == 32) FSB_TRY(configure_kernels<4>(c, n_tiles));
-  else if (th == 16) FSB_TRY(configure_kernels<2>(c, n_tiles));
-  else FSB_TRY(configure_kernels<1>(c, n_tiles));
-  if (th == 32) FSB_TRY(configure_fused<4>(c, n_tiles));
-  else if (th == 16) FSB_TRY(configure_fused<2>(c, n_tiles));
-  else FSB_TRY(configure_fused<1>(c, n_tiles));
+  int th = pick_tile_rows(c);
+  // the persistent kernels need every CTA resident at once: cooperative launch
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
   {
-    // the fused kernel needs every CTA resident at once: cooperative launch
-    int coop = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+    const char* mode = getenv("FSB_CG_MODE");
+    c->cg_one = coop != 0 && (!mode || mode[0] == 'o');
+  }
+  if (c->cg_one)
+  {
+    // the one-sweep kernel runs kNWOne consumer warps per CTA: same rows per warp, shorter tiles
+    th = th / 8 * kNWOne;
+    c->cg_grid_dir = c->cg_grid_upd = c->cg_grid_fused = 0;
+  }
+  else
+  {
+    const int64_t n_tiles = (int64_t)fsb_div_up(c->ld, kTileW) *
+                            fsb_div_up(c->shard.row_hi - c->shard.row_lo, th);
+    if (th == 32) FSB_TRY(configure_kernels<4>(c, n_tiles));
+    else if (th == 16) FSB_TRY(configure_kernels<2>(c, n_tiles));
+    else FSB_TRY(configure_kernels<1>(c, n_tiles));
+    if (th == 32) FSB_TRY(configure_fused<4>(c, n_tiles));
+    else if (th == 16) FSB_TRY(configure_fused<2>(c, n_tiles));
+    else FSB_TRY(configure_fused<1>(c, n_tiles));
+  }
+  {
     // Default: the persistent single-kernel solve (k_cg_solve) -- fastest at every size measured
     // (profiles/r01g).  FSB_CG_MODE=graph selects two launches per iteration in a CUDA graph.
     // Default: the one-sweep solve (fsb_cg_one.cu: one sweep and one reduction point per iteration,
@@ -1618,7 +1631,6 @@ int configure_cg(fsb_ctx* c)
     // (Eigen's two reduction points, 32 B per cell), FSB_CG_MODE=graph its two-kernel form.
     const char* mode = getenv("FSB_CG_MODE");
     c->cg_fused = coop != 0 && !(mode && mode[0] == 'g');
-    c->cg_one = coop != 0 && (!mode || mode[0] == 'o');
     // Sharded solves on short slabs are bound by the two cross-GPU reductions per iteration, and the
     // kernel-boundary form of that handshake (last CTA + one-warp combine) is lighter than the
     // in-kernel one where every CTA polls the mailbox: measured on 2 B200, 8.4 M cells per rank
@@ -1658,6 +1670,11 @@ int configure_cg(fsb_ctx* c)
   if (!fn || qres != cudaDriverEntryPointSuccess)
     return fsb_fail(c, FSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
   EncodeTiledFn encode = (EncodeTiledFn)fn;
+  if (c->cg_one)
+  {
+    c->cg_tile_rows = th; // its tensor maps are made by fsb_cg_one.cu
+    return FSB_OK;
+  }
   CUtensorMap halo_r, halo_p[2], inner_x, inner_r, code, inner_p[2];
   FSB_TRY(make_map(c, encode, &inner_p[0], c->cg_p[0], true, kTileW, th));
   FSB_TRY(make_map(c, encode, &inner_p[1], c->cg_p[1], true, kTileW, th));

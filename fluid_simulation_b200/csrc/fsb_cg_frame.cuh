@@ -134,6 +134,7 @@ struct TileWalk
   // so the system-scope fence before the reduction finds the peer stores already acknowledged.
   const int* list;
   int first, stride, n_total, k, n_pre;
+  int ahead; // list entry of tile k + 1, requested one tile early (its latency is off the critical path)
   __device__ __forceinline__ TileWalk(int first_tile, int stride_, int tiles_x_, int n_tiles,
                                       bool reverse = false, const int* list_ = nullptr,
                                       int prefix = 0)
@@ -145,6 +146,7 @@ struct TileWalk
     stride = stride_;
     n_total = n_tiles;
     k = 0;
+    ahead = 0;
     count = first_tile < n_tiles ? (n_tiles - 1 - first_tile) / stride_ + 1 : 0;
     // this CTA's list positions below `prefix`
     n_pre = (list && first_tile < prefix) ? (prefix - 1 - first_tile) / stride_ + 1 : 0;
@@ -156,7 +158,13 @@ struct TileWalk
     ty = 0;
     if (list)
     {
-      if (count > 0) decode();
+      if (count > 0)
+      {
+        const int t = __ldg(list + position(0));
+        tx = t & 0xffff;
+        ty = t >> 16;
+        if (count > 1) ahead = __ldg(list + position(1));
+      }
     }
     else
     {
@@ -164,25 +172,24 @@ struct TileWalk
       ty = start / tiles_x;
     }
   }
-  // list position of the k-th tile of this CTA: prefix entries ascending, then the rest in walk order
-  __device__ __forceinline__ int position() const
+  // list position of the kk-th tile of this CTA: prefix entries ascending, then the rest in walk order
+  __device__ __forceinline__ int position(int kk) const
   {
-    if (k < n_pre) return first + k * stride;
-    const int m = k - n_pre; // m-th of the (count - n_pre) non-prefix entries
+    if (kk < n_pre) return first + kk * stride;
+    const int m = kk - n_pre; // m-th of the (count - n_pre) non-prefix entries
     return rev ? first + (count - 1 - m) * stride : first + (n_pre + m) * stride;
-  }
-  __device__ __forceinline__ void decode()
-  {
-    const int t = __ldg(list + position());
-    tx = t & 0xffff;
-    ty = t >> 16;
   }
   __device__ __forceinline__ void next()
   {
     if (list)
     {
       ++k;
-      if (k < count) decode();
+      if (k < count)
+      {
+        tx = ahead & 0xffff;
+        ty = ahead >> 16;
+        if (k + 1 < count) ahead = __ldg(list + position(k + 1));
+      }
       return;
     }
     if (!rev)
@@ -320,6 +327,9 @@ struct RingPos
 // Kernel shapes: 8 consumer warps x RPW rows.  RPW = 2 (16-row tiles) when that still
 // gives every SM several tiles, else RPW = 1 (8-row tiles, small grids).
 constexpr int kNW = 8;
+// the one-sweep kernel (fsb_cg_one.cu) needs more registers per thread: 7 consumer warps + the producer
+// = 256 threads, 128 registers at two CTAs per SM
+constexpr int kNWOne = 7;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

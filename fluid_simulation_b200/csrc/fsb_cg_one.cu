@@ -43,6 +43,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "fsb_cg_frame.cuh"
 #include "fsb_cg_one_scalars.h"
@@ -330,10 +331,6 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
     const float* __restrict__ p_old = cur ? p_b : p_a;
     float* __restrict__ p_new = cur ? p_a : p_b;
     float* __restrict__ r_new = cur ? r_a : r_b;
-    float* const pp_lo = peers.p_lo[cur ^ 1];
-    float* const pp_hi = peers.p_hi[cur ^ 1];
-    float* const pr_lo = peers.r_lo[cur ^ 1];
-    float* const pr_hi = peers.r_hi[cur ^ 1];
     double acc[kNSums];
 #pragma unroll
     for (int n = 0; n < kNSums; ++n) acc[n] = 0.0;
@@ -349,7 +346,10 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
       const int j0 = sh.row_lo + t.ty * TH;
       const int jb = j0 + r0;
       // a tile holding one of the slab's two first / last rows stores into peer memory
-      pushed |= sharded && (t.ty == 0 || j0 + TH >= sh.row_hi - 1);
+      const bool push_tile = sharded && (t.ty == 0 || j0 + TH >= sh.row_hi - 1);
+      pushed |= push_tile;
+      const bool inside = (jb + RPW <= sh.row_hi) && (ci < ld); // all own rows of this lane are stored
+      const size_t o0 = (size_t)jb * ld + ci;
 
       // x and the previous direction do not pass through the ring: they are read and written by
       // this thread only, so the loads are simply issued before the wait for the tile
@@ -359,128 +359,157 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
       {
         xv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         pv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int j = jb + k;
-        if (with_x && j < sh.row_hi && ci < ld)
+        if (with_x && jb + k < sh.row_hi && ci < ld)
         {
-          const size_t o = (size_t)j * ld + ci;
-          xv[k] = *reinterpret_cast<const float4*>(x + o);
-          if (two_x) pv[k] = *reinterpret_cast<const float4*>(p_new + o); // p_{k-1}, overwritten below
+          xv[k] = *reinterpret_cast<const float4*>(x + o0 + (size_t)k * ld);
+          if (two_x) pv[k] = *reinterpret_cast<const float4*>(p_new + o0 + (size_t)k * ld); // p_{k-1}
         }
       }
-      mbar_wait_guarded(&full[rp.st], rp.round & 1);
+      mbar_wait(&full[rp.st], rp.round & 1);
 
       float4 pk[RPW + 4], rk[RPW + 2];
       uint32_t cd[RPW + 2];
       float hpc[RPW + 2]; // lanes 0 / 31: p_old of the halo-column cell, rows of the stage-1 block
-      float he[RPW];      // lanes 0 / 31: NEW direction of the halo-column cell of the own rows
+      float hfar[RPW], hr[RPW];
+      uint32_t hcd[RPW];
 #pragma unroll
       for (int i = 0; i < RPW + 4; ++i) pk[i] = *reinterpret_cast<const float4*>(sp + fo + i * kHaloW);
+      bool ok = inside && !push_tile;
 #pragma unroll
       for (int m = 0; m < RPW + 2; ++m)
       {
         rk[m] = *reinterpret_cast<const float4*>(sr + fo + m * kHaloW);
         cd[m] = *reinterpret_cast<const uint32_t*>(sc + co + m * kCodeW);
         hpc[m] = edge ? sp[hfo + (m + 1) * kHaloW] : 0.0f;
+        ok &= (cd[m] == kInterior4);
       }
-      // the update of iteration k for the halo-column cell of the own rows (lanes 0 / 31), with the
-      // same association of the sums as apply_a4 / direction4, so that it equals bit for bit what
-      // the owner of that cell stores:  q = A p, r' = r - alpha q, p' = D^-1 r' + beta p
 #pragma unroll
       for (int k = 0; k < RPW; ++k)
       {
-        he[k] = 0.0f;
+        hfar[k] = 0.0f;
+        hr[k] = 0.0f;
+        hcd[k] = 5u;
         if (edge)
         {
-          const int m = k + 1;
-          const float far = sp[hff + (m + 1) * kHaloW];
-          const float pc = hpc[m];
-          const float pw = west ? far : pk[m + 1].w;
-          const float pe = west ? pk[m + 1].x : far;
-          const float4 kf = lut[sc[hco + m * kCodeW]];
-          const float q = fmaf(kf.y, pc, kf.z * ((pw + pe) + (hpc[m - 1] + hpc[m + 1])));
-          const float rr = fmaf(nalpha, q, sr[hfo + m * kHaloW]);
-          he[k] = fmaf(beta, pc, kf.x * rr);
+          hfar[k] = sp[hff + (k + 2) * kHaloW];
+          hr[k] = sr[hfo + (k + 1) * kHaloW];
+          hcd[k] = sc[hco + (k + 1) * kCodeW];
         }
+        ok &= (hcd[k] == 5u);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[rp.st]); // everything is in registers
+      rp.advance(stages);
+      // FAST: every cell this warp touches in this tile (own rows, the rows above and below, the
+      // halo-column cells) is LIQUID with four non-SOLID neighbours, all own rows lie inside the
+      // slab and the grid, no peer stores: register constants, no table, no bounds logic
+      const bool fast = __all_sync(0xffffffffu, ok);
+
       // x += alpha p (odd iterations: the pending update of the previous iteration first, the same
       // rounding order as one update per iteration)
       if (with_x)
       {
 #pragma unroll
         for (int k = 0; k < RPW; ++k)
-        {
-          const int j = jb + k;
-          if (j < sh.row_hi && ci < ld)
+          if (jb + k < sh.row_hi && ci < ld)
           {
             float4 xn = xv[k];
             if (two_x) xn = fma4(alpha_prev, pv[k], xn);
             xn = fma4(alpha, pk[k + 2], xn);
-            *reinterpret_cast<float4*>(x + (size_t)j * ld + ci) = xn;
+            *reinterpret_cast<float4*>(x + o0 + (size_t)k * ld) = xn;
           }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[rp.st]); // everything is in registers
-      rp.advance(stages);
-
-      // ---- the update of iteration k on the warp's rows and one row above / below:
-      //      q = A p, r' = r - alpha q, p' = D^-1 r' + beta p     (stage-1 row m = grid row jb - 1 + m)
-      float4 rn[RPW + 2], pn[RPW + 2];
-#pragma unroll
-      for (int m = 0; m < RPW + 2; ++m)
-      {
-        const float4 pc = pk[m + 1];
-        float w = __shfl_up_sync(0xffffffffu, pc.w, 1);
-        float e = __shfl_down_sync(0xffffffffu, pc.x, 1);
-        if (edge) // lane 0: west neighbour, lane 31: east neighbour = the halo-column cell
-        {
-          if (west) w = hpc[m];
-          else e = hpc[m];
-        }
-        const float4 q = apply_a4(pc, w, e, pk[m], pk[m + 2], cd[m], lut, diag5, off);
-        rn[m] = fma4(nalpha, q, rk[m]);
-        pn[m] = direction4(rn[m], pc, cd[m], lut, inv5, beta);
       }
 
-      // ---- q' = A p' on the own rows, the five sums, the stores
+      auto body = [&](auto fast_c) {
+        constexpr bool FAST = decltype(fast_c)::value;
+        // the update of iteration k for the halo-column cell of the own rows (lanes 0 / 31), with
+        // the same association of the sums as apply_a4 / direction4, so that it equals bit for bit
+        // what the owner of that cell stores:  q = A p, r' = r - alpha q, p' = D^-1 r' + beta p
+        float he[RPW];
 #pragma unroll
-      for (int k = 0; k < RPW; ++k)
-      {
-        const int m = k + 1;
-        float w = __shfl_up_sync(0xffffffffu, pn[m].w, 1);
-        float e = __shfl_down_sync(0xffffffffu, pn[m].x, 1);
-        if (lane == 0) w = he[k];
-        if (lane == 31) e = he[k];
-        const uint32_t c4 = cd[m];
-        const float4 q2 = apply_a4(pn[m], w, e, pn[m - 1], pn[m + 1], c4, lut, diag5, off);
-        const int j = jb + k;
-        if (j < sh.row_hi && ci < ld)
+        for (int k = 0; k < RPW; ++k)
         {
-          const size_t o = (size_t)j * ld + ci;
-          *reinterpret_cast<float4*>(p_new + o) = pn[m];
-          *reinterpret_cast<float4*>(r_new + o) = rn[m];
-          if (sharded)
+          he[k] = 0.0f;
+          if (edge)
           {
-            // the slab's first / last two rows of p and first / last row of r also go straight
-            // into the neighbours' ghost rows (NVLink stores)
-            if (pp_lo && j <= sh.row_lo + 1) *reinterpret_cast<float4*>(pp_lo + o) = pn[m];
-            if (pp_hi && j >= sh.row_hi - 2) *reinterpret_cast<float4*>(pp_hi + o) = pn[m];
-            if (pr_lo && j == sh.row_lo) *reinterpret_cast<float4*>(pr_lo + o) = rn[m];
-            if (pr_hi && j == sh.row_hi - 1) *reinterpret_cast<float4*>(pr_hi + o) = rn[m];
+            const int m = k + 1;
+            const float pc = hpc[m];
+            const float pw = west ? hfar[k] : pk[m + 1].w;
+            const float pe = west ? pk[m + 1].x : hfar[k];
+            float4 kf = make_float4(inv5, diag5, off, 0.f);
+            if (!FAST) kf = lut[hcd[k]];
+            const float q = fmaf(kf.y, pc, kf.z * ((pw + pe) + (hpc[m - 1] + hpc[m + 1])));
+            const float rr = fmaf(nalpha, q, hr[k]);
+            he[k] = fmaf(beta, pc, kf.x * rr);
           }
-          float4 iv = make_float4(inv5, inv5, inv5, inv5);
-          if (c4 != kInterior4)
-            iv = make_float4(lut[c4 & 0xff].x, lut[(c4 >> 8) & 0xff].x, lut[(c4 >> 16) & 0xff].x,
-                             lut[c4 >> 24].x);
-          const float4 z = make_float4(iv.x * rn[m].x, iv.y * rn[m].y, iv.z * rn[m].z, iv.w * rn[m].w);
-          const float4 mq = make_float4(iv.x * q2.x, iv.y * q2.y, iv.z * q2.z, iv.w * q2.w);
-          acc[0] += (double)dot4(pn[m], q2);
-          acc[1] += (double)dot4(rn[m], z);
-          acc[2] += (double)dot4(rn[m], rn[m]);
-          acc[3] += (double)dot4(z, q2);
-          acc[4] += (double)dot4(q2, mq);
         }
-      }
+        // the same update on the warp's rows and one row above / below (stage-1 row m = grid row jb - 1 + m)
+        float4 rn[RPW + 2], pn[RPW + 2];
+#pragma unroll
+        for (int m = 0; m < RPW + 2; ++m)
+        {
+          const float4 pc = pk[m + 1];
+          float w = __shfl_up_sync(0xffffffffu, pc.w, 1);
+          float e = __shfl_down_sync(0xffffffffu, pc.x, 1);
+          if (edge) // lane 0: west neighbour, lane 31: east neighbour = the halo-column cell
+          {
+            if (west) w = hpc[m];
+            else e = hpc[m];
+          }
+          const uint32_t c4 = FAST ? kInterior4 : cd[m];
+          const float4 q = apply_a4(pc, w, e, pk[m], pk[m + 2], c4, lut, diag5, off);
+          rn[m] = fma4(nalpha, q, rk[m]);
+          pn[m] = direction4(rn[m], pc, c4, lut, inv5, beta);
+        }
+        // q' = A p' on the own rows, the five sums, the stores
+#pragma unroll
+        for (int k = 0; k < RPW; ++k)
+        {
+          const int m = k + 1;
+          float w = __shfl_up_sync(0xffffffffu, pn[m].w, 1);
+          float e = __shfl_down_sync(0xffffffffu, pn[m].x, 1);
+          if (edge)
+          {
+            if (west) w = he[k];
+            else e = he[k];
+          }
+          const uint32_t c4 = FAST ? kInterior4 : cd[m];
+          const float4 q2 = apply_a4(pn[m], w, e, pn[m - 1], pn[m + 1], c4, lut, diag5, off);
+          const int j = jb + k;
+          if (FAST || (j < sh.row_hi && ci < ld))
+          {
+            const size_t o = o0 + (size_t)k * ld;
+            *reinterpret_cast<float4*>(p_new + o) = pn[m];
+            *reinterpret_cast<float4*>(r_new + o) = rn[m];
+            if (!FAST && push_tile)
+            {
+              // the slab's first / last two rows of p and first / last row of r also go straight
+              // into the neighbours' ghost rows (NVLink stores)
+              float* const pp_lo = peers.p_lo[cur ^ 1];
+              float* const pp_hi = peers.p_hi[cur ^ 1];
+              float* const pr_lo = peers.r_lo[cur ^ 1];
+              float* const pr_hi = peers.r_hi[cur ^ 1];
+              if (pp_lo && j <= sh.row_lo + 1) *reinterpret_cast<float4*>(pp_lo + o) = pn[m];
+              if (pp_hi && j >= sh.row_hi - 2) *reinterpret_cast<float4*>(pp_hi + o) = pn[m];
+              if (pr_lo && j == sh.row_lo) *reinterpret_cast<float4*>(pr_lo + o) = rn[m];
+              if (pr_hi && j == sh.row_hi - 1) *reinterpret_cast<float4*>(pr_hi + o) = rn[m];
+            }
+            float4 iv = make_float4(inv5, inv5, inv5, inv5);
+            if (!FAST && c4 != kInterior4)
+              iv = make_float4(lut[c4 & 0xff].x, lut[(c4 >> 8) & 0xff].x, lut[(c4 >> 16) & 0xff].x,
+                               lut[c4 >> 24].x);
+            const float4 z = make_float4(iv.x * rn[m].x, iv.y * rn[m].y, iv.z * rn[m].z, iv.w * rn[m].w);
+            const float4 mq = make_float4(iv.x * q2.x, iv.y * q2.y, iv.z * q2.z, iv.w * q2.w);
+            acc[0] += (double)dot4(pn[m], q2);
+            acc[1] += (double)dot4(rn[m], z);
+            acc[2] += (double)dot4(rn[m], rn[m]);
+            acc[3] += (double)dot4(z, q2);
+            acc[4] += (double)dot4(q2, mq);
+          }
+        }
+      };
+      if (fast) body(std::true_type{});
+      else body(std::false_type{});
     }
     ++phase_id;
     one_reduce<NW>(acc, s, partials + (phase_id & 1u) * (kNSums * G), phase_id, sh, &ss, pushed);
@@ -531,8 +560,8 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
 template <int RPW>
 int configure_one_shape(fsb_ctx* c, int64_t n_tiles)
 {
-  constexpr int TH = kNW * RPW;
-  const int threads = (kNW + 1) * 32;
+  constexpr int TH = kNWOne * RPW;
+  const int threads = (kNWOne + 1) * 32;
   const int budget = (227 * 1024 - 2 * 2048) / 2; // two resident CTAs per SM
   int stages = std::max(2, std::min(kMaxStages, budget / OneStage<TH>::kBytes));
   if (const char* e = getenv("FSB_CG_STAGES")) // tuning knob for profiling runs
@@ -543,7 +572,7 @@ int configure_one_shape(fsb_ctx* c, int64_t n_tiles)
   const int smem = stages * OneStage<TH>::kBytes;
   if (smem > 227 * 1024 - 2048)
     return fsb_fail(c, FSB_ERR_INVALID, "CG ring of %d stages does not fit shared memory", stages);
-  auto kf = k_cg_solve1<kNW, RPW>;
+  auto kf = k_cg_solve1<kNWOne, RPW>;
   FSB_CUDA(c, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int occ = 1;
   FSB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, threads, smem));
@@ -561,8 +590,8 @@ int configure_one(fsb_ctx* c)
   if (c->cg_one_th == th) return FSB_OK;
   const int64_t n_tiles = (int64_t)fsb_div_up(c->ld, kTileW) *
                           fsb_div_up(c->shard.row_hi - c->shard.row_lo, th);
-  if (th == 32) FSB_TRY(configure_one_shape<4>(c, n_tiles));
-  else if (th == 16) FSB_TRY(configure_one_shape<2>(c, n_tiles));
+  if (th == 4 * kNWOne) FSB_TRY(configure_one_shape<4>(c, n_tiles));
+  else if (th == 2 * kNWOne) FSB_TRY(configure_one_shape<2>(c, n_tiles));
   else FSB_TRY(configure_one_shape<1>(c, n_tiles));
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -630,17 +659,17 @@ int fsb_k_cg_one_solve(fsb_ctx* c, const CgCoef& coef)
   int flags = c->cg_flags;
   void* args[] = {(void*)&maps, &c->cg_x, &c->cg_r, &c->cg_r2, &c->cg_p[0], &c->cg_p[1], &ld, &tiles_x,
                   &n_tiles, &stages, &cf, &c->scal, &c->partials, (void*)&sh, &peers, &flags};
-  const dim3 grid(c->cg_one_grid), block((kNW + 1) * 32);
+  const dim3 grid(c->cg_one_grid), block((kNWOne + 1) * 32);
   cudaError_t e;
-  if (th == 32)
-    e = cudaLaunchCooperativeKernel((void*)k_cg_solve1<kNW, 4>, grid, block, args,
-                                    (size_t)stages * OneStage<32>::kBytes, c->stream);
-  else if (th == 16)
-    e = cudaLaunchCooperativeKernel((void*)k_cg_solve1<kNW, 2>, grid, block, args,
-                                    (size_t)stages * OneStage<16>::kBytes, c->stream);
+  if (th == 4 * kNWOne)
+    e = cudaLaunchCooperativeKernel((void*)k_cg_solve1<kNWOne, 4>, grid, block, args,
+                                    (size_t)stages * OneStage<4 * kNWOne>::kBytes, c->stream);
+  else if (th == 2 * kNWOne)
+    e = cudaLaunchCooperativeKernel((void*)k_cg_solve1<kNWOne, 2>, grid, block, args,
+                                    (size_t)stages * OneStage<2 * kNWOne>::kBytes, c->stream);
   else
-    e = cudaLaunchCooperativeKernel((void*)k_cg_solve1<kNW, 1>, grid, block, args,
-                                    (size_t)stages * OneStage<8>::kBytes, c->stream);
+    e = cudaLaunchCooperativeKernel((void*)k_cg_solve1<kNWOne, 1>, grid, block, args,
+                                    (size_t)stages * OneStage<1 * kNWOne>::kBytes, c->stream);
   if (e != cudaSuccess)
     return fsb_fail(c, FSB_ERR_CUDA, "cooperative launch of the one-sweep CG solve failed: %s",
                     cudaGetErrorString(e));
