@@ -817,8 +817,9 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
       ro[k] = *reinterpret_cast<const float4*>(sr + io + k * kTileW);
       he[k] = edge ? sp[hfo + (k + 1) * kHaloW] : 0.0f;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]); // everything this warp needs is in registers
+    // the slot is released after the loop below has CONSUMED the staged values: an arrive does not wait
+    // for shared-memory loads still in flight (see fsb_cg_one.cu)
+    const int slot_done = st;
     if (++st == stages) { st = 0; ++round; }
 
     const int ci = t.tx * kTileW + (int)lane * 4;
@@ -857,6 +858,8 @@ k_cg_update(const __grid_constant__ CgMaps maps, float* __restrict__ x, float* _
         acc[1] += (double)dot4(rn, z);
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot_done]);
   }
 
   double tot[2] = {0.0, 0.0};
@@ -937,6 +940,11 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[N], CgScalars* s,
 {
   __shared__ double s_part[N][32];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // every thread orders its own global stores before the arrival (a proxy fence is not cumulative,
+  // see one_reduce in fsb_cg_one.cu)
+  fence_proxy_async_all();
+  if (pushed) __threadfence_system();
+  else __threadfence();
 #pragma unroll
   for (int n = 0; n < N; ++n)
   {
@@ -1375,8 +1383,7 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
           ro[k] = *reinterpret_cast<const float4*>(sr + io + k * kTileW);
           he[k] = edge ? sp[hfo + (k + 1) * kHaloW] : 0.0f;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[rp.st]);
+        const int slot_done = rp.st; // released after the loop below has consumed the staged values
         rp.advance(stages);
         const int ci = t.tx * kTileW + (int)lane * 4;
         const int jb = sh.row_lo + t.ty * TH + r0;
@@ -1417,6 +1424,8 @@ k_cg_solve(const __grid_constant__ SolveMaps maps, float* __restrict__ x, float*
             acc[1] += (double)dot4(rn, z);
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot_done]);
       }
       ++phase_id;
       grid_reduce<NW, 2, 1>(acc, s, part_b, phase_id, sh, &ss, pushed);
@@ -1661,7 +1670,8 @@ int configure_cg(fsb_ctx* c)
     c->cg_edge_first = knob("FSB_CG_EDGE_FIRST", 0);
     c->cg_flags = (knob("FSB_CG_SERP", 1) ? 1 : 0) | (knob("FSB_CG_XHINT", 0) ? 2 : 0) |
                   (knob("FSB_CG_PREFETCH", 1) ? 4 : 0) | (knob("FSB_CG_PHINT", 0) ? 8 : 0) |
-                  (keep << 4) | (knob("FSB_CG_XDEFER", 1) ? 128 : 0);
+                  (keep << 4) | (knob("FSB_CG_XDEFER", 1) ? 128 : 0) |
+                  (knob("FSB_CG_DEBUG_NOTILES", 0) ? 256 : 0) | (knob("FSB_CG_DEBUG_NOFAST", 0) ? 512 : 0);
   }
 
   void* fn = nullptr;

@@ -44,6 +44,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
+#include <vector>
 
 #include "fsb_cg_frame.cuh"
 #include "fsb_cg_one_scalars.h"
@@ -96,10 +97,19 @@ __device__ __forceinline__ void ld_mail2(const unsigned long long* p, unsigned l
 template <int NW>
 __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
                                            double* __restrict__ partials, unsigned phase_id,
-                                           const ShardArgs& sh, OneState* ss, bool pushed)
+                                           const ShardArgs& sh, OneState* ss, bool pushed,
+                                           double* __restrict__ dbg = nullptr)
 {
   __shared__ double s_part[kNSums][NW];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // EVERY thread orders its own global stores of this sweep (p / r / x rows, peer rows) before the
+  // arrival: a proxy fence is not cumulative -- the TMA (async proxy) loads of the next sweep, on
+  // this and on every other SM, are ordered only against generic-proxy stores whose issuing thread
+  // executed the fence itself.  (With the fence in lane 0 of warp 0 alone the solve was
+  // timing-dependent at 4096^2: iteration counts 8619-8622 instead of 8636.)
+  fence_proxy_async_all();
+  if (pushed) __threadfence_system();
+  else __threadfence();
 #pragma unroll
   for (int n = 0; n < kNSums; ++n)
   {
@@ -124,6 +134,8 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
     {
 #pragma unroll
       for (int n = 0; n < kNSums; ++n) partials[n * G + blockIdx.x] = tot[n];
+      if (dbg && phase_id <= 64) // FSB_CG_DEBUG_SUMS: this CTA's own sums of the sweep
+        for (int n = 0; n < kNSums; ++n) dbg[((size_t)(phase_id - 1) * G + blockIdx.x) * 10 + n] = tot[n];
       // the CTA's global stores (p / r / x rows, peer rows) must be visible to the TMA loads of the
       // next sweep on every SM (and GPU) before the arrival is
       fence_proxy_async_all();
@@ -211,6 +223,8 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
     }
     if (lane == 0)
     {
+      if (dbg && phase_id <= 64) // ... and the totals as this CTA sees them
+        for (int n = 0; n < kNSums; ++n) dbg[((size_t)(phase_id - 1) * gridDim.x + blockIdx.x) * 10 + 5 + n] = tot[n];
       ss->seq = seq;
       if (!ok)
       {
@@ -234,7 +248,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
             float* __restrict__ r_b, float* __restrict__ p_a, float* __restrict__ p_b, int ld,
             int tiles_x, int n_tiles, int stages, const CgCoef coef, CgScalars* __restrict__ s,
             double* __restrict__ partials, const __grid_constant__ ShardArgs sh,
-            const __grid_constant__ OnePeers peers, int flags)
+            const __grid_constant__ OnePeers peers, int flags, double* __restrict__ dbg)
 {
   constexpr int TH = NW * RPW;
   using St = OneStage<TH>;
@@ -265,7 +279,10 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
   }
   __syncthreads();
   const int* __restrict__ tile_list = s->tile_list; // fixed for the whole solve
-  const int n_walk = tile_list ? s->n_active_tiles : n_tiles;
+  // flags bit 8 (FSB_CG_DEBUG_NOTILES, measurement only): sweeps without tiles -- the time per
+  // "iteration" is then the bare cost of the barrier + reduction + scalar step
+  const bool no_tiles = (flags & 256) != 0;
+  const int n_walk = no_tiles ? 0 : tile_list ? s->n_active_tiles : n_tiles;
   const int n_prefix = tile_list ? s->n_prefix_tiles : 0;
   const int G = (int)gridDim.x;
 
@@ -276,27 +293,62 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
     RingPos rp = {0, 0};
     int cur = 0, sweep = -1;
     unsigned phase_id = 0;
+    int npre = 0; // leading tiles of the sweep whose loads are already out
+    // The next sweep's loads depend on the other CTAs' stores of this sweep -- that is, on every
+    // CTA having ARRIVED at the barrier -- but not on the scalars: they go out as soon as the
+    // arrival counter is complete, while warp 0 still folds the partials and advances the
+    // scalars.  (Sharded: the peers' boundary rows are only known to have landed once their
+    // mailbox entries are in, so there the loads wait for the release.)
+    const bool early = (flags & 4) != 0 && sh.world == 1;
+    auto issue = [&](const TileWalk& t, int cr) {
+      if (rp.round > 0) mbar_wait_guarded(&empty[rp.st], (rp.round - 1) & 1);
+      unsigned char* base = smem + rp.st * St::kBytes;
+      const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
+      mbar_expect_tx(&full[rp.st], St::kTx);
+      tma_load_2d(base + St::oP, &maps.halo_p[cr], c0 - 4, j0 - 2, &full[rp.st]);
+      tma_load_2d(base + St::oR, &maps.halo_r[cr], c0 - 4, j0 - 1, &full[rp.st]);
+      tma_load_2d(base + St::oC, &maps.code, c0 - 16, j0 - 1, &full[rp.st]);
+      rp.advance(stages);
+    };
     for (;;)
     {
       TileWalk t(blockIdx.x, G, tiles_x, n_walk, serp && (sweep & 1) == 0, tile_list, n_prefix);
-      for (int k = 0; k < t.count; ++k, t.next())
-      {
-        if (rp.round > 0) mbar_wait_guarded(&empty[rp.st], (rp.round - 1) & 1);
-        unsigned char* base = smem + rp.st * St::kBytes;
-        const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
-        mbar_expect_tx(&full[rp.st], St::kTx);
-        tma_load_2d(base + St::oP, &maps.halo_p[cur], c0 - 4, j0 - 2, &full[rp.st]);
-        tma_load_2d(base + St::oR, &maps.halo_r[cur], c0 - 4, j0 - 1, &full[rp.st]);
-        tma_load_2d(base + St::oC, &maps.code, c0 - 16, j0 - 1, &full[rp.st]);
-        rp.advance(stages);
-      }
+      int k = 0;
+      for (; k < npre; ++k) t.next();
+      for (; k < t.count; ++k, t.next()) issue(t, cur);
       ++phase_id;
+      npre = 0;
+      const RingPos pre = rp;
+      if (early)
+      {
+        const volatile unsigned int* cnt = &s->bar_count;
+        const unsigned int target = phase_id * (unsigned int)G;
+        {
+          SpinGuard g;
+          while (*cnt < target) g.tick();
+        }
+        __threadfence();
+        fence_proxy_async_all();
+        TileWalk tn(blockIdx.x, G, tiles_x, n_walk, serp && ((sweep + 1) & 1) == 0, tile_list, n_prefix);
+        const int want = min(stages, tn.count);
+        for (; npre < want; ++npre, tn.next()) issue(tn, cur ^ 1);
+      }
       {
         SpinGuard g;
         while (ss.released < phase_id) g.tick();
       }
       fence_proxy_async_all();
-      if (ss.done) return;
+      if (ss.done)
+      {
+        // nobody will consume the tiles already requested: let them land before the CTA may exit
+        RingPos w = pre;
+        for (int m = 0; m < npre; ++m)
+        {
+          mbar_wait_guarded(&full[w.st], w.round & 1);
+          w.advance(stages);
+        }
+        return;
+      }
       cur ^= 1;
       ++sweep;
     }
@@ -333,7 +385,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
     float* __restrict__ r_new = cur ? r_a : r_b;
     double acc[kNSums];
 #pragma unroll
-    for (int n = 0; n < kNSums; ++n) acc[n] = 0.0;
+    for (int n = 0; n < kNSums; ++n) acc[n] = no_tiles ? 1.0 : 0.0;
     bool pushed = false;
     TileWalk t(blockIdx.x, G, tiles_x, n_walk, serp && (sweep & 1) == 0, tile_list, n_prefix);
     for (int tk = 0; tk < t.count; ++tk, t.next())
@@ -374,7 +426,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
       uint32_t hcd[RPW];
 #pragma unroll
       for (int i = 0; i < RPW + 4; ++i) pk[i] = *reinterpret_cast<const float4*>(sp + fo + i * kHaloW);
-      bool ok = inside && !push_tile;
+      bool ok = inside && !push_tile && (flags & 512) == 0; // bit 9 (FSB_CG_DEBUG_NOFAST): table path only
 #pragma unroll
       for (int m = 0; m < RPW + 2; ++m)
       {
@@ -397,8 +449,12 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
         }
         ok &= (hcd[k] == 5u);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[rp.st]); // everything is in registers
+      // The ring slot is released only after everything staged has been CONSUMED by arithmetic (end of
+      // stage 1 below), not merely requested: an mbarrier arrive does not wait for the warp's
+      // shared-memory loads still in flight, and a slot released with loads outstanding can be
+      // refilled under them.  (Seen on B200 as a timing-dependent last-bit wobble of the sums that
+      // involve the halo-column cells, whose loads are the last ones issued.)
+      const int slot_done = rp.st;
       rp.advance(stages);
       // FAST: every cell this warp touches in this tile (own rows, the rows above and below, the
       // halo-column cells) is LIQUID with four non-SOLID neighbours, all own rows lie inside the
@@ -461,6 +517,8 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
           rn[m] = fma4(nalpha, q, rk[m]);
           pn[m] = direction4(rn[m], pc, c4, lut, inv5, beta);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot_done]);
         // q' = A p' on the own rows, the five sums, the stores
 #pragma unroll
         for (int k = 0; k < RPW; ++k)
@@ -512,7 +570,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
       else body(std::false_type{});
     }
     ++phase_id;
-    one_reduce<NW>(acc, s, partials + (phase_id & 1u) * (kNSums * G), phase_id, sh, &ss, pushed);
+    one_reduce<NW>(acc, s, partials + (phase_id & 1u) * (kNSums * G), phase_id, sh, &ss, pushed, dbg);
     if (iter_sweep)
     {
       alpha_prev = alpha;
@@ -657,8 +715,19 @@ int fsb_k_cg_one_solve(fsb_ctx* c, const CgCoef& coef)
   int ld = c->ld, stages = c->cg_one_stages;
   CgCoef cf = coef;
   int flags = c->cg_flags;
+  // FSB_CG_DEBUG_SUMS=<file prefix> (measurement / debugging only): per sweep and CTA, the CTA's own five
+  // sums and the totals as it sees them, for the first 64 sweeps, appended to <prefix>.<solve number>
+  static int dbg_solves = 0;
+  double* dbg = nullptr;
+  const char* dbg_path = getenv("FSB_CG_DEBUG_SUMS");
+  const size_t dbg_count = (size_t)64 * c->cg_one_grid * 10 + 8 + 64 * 8;
+  if (dbg_path)
+  {
+    FSB_CUDA(c, cudaMalloc(&dbg, sizeof(double) * dbg_count));
+    FSB_CUDA(c, cudaMemsetAsync(dbg, 0, sizeof(double) * dbg_count, c->stream));
+  }
   void* args[] = {(void*)&maps, &c->cg_x, &c->cg_r, &c->cg_r2, &c->cg_p[0], &c->cg_p[1], &ld, &tiles_x,
-                  &n_tiles, &stages, &cf, &c->scal, &c->partials, (void*)&sh, &peers, &flags};
+                  &n_tiles, &stages, &cf, &c->scal, &c->partials, (void*)&sh, &peers, &flags, &dbg};
   const dim3 grid(c->cg_one_grid), block((kNWOne + 1) * 32);
   cudaError_t e;
   if (th == 4 * kNWOne)
@@ -674,5 +743,19 @@ int fsb_k_cg_one_solve(fsb_ctx* c, const CgCoef& coef)
     return fsb_fail(c, FSB_ERR_CUDA, "cooperative launch of the one-sweep CG solve failed: %s",
                     cudaGetErrorString(e));
   c->launches += 1;
+  if (dbg)
+  {
+    std::vector<double> h(dbg_count);
+    FSB_CUDA(c, cudaMemcpyAsync(h.data(), dbg, sizeof(double) * dbg_count, cudaMemcpyDeviceToHost, c->stream));
+    FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dbg);
+    char name[512];
+    snprintf(name, sizeof name, "%s.%d", dbg_path, dbg_solves++);
+    if (FILE* f = fopen(name, "wb"))
+    {
+      fwrite(h.data(), sizeof(double), dbg_count, f);
+      fclose(f);
+    }
+  }
   return FSB_OK;
 }
