@@ -15,12 +15,21 @@ This is the configuration BASELINE.json's north_star quotes its single-GPU targe
 value   cell-updates/s = size_x*size_y*steps / device time, state resident in HBM
 e2e     same metric through the C ABI with HOST buffers: every step uploads the particle set
         from pinned host memory, runs fsb_step, and downloads the particle set again
-roofline  the CG iteration (one direction + one update sweep of the persistent k_cg_solve kernel),
-        which is >99 % of the step: algorithmic bytes = 45 B x cells per iteration
-        / (CUDA-event time of the CG loop on the library's stream / iterations), against
-        MEASURED_PEAKS.json hbm_gbs.  stage_roofline gives the same figure for every other stage.
-cpu_baseline  the reference's own sources (oracle/_ref) or the C restatement (oracle port) on one
-        host core, bounded sample (see `sample`), reported only
+roofline  the CG iteration of the persistent one-sweep solve kernel k_cg_solve1 (>99 % of the step):
+        achieved = bytes the kernel is DESIGNED to move per iteration (23 B x the cells of the tiles it
+        sweeps) / (CUDA-event time of the CG loop on the library's stream /
+        iterations), against MEASURED_PEAKS.json hbm_gbs.  frac_textbook does the same with the 45 B
+        per cell of SURVEY.md 8(d) (a stored q = Ap, x touched every iteration): it exceeds 1 because
+        the kernel does not move those bytes.  traffic / frac_dram: DRAM bytes per iteration from the
+        committed ncu capture of the same workload (profiles/), null when there is none.
+        stage_roofline gives the algorithmic-byte figure for every other stage.
+scale_cg8192  on every --gpus N line: BASELINE.json configs[3], the 8192^2 tank pressure solve to 1e-6
+        sharded over the N ranks (us per iteration, iterations/s), so that the north-star scaling
+        config is in the driver's record.
+cpu_baseline  the reference's own sources (oracle/_ref) on one host core on the SAME scene at the SAME
+        size: every stage of one step once, the CG capped at 20 iterations; time-to-1e-6 is that
+        per-iteration rate times the reference's own iteration count for this scene (17 821, from the
+        72-minute golden run, tests/golden/config2_picflip4096.npz), labelled as extrapolated
 
 Only the cpu_baseline / --impl reference legs touch oracle/.
 """
@@ -38,11 +47,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-ALG_BYTES_CG_PER_CELL = 45.0  # bytes per cell per CG iteration
-# dram__bytes_read.sum + dram__bytes_write.sum of the persistent k_cg_solve launch / its iterations, from
-# the committed ncu --set full capture (bytes per CG iteration, 4096^2)
-NCU_TRAFFIC = {("picflip4096", 1): 417.4e6, ("cg4096", 1): 417.4e6}
-NCU_TRAFFIC_SOURCE = "profiles/r01h_cg_solve_ncu_full.md"
+TEXTBOOK_BYTES_CG_PER_CELL = 45.0  # bytes per cell per CG iteration with a stored q
+# bytes per swept cell and iteration the solve kernels are designed to move
+DESIGN_BYTES_CG_PER_CELL = {"one-sweep": 23.0, "persistent": 32.0, "graph": 32.0}
+# DRAM bytes per CG iteration (dram__bytes_read.sum + dram__bytes_write.sum of the persistent launch /
+# its iterations) from the committed ncu --set full captures, keyed "<workload>/<n_gpus>/<mode>"
+NCU_TRAFFIC_FILE = os.path.join("profiles", "r02_cg_traffic.json")
+# the reference's own iteration count to 1e-6 on the first step of the picflip4096 scene
+# (tests/golden/config2_picflip4096.npz, oracle/_ref, 4343 s of CPU time)
+REFERENCE_ITERS = {"picflip4096": 17821}
 
 WORKLOADS = {
     # name: (n, step kind, pic_ratio, cg tol, cg cap, particles per cell side)
@@ -151,82 +164,147 @@ def step_kind(mod, name):
 
 
 # --------------------------------------------------------------------------- reference arm --
-def run_cpu_reference(wl, name, steps, warmup, gpu_iters_hint=None):
+def run_cpu_reference(wl, name, steps, warmup, gpu_iters_hint=None, parts=None, budget_s=150.0):
     """Times the reference's CPU implementation (one core: the reference is single-threaded,
-    src/FluidSolver.cpp:3,418-420) on a bounded sample of the workload.
+    src/FluidSolver.cpp:3,418-420) on a bounded sample of the SAME scene at the SAME size.
 
-    Sample: the same scene at the workload's grid size when that fits a ~30 s budget, else at the
-    largest power-of-two size that does; the step is run stage by stage with the CG capped at
-    `cg_sample_iters` iterations, and the converged-step time is extrapolated as
-    t_non_cg + iterations_to_tol * t_per_iteration with iterations_to_tol taken from the GPU run
-    (or the O(N) law measured at 256^2 when no GPU figure is given).  Labelled as extrapolated."""
+    Sample step 0: every stage of one step, once, stage by stage, with the CG capped at 20
+    iterations (4096^2: about 28 s).  Further sample steps (the reference arm is asked for K of
+    them): the pressure system assembled again and iterated for a few iterations, as many as the
+    time budget allows per step.  Nothing is scaled in cells.  The converged-step time is
+        t(all stages but the CG loop) + iterations_to_tol * t(per CG iteration)
+    with iterations_to_tol the reference's OWN count where it is known (REFERENCE_ITERS: the golden
+    run of this scene), else the GPU's count for the same scene -- labelled as extrapolated: only
+    the iteration count is, every time in the formula was measured at full size."""
     import oracle_lib as ol
     import scenes
     kind_name = "reference" if ol.available("fsr") else "port"
     lib = ol.OracleLib("fsr" if kind_name == "reference" else "fso")
     n = wl["n"]
-    budget_cells = 1024 * 1024  # ~20-30 s of single-core work per sampled step
-    n_s = n
-    while n_s * n_s > budget_cells:
-        n_s //= 2
-    dt = np.float32(0.01 * 64.0 / n_s)
-    s = lib.sim(n_s, n_s, 1.0, 1.0, float(dt), wl["pic_ratio"])
-    cg_sample_iters = 20
-    s.set_cg(cg_sample_iters, wl["tol"])
+    dt = np.float32(0.01 * 64.0 / n)
+    s = lib.sim(n, n, 1.0, 1.0, float(dt), wl["pic_ratio"])
     grav = float(np.float32(-9.82))
     if wl["kind"] == "cg":
-        lab, u0, v0 = tank_fields(n_s)
+        lab, u0, v0 = tank_fields(n)
         s.set_cell_types(lab)
-        parts = np.zeros((0, 4), dtype=np.float32)
+        n_part = 0
     else:
-        parts = scenes.tank_particles(n_s, np.random.default_rng(1234), wl["per_side"])
+        if parts is None:
+            parts = scenes.tank_particles(n, np.random.default_rng(1234), wl["per_side"])
         s.set_particles(parts)
-    results = []
-    for it in range(max(1, min(steps, 2)) + min(warmup, 1)):
-        t0 = time.perf_counter()
-        if wl["kind"] == "cg":
-            s.set_grid(ol.U_FRONT, u0); s.set_grid(ol.V_FRONT, v0)
-            t0 = time.perf_counter()
-            t1 = t0; s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
-        elif wl["kind"] == "sl":
-            s.classify_cells(); s.advect_velocity_sl(float(dt)); s.add_acceleration(0.0, grav, float(dt))
-            s.enforce_dirichlet()
-            t1 = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
-            s.enforce_dirichlet(); s.advect_particles_grid(float(dt))
-        else:
-            s.classify_cells(); s.p2g_spread(); s.save_previous()
-            s.add_acceleration(0.0, grav, float(dt)); s.enforce_dirichlet(); s.extend_velocity(2)
-            t1 = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
-            s.enforce_dirichlet(); s.update_diff(); s.g2p(ol.G2P_PICFLIP, wl["pic_ratio"])
-            s.advect_particles(float(dt), True)
-        t3 = time.perf_counter()
-        iters_done = max(1, s.cg_info()[0])
-        results.append((t3 - t0, t2 - t1, iters_done))
-    tot, solve, iters_done = results[-1]
-    # assembly + patch share of the solve: time a zero-iteration solve
-    s.set_cg(0, wl["tol"])
+        n_part = parts.shape[0]
+    cap0 = 20
+    s.set_cg(cap0, wl["tol"])
+    t_start = time.perf_counter()
+    t0 = time.perf_counter()
     if wl["kind"] == "cg":
         s.set_grid(ol.U_FRONT, u0); s.set_grid(ol.V_FRONT, v0)
-    t1 = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
-    solve0 = t2 - t1
-    t_iter = max(solve - solve0, 1e-9) / iters_done
-    t_non_cg = tot - solve + solve0
-    scale = (n * n) / float(n_s * n_s)
-    iters_to_tol = gpu_iters_hint if gpu_iters_hint else int(3.2 * n)  # O(N): ~800 at 256^2
-    step_time_full = scale * (t_non_cg + iters_to_tol * t_iter)
-    value = n * n / step_time_full
+        t0 = time.perf_counter()
+        t1 = t0; s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
+    elif wl["kind"] == "sl":
+        s.classify_cells(); s.advect_velocity_sl(float(dt)); s.add_acceleration(0.0, grav, float(dt))
+        s.enforce_dirichlet()
+        t1 = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
+        s.enforce_dirichlet(); s.advect_particles_grid(float(dt))
+    else:
+        s.classify_cells(); s.p2g_spread(); s.save_previous()
+        s.add_acceleration(0.0, grav, float(dt)); s.enforce_dirichlet(); s.extend_velocity(2)
+        t1 = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); t2 = time.perf_counter()
+        s.enforce_dirichlet(); s.update_diff(); s.g2p(ol.G2P_PICFLIP, wl["pic_ratio"])
+        s.advect_particles(float(dt), True)
+    t3 = time.perf_counter()
+    step_times = [t3 - t0]
+    solve_samples = [(t2 - t1, max(1, s.cg_info()[0]))]
+    # further sample steps: assembly + a few iterations of the next step's system
+    per_step = max(0.0, budget_s - (t3 - t_start)) / max(1, steps - 1)
+    for k in range(1, max(1, steps)):
+        t_it = solve_samples[0][0] / (solve_samples[0][1] + 24.0)  # rough: assembly ~ 24 iterations
+        cap = int(max(1, min(cap0, per_step / max(t_it, 1e-9) - 24)))
+        s.set_cg(cap, wl["tol"])
+        if wl["kind"] == "cg":
+            s.set_grid(ol.U_FRONT, u0); s.set_grid(ol.V_FRONT, v0)
+        ta = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); tb = time.perf_counter()
+        solve_samples.append((tb - ta, max(1, s.cg_info()[0])))
+        step_times.append(tb - ta)
+    # per-iteration time and assembly + patch time from the solves (least squares over the samples,
+    # or a zero-iteration solve when there is only one)
+    if len(set(c for _, c in solve_samples)) >= 2:
+        A = np.array([[1.0, c] for _, c in solve_samples]); y = np.array([t for t, _ in solve_samples])
+        (solve0, t_iter), *_ = np.linalg.lstsq(A, y, rcond=None)
+        solve0, t_iter = float(max(solve0, 0.0)), float(max(t_iter, 1e-9))
+    else:
+        s.set_cg(0, wl["tol"])
+        if wl["kind"] == "cg":
+            s.set_grid(ol.U_FRONT, u0); s.set_grid(ol.V_FRONT, v0)
+        ta = time.perf_counter(); s.pressure_solve(float(dt), float(dt)); solve0 = time.perf_counter() - ta
+        t_iter = max(solve_samples[0][0] - solve0, 1e-9) / solve_samples[0][1]
+    t_non_cg = (t3 - t0) - (t2 - t1) + solve0
+    iters_to_tol = REFERENCE_ITERS.get(name) or gpu_iters_hint or int(3.2 * n)
+    iters_src = ("the reference's own count for this scene (golden run)" if name in REFERENCE_ITERS
+                 else "the GPU's count for this scene" if gpu_iters_hint else "the O(N) law 3.2 N")
+    step_time_full = t_non_cg + iters_to_tol * t_iter
     what = "pressure solve" if wl["kind"] == "cg" else f"{wl['kind']} step"
-    sample = (f"{kind_name} build, 1 thread: one {what} of the tank scene at {n_s}^2 "
-              f"({parts.shape[0]} particles) run stage by stage with CG capped at {cg_sample_iters} "
-              f"iterations: non-CG {t_non_cg:.2f} s, {t_iter * 1e3:.2f} ms per CG iteration; "
-              f"scaled x{scale:.0f} in cells to {n}^2 and extrapolated to {iters_to_tol} CG "
-              f"iterations (time-to-1e-6 is EXTRAPOLATED, not run)")
-    return {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": kind_name,
+    sample = (f"{kind_name} build, 1 thread, SAME scene and size ({n}^2, {n_part} particles): one {what} run "
+              f"stage by stage with the CG capped at {cap0} iterations ({step_times[0]:.1f} s)"
+              + (f", then {len(step_times) - 1} more sample steps = the pressure system assembled and iterated "
+                 f"{solve_samples[-1][1]} times" if len(step_times) > 1 else "")
+              + f": all stages but the CG loop {t_non_cg:.2f} s, {t_iter * 1e3:.1f} ms per CG iteration; "
+              f"converged-step time = {t_non_cg:.1f} s + {iters_to_tol} x {t_iter * 1e3:.1f} ms = {step_time_full:.0f} s "
+              f"with the iteration count taken from {iters_src} (time-to-1e-6 is EXTRAPOLATED in the "
+              f"iteration count only; nothing is scaled in cells)")
+    return {"value": n * n / step_time_full, "unit": "cell-updates/s", "cores": 1, "kind": kind_name,
             "sample": sample, "host_cores_available": os.cpu_count(),
-            "cg_iters_per_s": (1.0 / (t_iter * scale))}
+            "cg_iters_per_s": 1.0 / t_iter, "sample_step_s": step_times,
+            "non_cg_s": t_non_cg, "converged_step_s_extrapolated": step_time_full}
 
 
 # ------------------------------------------------------------------------------- our arm --
+def scale_cg8192(capi, sharding, dist, torch, local_rank, world, log):
+    """The 8192^2 tank pressure solve (BASELINE.json configs[3]) to 1e-6, rows split over the ranks:
+    one capped warm-up solve, one timed solve.  Device time of the CG loop, max over ranks."""
+    n = 8192
+    dt = float(np.float32(0.01 * 64.0 / n))
+    lab, u0, v0 = tank_fields(n)
+    g = capi.Sim(n, n, 1.0, 1.0, dt, 0.02, device=local_rank)
+    g.set_cell_types(lab)
+    del lab
+    if world > 1:
+        sharding.connect(g, dist, torch.device("cuda", local_rank))
+    out = {}
+    for cap, timed in ((200, False), (400000, True)):
+        g.set_grid(capi.U_FRONT, u0); g.set_grid(capi.V_FRONT, v0)
+        g.set_cg(cap, 1e-6)
+        g.synchronize()
+        if world > 1:
+            dist.barrier()
+        g.profile_enable(True)
+        g.profile_read()
+        g.pressure_solve(dt, dt)
+        g.synchronize()
+        prof = g.profile_read()
+        g.profile_enable(False)
+        if not timed:
+            continue
+        cg_ms = prof["cg"][0]
+        if world > 1:
+            t = torch.tensor([cg_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cg_ms = float(t.item())
+        it, relres = g.cg_info()
+        mode = {1: "graph", 4: "one-sweep"}.get(g.cg_launch_mode(), "persistent")
+        out = {"workload": "8192^2 pressure Poisson solve (tank labels, swirl + gravity field), Jacobi-PCG to "
+                           "1e-06, row slabs over the ranks", "n_gpus": world, "iterations": int(it),
+               "relres": float(relres), "cg_ms": cg_ms, "us_per_iteration": 1e3 * cg_ms / max(it, 1),
+               "cg_iters_per_s": it / (cg_ms * 1e-3) if cg_ms else None, "mode": mode,
+               "swept_cells_per_rank": g.cg_swept_cells()}
+        log(f"scale_cg8192: {out}")
+    if world > 1:
+        g.shard_disconnect()
+        dist.barrier()
+    g.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -237,6 +315,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-optin", action="store_true", help="skip the opt-in multigrid side measurement")
+    ap.add_argument("--no-scale", action="store_true", help="skip the 8192^2 CG side measurement")
     ap.add_argument("--cg-cap", type=int, default=None, help="override the CG iteration cap (debug)")
     ap.add_argument("--precond", default="jacobi", choices=["jacobi", "mg"],
                     help="jacobi: the reference's preconditioner (headline); mg: the opt-in multigrid "
@@ -274,9 +353,13 @@ def main():
             except Exception:
                 hint = None
         cb = run_cpu_reference(wl, args.workload, args.steps, args.warmup, hint)
+        # ms_per_step: the sample steps as they were actually timed (so that steps x ms_per_step is the
+        # timed region of THIS run); value: the converged step, extrapolated in the iteration count
+        timed = cb.pop("sample_step_s")
         line = {"impl": "reference", "metric": "cell_updates_per_s", "value": cb["value"],
                 "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * n * n / cb["value"],
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(timed) / max(1, len(timed)),
+                "ms_per_converged_step_extrapolated": 1e3 * cb["converged_step_s_extrapolated"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {"workload": cfg_name},
                 "cpu_baseline": cb,
@@ -426,7 +509,8 @@ def main():
                # the e2e steps continue the same simulation: later steps, other iteration counts
                "cg_iters_per_step": e2e_iters / args.steps}
 
-    cg_mode = {1: "graph", 3: "multigrid"}.get(sim.cg_launch_mode(), "persistent")
+    cg_mode = {1: "graph", 3: "multigrid", 4: "one-sweep"}.get(sim.cg_launch_mode(), "persistent")
+    swept_cells = sim.cg_swept_cells()  # per rank, per iteration (cells of the tiles the sweeps visit)
 
     # ---- side measurement, not the headline: the same steps with the opt-in multigrid preconditioner
     optin = None
@@ -456,6 +540,14 @@ def main():
                 sim.set_preconditioner(capi.PRECOND_JACOBI)
             except Exception:
                 pass
+    # ---- side measurement on every line: BASELINE.json configs[3], the 8192^2 pressure solve to 1e-6
+    # sharded over the `world` ranks (north_star: ">= 6x strong scaling from 1 to 8 GPUs")
+    scale = None
+    if not args.no_scale and args.workload != "cg8192" and args.precond == "jacobi":
+        try:
+            scale = scale_cg8192(capi, sharding, dist, torch, local_rank, world, log)
+        except Exception as e:  # a side measurement must never cost the headline line
+            scale = {"error": str(e)[:300]}
     if world > 1:
         sim.shard_disconnect()
         dist.barrier()
@@ -466,9 +558,23 @@ def main():
     peak, peak_src = measured_peak_gbs()
     cg_ms, _ = prof["cg"]
     it_ms = cg_ms / max(iters_total, 1)
-    # per GPU: each rank sweeps 1/world of the rows per iteration
-    alg_bytes = ALG_BYTES_CG_PER_CELL * n * n / world
-    achieved = alg_bytes / (it_ms * 1e-3) / 1e9 if iters_total else 0.0
+    # per GPU: each rank sweeps the active tiles of its 1/world of the rows per iteration
+    design_b = DESIGN_BYTES_CG_PER_CELL.get(cg_mode)
+    if not swept_cells:
+        swept_cells = n * n // world
+    design_bytes = (design_b or TEXTBOOK_BYTES_CG_PER_CELL) * swept_cells
+    textbook_bytes = TEXTBOOK_BYTES_CG_PER_CELL * n * n / world
+    achieved = design_bytes / (it_ms * 1e-3) / 1e9 if iters_total else 0.0
+    achieved_textbook = textbook_bytes / (it_ms * 1e-3) / 1e9 if iters_total else 0.0
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, NCU_TRAFFIC_FILE)))
+        ent = tr.get(f"{args.workload}/{world}/{cg_mode}") or (
+            tr.get(f"cg{n}/{world}/{cg_mode}") if wl["kind"] != "cg" else None)
+        if ent:
+            traffic, traffic_src = float(ent["dram_bytes_per_iteration"]), ent["source"]
+    except Exception:
+        pass
     stages = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
     # every stage against the HBM roofline: algorithmic bytes of SURVEY.md 8(d) (C cells, P
     # particles; the cell sort is overhead and has no algorithmic bytes) / CUDA-event time
@@ -485,19 +591,26 @@ def main():
             gbs = nbytes / (t_ms * 1e-3) / 1e9
             stage_roofline[name] = {"ms": round(t_ms, 4), "alg_gb": round(nbytes / 1e9, 4),
                                     "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 3)}
+    kernel = {"multigrid": "OPT-IN multigrid-preconditioned CG iteration (one V-cycle + four sweeps; NOT the "
+                           "reference's Jacobi iteration: no byte accounting applies)",
+              "one-sweep": "k_cg_solve1 (persistent cooperative kernel, the whole solve is ONE launch; ONE sweep "
+                           "and one reduction point per CG iteration): figures are per CG iteration",
+              "persistent": "k_cg_solve (persistent cooperative kernel, the whole solve is ONE launch): "
+                            "figures are per CG iteration = one direction sweep + one update sweep",
+              "graph": "CG iteration = k_cg_direction + k_cg_update (2 launches in a CUDA graph)"}[cg_mode]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, world)),
-                "traffic_source": NCU_TRAFFIC_SOURCE if (args.workload, world) in NCU_TRAFFIC else None,
-                "kernel": ("OPT-IN multigrid-preconditioned CG iteration (one V-cycle + four sweeps; NOT the "
-                           "reference's Jacobi iteration: the 45 B/cell accounting does not apply)"
-                           if cg_mode == "multigrid" else
-                           "k_cg_solve (persistent cooperative kernel, the whole solve is ONE launch): "
-                           "figures are per CG iteration = one direction sweep + one update sweep"
-                           if cg_mode != "graph" else
-                           "CG iteration = k_cg_direction + k_cg_update (2 launches in a CUDA graph)")
-                          + (", per GPU, slab halos + dot products over peer memory" if world > 1 else ""),
-                "algorithmic_bytes_per_iteration": alg_bytes,
-                "design_bytes_per_iteration": 32.0 * n * n / world,
+                "frac": achieved / peak,
+                "what": (f"bytes the kernel is designed to move: {design_b:g} B x the {swept_cells} cells of the "
+                         f"tiles it sweeps per iteration on one GPU" if design_b else "no byte accounting"),
+                "achieved_textbook": achieved_textbook, "frac_textbook": achieved_textbook / peak,
+                "what_textbook": "45 B x all cells (SURVEY.md 8d: stored q = Ap, x touched every iteration); "
+                                 "above 1 because the kernel does not move those bytes",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "frac_dram": (traffic / (it_ms * 1e-3) / 1e9 / peak) if traffic and iters_total else None,
+                "kernel": kernel + (", per GPU, slab halos + sums over peer memory" if world > 1 else ""),
+                "design_bytes_per_iteration": design_bytes,
+                "textbook_bytes_per_iteration": textbook_bytes,
+                "swept_cells_per_iteration": swept_cells,
                 "iterations_per_launch": (iters_total / args.steps) if cg_mode != "graph" else 0.5,
                 "avg_iteration_us": it_ms * 1e3, "peak_source": peak_src,
                 "cg_share_of_step": cg_ms / ms if ms else None}
@@ -512,6 +625,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         try:
             cpu = run_cpu_reference(wl, args.workload, 1, 0, int(round(iters_total / args.steps)))
+            cpu.pop("sample_step_s", None)
         except Exception as e:  # the reported baseline must never cost the headline line
             cpu = {"error": str(e)[:200]}
 
@@ -526,8 +640,8 @@ def main():
                    "l2": (f"inputs larger than L2 ({n_part * 16 / 1e9:.1f} GB particles, "
                           f"{n * n * 4 / 1e6:.0f} MB per grid)")
                    if n >= 4096 else "working set may fit L2: latency-bound, see DESIGN.md",
-                   "parallelism": (f"CG sharded over {world} row slabs (peer-memory halo stores + mailbox "
-                                   f"reductions over NVLink), other stages replicated")
+                   "parallelism": (f"CG sharded over {world} row slabs (peer-memory halo stores + one mailbox "
+                                   f"reduction per iteration over NVLink), other stages replicated")
                    if world > 1 else "single GPU"},
         "cg_iters_per_step": iters_total / args.steps,
         "cg_iters_per_s": iters_total / (cg_ms * 1e-3) if cg_ms else None,
@@ -540,6 +654,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "optin_multigrid": optin,
+        "scale_cg8192": scale,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

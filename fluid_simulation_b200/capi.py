@@ -104,6 +104,7 @@ SIGNATURES = {
     "fsb_profile_read": (_i, [_p, _p, _p]),
     "fsb_launch_count": (_l, [_p]),
     "fsb_cg_launch_mode": (_i, [_p]),
+    "fsb_cg_swept_cells": (C.c_int64, [_p]),
     "fsb_timer_start": (_i, [_p]),
     "fsb_timer_stop": (_i, [_p, C.POINTER(_f)]),
 }
@@ -321,6 +322,10 @@ class Sim:
 
     def launch_count(self):
         return _lib.fsb_launch_count(self.h)
+
+    def cg_swept_cells(self):
+        """Cells the CG sweeps of the last solve visited per iteration on this rank."""
+        return int(_lib.fsb_cg_swept_cells(self.h))
 
     def cg_launch_mode(self):
         """0 not configured yet, 1 two kernels per iteration (CUDA graph), 2 persistent kernel."""

@@ -1212,6 +1212,16 @@ int fsb_profile_read(fsb_ctx* c, float* ms, int* calls)
   return FSB_OK;
 }
 int64_t fsb_launch_count(const fsb_ctx* c) { return c ? c->launches : 0; }
+int64_t fsb_cg_swept_cells(const fsb_ctx* c)
+{
+  if (!c || c->cg_tile_rows == 0) return 0;
+  const int rows = (c->shard.world > 1 ? c->shard.row_hi - c->shard.row_lo : c->ny);
+  const int64_t tiles_x = (c->ld + 127) / 128;
+  const int64_t n_tiles = tiles_x * ((rows + c->cg_tile_rows - 1) / c->cg_tile_rows);
+  const int64_t n = (c->cg_skip_tiles && c->scal_h) ? (int64_t)c->cg_last_active_tiles : n_tiles;
+  return (n > 0 ? n : n_tiles) * 128 * c->cg_tile_rows;
+}
+
 int fsb_cg_launch_mode(const fsb_ctx* c)
 {
   if (!c) return 0;

@@ -469,6 +469,10 @@ __global__ void k_cg_combine(const ShardArgs sh, CgScalars* __restrict__ s)
   {
     s->comm_error = 1;
     s->done = 1;
+    s->comm_diag[0] = 1000000000ull + TYPE; // a kernel-boundary wait (TYPE 2: the end-of-solve barrier)
+    s->comm_diag[1] = 0;
+    s->comm_diag[2] = want;
+    s->comm_diag[3] = 0;
   }
   s->seq[TYPE] = want;
 }
@@ -940,11 +944,9 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[N], CgScalars* s,
 {
   __shared__ double s_part[N][32];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // every thread orders its own global stores before the arrival (a proxy fence is not cumulative,
-  // see one_reduce in fsb_cg_one.cu)
+  // every thread orders its own generic-proxy stores against the async proxy (a proxy fence is not
+  // cumulative, see one_reduce in fsb_cg_one.cu)
   fence_proxy_async_all();
-  if (pushed) __threadfence_system();
-  else __threadfence();
 #pragma unroll
   for (int n = 0; n < N; ++n)
   {
@@ -1671,7 +1673,18 @@ int configure_cg(fsb_ctx* c)
     c->cg_flags = (knob("FSB_CG_SERP", 1) ? 1 : 0) | (knob("FSB_CG_XHINT", 0) ? 2 : 0) |
                   (knob("FSB_CG_PREFETCH", 1) ? 4 : 0) | (knob("FSB_CG_PHINT", 0) ? 8 : 0) |
                   (keep << 4) | (knob("FSB_CG_XDEFER", 1) ? 128 : 0) |
-                  (knob("FSB_CG_DEBUG_NOTILES", 0) ? 256 : 0) | (knob("FSB_CG_DEBUG_NOFAST", 0) ? 512 : 0);
+                  (knob("FSB_CG_DEBUG_NOTILES", 0) ? 256 : 0) | (knob("FSB_CG_DEBUG_NOFAST", 0) ? 512 : 0) |
+                  // sharded one-sweep solve: bit 11 -- GPU-scope instead of system-scope fence after the
+                  // mailbox poll, bit 12 -- the same for the fence in front of the post.  Default: GPU
+                  // scope.  Measured on 2 B200 (bare reduction, sweeps without tiles): 27.8 us per
+                  // reduction with both at system scope, 14.8 with the poll fence at GPU scope, 13.6 with
+                  // both (one GPU: 7.8).  Why it is enough: the boundary rows and the mailbox entry are
+                  // stored into THIS GPU's memory by the peer, which fences at system scope between the
+                  // two (every CTA that stored peer rows does, before it arrives at its own barrier); what
+                  // reads them here are TMA loads issued after the entry was seen, through the L2 that
+                  // received them.  FSB_CG_POLL_FENCE_SYS=1 / FSB_CG_POST_FENCE_SYS=1 restore the
+                  // system-scope fences.
+                  (knob("FSB_CG_POLL_FENCE_SYS", 0) ? 0 : 2048) | (knob("FSB_CG_POST_FENCE_SYS", 0) ? 0 : 4096);
   }
 
   void* fn = nullptr;
@@ -1974,6 +1987,7 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
   // waits for the poll.  Launches after convergence return immediately.
   fsb_prof_begin(c, FSB_PROF_CG);
   CgScalars fin = c->scal_h[0];
+  c->cg_last_active_tiles = fin.tile_list ? fin.n_active_tiles : 0;
   if (getenv("FSB_CG_VERBOSE"))
     fprintf(stderr, "[fsb] solve: %d liquid cells, active tiles %d (list %s), tile rows %d, mode %s\n",
             fin.n_liquid, fin.n_active_tiles, fin.tile_list ? "on" : "off", c->cg_tile_rows,
@@ -2077,7 +2091,12 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     if (c->scal_h[0].comm_error || fin.comm_error)
     {
       FSB_CUDA(c, cudaMemsetAsync(&c->scal->comm_error, 0, sizeof(int), c->stream));
-      return fsb_fail(c, FSB_ERR_COMM, "a peer rank did not answer within the mailbox time-out");
+      const CgScalars& q = c->scal_h[0];
+      return fsb_fail(c, FSB_ERR_COMM,
+                      "a peer rank did not answer within the mailbox time-out (rank %d of %d, iteration %d; "
+                      "gave up in reduction %llu on rank/word %llu.%llu, expected tag %llu, saw word %llx)",
+                      c->shard.rank, c->shard.world, fin.iter, q.comm_diag[0], q.comm_diag[1] / 16,
+                      q.comm_diag[1] % 16, q.comm_diag[2], q.comm_diag[3]);
     }
   }
   fsb_prof_end(c, FSB_PROF_CG);

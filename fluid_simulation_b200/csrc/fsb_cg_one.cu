@@ -98,18 +98,15 @@ template <int NW>
 __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
                                            double* __restrict__ partials, unsigned phase_id,
                                            const ShardArgs& sh, OneState* ss, bool pushed,
-                                           double* __restrict__ dbg = nullptr)
+                                           int sys_flags, double* __restrict__ dbg = nullptr)
 {
   __shared__ double s_part[kNSums][NW];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // EVERY thread orders its own global stores of this sweep (p / r / x rows, peer rows) before the
-  // arrival: a proxy fence is not cumulative -- the TMA (async proxy) loads of the next sweep, on
-  // this and on every other SM, are ordered only against generic-proxy stores whose issuing thread
-  // executed the fence itself.  (With the fence in lane 0 of warp 0 alone the solve was
-  // timing-dependent at 4096^2: iteration counts 8619-8622 instead of 8636.)
+  // Every thread orders its own generic-proxy stores of this sweep against the async proxy (the TMA
+  // loads of the next sweep): a proxy fence is not cumulative.  Visibility at GPU / system scope
+  // follows from lane 0's fence below, which is cumulative over everything the CTA barrier in
+  // between has ordered before it (the pattern of cooperative-groups grid.sync()).
   fence_proxy_async_all();
-  if (pushed) __threadfence_system();
-  else __threadfence();
 #pragma unroll
   for (int n = 0; n < kNSums; ++n)
   {
@@ -130,10 +127,14 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       tot[n] = v;
     }
+    // partials: one 64-byte record per CTA (five sums), two regions used alternately
+    unsigned int arrived = 0;
     if (lane == 0)
     {
-#pragma unroll
-      for (int n = 0; n < kNSums; ++n) partials[n * G + blockIdx.x] = tot[n];
+      double2* rec = reinterpret_cast<double2*>(partials + (size_t)blockIdx.x * 8);
+      rec[0] = make_double2(tot[0], tot[1]);
+      rec[1] = make_double2(tot[2], tot[3]);
+      partials[(size_t)blockIdx.x * 8 + 4] = tot[4];
       if (dbg && phase_id <= 64) // FSB_CG_DEBUG_SUMS: this CTA's own sums of the sweep
         for (int n = 0; n < kNSums; ++n) dbg[((size_t)(phase_id - 1) * G + blockIdx.x) * 10 + n] = tot[n];
       // the CTA's global stores (p / r / x rows, peer rows) must be visible to the TMA loads of the
@@ -141,27 +142,40 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
       fence_proxy_async_all();
       if (pushed) __threadfence_system();
       else __threadfence();
-      atomicAdd(&s->bar_count, 1u);
+      arrived = atomicAdd(&s->bar_count, 1u) + 1u;
     }
-    __syncwarp();
-    if (sh.world == 1 || blockIdx.x == 0)
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    const unsigned int target = phase_id * (unsigned int)G;
+    // Who folds the partials: single GPU -- every CTA, as soon as the counter is complete (no
+    // broadcast hop); sharded -- the CTA that arrived LAST (it needs no wait at all), which then posts
+    // the slab's sums into every rank's mailbox.
+    const bool folder = sh.world == 1 || arrived == target;
+    if (folder)
     {
-      const volatile unsigned int* cnt = &s->bar_count;
-      const unsigned int target = phase_id * (unsigned int)G;
+      if (sh.world == 1)
       {
+        const volatile unsigned int* cnt = &s->bar_count;
         SpinGuard g;
         while (*cnt < target) g.tick();
       }
       __threadfence();
-      const volatile double* part = partials;
+#pragma unroll
+      for (int n = 0; n < kNSums; ++n) tot[n] = 0.0;
+      // every lane adds the records lane, lane + 32, ... in that order, then a butterfly: one fixed
+      // order of additions, the same on every CTA
+#pragma unroll 5
+      for (int k = (int)lane; k < G; k += 32)
+      {
+        const double2* rec = reinterpret_cast<const double2*>(partials + (size_t)k * 8);
+        const double2 a = __ldcg(rec), b2 = __ldcg(rec + 1);
+        const double c = __ldcg(partials + (size_t)k * 8 + 4);
+        tot[0] += a.x; tot[1] += a.y; tot[2] += b2.x; tot[3] += b2.y; tot[4] += c;
+      }
 #pragma unroll
       for (int n = 0; n < kNSums; ++n)
       {
-        double v = 0.0;
-        for (int k = (int)lane; k < G; k += 32) v += part[n * G + k];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        tot[n] = v;
+        for (int o = 16; o > 0; o >>= 1) tot[n] += __shfl_xor_sync(0xffffffffu, tot[n], o);
       }
     }
     bool ok = true;
@@ -169,14 +183,16 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
     if (sh.world > 1)
     {
       const unsigned long long tag = seq & 0xffffffffull;
-      if (blockIdx.x == 0)
+      if (folder)
       {
-        // every local CTA's arrival (and its peer rows, fenced at system scope) precedes the entry
-        __threadfence_system();
+        // every local CTA's arrival (and its peer rows, each fenced at system scope by the CTA that
+        // stored them) precedes the entry
+        if (sys_flags & 2) __threadfence();
+        else __threadfence_system();
         if ((int)lane < sh.world)
         {
-          unsigned long long* out = reinterpret_cast<unsigned long long*>(sh.mail[lane]) +
-                                    kOneMailWord + sh.rank * kOneMailStride;
+          unsigned long long* out = reinterpret_cast<unsigned long long*>(sh.mail[lane]) + kOneMailWord +
+                                    ((int)(seq & 1ull) * kMaxRanks + sh.rank) * kOneMailStride;
 #pragma unroll
           for (int n = 0; n < kNSums; ++n)
           {
@@ -191,7 +207,7 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
       if ((int)lane < sh.world)
       {
         const unsigned long long* in = reinterpret_cast<const unsigned long long*>(sh.mail[sh.rank]) +
-                                       kOneMailWord + lane * kOneMailStride;
+                                       kOneMailWord + ((int)(seq & 1ull) * kMaxRanks + (int)lane) * kOneMailStride;
         const unsigned long long t0 = global_ns();
         unsigned int spins = 0;
 #pragma unroll
@@ -204,6 +220,13 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
             if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
             if ((++spins & 1023u) == 0 && global_ns() - t0 > kMailTimeoutNs)
             {
+              if (ok && blockIdx.x == 0)
+              {
+                s->comm_diag[0] = (unsigned long long)(phase_id);
+                s->comm_diag[1] = lane * 16ull + n;
+                s->comm_diag[2] = tag;
+                s->comm_diag[3] = w0;
+              }
               ok = false;
               break;
             }
@@ -212,7 +235,10 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
         }
       }
       ok = __all_sync(0xffffffffu, ok);
-      __threadfence_system(); // acquire: the peers' boundary rows were stored before their entries
+      // acquire: the peers' boundary rows were stored (and fenced) before their entries; they live in
+      // THIS GPU's memory and the next sweep reads them with TMA loads issued after this point
+      if (sys_flags & 1) __threadfence();
+      else __threadfence_system();
 #pragma unroll
       for (int n = 0; n < kNSums; ++n)
       {
@@ -298,8 +324,13 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
     // CTA having ARRIVED at the barrier -- but not on the scalars: they go out as soon as the
     // arrival counter is complete, while warp 0 still folds the partials and advances the
     // scalars.  (Sharded: the peers' boundary rows are only known to have landed once their
-    // mailbox entries are in, so there the loads wait for the release.)
-    const bool early = (flags & 4) != 0 && sh.world == 1;
+    // mailbox entries are in, so tiles next to a slab boundary wait for the release.)
+    const bool early = (flags & 4) != 0;
+    // sharded: tiles that read a neighbour's ghost rows wait for the release (the peers' entries)
+    auto needs_peer = [&](const TileWalk& t) {
+      const int j0 = sh.row_lo + t.ty * TH;
+      return sh.world > 1 && ((sh.rank > 0 && t.ty == 0) || (sh.rank < sh.world - 1 && j0 + TH + 2 > sh.row_hi));
+    };
     auto issue = [&](const TileWalk& t, int cr) {
       if (rp.round > 0) mbar_wait_guarded(&empty[rp.st], (rp.round - 1) & 1);
       unsigned char* base = smem + rp.st * St::kBytes;
@@ -331,7 +362,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
         fence_proxy_async_all();
         TileWalk tn(blockIdx.x, G, tiles_x, n_walk, serp && ((sweep + 1) & 1) == 0, tile_list, n_prefix);
         const int want = min(stages, tn.count);
-        for (; npre < want; ++npre, tn.next()) issue(tn, cur ^ 1);
+        for (; npre < want && !needs_peer(tn); ++npre, tn.next()) issue(tn, cur ^ 1);
       }
       {
         SpinGuard g;
@@ -570,7 +601,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
       else body(std::false_type{});
     }
     ++phase_id;
-    one_reduce<NW>(acc, s, partials + (phase_id & 1u) * (kNSums * G), phase_id, sh, &ss, pushed, dbg);
+    one_reduce<NW>(acc, s, partials + (phase_id & 1u) * (8 * G), phase_id, sh, &ss, pushed, (flags >> 11) & 3, dbg);
     if (iter_sweep)
     {
       alpha_prev = alpha;
@@ -670,7 +701,7 @@ int configure_one(fsb_ctx* c)
 
 } // namespace
 
-int fsb_cg_one_partials(const fsb_ctx* c) { return 2 * kNSums * std::max(c->cg_one_grid, c->sm_count * 2); }
+int fsb_cg_one_partials(const fsb_ctx* c) { return 2 * 8 * std::max(c->cg_one_grid, c->sm_count * 2); }
 
 // Called after the set-up (k_cg_build*: x = 0, r = b, stencil codes, |b|^2 and the threshold in
 // the CG scalars, the active-tile list) with the solve not yet finished.
@@ -681,7 +712,7 @@ int fsb_k_cg_one_solve(fsb_ctx* c, const CgCoef& coef)
   const ShardArgs& sh = c->shard;
   int tiles_x = fsb_div_up(c->ld, kTileW);
   int n_tiles = tiles_x * fsb_div_up(sh.row_hi - sh.row_lo, th);
-  const int need = 2 * kNSums * c->cg_one_grid;
+  const int need = 2 * 8 * c->cg_one_grid;
   if (need > c->partials_cap)
     return fsb_fail(c, FSB_ERR_INVALID, "partials buffer too small for the one-sweep solve");
   {

@@ -39,6 +39,9 @@ struct CgScalars
   // and a flag raised when a peer did not answer in time
   unsigned long long seq[4];
   int comm_error;
+  // where a mailbox wait gave up (diagnostics for FSB_ERR_COMM): sweep, missing rank, expected tag,
+  // word seen
+  unsigned long long comm_diag[4];
   // software grid barrier of the persistent solve kernel: arrivals so far / last released phase
   unsigned int bar_count;
   unsigned int bar_release;
@@ -60,9 +63,13 @@ struct CgScalars
 //   combine kernel waits for all `world` entries and adds them in rank order, so
 //   all ranks derive bit-identical alpha / beta / `done`.  No NCCL call in the loop.
 constexpr int kMaxRanks = 8;
-constexpr int kMailTypes = 8; // 0: p.Ap, 1: (|r|^2, r.z), 2: end-of-solve barrier; 4-7: one-sweep solve
-// the one-sweep solve (fsb_cg_one.cu) posts five doubles per reduction: rank q's entry is the 16
-// self-validating words starting at word kOneMailWord + q * kOneMailStride of a mailbox
+constexpr int kMailTypes = 12; // 0: p.Ap, 1: (|r|^2, r.z), 2: end-of-solve barrier; 4-11: one-sweep solve
+// the one-sweep solve (fsb_cg_one.cu) posts five doubles per reduction: rank q's entry of reduction
+// number `seq` is the 16 self-validating words starting at word
+// kOneMailWord + ((seq & 1) * kMaxRanks + q) * kOneMailStride of a mailbox.  Two entries per rank,
+// used alternately: a rank can only post reduction n + 2 after it has received every rank's n + 1,
+// and a rank posts n + 1 only after all of its CTAs have finished reading the entries of n -- so an
+// entry is never overwritten while somebody may still have to read it.
 constexpr int kOneMailWord = 4 * kMaxRanks * 4;
 constexpr int kOneMailStride = 16;
 
@@ -165,6 +172,7 @@ struct fsb_ctx
   int* cg_tile_flags = nullptr;
   int* cg_tile_list = nullptr;
   int cg_tile_cap = 0;
+  int cg_last_active_tiles = 0; // active-tile count of the last solve (measurement)
   int cg_grid_fused = 0, cg_fused_stages = 0, cg_fused_stage_bytes = 0;
   int max_iters = 100;
   float tol = 1.1920929e-7f;

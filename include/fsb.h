@@ -293,6 +293,10 @@ int fsb_profile_read(fsb_ctx* ctx, float* ms, int* calls);
  * 3 the last solve was a multigrid-preconditioned CG (FSB_PRECOND_MULTIGRID),
  * 4 one persistent cooperative kernel with ONE sweep and one reduction per iteration (default) */
 int fsb_cg_launch_mode(const fsb_ctx* ctx);
+/* cells the sweeps of the last pressure solve visited per iteration on THIS rank: the cells of the
+ * tiles that hold at least one LIQUID cell (all tiles of the rank's rows when the active-tile list is
+ * off); 0 before the first solve.  Measurement only: the byte count of the roofline figure. */
+int64_t fsb_cg_swept_cells(const fsb_ctx* ctx);
 /* number of kernels this library launched on the context since creation */
 int64_t fsb_launch_count(const fsb_ctx* ctx);
 /* a pair of events around an arbitrary region of this context's stream */
