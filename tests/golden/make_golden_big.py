@@ -7,6 +7,7 @@ container; the outputs are committed and the GPU tests read them.
     python tests/golden/make_golden_big.py config0     # ~2 s   examples/simple.cpp scene, 100 steps
     python tests/golden/make_golden_big.py config1     # ~2 min 1024^2 semi-Lagrangian dam-break, 3 steps
     python tests/golden/make_golden_big.py config2     # ~35 min 4096^2 PIC/FLIP tank, one step, CG to 1e-6
+    python tests/golden/make_golden_big.py cg4096      # ~40 min 4096^2 tank pressure solve (analytic input) to 1e-6
     python tests/golden/make_golden_big.py cg8192c     # ~5 min 8192^2 tank pressure solve, 40 iterations
 
 The CG inside is the restated Eigen loop of the shim (dots accumulated in double, see
@@ -107,6 +108,31 @@ def config2(ref):
     np.savez_compressed(os.path.join(HERE, "config2_picflip4096.npz"), **out)
 
 
+def cg4096(ref):
+    """bench.py's cg4096 workload: the 4096^2 tank pressure system with the ANALYTIC input field
+    (`tank_fields`: both sides get bit-identical u, v, labels), solved to 1e-6 by the reference.
+    Unlike config 2 -- whose right-hand side is the divergence of a P2G result and therefore differs
+    between implementations at the 1e-5 level of the transfer, mostly as grid-scale noise -- this pins
+    the iteration count for identical inputs."""
+    import bench
+    n = 4096
+    dt = float(np.float32(0.01 * 64.0 / n))
+    lab, u0, v0 = bench.tank_fields(n)
+    s = ref.sim(n, n, 1.0, 1.0, dt, 0.02)
+    s.set_cell_types(lab)
+    s.set_grid(ol.U_FRONT, u0); s.set_grid(ol.V_FRONT, v0)
+    s.set_cg(400000, 1e-6)
+    t0 = time.time()
+    s.pressure_solve(dt, dt)
+    pr = s.get_pressure()
+    out = {"n": n, "dt": dt, "cg": np.array(s.cg_info(), dtype=np.float64), "seconds": time.time() - t0,
+           "pressure_ds16": pr[::16, ::16].copy(),
+           "pressure_l2": float(np.sqrt((pr.astype(np.float64) ** 2).sum())),
+           "u_ds16": s.get_grid(ol.U_FRONT)[::16, ::16].copy(), "v_ds16": s.get_grid(ol.V_FRONT)[::16, ::16].copy()}
+    print("cg4096", s.cg_info(), f"{out['seconds']:.0f}s", flush=True)
+    np.savez_compressed(os.path.join(HERE, "cg4096_solve.npz"), **out)
+
+
 def cg8192c(ref):
     """BASELINE.json configs[3] sample: the 8192^2 tank pressure system of bench.py (`tank_fields`),
     the first 40 iterations of the restated Eigen loop: iterate x_40 (down-sampled) and the
@@ -134,7 +160,7 @@ def cg8192c(ref):
 if __name__ == "__main__":
     assert ol.available("fsr"), "build oracle/_ref first: make -C oracle ref"
     ref = ol.OracleLib("fsr")
-    jobs = {"config0": config0, "config1": config1, "config2": config2, "cg8192c": cg8192c}
+    jobs = {"config0": config0, "config1": config1, "config2": config2, "cg4096": cg4096, "cg8192c": cg8192c}
     for name in sys.argv[1:]:
         t0 = time.time()
         jobs[name](ref)
