@@ -1684,7 +1684,8 @@ int configure_cg(fsb_ctx* c)
                   // reads them here are TMA loads issued after the entry was seen, through the L2 that
                   // received them.  FSB_CG_POLL_FENCE_SYS=1 / FSB_CG_POST_FENCE_SYS=1 restore the
                   // system-scope fences.
-                  (knob("FSB_CG_POLL_FENCE_SYS", 0) ? 0 : 2048) | (knob("FSB_CG_POST_FENCE_SYS", 0) ? 0 : 4096);
+                  (knob("FSB_CG_POLL_FENCE_SYS", 0) ? 0 : 2048) | (knob("FSB_CG_POST_FENCE_SYS", 0) ? 0 : 4096) |
+                  (knob("FSB_CG_DEBUG_TIMES", 0) ? 8192 : 0) | (knob("FSB_CG_ROTATE", 0) ? 16384 : 0);
   }
 
   void* fn = nullptr;

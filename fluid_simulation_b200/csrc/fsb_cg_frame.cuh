@@ -135,10 +135,16 @@ struct TileWalk
   const int* list;
   int first, stride, n_total, k, n_pre;
   int ahead; // list entry of tile k + 1, requested one tile early (its latency is off the critical path)
+  // rot != 0: round r of the walk gives this CTA the list position r * stride + (first + r * rot) %
+  // stride instead of r * stride + first, so that a CTA's tiles do not all sit in the same few tile
+  // columns (stride 296 over 32 tile columns: every fourth tile of CTAs 0, 7 mod 8 would be a wall
+  // tile, which takes the slower table path).  Only without a prefix.
+  int rot;
   __device__ __forceinline__ TileWalk(int first_tile, int stride_, int tiles_x_, int n_tiles,
                                       bool reverse = false, const int* list_ = nullptr,
-                                      int prefix = 0)
+                                      int prefix = 0, int rot_ = 0)
   {
+    rot = (list_ && prefix == 0) ? rot_ : 0;
     tiles_x = tiles_x_;
     rev = reverse;
     list = list_;
@@ -148,6 +154,11 @@ struct TileWalk
     k = 0;
     ahead = 0;
     count = first_tile < n_tiles ? (n_tiles - 1 - first_tile) / stride_ + 1 : 0;
+    if (rot)
+    {
+      const int full = n_tiles / stride_, rem = n_tiles - full * stride_;
+      count = full + (((first_tile + full * rot) % stride_ < rem) ? 1 : 0);
+    }
     // this CTA's list positions below `prefix`
     n_pre = (list && first_tile < prefix) ? (prefix - 1 - first_tile) / stride_ + 1 : 0;
     if (n_pre > count) n_pre = count;
@@ -177,7 +188,9 @@ struct TileWalk
   {
     if (kk < n_pre) return first + kk * stride;
     const int m = kk - n_pre; // m-th of the (count - n_pre) non-prefix entries
-    return rev ? first + (count - 1 - m) * stride : first + (n_pre + m) * stride;
+    const int r = rev ? (count - 1 - m) : (n_pre + m);
+    if (rot) return r * stride + (first + r * rot) % stride;
+    return first + r * stride;
   }
   __device__ __forceinline__ void next()
   {

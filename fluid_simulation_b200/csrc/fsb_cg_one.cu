@@ -115,10 +115,20 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
     if (lane == 0) s_part[n][warp] = acc[n];
   }
   consumer_sync(NW * 32);
+  __shared__ double s_fold[kNSums][NW];
+  __shared__ int s_folder;
+  const int G = (int)gridDim.x;
+  const unsigned int target = phase_id * (unsigned int)G;
+  double tot[kNSums];
+#pragma unroll
+  for (int n = 0; n < kNSums; ++n) tot[n] = 0.0;
+  // FSB_CG_DEBUG_TIMES (with FSB_CG_DEBUG_SUMS): %globaltimer stamps of reductions 100..163 instead of the sums
+  double* tdbg = nullptr;
+  if (dbg && (sys_flags & 4) && threadIdx.x == 0 && phase_id >= 100 && phase_id < 164)
+    tdbg = dbg + ((size_t)(phase_id - 100) * G + blockIdx.x) * 10;
+#define FSB_STAMP(i) do { if (tdbg) tdbg[i] = (double)global_ns(); } while (0)
   if (warp == 0)
   {
-    const int G = (int)gridDim.x;
-    double tot[kNSums];
 #pragma unroll
     for (int n = 0; n < kNSums; ++n)
     {
@@ -127,57 +137,84 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       tot[n] = v;
     }
+    FSB_STAMP(0);
     // partials: one 64-byte record per CTA (five sums), two regions used alternately
-    unsigned int arrived = 0;
     if (lane == 0)
     {
       double2* rec = reinterpret_cast<double2*>(partials + (size_t)blockIdx.x * 8);
       rec[0] = make_double2(tot[0], tot[1]);
       rec[1] = make_double2(tot[2], tot[3]);
       partials[(size_t)blockIdx.x * 8 + 4] = tot[4];
-      if (dbg && phase_id <= 64) // FSB_CG_DEBUG_SUMS: this CTA's own sums of the sweep
+      if (dbg && !(sys_flags & 4) && phase_id <= 64) // FSB_CG_DEBUG_SUMS: this CTA's own sums of the sweep
         for (int n = 0; n < kNSums; ++n) dbg[((size_t)(phase_id - 1) * G + blockIdx.x) * 10 + n] = tot[n];
       // the CTA's global stores (p / r / x rows, peer rows) must be visible to the TMA loads of the
       // next sweep on every SM (and GPU) before the arrival is
       fence_proxy_async_all();
       if (pushed) __threadfence_system();
       else __threadfence();
-      arrived = atomicAdd(&s->bar_count, 1u) + 1u;
-    }
-    arrived = __shfl_sync(0xffffffffu, arrived, 0);
-    const unsigned int target = phase_id * (unsigned int)G;
-    // Who folds the partials: single GPU -- every CTA, as soon as the counter is complete (no
-    // broadcast hop); sharded -- the CTA that arrived LAST (it needs no wait at all), which then posts
-    // the slab's sums into every rank's mailbox.
-    const bool folder = sh.world == 1 || arrived == target;
-    if (folder)
-    {
+      // Who folds the partials: single GPU -- every CTA, as soon as the counter is complete (no
+      // broadcast hop); sharded -- the CTA that arrived LAST (it needs no wait at all), which then
+      // posts the slab's sums into every rank's mailbox.
+      int folder = 1;
       if (sh.world == 1)
       {
+        atomicAdd(&s->bar_count, 1u); // no return value needed: a reduction, not a round trip
+        FSB_STAMP(1);
         const volatile unsigned int* cnt = &s->bar_count;
         SpinGuard g;
         while (*cnt < target) g.tick();
       }
-      __threadfence();
-#pragma unroll
-      for (int n = 0; n < kNSums; ++n) tot[n] = 0.0;
-      // every lane adds the records lane, lane + 32, ... in that order, then a butterfly: one fixed
-      // order of additions, the same on every CTA
-#pragma unroll 5
-      for (int k = (int)lane; k < G; k += 32)
+      else
       {
-        const double2* rec = reinterpret_cast<const double2*>(partials + (size_t)k * 8);
-        const double2 a = __ldcg(rec), b2 = __ldcg(rec + 1);
-        const double c = __ldcg(partials + (size_t)k * 8 + 4);
-        tot[0] += a.x; tot[1] += a.y; tot[2] += b2.x; tot[3] += b2.y; tot[4] += c;
+        folder = (atomicAdd(&s->bar_count, 1u) + 1u == target) ? 1 : 0;
+        FSB_STAMP(1);
       }
+      if (folder) __threadfence();
+      s_folder = folder;
+      FSB_STAMP(2);
+    }
+  }
+  consumer_sync(NW * 32);
+  const bool folder = s_folder != 0;
+  if (folder)
+  {
+    // the fold is done by the whole CTA: thread t adds the records t, t + NW * 32, ... (at most two),
+    // a butterfly inside each warp, then warp 0 adds the NW warp sums in warp order -- one fixed order
+    // of additions, the same on every CTA; all loads are in flight together
+    double f[kNSums];
+#pragma unroll
+    for (int n = 0; n < kNSums; ++n) f[n] = 0.0;
+    for (int k = (int)threadIdx.x; k < G; k += NW * 32)
+    {
+      const double2* rec = reinterpret_cast<const double2*>(partials + (size_t)k * 8);
+      const double2 a = __ldcg(rec), b2 = __ldcg(rec + 1);
+      const double c = __ldcg(partials + (size_t)k * 8 + 4);
+      f[0] += a.x; f[1] += a.y; f[2] += b2.x; f[3] += b2.y; f[4] += c;
+    }
+#pragma unroll
+    for (int n = 0; n < kNSums; ++n)
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) f[n] += __shfl_xor_sync(0xffffffffu, f[n], o);
+      if (lane == 0) s_fold[n][warp] = f[n];
+    }
+    consumer_sync(NW * 32);
+    if (warp == 0)
+    {
 #pragma unroll
       for (int n = 0; n < kNSums; ++n)
       {
+        double v = 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot[n] += __shfl_xor_sync(0xffffffffu, tot[n], o);
+        for (int w = 0; w < NW; ++w) v += s_fold[n][w];
+        tot[n] = v;
       }
     }
+  }
+  if (warp == 0)
+  {
+    FSB_STAMP(3);
+    if (tdbg) tdbg[7] = folder ? 1.0 : 0.0;
     bool ok = true;
     const unsigned long long seq = ss->seq + 1;
     if (sh.world > 1)
@@ -201,6 +238,7 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
           }
         }
       }
+      FSB_STAMP(4);
       double v[kNSums];
 #pragma unroll
       for (int n = 0; n < kNSums; ++n) v[n] = 0.0;
@@ -235,10 +273,11 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
         }
       }
       ok = __all_sync(0xffffffffu, ok);
-      // acquire: the peers' boundary rows were stored (and fenced) before their entries; they live in
-      // THIS GPU's memory and the next sweep reads them with TMA loads issued after this point
-      if (sys_flags & 1) __threadfence();
-      else __threadfence_system();
+      FSB_STAMP(5);
+      // the peers' boundary rows were stored, and fenced at system scope, before their entries; they
+      // live in THIS GPU's memory and the next sweep reads them with TMA loads that the producer issues
+      // only after it has seen the release below (FSB_CG_POLL_FENCE_SYS=1: a system-scope fence here)
+      if (!(sys_flags & 1)) __threadfence_system();
 #pragma unroll
       for (int n = 0; n < kNSums; ++n)
       {
@@ -249,7 +288,7 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
     }
     if (lane == 0)
     {
-      if (dbg && phase_id <= 64) // ... and the totals as this CTA sees them
+      if (dbg && !(sys_flags & 4) && phase_id <= 64) // ... and the totals as this CTA sees them
         for (int n = 0; n < kNSums; ++n) dbg[((size_t)(phase_id - 1) * gridDim.x + blockIdx.x) * 10 + 5 + n] = tot[n];
       ss->seq = seq;
       if (!ok)
@@ -263,6 +302,7 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
       }
       __threadfence_block();
       ss->released = phase_id;
+      FSB_STAMP(6);
     }
   }
   consumer_sync(NW * 32);
@@ -308,6 +348,10 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
   // flags bit 8 (FSB_CG_DEBUG_NOTILES, measurement only): sweeps without tiles -- the time per
   // "iteration" is then the bare cost of the barrier + reduction + scalar step
   const bool no_tiles = (flags & 256) != 0;
+  // FSB_CG_ROTATE=1: rotate the CTA -> tile assignment from round to round (TileWalk::rot).  Measured
+  // at 4096^2: no gain (69.8 vs 69.2 us per iteration) -- the 11 us between the first and the last CTA
+  // reaching the barrier are not the wall tiles' slower path -- so it is off by default.
+  const int rot = (flags & 16384) ? 1 : 0;
   const int n_walk = no_tiles ? 0 : tile_list ? s->n_active_tiles : n_tiles;
   const int n_prefix = tile_list ? s->n_prefix_tiles : 0;
   const int G = (int)gridDim.x;
@@ -343,7 +387,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
     };
     for (;;)
     {
-      TileWalk t(blockIdx.x, G, tiles_x, n_walk, serp && (sweep & 1) == 0, tile_list, n_prefix);
+      TileWalk t(blockIdx.x, G, tiles_x, n_walk, serp && (sweep & 1) == 0, tile_list, n_prefix, rot);
       int k = 0;
       for (; k < npre; ++k) t.next();
       for (; k < t.count; ++k, t.next()) issue(t, cur);
@@ -360,7 +404,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
         }
         __threadfence();
         fence_proxy_async_all();
-        TileWalk tn(blockIdx.x, G, tiles_x, n_walk, serp && ((sweep + 1) & 1) == 0, tile_list, n_prefix);
+        TileWalk tn(blockIdx.x, G, tiles_x, n_walk, serp && ((sweep + 1) & 1) == 0, tile_list, n_prefix, rot);
         const int want = min(stages, tn.count);
         for (; npre < want && !needs_peer(tn); ++npre, tn.next()) issue(tn, cur ^ 1);
       }
@@ -418,7 +462,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
 #pragma unroll
     for (int n = 0; n < kNSums; ++n) acc[n] = no_tiles ? 1.0 : 0.0;
     bool pushed = false;
-    TileWalk t(blockIdx.x, G, tiles_x, n_walk, serp && (sweep & 1) == 0, tile_list, n_prefix);
+    TileWalk t(blockIdx.x, G, tiles_x, n_walk, serp && (sweep & 1) == 0, tile_list, n_prefix, rot);
     for (int tk = 0; tk < t.count; ++tk, t.next())
     {
       const unsigned char* base = smem + rp.st * St::kBytes;
@@ -601,7 +645,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
       else body(std::false_type{});
     }
     ++phase_id;
-    one_reduce<NW>(acc, s, partials + (phase_id & 1u) * (8 * G), phase_id, sh, &ss, pushed, (flags >> 11) & 3, dbg);
+    one_reduce<NW>(acc, s, partials + (phase_id & 1u) * (8 * G), phase_id, sh, &ss, pushed, (flags >> 11) & 7, dbg);
     if (iter_sweep)
     {
       alpha_prev = alpha;
@@ -615,7 +659,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
   {
     // the solve ended on an iteration whose x update was deferred: x += alpha p of that iteration.
     // Same tile -> thread mapping as the sweeps; p is exactly zero outside LIQUID cells.
-    TileWalk t(blockIdx.x, G, tiles_x, n_walk, false, tile_list, n_prefix);
+    TileWalk t(blockIdx.x, G, tiles_x, n_walk, false, tile_list, n_prefix, rot);
     for (int tk = 0; tk < t.count; ++tk, t.next())
     {
       const int ci = t.tx * kTileW + (int)lane * 4;
