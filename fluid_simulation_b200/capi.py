@@ -381,6 +381,32 @@ class Sim:
         self._ck(_lib.fsb_slab_boundary_take(self.h, _ptr(parts), _ptr(ids)))
         return parts, ids
 
+    # the same calls with raw pointers (host or device memory: the library copies with
+    # cudaMemcpyDefault and returns after the copy has completed)
+    def slab_add_ptr(self, parts_ptr, ids_ptr, n):
+        if n:
+            self._ck(_lib.fsb_slab_add(self.h, C.c_void_p(parts_ptr), C.c_void_p(ids_ptr), int(n)))
+
+    def slab_take_ptr(self, dest, parts_ptr, ids_ptr):
+        self._ck(_lib.fsb_slab_take(self.h, dest, C.c_void_p(parts_ptr), C.c_void_p(ids_ptr)))
+
+    def slab_boundary_count(self, side):
+        n = _l()
+        self._ck(_lib.fsb_slab_boundary(self.h, side, C.byref(n)))
+        return int(n.value)
+
+    def slab_boundary_take_ptr(self, parts_ptr, ids_ptr):
+        self._ck(_lib.fsb_slab_boundary_take(self.h, C.c_void_p(parts_ptr), C.c_void_p(ids_ptr)))
+
+    def slab_get_ptr(self, parts_ptr, ids_ptr):
+        self._ck(_lib.fsb_slab_get(self.h, C.c_void_p(parts_ptr), C.c_void_p(ids_ptr)))
+
+    def get_rows_ptr(self, which, lo, hi, ptr):
+        self._ck(_lib.fsb_get_rows(self.h, which, lo, hi, C.c_void_p(ptr)))
+
+    def set_rows_ptr(self, which, lo, hi, ptr):
+        self._ck(_lib.fsb_set_rows(self.h, which, lo, hi, C.c_void_p(ptr)))
+
     def slab_get(self):
         n = self.num_particles()
         parts, ids = np.empty((n, 4), dtype=np.float32), np.empty(n, dtype=np.int32)

@@ -416,9 +416,17 @@ int fsb_set_gravity(fsb_ctx* c, float ax, float ay)
 }
 
 // ---------------------------------------------------------------- particles
+// On a slab-partitioned context (fsb_slab_configure with world > 1) the index map holds GLOBAL
+// particle ids (and -1 for retired ghosts), not a permutation of 0 .. n-1: the calls that treat it as
+// one -- or that hand out ids starting at the local count -- are refused; fsb_slab_get / _add are
+// their slab forms.
+#define REFUSE_ON_SLAB(c, what) \
+  return fsb_fail((c), FSB_ERR_INVALID, what " on a slab-partitioned context: use the fsb_slab_* calls")
+
 int fsb_append_particles(fsb_ctx* c, const float* aos4, int64_t n)
 {
   CHECK_CTX(c);
+  if (c->slab_partitioned) REFUSE_ON_SLAB(c, "fsb_append_particles");
   if (n < 0 || (n > 0 && !aos4)) return fsb_fail(c, FSB_ERR_INVALID, "bad particle buffer");
   if (n == 0) return FSB_OK;
   FSB_TRY(ensure_particle_capacity(c, c->n + n));
@@ -434,6 +442,7 @@ int fsb_set_particles(fsb_ctx* c, const float* aos4, int64_t n)
 {
   CHECK_CTX(c);
   c->n = 0;
+  c->slab_partitioned = false; // a fresh, whole set (to be distributed again if the context is a slab)
   c->sort_valid = false;
   return fsb_append_particles(c, aos4, n);
 }
@@ -441,6 +450,7 @@ int64_t fsb_num_particles(const fsb_ctx* c) { return c ? c->n : 0; }
 int fsb_get_particles(fsb_ctx* c, float* aos4)
 {
   CHECK_CTX(c);
+  if (c->slab_partitioned) REFUSE_ON_SLAB(c, "fsb_get_particles");
   if (c->n == 0) return FSB_OK;
   if (!aos4) return fsb_fail(c, FSB_ERR_INVALID, "null particle buffer");
   // part[pcur^1] is scratch outside the sort
@@ -456,6 +466,7 @@ int fsb_emit_source(fsb_ctx* c, float x_min, float x_max, float y_min, float y_m
 {
   CHECK_CTX(c);
   if (n_added) *n_added = 0;
+  if (c->slab_partitioned) REFUSE_ON_SLAB(c, "fsb_emit_source");
   // src/FluidDomain.cpp:37-41: increments are formed in double and rounded;
   // the coordinates are accumulated by repeated float addition
   const float x_incr = (float)(delta_x / 2.5);
@@ -754,6 +765,7 @@ int fsb_slab_add(fsb_ctx* c, const float* aos4, const int32_t* ids, int64_t n)
   c->n += n;
   c->sort_valid = false;
   c->slab_grouped = false;
+  c->slab_partitioned = true; // ids given by the caller: global ids
   return FSB_OK;
 }
 int fsb_slab_sort_out(fsb_ctx* c, int64_t* counts)
@@ -797,6 +809,7 @@ int fsb_slab_keep_own(fsb_ctx* c)
   c->n = n;
   c->sort_valid = false;
   c->slab_grouped = false;
+  if (c->slab_world > 1) c->slab_partitioned = true;
   return FSB_OK;
 }
 int fsb_slab_boundary(fsb_ctx* c, int side, int64_t* n)
@@ -951,6 +964,7 @@ int fsb_save_state(fsb_ctx* c, const char* path)
 {
   CHECK_CTX(c);
   if (!path) return fsb_fail(c, FSB_ERR_INVALID, "null path");
+  if (c->slab_partitioned) REFUSE_ON_SLAB(c, "fsb_save_state");
   FILE* f = fopen(path, "wb");
   if (!f) return fsb_fail(c, FSB_ERR_INVALID, "cannot open %s for writing", path);
   FileCloser guard(f);
@@ -1001,79 +1015,99 @@ int fsb_save_state(fsb_ctx* c, const char* path)
   return FSB_OK;
 }
 
-int fsb_load_state(fsb_ctx* c, const char* path)
+// Transactional: the whole file is read into host memory and validated (header fields, sizes against
+// the file length, the particle index map) BEFORE the context is touched; a rejected or truncated
+// file leaves the running simulation exactly as it was.  No C++ exception crosses the C ABI.
+static int load_state_impl(fsb_ctx* c, const char* path)
 {
-  CHECK_CTX(c);
-  if (!path) return fsb_fail(c, FSB_ERR_INVALID, "null path");
   FILE* f = fopen(path, "rb");
   if (!f) return fsb_fail(c, FSB_ERR_INVALID, "cannot open %s", path);
   FileCloser guard(f);
   StateHeader hd;
   if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, kStateMagic, 8) != 0 || hd.version != 1)
     return fsb_fail(c, FSB_ERR_INVALID, "%s is not a version-1 FSBSTATE file", path);
-  if (hd.nx != c->nx || hd.ny != c->ny || hd.n_particles < 0)
-  {
+  if (hd.nx != c->nx || hd.ny != c->ny)
     return fsb_fail(c, FSB_ERR_INVALID, "%s holds a %dx%d domain, the context is %dx%d", path, hd.nx,
                     hd.ny, c->nx, c->ny);
-  }
+  auto pos_finite = [](float v) { return std::isfinite(v) && v > 0.0f; };
+  if (!pos_finite(hd.dx) || !pos_finite(hd.dy) || !pos_finite(hd.pool_dx) || !pos_finite(hd.pool_dy) ||
+      !std::isfinite(hd.density) || !std::isfinite(hd.pic_ratio) || !std::isfinite(hd.grav_x) ||
+      !std::isfinite(hd.grav_y) || !std::isfinite(hd.tol) || hd.pool_nx <= 0 || hd.pool_ny <= 0 ||
+      (hd.integrator != FSB_INTEGRATOR_EULER && hd.integrator != FSB_INTEGRATOR_RK3))
+    return fsb_fail(c, FSB_ERR_INVALID, "%s: header fields out of range", path);
   const size_t cells = (size_t)c->nx * c->ny;
-  std::vector<float> buf(std::max(cells, (size_t)hd.n_particles * 4));
+  // the file length fixes how many particles it can hold: no allocation from an unchecked count
+  if (fseek(f, 0, SEEK_END) != 0) return fsb_fail(c, FSB_ERR_INVALID, "%s: cannot seek", path);
+  const long long file_len = ftell(f);
+  const long long fixed = (long long)sizeof hd + (long long)cells * (1 + 8 * (long long)sizeof(float));
+  if (hd.n_particles < 0 || hd.n_particles > INT32_MAX || file_len < fixed ||
+      (file_len - fixed) != hd.n_particles * (long long)(4 * sizeof(float) + sizeof(int)))
+    return fsb_fail(c, FSB_ERR_INVALID, "%s is truncated or its particle count (%lld) does not match its length",
+                    path, (long long)hd.n_particles);
+  if (fseek(f, (long)sizeof hd, SEEK_SET) != 0) return fsb_fail(c, FSB_ERR_INVALID, "%s: cannot seek", path);
+  const int64_t np = hd.n_particles;
   std::vector<uint8_t> lab(cells);
-  int rc = FSB_OK;
-  bool ok = fread(lab.data(), 1, cells, f) == cells;
-  if (ok) rc = fsb_set_cell_types(c, lab.data());
-  c->diff_pending = false;
-  for (int w = FSB_U_FRONT; ok && rc == FSB_OK && w <= FSB_V_DIFF; ++w)
+  std::vector<float> grids(8 * cells), parts((size_t)np * 4);
+  std::vector<int> orig((size_t)np);
+  bool ok = fread(lab.data(), 1, cells, f) == cells &&
+            fread(grids.data(), sizeof(float), 8 * cells, f) == 8 * cells &&
+            (np == 0 || (fread(parts.data(), 4 * sizeof(float), (size_t)np, f) == (size_t)np &&
+                         fread(orig.data(), sizeof(int), (size_t)np, f) == (size_t)np));
+  guard.close();
+  if (!ok) return fsb_fail(c, FSB_ERR_INVALID, "%s is truncated", path);
+  for (size_t k = 0; k < cells; ++k)
+    if (lab[k] > FSB_SOLID) return fsb_fail(c, FSB_ERR_INVALID, "%s: cell label out of range", path);
   {
-    ok = fread(buf.data(), sizeof(float), cells, f) == cells;
-    if (ok) rc = fsb_set_grid(c, w, buf.data());
-    // the staging vector is reused: the copy must have left it before the next read
-    if (ok && rc == FSB_OK) rc = fsb_synchronize(c);
-  }
-  if (ok && rc == FSB_OK)
-  {
-    const int64_t np = hd.n_particles;
-    c->n = 0;
-    c->sort_valid = false;
-    if (np > 0)
+    // the map must be a permutation of 0 .. n-1 (it indexes the caller-order buffer on read-back)
+    std::vector<uint8_t> seen((size_t)np, 0);
+    for (int64_t k = 0; k < np; ++k)
     {
-      rc = ensure_particle_capacity(c, np);
-      ok = rc == FSB_OK && fread(buf.data(), 4 * sizeof(float), (size_t)np, f) == (size_t)np;
-      if (ok)
-      {
-        FSB_CUDA(c, cudaMemcpyAsync(c->part[c->pcur], buf.data(), sizeof(float4) * np,
-                                    cudaMemcpyHostToDevice, c->stream));
-        FSB_CUDA(c, cudaStreamSynchronize(c->stream));
-        ok = fread(buf.data(), sizeof(int), (size_t)np, f) == (size_t)np;
-      }
-      if (ok)
-      {
-        // the map must be a permutation of 0 .. n-1 (it indexes the caller-order buffer on read-back)
-        const int* o = reinterpret_cast<const int*>(buf.data());
-        std::vector<uint8_t> seen((size_t)np, 0);
-        for (int64_t k = 0; k < np && ok; ++k)
-        {
-          ok = o[k] >= 0 && o[k] < np && !seen[(size_t)o[k]];
-          if (ok) seen[(size_t)o[k]] = 1;
-        }
-        if (!ok)
-          return fsb_fail(c, FSB_ERR_INVALID, "%s: the particle index map is not a permutation", path);
-        FSB_CUDA(c, cudaMemcpyAsync(c->orig[c->pcur], buf.data(), sizeof(int) * np,
-                                    cudaMemcpyHostToDevice, c->stream));
-        FSB_CUDA(c, cudaStreamSynchronize(c->stream));
-        c->n = np;
-      }
+      if (orig[(size_t)k] < 0 || orig[(size_t)k] >= np || seen[(size_t)orig[(size_t)k]])
+        return fsb_fail(c, FSB_ERR_INVALID, "%s: the particle index map is not a permutation", path);
+      seen[(size_t)orig[(size_t)k]] = 1;
     }
   }
-  guard.close();
-  if (rc != FSB_OK) return rc;
-  if (!ok) return fsb_fail(c, FSB_ERR_INVALID, "%s is truncated", path);
+  // ---- everything checked: now the context changes
+  if (np > 0) FSB_TRY(ensure_particle_capacity(c, np));
+  FSB_TRY(fsb_set_cell_types(c, lab.data()));
+  c->diff_pending = false;
+  for (int w = FSB_U_FRONT; w <= FSB_V_DIFF; ++w) FSB_TRY(fsb_set_grid(c, w, grids.data() + (size_t)w * cells));
+  c->n = 0;
+  c->sort_valid = false;
+  if (np > 0)
+  {
+    FSB_CUDA(c, cudaMemcpyAsync(c->part[c->pcur], parts.data(), sizeof(float4) * np, cudaMemcpyHostToDevice,
+                                c->stream));
+    FSB_CUDA(c, cudaMemcpyAsync(c->orig[c->pcur], orig.data(), sizeof(int) * np, cudaMemcpyHostToDevice,
+                                c->stream));
+  }
+  FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n = np;
   c->dx = hd.dx; c->dy = hd.dy; c->density = hd.density; c->pic_ratio = hd.pic_ratio;
   c->grav_x = hd.grav_x; c->grav_y = hd.grav_y; c->integrator = hd.integrator;
   c->max_iters = hd.max_iters; c->tol = hd.tol;
   c->pool_dx = hd.pool_dx; c->pool_dy = hd.pool_dy; c->pool_nx = hd.pool_nx; c->pool_ny = hd.pool_ny;
   c->pressure_valid = false;
   return FSB_OK;
+}
+
+int fsb_load_state(fsb_ctx* c, const char* path)
+{
+  CHECK_CTX(c);
+  if (!path) return fsb_fail(c, FSB_ERR_INVALID, "null path");
+  if (c->slab_partitioned) REFUSE_ON_SLAB(c, "fsb_load_state");
+  try
+  {
+    return load_state_impl(c, path);
+  }
+  catch (const std::bad_alloc&)
+  {
+    return fsb_fail(c, FSB_ERR_NOMEM, "out of host memory while reading %s", path);
+  }
+  catch (const std::exception& e)
+  {
+    return fsb_fail(c, FSB_ERR_INVALID, "reading %s failed: %s", path, e.what());
+  }
 }
 
 // ------------------------------------------------------------------ sharding

@@ -198,6 +198,7 @@ struct fsb_ctx
   int slab_world = 1, slab_rank = 0, slab_lo = 0, slab_hi = 0;
   int64_t slab_count[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // group sizes after fsb_slab_sort_out
   bool slab_grouped = false;
+  bool slab_partitioned = false; // the set holds a slab's particles with GLOBAL ids (after keep_own / add)
   float4* slab_buf_part = nullptr; // boundary-row selection
   int* slab_buf_orig = nullptr;
   int64_t slab_buf_cap = 0;

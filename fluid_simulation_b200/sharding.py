@@ -122,121 +122,130 @@ class LocalSlabs:
 
 
 class DistSlabs:
-    """One rank of a torch.distributed job (gloo on CPU tensors, or NCCL with device="cuda").
-    Same call sequence as LocalSlabs; buffers travel as torch tensors staged through the host.
-    Round-1 status: the gloo transport is verified on a B200 (two ranks sharing one GPU,
-    tests/test_multi_gpu.py); the NCCL transport's first version deadlocked in ungrouped
-    isend / recv pairs, was rewritten with batch_isend_irecv and has NOT been re-run (the round's GPU
-    budget was spent): its test is opt-in (FSB_TEST_NCCL_SLABS=1)."""
+    """One rank of a torch.distributed job.  Same call sequence as LocalSlabs.  All buffers are torch
+    tensors on `device` -- CUDA tensors with the NCCL backend, CPU tensors with gloo -- and the library
+    reads / writes them through their raw pointers (fsb_slab_add / _take / fsb_get_rows / fsb_set_rows
+    take host or device memory): with NCCL nothing is staged through the host.  Point-to-point
+    transfers are issued as ONE batch_isend_irecv group (an ungrouped send / recv pair in opposite
+    directions between two ranks deadlocks under NCCL); the library's copies run on the context's own
+    stream and have completed when its calls return, the collectives are waited for before the library
+    touches a buffer."""
 
     def __init__(self, sim, dist=None, device=None):
         import torch
         if dist is None:
             import torch.distributed as dist
-        self.torch, self.dist, self.device = torch, dist, device
+        self.torch, self.dist = torch, dist
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
         self.sim = sim
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.lo, self.hi = sim.slab_configure(self.rank, self.world)
         self.rows = [slab_rows(sim.ny, self.world, q) for q in range(self.world)]
+        self.max_rows = max(hi - lo for lo, hi in self.rows)
 
-    def _t(self, a):
-        t = self.torch.from_numpy(np.ascontiguousarray(a))
-        return t.to(self.device) if self.device is not None else t
+    def _sync(self):
+        if self.device.type == "cuda":
+            self.torch.cuda.synchronize(self.device)
+
+    def _pair(self, n):
+        torch = self.torch
+        return (torch.empty((max(n, 1), 4), dtype=torch.float32, device=self.device),
+                torch.empty(max(n, 1), dtype=torch.int32, device=self.device))
 
     def _exchange(self, outgoing):
-        """outgoing[d] = (parts, ids) or None; returns the list of (parts, ids) received."""
+        """outgoing[d] = (parts tensor, ids tensor, n) or None; returns [(parts, ids, n)] received."""
         torch, dist = self.torch, self.dist
-        n_out = torch.tensor([0 if o is None else o[1].shape[0] for o in outgoing], dtype=torch.int64)
-        n_out = n_out.to(self.device) if self.device is not None else n_out
+        n_out = torch.tensor([0 if o is None else o[2] for o in outgoing], dtype=torch.int64, device=self.device)
         table = [torch.empty_like(n_out) for _ in range(self.world)]
-        dist.all_gather(table, n_out)  # table[q][d] = what q sends to d (gloo has no all-to-all)
-        n_in = [int(table[q][self.rank].item()) for q in range(self.world)]
-        recv = []
-        if dist.get_backend() == "nccl":
-            # NCCL point-to-point calls must be issued as ONE group: an ungrouped send / recv pair in
-            # opposite directions between two ranks deadlocks (each send kernel waits for the peer's
-            # recv, which is queued behind the peer's own send)
-            ops, bufs = [], []
-            for q in range(self.world):
-                if q != self.rank and outgoing[q] is not None and outgoing[q][1].shape[0]:
-                    ops.append(dist.P2POp(dist.isend, self._t(outgoing[q][0]), q))
-                    ops.append(dist.P2POp(dist.isend, self._t(outgoing[q][1]), q))
-            for q in range(self.world):
-                if q != self.rank and n_in[q]:
-                    p = torch.empty((n_in[q], 4), dtype=torch.float32, device=self.device)
-                    i = torch.empty(n_in[q], dtype=torch.int32, device=self.device)
-                    ops.append(dist.P2POp(dist.irecv, p, q))
-                    ops.append(dist.P2POp(dist.irecv, i, q))
-                    bufs.append((p, i))
-            if ops:
-                for r in dist.batch_isend_irecv(ops):
-                    r.wait()
-                torch.cuda.synchronize()
-            return [(p.cpu().numpy(), i.cpu().numpy()) for p, i in bufs]
-        reqs = []
+        dist.all_gather(table, n_out)  # table[q][d] = what q sends to d
+        n_in = [int(v) for v in torch.stack(table)[:, self.rank].cpu().tolist()]
+        ops, recv = [], []
         for q in range(self.world):
-            if q != self.rank and outgoing[q] is not None and outgoing[q][1].shape[0]:
-                reqs.append(dist.isend(self._t(outgoing[q][0]), q))
-                reqs.append(dist.isend(self._t(outgoing[q][1]), q))
+            if q != self.rank and outgoing[q] is not None and outgoing[q][2]:
+                p, i, n = outgoing[q]
+                ops.append(dist.P2POp(dist.isend, p[:n], q))
+                ops.append(dist.P2POp(dist.isend, i[:n], q))
         for q in range(self.world):
             if q != self.rank and n_in[q]:
-                p = torch.empty((n_in[q], 4), dtype=torch.float32, device=self.device)
-                i = torch.empty(n_in[q], dtype=torch.int32, device=self.device)
-                dist.recv(p, q)
-                dist.recv(i, q)
-                recv.append((p.cpu().numpy(), i.cpu().numpy()))
-        for r in reqs:
-            r.wait()
+                p, i = self._pair(n_in[q])
+                ops.append(dist.P2POp(dist.irecv, p[:n_in[q]], q))
+                ops.append(dist.P2POp(dist.irecv, i[:n_in[q]], q))
+                recv.append((p, i, n_in[q]))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+            self._sync()
         return recv
 
     def distribute(self):
         self.sim.slab_sort_out(self.world)
         self.sim.slab_keep_own()
 
-    def step(self, kind, dt):
-        s, torch, dist = self.sim, self.torch, self.dist
-        out = [None] * self.world
-        if self.rank > 0:
-            out[self.rank - 1] = s.slab_boundary(0)
-        if self.rank + 1 < self.world:
-            out[self.rank + 1] = s.slab_boundary(1)
-        for parts, ids in self._exchange(out):
-            s.slab_add(parts, ids)
-        s.slab_step_a(kind)
+    def _boundary(self, side):
+        n = self.sim.slab_boundary_count(side)
+        p, i = self._pair(n)
+        if n:
+            self.sim.slab_boundary_take_ptr(p.data_ptr(), i.data_ptr())
+        return p, i, n
+
+    def _gather_rows(self):
+        """Every rank's label / u / v rows to every rank.  Slabs differ by a row when ny is not a multiple
+        of the world size: the buffers are padded to the tallest slab (all_gather wants equal shapes)."""
+        torch, dist, s = self.torch, self.dist, self.sim
         for which in (ROWS_LABELS, U_FRONT, V_FRONT):
-            mine = self._t(s.get_rows(which, self.lo, self.hi))
-            slabs = [torch.empty((hi - lo, s.nx), dtype=mine.dtype, device=mine.device)
-                     for lo, hi in self.rows]
+            dtype = torch.uint8 if which == ROWS_LABELS else torch.float32
+            mine = torch.zeros((self.max_rows, s.nx), dtype=dtype, device=self.device)
+            s.get_rows_ptr(which, self.lo, self.hi, mine.data_ptr())
+            slabs = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(slabs, mine)
+            self._sync()
             for q, (lo, hi) in enumerate(self.rows):
                 if q != self.rank:
-                    s.set_rows(which, lo, hi, slabs[q].cpu().numpy())
+                    s.set_rows_ptr(which, lo, hi, slabs[q].data_ptr())
+
+    def step(self, kind, dt):
+        s = self.sim
+        out = [None] * self.world
+        if self.rank > 0:
+            out[self.rank - 1] = self._boundary(0)
+        if self.rank + 1 < self.world:
+            out[self.rank + 1] = self._boundary(1)
+        for p, i, n in self._exchange(out):
+            s.slab_add_ptr(p.data_ptr(), i.data_ptr(), n)
+        s.slab_step_a(kind)
+        self._gather_rows()
         s.slab_step_b(kind, dt)
         s.slab_step_c(kind, dt)
         counts = s.slab_sort_out(self.world)
-        out = [s.slab_take(d, counts[d]) if d != self.rank and counts[d] else None
-               for d in range(self.world)]
+        out = [None] * self.world
+        for d in range(self.world):
+            if d != self.rank and counts[d]:
+                p, i = self._pair(counts[d])
+                s.slab_take_ptr(d, p.data_ptr(), i.data_ptr())
+                out[d] = (p, i, counts[d])
         s.slab_keep_own()
-        for parts, ids in self._exchange(out):
-            s.slab_add(parts, ids)
+        for p, i, n in self._exchange(out):
+            s.slab_add_ptr(p.data_ptr(), i.data_ptr(), n)
         return sum(c for d, c in enumerate(counts) if d != self.rank)
 
     def particles(self):
-        """The whole set in global-id order, gathered on every rank."""
+        """The whole set in global-id order, gathered on every rank (tests; small scenes)."""
         torch, dist = self.torch, self.dist
-        parts, ids = self.sim.slab_get()
-        n = torch.tensor([ids.shape[0]], dtype=torch.int64)
-        n = n.to(self.device) if self.device is not None else n
+        n_own = self.sim.num_particles()
+        n = torch.tensor([n_own], dtype=torch.int64, device=self.device)
         ns = [torch.empty_like(n) for _ in range(self.world)]
         dist.all_gather(ns, n)
         ns = [int(v.item()) for v in ns]
         cap = max(ns) if ns else 0
-        pp = np.zeros((cap, 4), dtype=np.float32); pp[:ids.shape[0]] = parts
-        ii = np.zeros(cap, dtype=np.int32); ii[:ids.shape[0]] = ids
-        gp = [torch.empty((cap, 4), dtype=torch.float32, device=self.device) for _ in range(self.world)]
-        gi = [torch.empty(cap, dtype=torch.int32, device=self.device) for _ in range(self.world)]
-        dist.all_gather(gp, self._t(pp))
-        dist.all_gather(gi, self._t(ii))
+        pp, ii = self._pair(cap)
+        pp.zero_(); ii.zero_()
+        if n_own:
+            self.sim.slab_get_ptr(pp.data_ptr(), ii.data_ptr())
+        gp = [torch.empty_like(pp) for _ in range(self.world)]
+        gi = [torch.empty_like(ii) for _ in range(self.world)]
+        dist.all_gather(gp, pp)
+        dist.all_gather(gi, ii)
+        self._sync()
         out = np.empty((sum(ns), 4), dtype=np.float32)
         for q in range(self.world):
             out[gi[q][:ns[q]].cpu().numpy()] = gp[q][:ns[q]].cpu().numpy()

@@ -704,6 +704,74 @@ def test_state_file_round_trip_continues_bit_identically(capi, tmp_path):
         b.load_state(str(tmp_path / "missing.fsb"))
 
 
+def test_rejected_state_files_leave_the_simulation_untouched(capi, tmp_path):
+    """fsb_load_state validates the whole file before it touches the context: truncated files, a
+    particle count that does not match the file length (an absurd count must not turn into an
+    allocation), header fields out of range and an index map that is not a permutation are refused,
+    and the running simulation continues exactly as if the call had not been made."""
+    n = 48
+    a = capi.Sim(n, n, 1.0, 1.0, 0.01, 0.05)
+    a.emit_source(*scenes.dam_break_args(n))
+    a.step(STEP_PICFLIP, 0.01)
+    good = str(tmp_path / "good.fsb")
+    a.save_state(good)
+    raw = bytearray(open(good, "rb").read())
+    before = (a.get_cell_types(), a.get_particles(), a.get_grid(U_FRONT), a.get_grid(V_BACK))
+    import struct
+    off_np = 72  # StateHeader::n_particles (fsb_api.cu)
+    assert struct.unpack("<q", bytes(raw[off_np:off_np + 8]))[0] == a.num_particles()
+
+    def variant(name, edit):
+        b = bytearray(raw)
+        edit(b)
+        path = str(tmp_path / name)
+        open(path, "wb").write(b)
+        return path
+
+    def set_count(b, v):
+        b[off_np:off_np + 8] = struct.pack("<q", v)
+
+    bad = [variant("trunc_grids.fsb", lambda b: b.__delitem__(slice(len(b) // 3, None))),
+           variant("trunc_tail.fsb", lambda b: b.__delitem__(slice(len(b) - 5, None))),
+           variant("huge_count.fsb", lambda b: set_count(b, 1 << 40)),
+           variant("negative_count.fsb", lambda b: set_count(b, -3)),
+           variant("count_plus_one.fsb", lambda b: set_count(b, a.num_particles() + 1)),
+           variant("bad_map.fsb", lambda b: b.__setitem__(slice(len(b) - 4, None), struct.pack("<i", 0) if
+                                                          struct.unpack("<i", bytes(b[-4:]))[0] != 0 else struct.pack("<i", 1))),
+           variant("empty.fsb", lambda b: b.__delitem__(slice(0, None)))]
+    for path in bad:
+        with pytest.raises(RuntimeError):
+            a.load_state(path)
+        now = (a.get_cell_types(), a.get_particles(), a.get_grid(U_FRONT), a.get_grid(V_BACK))
+        for x, y in zip(before, now):
+            assert np.array_equal(x, y), path
+    a.load_state(good)  # and the good file still loads
+    assert np.array_equal(a.get_particles(), before[1])
+
+
+def test_whole_set_calls_are_refused_on_a_slab_partitioned_context(capi, tmp_path):
+    """After fsb_slab_keep_own the index map holds global ids: fsb_get_particles (which un-permutes
+    through it), fsb_save_state, fsb_append_particles and fsb_emit_source return an error instead of
+    writing out of bounds / colliding ids; fsb_set_particles starts over with a whole set."""
+    n = 64
+    g = capi.Sim(n, n, 1.0, 1.0, 0.01, 0.05)
+    g.emit_source(*scenes.dam_break_args(n))
+    whole = g.get_particles()
+    g.slab_configure(1, 2)
+    assert np.array_equal(g.get_particles(), whole)  # still the whole set: fine
+    g.slab_sort_out(2)
+    g.slab_keep_own()
+    assert 0 < g.num_particles() < whole.shape[0]
+    for call in (g.get_particles, lambda: g.save_state(str(tmp_path / "x.fsb")),
+                 lambda: g.append_particles(whole[:3]), lambda: g.emit_source(*scenes.dam_break_args(n))):
+        with pytest.raises(RuntimeError):
+            call()
+    parts, ids = g.slab_get()
+    assert parts.shape[0] == g.num_particles() and np.array_equal(parts, whole[ids])
+    g.set_particles(whole)
+    assert np.array_equal(g.get_particles(), whole)
+
+
 @pytest.mark.parametrize("kind", [STEP_PICFLIP, STEP_SL])
 def test_edge_cases_empty_set_tiny_grid_and_particles_in_wall_cells(capi, port, kind):
     """No particles at all on the smallest grid the library accepts, and particles everywhere in

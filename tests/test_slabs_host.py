@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NY, NX = 24, 8
+NY, NX = 25, 8  # 25 rows: the slabs of 2 / 3 / 4 ranks differ in height (padded row all-gather)
 
 
 class FakeSim:
@@ -68,6 +68,46 @@ class FakeSim:
 
     def slab_get(self):
         return self.parts.copy(), self.ids.copy()
+
+    # the raw-pointer forms DistSlabs uses (host memory here; device memory with NCCL on a GPU)
+    @staticmethod
+    def _view(ptr, shape, dtype):
+        import ctypes
+        n = int(np.prod(shape))
+        if n == 0:
+            return np.empty(shape, dtype=dtype)
+        buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def slab_add_ptr(self, pp, ip, n):
+        if n:
+            self.slab_add(self._view(pp, (n, 4), np.float32).copy(), self._view(ip, (n,), np.int32).copy())
+
+    def slab_take_ptr(self, dest, pp, ip):
+        parts, ids = self.slab_take(dest, self.groups[dest].size)
+        self._view(pp, parts.shape, np.float32)[:] = parts
+        self._view(ip, ids.shape, np.int32)[:] = ids
+
+    def slab_boundary_count(self, side):
+        self._sel = self.slab_boundary(side)
+        return self._sel[1].shape[0]
+
+    def slab_boundary_take_ptr(self, pp, ip):
+        parts, ids = self._sel
+        self._view(pp, parts.shape, np.float32)[:] = parts
+        self._view(ip, ids.shape, np.int32)[:] = ids
+
+    def slab_get_ptr(self, pp, ip):
+        self._view(pp, self.parts.shape, np.float32)[:] = self.parts
+        self._view(ip, self.ids.shape, np.int32)[:] = self.ids
+
+    def get_rows_ptr(self, which, lo, hi, ptr):
+        a = self.get_rows(which, lo, hi)
+        self._view(ptr, a.shape, a.dtype)[:] = a
+
+    def set_rows_ptr(self, which, lo, hi, ptr):
+        dtype = np.uint8 if which == 8 else np.float32
+        self.set_rows(which, lo, hi, self._view(ptr, (hi - lo, self.nx), dtype).copy())
 
     def get_rows(self, which, lo, hi):
         return (self.labels if which == 8 else self.grids[which])[lo:hi].copy()
