@@ -305,6 +305,52 @@ def scale_cg8192(capi, sharding, dist, torch, local_rank, world, log):
     return out
 
 
+def config4_slabs(capi, sharding, dist, torch, local_rank, world, log, n=16384):
+    """BASELINE.json configs[4]: the 16384^2 PIC/FLIP step on `world` GPUs -- particles partitioned by
+    row slab (ghost rows and migration over NCCL, device buffers), the pressure CG sharded over the same
+    slabs, the grid stages replicated.  The tank is filled on the device by fsb_emit_source (4 particles
+    per cell, at rest); every rank emits the whole lattice, keeps its slab and frees nothing else.
+    One warm-up step with the CG capped, one timed step to 1e-6."""
+    dt = float(np.float32(0.01 * 64.0 / n))
+    d = 1.0 / n
+    g = capi.Sim(n, n, 1.0, 1.0, dt, 0.02, device=local_rank)
+    n_all = g.emit_source(1.25 * d, 1.0 - d, 1.25 * d, 15.0 / 16.0, 1.25 * d, 1.25 * d, 0.0, 0.0)
+    dev = torch.device("cuda", local_rank)
+    slabs = sharding.DistSlabs(g, dist, dev)
+    slabs.distribute()
+    n_own = g.num_particles()
+    sharding.connect(g, dist, dev)
+    log(f"config4: {n_all} particles, {n_own} on this rank, rows {slabs.lo}..{slabs.hi}")
+    g.set_cg(100, 1e-6)
+    slabs.step(capi.STEP_PICFLIP, dt)
+    g.synchronize(); dist.barrier()
+    g.set_cg(400000, 1e-6)
+    g.profile_enable(True); g.profile_read()
+    t0 = time.perf_counter()
+    g.timer_start()
+    moved = slabs.step(capi.STEP_PICFLIP, dt)
+    ms = g.timer_stop()
+    torch.cuda.synchronize(); dist.barrier()
+    wall = time.perf_counter() - t0
+    prof = g.profile_read(); g.profile_enable(False)
+    it, relres = g.cg_info()
+    t = torch.tensor([ms, prof["cg"][0], wall * 1e3], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, cg_ms, wall_ms = (float(v) for v in t.tolist())
+    out = {"workload": f"{n}^2 picflip full step on {world} GPUs: particle slabs (NCCL, device buffers) + sharded "
+                       f"Jacobi-PCG to 1e-06, tank scene 4 particles/cell (device-emitted lattice, at rest)",
+           "n_gpus": world, "particles": int(n_all), "particles_per_rank": int(n_own),
+           "ms_per_step": ms, "wall_ms_per_step": wall_ms, "cell_updates_per_s": n * n / (wall_ms * 1e-3),
+           "cg_iterations": int(it), "cg_relres": float(relres), "cg_us_per_iteration": 1e3 * cg_ms / max(it, 1),
+           "migrated_from_this_rank": int(moved),
+           "stage_ms": {k: round(v[0], 3) for k, v in prof.items()}}
+    log(f"config4: {out}")
+    g.shard_disconnect()
+    dist.barrier()
+    g.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -315,7 +361,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-optin", action="store_true", help="skip the opt-in multigrid side measurement")
-    ap.add_argument("--no-scale", action="store_true", help="skip the 8192^2 CG side measurement")
+    ap.add_argument("--no-scale", action="store_true", help="skip the 8192^2 CG (and, on 8 GPUs, the 16384^2 step) "
+                                                            "side measurements")
+    ap.add_argument("--config4", type=int, default=0, metavar="N",
+                    help="run the particle-slab side measurement at N^2 on any multi-GPU world (debug)")
     ap.add_argument("--cg-cap", type=int, default=None, help="override the CG iteration cap (debug)")
     ap.add_argument("--precond", default="jacobi", choices=["jacobi", "mg"],
                     help="jacobi: the reference's preconditioner (headline); mg: the opt-in multigrid "
@@ -548,7 +597,19 @@ def main():
             scale = scale_cg8192(capi, sharding, dist, torch, local_rank, world, log)
         except Exception as e:  # a side measurement must never cost the headline line
             scale = {"error": str(e)[:300]}
-    if world > 1:
+    # ---- side measurement on the 8-GPU line: BASELINE.json configs[4] (16384^2 on the whole box)
+    config4 = None
+    if (world == 8 or args.config4) and world > 1 and not args.no_scale and args.precond == "jacobi":
+        sim.shard_disconnect()
+        sim.close()  # its 5 GB of particles and grids are not needed any more
+        try:
+            config4 = config4_slabs(capi, sharding, dist, torch, local_rank, world, log,
+                                    n=args.config4 if args.config4 else 16384)
+        except Exception as e:
+            config4 = {"error": str(e)[:300]}
+        dist.barrier()
+        dist.destroy_process_group()
+    elif world > 1:
         sim.shard_disconnect()
         dist.barrier()
         dist.destroy_process_group()
@@ -655,6 +716,7 @@ def main():
         "cpu_baseline": cpu,
         "optin_multigrid": optin,
         "scale_cg8192": scale,
+        "config4_picflip16384": config4,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -36,9 +36,6 @@ def test_particle_slabs_over_torch_distributed(built, backend):
     one-GPU box); nccl: one rank per GPU, needs 2 GPUs."""
     import torch
     if backend == "nccl":
-        if os.environ.get("FSB_TEST_NCCL_SLABS") != "1":
-            pytest.skip("NCCL transport of the particle slabs: rewritten after a deadlock, not re-run "
-                        "in round 1 (set FSB_TEST_NCCL_SLABS=1 on a 2-GPU box)")
         if torch.cuda.device_count() < 2:
             pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
