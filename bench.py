@@ -76,6 +76,10 @@ WORKLOADS = {
     "cg8192": dict(n=8192, kind="cg", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=0),
     "cg4096": dict(n=4096, kind="cg", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=0),
     "cg1024": dict(n=1024, kind="cg", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=0),
+    # one rank's share of cg8192 on 8 / 4 GPUs as a single-GPU workload (8192 columns x 1024 / 2048 rows,
+    # same cell size): the per-rank sweep without any cross-GPU traffic (tuning aid, capped)
+    "cg8192slab8": dict(n=8192, ny=1024, kind="cg", pic_ratio=0.02, tol=1e-6, cap=2000, per_side=0),
+    "cg8192slab4": dict(n=8192, ny=2048, kind="cg", pic_ratio=0.02, tol=1e-6, cap=2000, per_side=0),
 }
 
 
@@ -142,17 +146,18 @@ def tank_particles(n, per_side, seed=1234):
     return scenes.tank_particles(n, np.random.default_rng(seed), per_side)
 
 
-def tank_fields(n):
+def tank_fields(n, ny=None):
     """CG-only workloads: labels of the tank scene (SOLID border, LIQUID below 15/16, AIR cap) and a
     velocity field = analytic swirl + one gravity kick, sampled at the MAC face positions."""
     dx = 1.0 / n
-    lab = np.full((n, n), 1, dtype=np.uint8)
-    lab[1:int(15.0 / 16.0 * n), 1:-1] = 0
+    ny = n if ny is None else ny
+    lab = np.full((ny, n), 1, dtype=np.uint8)
+    lab[1:int(15.0 / 16.0 * ny), 1:-1] = 0
     lab[0, :] = lab[-1, :] = 2
     lab[:, 0] = lab[:, -1] = 2
-    i = np.arange(n, dtype=np.float64)
-    xu, yu = (i * dx)[None, :], ((i + 0.5) * dx)[:, None]
-    xv, yv = ((i + 0.5) * dx)[None, :], (i * dx)[:, None]
+    i, j = np.arange(n, dtype=np.float64), np.arange(ny, dtype=np.float64)
+    xu, yu = (i * dx)[None, :], ((j + 0.5) * dx)[:, None]
+    xv, yv = ((i + 0.5) * dx)[None, :], (j * dx)[:, None]
     u = (np.sin(np.pi * xu) * np.cos(np.pi * yu)).astype(np.float32)
     v = (-np.cos(np.pi * xv) * np.sin(np.pi * yv) - 9.82 * 0.01 * 64.0 / n).astype(np.float32)
     return lab, u, v
@@ -433,16 +438,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     dt = float(np.float32(0.01 * 64.0 / n))
-    sim = capi.Sim(n, n, 1.0, 1.0, dt, wl["pic_ratio"], device=local_rank)
+    ny = wl.get("ny", n)
+    sim = capi.Sim(n, ny, 1.0, float(ny) / float(n), dt, wl["pic_ratio"], device=local_rank)
     sim.set_cg(wl["cap"], wl["tol"])
     if args.precond == "mg":
         sim.set_preconditioner(capi.PRECOND_MULTIGRID)
     cg_only = wl["kind"] == "cg"
     if cg_only:
-        lab, u0, v0 = tank_fields(n)
-        hu = torch.empty((n, n), dtype=torch.float32, pin_memory=True); hu.numpy()[:] = u0
-        hv = torch.empty((n, n), dtype=torch.float32, pin_memory=True); hv.numpy()[:] = v0
-        hp = torch.empty((n, n), dtype=torch.float32, pin_memory=True)
+        lab, u0, v0 = tank_fields(n, ny)
+        hu = torch.empty((ny, n), dtype=torch.float32, pin_memory=True); hu.numpy()[:] = u0
+        hv = torch.empty((ny, n), dtype=torch.float32, pin_memory=True); hv.numpy()[:] = v0
+        hp = torch.empty((ny, n), dtype=torch.float32, pin_memory=True)
         sim.set_cell_types(lab)
         n_part = 0
         del u0, v0
@@ -525,7 +531,7 @@ def main():
         prof["cg"] = (cg_ms_max, prof["cg"][1])
     ms_per_step = ms / args.steps
     # N > 1 is STRONG scaling of the same workload: total work fixed, CG rows split over N GPUs
-    value = n * n * args.steps / (ms * 1e-3)
+    value = n * ny * args.steps / (ms * 1e-3)
 
     # ---- e2e: host buffers in and out every step
     e2e = None
@@ -551,9 +557,9 @@ def main():
             t = torch.tensor([et], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             et = float(t.item())
-        h2d = 2 * n * n * 4 if cg_only else n_part * 16
-        d2h = n * n * 4 if cg_only else n_part * 16
-        e2e = {"value": n * n * args.steps / et, "unit": "cell-updates/s",
+        h2d = 2 * n * ny * 4 if cg_only else n_part * 16
+        d2h = n * ny * 4 if cg_only else n_part * 16
+        e2e = {"value": n * ny * args.steps / et, "unit": "cell-updates/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                # the e2e steps continue the same simulation: later steps, other iteration counts
                "cg_iters_per_step": e2e_iters / args.steps}
@@ -579,7 +585,7 @@ def main():
                              "and stopping rule, NOT the reference's Jacobi-PCG (no parity claim, not the "
                              "headline)",
                      "ms_per_step": ms_mg / args.steps,
-                     "cell_updates_per_s": n * n * args.steps / (ms_mg * 1e-3),
+                     "cell_updates_per_s": n * ny * args.steps / (ms_mg * 1e-3),
                      "cg_iters_per_step": it_mg / args.steps, "relres": sim.cg_info()[1],
                      "multigrid_used": mode_mg == 3}
         except Exception as e:  # a side measurement must never cost the headline line
@@ -622,9 +628,9 @@ def main():
     # per GPU: each rank sweeps the active tiles of its 1/world of the rows per iteration
     design_b = DESIGN_BYTES_CG_PER_CELL.get(cg_mode)
     if not swept_cells:
-        swept_cells = n * n // world
+        swept_cells = n * ny // world
     design_bytes = (design_b or TEXTBOOK_BYTES_CG_PER_CELL) * swept_cells
-    textbook_bytes = TEXTBOOK_BYTES_CG_PER_CELL * n * n / world
+    textbook_bytes = TEXTBOOK_BYTES_CG_PER_CELL * n * ny / world
     achieved = design_bytes / (it_ms * 1e-3) / 1e9 if iters_total else 0.0
     achieved_textbook = textbook_bytes / (it_ms * 1e-3) / 1e9 if iters_total else 0.0
     traffic, traffic_src = None, None
@@ -639,7 +645,7 @@ def main():
     stages = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
     # every stage against the HBM roofline: algorithmic bytes of SURVEY.md 8(d) (C cells, P
     # particles; the cell sort is overhead and has no algorithmic bytes) / CUDA-event time
-    C, P = float(n * n), float(n_part)
+    C, P = float(n * ny), float(n_part)
     # classification rides on the cell sort's counting pass (one read of the particle set for both),
     # so the two are timed together; the sort itself is overhead of the deterministic P2G
     alg = {"classify+sort": 8 * P + C, "p2g": 16 * P + 8 * C, "extend": 17 * C, "rhs": 13 * C,

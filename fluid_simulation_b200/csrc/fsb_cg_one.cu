@@ -325,6 +325,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool serp = (flags & 1) != 0; // consecutive sweeps walk the tile list in opposite directions
   const bool xdefer = (flags & 128) != 0;
+  const bool xhint = (flags & 2) != 0;
 
   load_lut(lut, coef);
   if (threadIdx.x == 0)
@@ -375,13 +376,26 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
       const int j0 = sh.row_lo + t.ty * TH;
       return sh.world > 1 && ((sh.rank > 0 && t.ty == 0) || (sh.rank < sh.world - 1 && j0 + TH + 2 > sh.row_hi));
     };
+    // FSB_CG_PHINT=1: the old direction and residual are dead once this sweep has read them (the next
+    // sweep overwrites them): evict-first, so that the L2 keeps what this sweep WRITES, which is what
+    // the next sweep reads
+    const bool dead_hint = (flags & 8) != 0;
+    const uint64_t pol_dead = l2_policy_evict_first();
     auto issue = [&](const TileWalk& t, int cr) {
       if (rp.round > 0) mbar_wait_guarded(&empty[rp.st], (rp.round - 1) & 1);
       unsigned char* base = smem + rp.st * St::kBytes;
       const int c0 = t.tx * kTileW, j0 = sh.row_lo + t.ty * TH;
       mbar_expect_tx(&full[rp.st], St::kTx);
-      tma_load_2d(base + St::oP, &maps.halo_p[cr], c0 - 4, j0 - 2, &full[rp.st]);
-      tma_load_2d(base + St::oR, &maps.halo_r[cr], c0 - 4, j0 - 1, &full[rp.st]);
+      if (dead_hint)
+      {
+        tma_load_2d_hint(base + St::oP, &maps.halo_p[cr], c0 - 4, j0 - 2, &full[rp.st], pol_dead);
+        tma_load_2d_hint(base + St::oR, &maps.halo_r[cr], c0 - 4, j0 - 1, &full[rp.st], pol_dead);
+      }
+      else
+      {
+        tma_load_2d(base + St::oP, &maps.halo_p[cr], c0 - 4, j0 - 2, &full[rp.st]);
+        tma_load_2d(base + St::oR, &maps.halo_r[cr], c0 - 4, j0 - 1, &full[rp.st]);
+      }
       tma_load_2d(base + St::oC, &maps.code, c0 - 16, j0 - 1, &full[rp.st]);
       rp.advance(stages);
     };
@@ -488,8 +502,17 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
         pv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (with_x && jb + k < sh.row_hi && ci < ld)
         {
-          xv[k] = *reinterpret_cast<const float4*>(x + o0 + (size_t)k * ld);
-          if (two_x) pv[k] = *reinterpret_cast<const float4*>(p_new + o0 + (size_t)k * ld); // p_{k-1}
+          if (xhint)
+          {
+            // FSB_CG_XHINT=1: x (and the previous direction, read once more) are pure streams
+            xv[k] = __ldcs(reinterpret_cast<const float4*>(x + o0 + (size_t)k * ld));
+            if (two_x) pv[k] = __ldcs(reinterpret_cast<const float4*>(p_new + o0 + (size_t)k * ld));
+          }
+          else
+          {
+            xv[k] = *reinterpret_cast<const float4*>(x + o0 + (size_t)k * ld);
+            if (two_x) pv[k] = *reinterpret_cast<const float4*>(p_new + o0 + (size_t)k * ld); // p_{k-1}
+          }
         }
       }
       mbar_wait(&full[rp.st], rp.round & 1);
@@ -547,7 +570,8 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
             float4 xn = xv[k];
             if (two_x) xn = fma4(alpha_prev, pv[k], xn);
             xn = fma4(alpha, pk[k + 2], xn);
-            *reinterpret_cast<float4*>(x + o0 + (size_t)k * ld) = xn;
+            if (xhint) __stcs(reinterpret_cast<float4*>(x + o0 + (size_t)k * ld), xn);
+            else *reinterpret_cast<float4*>(x + o0 + (size_t)k * ld) = xn;
           }
       }
 
@@ -696,7 +720,11 @@ int configure_one_shape(fsb_ctx* c, int64_t n_tiles)
   constexpr int TH = kNWOne * RPW;
   const int threads = (kNWOne + 1) * 32;
   const int budget = (227 * 1024 - 2 * 2048) / 2; // two resident CTAs per SM
-  int stages = std::max(2, std::min(kMaxStages, budget / OneStage<TH>::kBytes));
+  // Ring depth: 3.  Deeper rings fit (5 stages of 21 KB at two CTAs per SM) but measured slower -- one
+  // B200, same box: 4096^2 76.7 (5 stages) / 74.8 (4) / 72.7 (3) / 73.3 (2) us per iteration, the
+  // 8192 x 1024 slab of an 8-GPU solve 42.0 / 39.2 / 39.9 (5 / 3 / 2), 8192^2 291.9 / 279.1 (5 / 3): the
+  // shared memory a shorter ring leaves free goes to the L1, through which x and the spilled registers pass.
+  int stages = std::max(2, std::min(3, budget / OneStage<TH>::kBytes));
   if (const char* e = getenv("FSB_CG_STAGES")) // tuning knob for profiling runs
   {
     const int v = atoi(e);
