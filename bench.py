@@ -62,7 +62,10 @@ WORKLOADS = {
     "picflip4096": dict(n=4096, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
     "picflip2048": dict(n=2048, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
     "picflip1024": dict(n=1024, kind="picflip", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
-    "sl1024": dict(n=1024, kind="sl", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2),
+    # BASELINE.json configs[1]: 1024^2 semi-Lagrangian + CG, synthetic dam-break (the FluidSource box of
+    # examples/simple.cpp:29 scaled to the grid, 6.25 particles per cell: 2.27e6 particles)
+    "sl1024": dict(n=1024, kind="sl", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2, scene="dam"),
+    "sl4096": dict(n=4096, kind="sl", pic_ratio=0.02, tol=1e-6, cap=400000, per_side=2, scene="dam"),
     # BASELINE.json configs[4]: 16384^2 full PIC/FLIP step.  1.0e9 particles: the tank is filled on
     # the device by fsb_emit_source (the reference's FluidSource lattice, src/FluidDomain.cpp:34-50,
     # at delta/2 spacing starting a quarter cell in: 4 particles per cell at the stratum centres,
@@ -392,7 +395,9 @@ def main():
         cfg_name = (f"{n}^2 pressure Poisson solve only (tank labels, swirl + gravity field), "
                     f"Jacobi-PCG to {wl['tol']:g} relative residual")
     else:
-        cfg_name = (f"{n}^2 {wl['kind']} full step, tank scene {wl['per_side']**2} particles/cell"
+        scene = ("dam-break scene 6.25 particles/cell" if wl.get("scene") == "dam"
+                 else f"tank scene {wl['per_side']**2} particles/cell")
+        cfg_name = (f"{n}^2 {wl['kind']} full step, {scene}"
                     f"{' (device-emitted lattice, at rest)' if wl.get('emit') else ''}, "
                     f"pic_ratio {wl['pic_ratio']}, CG to {wl['tol']:g} relative residual")
 
@@ -461,7 +466,12 @@ def main():
         kind = step_kind(capi, wl["kind"])
         log(f"scene emitted on the device: {n_part} particles")
     else:
-        parts = tank_particles(n, wl["per_side"])
+        if wl.get("scene") == "dam":
+            import scenes
+            sim.emit_source(*scenes.dam_break_args(n))
+            parts = sim.get_particles()
+        else:
+            parts = tank_particles(n, wl["per_side"])
         n_part = parts.shape[0]
         host = torch.empty((n_part, 4), dtype=torch.float32, pin_memory=True)
         host.numpy()[:] = parts

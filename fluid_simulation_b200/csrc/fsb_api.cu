@@ -237,6 +237,7 @@ int fsb_create(fsb_ctx** out, int size_x, int size_y, float length_x, float leng
   c->grav_x = 0.0f;
   c->grav_y = (float)-9.82; // src/FluidSolver.cpp:232
   if (const char* e = getenv("FSB_STAGE_KERNELS")) c->stage_v1 = (strcmp(e, "v1") == 0);
+  if (const char* e = getenv("FSB_SL_ATOMIC")) c->sl_atomic = atoi(e) != 0;
   if (const char* e = getenv("FSB_MG_MAX_ITERS")) c->mg_max_iters = std::max(1, atoi(e));
   if (const char* e = getenv("FSB_MG_SWEEPS")) c->mg_sweeps = std::max(1, std::min(8, atoi(e)));
   memset(c->prof_ms, 0, sizeof c->prof_ms);
@@ -313,6 +314,7 @@ void fsb_destroy(fsb_ctx* c)
   cudaFree(c->sort_key); cudaFree(c->sort_rank); cudaFree(c->sort_idx);
   for (int k = 0; k < c->n_ipc_opened; ++k) cudaIpcCloseMemHandle(c->ipc_opened[k]);
   cudaFree(c->peer_x_dev); cudaFree(c->mail_local);
+  fsb_sl_free(c);
   fsb_mg_free(c);
   cudaFree(c->slab_buf_part); cudaFree(c->slab_buf_orig); cudaFree(c->slab_ctr);
   cudaFree(c->cg_tile_flags); cudaFree(c->cg_tile_list);

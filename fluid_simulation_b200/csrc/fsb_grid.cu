@@ -398,6 +398,17 @@ int fsb_k_advect_velocity_sl(fsb_ctx* c, float dt)
 {
   const size_t bytes = (size_t)c->ld * c->ny * sizeof(float);
   fsb_prof_begin(c, FSB_PROF_ADVECT_SL);
+  if (!c->stage_v1 && !c->sl_atomic)
+  {
+    // the deterministic gather (fsb_sl.cu): bit-identical to the reference's face order
+    int done = 0;
+    FSB_TRY(fsb_k_advect_velocity_sl_gather(c, dt, &done));
+    if (done)
+    {
+      fsb_prof_end(c, FSB_PROF_ADVECT_SL);
+      return FSB_OK;
+    }
+  }
   FSB_CUDA(c, cudaMemsetAsync(fsb_ub(c), 0, bytes, c->stream));
   FSB_CUDA(c, cudaMemsetAsync(fsb_vb(c), 0, bytes, c->stream));
   const GridDims d = dims(c);

@@ -183,6 +183,13 @@ struct fsb_ctx
   // materialised only when somebody reads it
   bool diff_pending = false;
 
+  // semi-Lagrangian velocity advection (fsb_sl.cu): one 16-byte record per face, largest displacement
+  void *sl_rec_u = nullptr, *sl_rec_v = nullptr;
+  int* sl_maxd = nullptr;
+  size_t sl_cells = 0;
+  int sl_reach = 0;         // reach (source cells) of the last gather
+  bool sl_atomic = false;   // FSB_SL_ATOMIC=1: the first-generation float-atomics scatter
+
   // row-slab sharding (fsb_shard_*); world == 1: not sharded
   ShardArgs shard = {1, 0, 0, 0, {nullptr}};
   MailSlot* mail_local = nullptr;
@@ -283,6 +290,9 @@ int fsb_k_slab_sort_out(fsb_ctx* c, int64_t* counts);
 int fsb_k_slab_row_select(fsb_ctx* c, int row, int64_t* n_out);
 int fsb_k_emit_source_dev(fsb_ctx* c, int64_t first, const float* xs_dev, const float* ys_dev,
                           int64_t count_x, int64_t count_y, float vel_x, float vel_y);
+// semi-Lagrangian velocity advection as a deterministic gather: fsb_sl.cu
+int fsb_k_advect_velocity_sl_gather(fsb_ctx* c, float dt, int* done);
+void fsb_sl_free(fsb_ctx* c);
 // pressure: fsb_cg.cu
 int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichlet = false);
 void fsb_cg_reconfigure(fsb_ctx* c); // drop the CG launch configuration and graph (sharding changed)
