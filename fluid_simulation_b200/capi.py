@@ -69,6 +69,7 @@ SIGNATURES = {
     "fsb_add_acceleration": (_i, [_p, _f, _f, _f]),
     "fsb_enforce_dirichlet": (_i, [_p]),
     "fsb_extend_velocity": (_i, [_p, _i]),
+    "fsb_extend_velocity_averaging": (_i, [_p, _i]),
     "fsb_pressure_solve": (_i, [_p, _f, _f]),
     "fsb_update_diff": (_i, [_p]),
     "fsb_g2p": (_i, [_p, _i, _f]),
@@ -270,6 +271,9 @@ class Sim:
 
     def extend_velocity(self, n_iter=2):
         self._ck(_lib.fsb_extend_velocity(self.h, n_iter))
+
+    def extend_velocity_avg(self, n_iter=2):
+        self._ck(_lib.fsb_extend_velocity_averaging(self.h, n_iter))
 
     def pressure_solve(self, density=None, dt=0.01):
         self._ck(_lib.fsb_pressure_solve(self.h, self.density if density is None else density, dt))

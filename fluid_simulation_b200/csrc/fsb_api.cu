@@ -613,6 +613,13 @@ int fsb_extend_velocity(fsb_ctx* c, int n_iterations)
   FSB_TRY(flush_diff(c));
   return fsb_k_extend_velocity(c, n_iterations);
 }
+int fsb_extend_velocity_averaging(fsb_ctx* c, int n_iterations)
+{
+  CHECK_CTX(c);
+  if (n_iterations < 0) return fsb_fail(c, FSB_ERR_INVALID, "negative iteration count");
+  FSB_TRY(flush_diff(c));
+  return fsb_k_extend_velocity_avg(c, n_iterations);
+}
 int fsb_pressure_solve(fsb_ctx* c, float density, float dt)
 {
   CHECK_CTX(c);

@@ -394,6 +394,103 @@ int fsb_k_extend_velocity(fsb_ctx* c, int n_iter)
   return FSB_OK;
 }
 
+// ----------------------------------------------- extendVelocityAvarageing --
+// src/FluidSolver.cpp:625-707 (no step calls it).  A non-SOLID cell without the validity mark takes the
+// mean of the cell-centred back-buffer velocities of its marked neighbours and writes it to BOTH of its
+// faces per component (include/MacGrid.h:124-133) -- faces it shares with its neighbours -- so within a
+// sweep a cell sees what the cells scanned before it wrote: the result depends on the row-major scan
+// order.  The dependences are local, though: cell (i, j) reads faces written by (i-2..i-1, j),
+// (i-1..i+1, j-1) and (i, j-2) among the cells scanned before it, and cells scanned after it that write
+// a face it reads are (i+1..i+2, j), (i-1..i+1, j+1), (i, j+2).  With t = i + 2 j every such earlier
+// cell has a smaller t and every later one a larger t, so the cells of one t are mutually independent:
+// the sweep runs as nx + 2 ny - 2 wavefronts of one CTA, bit-identical to the sequential scan.
+namespace {
+
+__global__ void k_extend_avg_init(const float* __restrict__ uf, const float* __restrict__ vf,
+                                  float* __restrict__ ub, float* __restrict__ vb,
+                                  const uint8_t* __restrict__ cell, uint8_t* __restrict__ m0,
+                                  uint8_t* __restrict__ m1, const GridDims d, int* __restrict__ bad_border)
+{
+  int i, j;
+  if (!cell_of_thread(d, &i, &j)) return;
+  const size_t k = i + (size_t)j * d.ld;
+  const uint8_t ct = cell[k];
+  const uint8_t m = ct == FSB_LIQUID ? 1 : 0;
+  m0[k] = m;
+  m1[k] = m;
+  ub[k] = uf[k];
+  vb[k] = vf[k];
+  // the reference indexes (i +- 1, j +- 1) and (i + 2, j) / (i, j + 2) of non-SOLID cells without a
+  // clamp (it asserts): a classified grid has a SOLID border, anything else is refused
+  if ((i == 0 || j == 0 || i == d.nx - 1 || j == d.ny - 1) && ct != FSB_SOLID) *bad_border = 1;
+}
+
+__global__ void __launch_bounds__(1024)
+k_extend_avg_sweep(float* __restrict__ ub, float* __restrict__ vb, const uint8_t* __restrict__ cell,
+                   const uint8_t* __restrict__ mf, uint8_t* __restrict__ mb, const GridDims d)
+{
+  const int nx = d.nx, ny = d.ny, ld = d.ld;
+  auto ubc = [&](int i, int j) { return (ub[i + (size_t)j * ld] + ub[i + 1 + (size_t)j * ld]) / 2.0f; };
+  auto vbc = [&](int i, int j) { return (vb[i + (size_t)j * ld] + vb[i + (size_t)(j + 1) * ld]) / 2.0f; };
+  for (int t = 0; t <= nx - 1 + 2 * (ny - 1); ++t)
+  {
+    const int j_lo = max(0, (t - (nx - 1) + 1) / 2), j_hi = min(ny - 1, t / 2);
+    for (int j = j_lo + (int)threadIdx.x; j <= j_hi; j += (int)blockDim.x)
+    {
+      const int i = t - 2 * j;
+      const size_t k = i + (size_t)j * ld;
+      if (mf[k] == 0 && cell[k] != FSB_SOLID)
+      {
+        float nvx = 0.0f, nvy = 0.0f;
+        int n = 0;
+        if (mf[k - 1] == 1) { nvx += ubc(i - 1, j); nvy += vbc(i - 1, j); n++; }
+        if (mf[k - ld] == 1) { nvx += ubc(i, j - 1); nvy += vbc(i, j - 1); n++; }
+        if (mf[k + ld] == 1) { nvx += ubc(i, j + 1); nvy += vbc(i, j + 1); n++; }
+        if (mf[k + 1] == 1) { nvx += ubc(i + 1, j); nvy += vbc(i + 1, j); n++; }
+        if (n > 0)
+        {
+          nvx /= (float)n;
+          nvy /= (float)n;
+          ub[k] = nvx; ub[k + 1] = nvx;
+          vb[k] = nvy; vb[k + ld] = nvy;
+          mb[k] = 1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+} // namespace
+
+int fsb_k_extend_velocity_avg(fsb_ctx* c, int n_iter)
+{
+  const GridDims d = dims(c);
+  int* flag = nullptr;
+  FSB_CUDA(c, cudaMalloc(&flag, sizeof(int)));
+  FSB_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+  k_extend_avg_init<<<cell_grid(c), kBlock, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c),
+                                                              c->cell, c->mask_x[c->mask_front],
+                                                              c->mask_x[c->mask_front ^ 1], d, flag);
+  FSB_LAUNCHED(c);
+  int bad = 0;
+  FSB_CUDA(c, cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  FSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(flag);
+  if (bad)
+    return fsb_fail(c, FSB_ERR_INVALID, "extendVelocityAvarageing needs SOLID border cells (the reference "
+                                        "indexes past the border of a non-SOLID border cell)");
+  for (int it = 0; it < n_iter; ++it)
+  {
+    k_extend_avg_sweep<<<1, 1024, 0, c->stream>>>(fsb_ub(c), fsb_vb(c), c->cell, c->mask_x[c->mask_front],
+                                                   c->mask_x[c->mask_front ^ 1], d);
+    FSB_LAUNCHED(c);
+    c->mask_front ^= 1; // swapValidMaskBuffer, :703
+  }
+  c->front ^= 1; // swapVelocityBuffers, :706
+  return FSB_OK;
+}
+
 int fsb_k_advect_velocity_sl(fsb_ctx* c, float dt)
 {
   const size_t bytes = (size_t)c->ld * c->ny * sizeof(float);

@@ -275,6 +275,7 @@ int fsb_k_add_acceleration(fsb_ctx* c, float ax, float ay, float dt);
 int fsb_k_enforce_dirichlet(fsb_ctx* c);
 int fsb_k_prev_gravity_dirichlet(fsb_ctx* c, float ax, float ay, float dt, int save_prev);
 int fsb_k_extend_velocity(fsb_ctx* c, int n_iter);
+int fsb_k_extend_velocity_avg(fsb_ctx* c, int n_iter);
 int fsb_k_advect_velocity_sl(fsb_ctx* c, float dt);
 // particle stages: fsb_particles.cu
 int fsb_k_sort_particles(fsb_ctx* c, bool mark_labels = false);

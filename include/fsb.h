@@ -177,8 +177,13 @@ int fsb_add_external_force(fsb_ctx* ctx, float fx, float fy, float dt);
  * particle-set order; other faces keep the back buffer's value; swap.  The reference scans all
  * particles per face; the device scans the face's 3x3 cells of the cell-sorted set. */
 int fsb_p2g_gather(fsb_ctx* ctx);
-/* (extendVelocityAvarageing :625-707 is not provided: its two-face writes make every sweep
- * depend on the scan order) */
+/* extendVelocityAvarageing src/FluidSolver.cpp:625-707 -- per-CELL validity (the x masks of the pool);
+ * an unmarked non-SOLID cell takes the mean of the cell-centred back-buffer velocities of its marked
+ * neighbours (order (i-1,j), (i,j-1), (i,j+1), (i+1,j)) and writes it to both of its faces per
+ * component, so a sweep depends on the row-major scan order: the device runs it as skewed wavefronts
+ * (t = i + 2 j) that reproduce the sequential scan bit for bit.  Masks swapped per sweep, velocities
+ * at the end.  FSB_ERR_INVALID unless the border cells are SOLID (the reference asserts there). */
+int fsb_extend_velocity_averaging(fsb_ctx* ctx, int n_iterations);
 
 /* ---- fused steps: FluidSolver::step* src/FluidSolver.cpp:99-251 ------- */
 

@@ -514,6 +514,57 @@ void fso_add_external_force(void* h, float fx, float fy, float dt)
       }
 }
 
+/* src/FluidSolver.cpp:625-707  extendVelocityAvarageing (not called by any step).  One validity mask
+ * per CELL (the x masks of the pool); a non-SOLID cell without the mask takes the mean of the
+ * cell-centred back-buffer velocities ((face + next face) / 2, include/MacGrid.h:56-65) of its masked
+ * neighbours, visited in the order (i-1,j), (i,j-1), (i,j+1), (i+1,j), and writes it to BOTH of its
+ * faces per component (:124-133) -- so a sweep depends on the scan order (row-major), which this
+ * restatement keeps.  Masks are swapped after every sweep, velocities once at the end. */
+void fso_extend_velocity_avg(void* h, int n_iterations)
+{
+  Ctx* c = (Ctx*)h;
+  float *uf = UF(c), *vf = VF(c), *ub = UB(c), *vb = VB(c);
+  for (int j = 0; j < c->ny; ++j)
+    for (int i = 0; i < c->nx; ++i)
+    {
+      const uint8_t m = cell_type(c, i, j) == LIQUID ? 1 : 0;
+      c->mask_x[c->mask_front][AT(c, i, j)] = m;
+      c->mask_x[c->mask_front ^ 1][AT(c, i, j)] = m;
+      ub[AT(c, i, j)] = uf[AT(c, i, j)];
+      vb[AT(c, i, j)] = vf[AT(c, i, j)];
+    }
+#define UBC(i, j) ((ub[AT(c, i, j)] + ub[AT(c, (i) + 1, j)]) / 2)
+#define VBC(i, j) ((vb[AT(c, i, j)] + vb[AT(c, i, (j) + 1)]) / 2)
+  for (int iter = 0; iter < n_iterations; ++iter)
+  {
+    const uint8_t* mf = c->mask_x[c->mask_front];
+    uint8_t* mb = c->mask_x[c->mask_front ^ 1];
+    for (int j = 0; j < c->ny; ++j)
+      for (int i = 0; i < c->nx; ++i)
+        if (mf[AT(c, i, j)] == 0 && cell_type(c, i, j) != SOLID)
+        {
+          float nvx = 0, nvy = 0;
+          int n = 0;
+          if (mf[AT(c, i - 1, j)] == 1) { nvx += UBC(i - 1, j); nvy += VBC(i - 1, j); n++; }
+          if (mf[AT(c, i, j - 1)] == 1) { nvx += UBC(i, j - 1); nvy += VBC(i, j - 1); n++; }
+          if (mf[AT(c, i, j + 1)] == 1) { nvx += UBC(i, j + 1); nvy += VBC(i, j + 1); n++; }
+          if (mf[AT(c, i + 1, j)] == 1) { nvx += UBC(i + 1, j); nvy += VBC(i + 1, j); n++; }
+          if (n > 0)
+          {
+            nvx /= n;
+            nvy /= n;
+            ub[AT(c, i, j)] = nvx; ub[AT(c, i + 1, j)] = nvx;
+            vb[AT(c, i, j)] = nvy; vb[AT(c, i, j + 1)] = nvy;
+            mb[AT(c, i, j)] = 1;
+          }
+        }
+    c->mask_front ^= 1;
+  }
+#undef UBC
+#undef VBC
+  c->front ^= 1;
+}
+
 /* src/FluidSolver.cpp:816-871  transferVelocityToGridGather: for every face the particles whose
  * hat weight 1 - (|dx|/deltaX + |dy|/deltaY) is >= 1, i.e. (numerically) ON the face position;
  * mean of their velocities, written to the back buffer, swap (not called by any step) */

@@ -68,6 +68,9 @@ void FSX(advect_particles_grid)(void* h, float dt);
 void FSX(add_external_force)(void* h, float fx, float fy, float dt);
 /* transferVelocityToGridGather src/FluidSolver.cpp:816-871 */
 void FSX(p2g_gather)(void* h);
+/* extendVelocityAvarageing src/FluidSolver.cpp:625-707 (border cells must be SOLID: the reference
+ * asserts on the index otherwise) */
+void FSX(extend_velocity_avg)(void* h, int n_iterations);
 /* One frame as examples/simple.cpp:73-82 draws it: Renderer::clearCanvas, renderGridCellsToCanvas,
  * renderParticlesToCanvas (src/Renderer.cpp:14-56,141-162) on a width x height canvas over the
  * world-space area, converted to bytes like writeCanvasToPpm (:217-248).  rgb: width*height*3. */

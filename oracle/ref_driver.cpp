@@ -219,6 +219,10 @@ void fsr_p2g_gather(void* h)
   C(h)->solver.transferVelocityToGridGather(C(h)->domain.markerParticleSet(),
                                             C(h)->domain.macGrid());
 }
+void fsr_extend_velocity_avg(void* h, int n_iterations)
+{
+  C(h)->solver.extendVelocityAvarageing(C(h)->domain.macGrid(), n_iterations);
+}
 void fsr_render_rgb(void* h, int width, int height, float x_min, float x_max, float y_min,
                     float y_max, uint8_t* rgb)
 {

@@ -84,6 +84,14 @@ def uncalled_vectors(ref):
     s.p2g_gather()
     for w in range(4):
         out[f"gather_grid{w}"] = s.get_grid(w)
+    # extendVelocityAvarageing (src/FluidSolver.cpp:625-707) from the same inputs, 1 / 2 / 3 sweeps
+    for it in (1, 2, 3):
+        s.set_cell_types(lab)
+        for w, f in fields.items():
+            s.set_grid(w, f)
+        s.extend_velocity_avg(it)
+        for w in range(4):
+            out[f"extavg{it}_grid{w}"] = s.get_grid(w)
     np.savez_compressed(os.path.join(HERE, "uncalled_24x20.npz"), **out)
 
 

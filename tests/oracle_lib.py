@@ -59,6 +59,7 @@ _SIGS = {
     "step": (_i, [_p, _i, _f]),
     "add_external_force": (None, [_p, _f, _f, _f]),
     "p2g_gather": (None, [_p]),
+    "extend_velocity_avg": (None, [_p, _i]),
     "render_rgb": (None, [_p, _i, _i, _f, _f, _f, _f, _p]),
 }
 
@@ -199,6 +200,9 @@ class OracleSim:
 
     def p2g_gather(self):
         self.L._p2g_gather(self.h)
+
+    def extend_velocity_avg(self, n_iter=2):
+        self.L._extend_velocity_avg(self.h, n_iter)
 
     def render_rgb(self, width, height, area=(0.0, 1.0, 0.0, 1.0)):
         a = np.zeros((height, width, 3), dtype=np.uint8)

@@ -681,6 +681,34 @@ def test_uncalled_solver_routines_bit_exact(capi, checkers, nx, ny):
         assert np.array_equal(g.get_particles(), c.get_particles())
 
 
+@pytest.mark.parametrize("nx,ny", SIZES + [(300, 200), (1030, 520)])
+def test_extend_velocity_averaging_is_bit_exact(capi, checkers, nx, ny):
+    """extendVelocityAvarageing (src/FluidSolver.cpp:625-707, called by no step): its result depends on
+    the row-major scan order; the device runs skewed wavefronts (t = i + 2 j) that reproduce the
+    sequential scan -- bit-exact against the compiled reference and the port for 0 - 4 sweeps, including
+    the masks' ping-pong and the final buffer swap; a non-SOLID border cell is refused (the reference
+    asserts on the index there)."""
+    rng = np.random.default_rng(43)
+    for chk in checkers:
+        for n_iter in (0, 1, 2, 3, 4):
+            if nx * ny > 100000 and (n_iter not in (2, 3) or chk.prefix != "fso"):
+                continue
+            g, c = make_pair(capi, chk, nx, ny)
+            load_state((g, c), rng, nx, ny, with_particles=False)
+            for s in (g, c):
+                s.extend_velocity_avg(n_iter)
+            assert_grids_equal(g, c)
+            # the individual extension run afterwards starts from the masks the averaging one left
+            for s in (g, c):
+                s.extend_velocity(1)
+            assert_grids_equal(g, c)
+    g, _ = make_pair(capi, checkers[0], 16, 16)
+    lab = np.full((16, 16), scenes.AIR, dtype=np.uint8)
+    g.set_cell_types(lab)
+    with pytest.raises(RuntimeError):
+        g.extend_velocity_avg(1)
+
+
 def test_frames_are_byte_identical_to_the_reference_renderer(capi, checkers, tmp_path):
     """fsb_render_rgb / fsb_write_ppm against Renderer + Canvas of the reference (compiled into
     oracle/_ref) and the C restatement: the frame of examples/simple.cpp, full view, odd canvas

@@ -160,6 +160,15 @@ def test_port_matches_golden_uncalled_routines(checkers):
         for w in range(4):
             assert np.array_equal(s.get_grid(w), z[f"gather_grid{w}"]), ("gather", w)
         assert (z["gather_grid0"] != z["force_grid2"]).sum() >= 5  # planted particles were selected
+        # extendVelocityAvarageing (src/FluidSolver.cpp:625-707), 1 / 2 / 3 sweeps
+        for it in (1, 2, 3):
+            s.set_cell_types(z["labels"])
+            for w in range(4):
+                s.set_grid(w, z[f"in_grid{w}"])
+            s.extend_velocity_avg(it)
+            for w in range(4):
+                assert np.array_equal(s.get_grid(w), z[f"extavg{it}_grid{w}"]), ("extend_avg", it, w)
+        assert (z["extavg2_grid0"] != z["in_grid2"]).sum() > 20  # it did extend something
 
 
 def test_port_matches_golden_frames(checkers):
