@@ -123,6 +123,7 @@ k_sl_gather(const float4* __restrict__ rec_u, const float4* __restrict__ rec_v, 
   const float4* __restrict__ rec = blockIdx.z == 0 ? rec_u : rec_v;
   float* __restrict__ out = blockIdx.z == 0 ? ub : vb;
   const int a0 = blockIdx.x * kTW, b0 = blockIdx.y * kTH;
+  int any_valid = 0;
   for (int t = threadIdx.x; t < SW * SH; t += kTW * kTH)
   {
     const int lx = t % SW, ly = t / SW;
@@ -130,11 +131,18 @@ k_sl_gather(const float4* __restrict__ rec_u, const float4* __restrict__ rec_v, 
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sx >= 0 && sx < nx && sy >= 0 && sy < ny) r = rec[sx + (size_t)sy * nx];
     s_rec[ly][lx] = r;
+    any_valid |= (__float_as_uint(r.w) & 0x80000000u) != 0u;
   }
-  __syncthreads();
+  // a window without a single traced face (air, solid): the nodes keep the zero of the cleared buffer
+  any_valid = __syncthreads_or(any_valid);
   const int tx = threadIdx.x % kTW, ty = threadIdx.x / kTW;
   const int a = a0 + tx, b = b0 + ty;
   if (a >= nx || b >= ny) return;
+  if (!any_valid)
+  {
+    out[a + (size_t)b * ld] = 0.0f;
+    return;
+  }
   float acc = 0.0f; // the zeroed back buffer, :712-719
   // the reference's source order: rows ascending, columns ascending within a row
 #pragma unroll 1
