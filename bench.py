@@ -313,6 +313,56 @@ def scale_cg8192(capi, sharding, dist, torch, local_rank, world, log):
     return out
 
 
+def small_configs(capi, local_rank, log):
+    """BASELINE.json configs[0] and configs[1] on the device, as side measurements of the one-GPU line:
+    the examples/simple.cpp scene (64^2, one source, dt 0.01, 100 x stepPICFLIP with the reference's own
+    CG settings: cap 100, tolerance FLT_EPSILON) and the 1024^2 semi-Lagrangian dam-break with the CG
+    run to 1e-6.  Parity of both against golden vectors of the compiled reference:
+    tests/test_gpu_goldens_big.py."""
+    import scenes
+    out = {}
+    g = capi.Sim(64, 64, 1.0, 1.0, 0.01, 0.05, device=local_rank)
+    g.emit_source(*scenes.dam_break_args(64))
+    for _ in range(5):
+        g.step(capi.STEP_PICFLIP, 0.01)
+    g.synchronize()
+    g.timer_start()
+    it = 0
+    for _ in range(100):
+        g.step(capi.STEP_PICFLIP, 0.01)
+        it += g.cg_info()[0]
+    ms = g.timer_stop()
+    out["config0_simple64"] = {"workload": "examples/simple.cpp scene: 64^2, 7800 particles, PIC/FLIP 0.05, dt 0.01, "
+                                           "100 steps, CG cap 100 / tolerance FLT_EPSILON (the reference's defaults)",
+                               "ms_per_step": ms / 100, "cell_updates_per_s": 64 * 64 * 100 / (ms * 1e-3),
+                               "cg_iters_per_step": it / 100}
+    g.close()
+    n = 1024
+    dt = float(np.float32(0.01 * 64.0 / n))
+    g = capi.Sim(n, n, 1.0, 1.0, dt, 0.02, device=local_rank)
+    g.set_cg(400000, 1e-6)
+    n_part = g.emit_source(*scenes.dam_break_args(n))
+    for _ in range(3):
+        g.step(capi.STEP_SL, dt)
+    g.synchronize()
+    g.profile_enable(True); g.profile_read()
+    g.timer_start()
+    it = 0
+    for _ in range(5):
+        g.step(capi.STEP_SL, dt)
+        it += g.cg_info()[0]
+    ms = g.timer_stop()
+    prof = g.profile_read()
+    out["config1_sl1024"] = {"workload": "1024^2 semi-Lagrangian step (RK3 back-trace, deterministic gather) + CG to "
+                                         "1e-06, dam-break scene", "particles": int(n_part),
+                             "ms_per_step": ms / 5, "cell_updates_per_s": n * n * 5 / (ms * 1e-3),
+                             "cg_iters_per_step": it / 5, "cg_us_per_iteration": 1e3 * prof["cg"][0] / max(it, 1),
+                             "stage_ms_per_step": {k: round(v[0] / 5, 4) for k, v in prof.items() if v[0] > 0}}
+    g.close()
+    log(f"small configs: {out}")
+    return out
+
+
 def config4_slabs(capi, sharding, dist, torch, local_rank, world, log, n=16384):
     """BASELINE.json configs[4]: the 16384^2 PIC/FLIP step on `world` GPUs -- particles partitioned by
     row slab (ghost rows and migration over NCCL, device buffers), the pressure CG sharded over the same
@@ -613,6 +663,13 @@ def main():
             scale = scale_cg8192(capi, sharding, dist, torch, local_rank, world, log)
         except Exception as e:  # a side measurement must never cost the headline line
             scale = {"error": str(e)[:300]}
+    # ---- side measurements on the one-GPU line: BASELINE.json configs[0] and configs[1]
+    small = None
+    if world == 1 and not args.no_scale and args.precond == "jacobi":
+        try:
+            small = small_configs(capi, local_rank, log)
+        except Exception as e:
+            small = {"error": str(e)[:300]}
     # ---- side measurement on the 8-GPU line: BASELINE.json configs[4] (16384^2 on the whole box)
     config4 = None
     if (world == 8 or args.config4) and world > 1 and not args.no_scale and args.precond == "jacobi":
@@ -733,6 +790,7 @@ def main():
         "optin_multigrid": optin,
         "scale_cg8192": scale,
         "config4_picflip16384": config4,
+        "small_configs": small,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

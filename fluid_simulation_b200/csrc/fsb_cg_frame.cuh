@@ -66,6 +66,23 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// An arrive that cannot be issued before the value `dep` is available: its address is formed from a
+// term that is always zero (bit 1 of a square) but that the assembler cannot fold away.  Used to
+// release a ring slot as soon as the shared-memory loads that produced `dep` have RETURNED -- an
+// mbarrier arrive by itself does not wait for the warp's loads in flight.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep)
+{
+  asm volatile(
+      "{\n"
+      ".reg .b32 t;\n"
+      "mul.lo.u32 t, %1, %1;\n"
+      "and.b32 t, t, 2;\n"
+      "add.u32 t, t, %0;\n"
+      "mbarrier.arrive.shared::cta.b64 _, [t];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(dep)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
   asm volatile(

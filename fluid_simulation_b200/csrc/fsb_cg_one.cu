@@ -515,6 +515,19 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
           }
         }
       }
+      // the NEXT tile's x and previous-direction rows into the L2 now: its loads, one tile from here,
+      // find them there instead of in DRAM (no registers held in between)
+      if (with_x && tk + 1 < t.count && lane < 4 * RPW * (two_x ? 2 : 1))
+      {
+        const int ntx = t.list ? (t.ahead & 0xffff) : t.tx, nty = t.list ? (t.ahead >> 16) : t.ty;
+        const int row = (int)lane >> 2 & (RPW - 1), which = (int)lane / (4 * RPW);
+        const int nj = sh.row_lo + nty * TH + r0 + row, nci = ntx * kTileW + ((int)lane & 3) * 32;
+        if (t.list && nj < sh.row_hi && nci < ld)
+        {
+          const float* a = (which ? p_new : x) + (size_t)nj * ld + nci;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+      }
       mbar_wait(&full[rp.st], rp.round & 1);
 
       float4 pk[RPW + 4], rk[RPW + 2];
@@ -547,12 +560,24 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
         }
         ok &= (hcd[k] == 5u);
       }
-      // The ring slot is released only after everything staged has been CONSUMED by arithmetic (end of
-      // stage 1 below), not merely requested: an mbarrier arrive does not wait for the warp's
-      // shared-memory loads still in flight, and a slot released with loads outstanding can be
-      // refilled under them.  (Seen on B200 as a timing-dependent last-bit wobble of the sums that
-      // involve the halo-column cells, whose loads are the last ones issued.)
-      const int slot_done = rp.st;
+      // The ring slot is released only after everything staged has ARRIVED in registers, not merely been
+      // requested: an mbarrier arrive does not wait for the warp's shared-memory loads still in flight,
+      // and a slot released with loads outstanding can be refilled under them.  (Seen on B200 as a
+      // timing-dependent last-bit wobble of the sums that involve the halo-column cells, whose loads are
+      // the last ones issued.)  The arrive is therefore made data-dependent on every load of the tile:
+      // one word of each, OR-ed together and folded over the warp.
+      {
+        uint32_t dep = 0;
+#pragma unroll
+        for (int i = 0; i < RPW + 4; ++i) dep |= __float_as_uint(pk[i].w) | __float_as_uint(pk[i].x);
+#pragma unroll
+        for (int m = 0; m < RPW + 2; ++m)
+          dep |= __float_as_uint(rk[m].w) | __float_as_uint(rk[m].x) | cd[m] | __float_as_uint(hpc[m]);
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) dep |= __float_as_uint(hfar[k]) | __float_as_uint(hr[k]) | hcd[k];
+        dep = __reduce_or_sync(0xffffffffu, dep); // every lane's loads, and the warp converges here
+        if (lane == 0) mbar_arrive_after(&empty[rp.st], dep);
+      }
       rp.advance(stages);
       // FAST: every cell this warp touches in this tile (own rows, the rows above and below, the
       // halo-column cells) is LIQUID with four non-SOLID neighbours, all own rows lie inside the
@@ -616,8 +641,6 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
           rn[m] = fma4(nalpha, q, rk[m]);
           pn[m] = direction4(rn[m], pc, c4, lut, inv5, beta);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[slot_done]);
         // q' = A p' on the own rows, the five sums, the stores
 #pragma unroll
         for (int k = 0; k < RPW; ++k)
