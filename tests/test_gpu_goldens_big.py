@@ -96,12 +96,12 @@ def test_config2_picflip4096_one_step(capi):
     it, err = g.cg_info()
     it_ref, err_ref = g2["cg"]
     assert err < 1e-6 and err_ref < 1e-6
-    # "comparable iteration counts": the reference (restated Eigen loop, dot products in double, five
-    # rounded products per matrix row) needs 17 821 iterations, the CUDA path (FMA stencil, fp32 products
-    # inside the dot products) 20 678 -- both with either of its solve kernels.  At 512^2 - 1024^2 the two
-    # agree within 0.2 - 2 % (test_config1, tests/multi_gpu_cg_check.py); at 1.5e7 unknowns and 2e4
-    # iterations of fp32 CG the count is set by rounding-level loss of orthogonality and is
-    # implementation-dependent (an Eigen binary, with fp32 packet sums, would give a third number).
+    # "comparable iteration counts": the reference needs 17 821 iterations here, the CUDA path 20 678 (with
+    # either of its solve kernels).  The difference is NOT the solver: on bit-identical input (the analytic
+    # field of test_cg4096_same_input_same_iteration_count below) both take exactly 8 636 iterations at this
+    # size.  Here the right-hand side is the divergence of a P2G result, which the two implementations sum
+    # in different orders (1e-5 field-relative): a grid-scale perturbation of b of the size
+    # of b's own smooth part for this divergence-free swirl, and the relative stopping rule does the rest.
     assert abs(it - it_ref) <= 0.20 * it_ref, (it, it_ref)
     pr = g.get_pressure()
     pr_ds, ref_ds = pr[::16, ::16].astype(np.float64), g2["pressure_ds16"].astype(np.float64)
@@ -114,3 +114,55 @@ def test_config2_picflip4096_one_step(capi):
     assert np.abs(p[::4099, :2] - g2["particles_ds"][:, :2]).max() < 1e-6
     assert np.abs(p[::4099, 2:] - g2["particles_ds"][:, 2:]).max() < 2e-3 * np.abs(g2["particles_ds"][:, 2:]).max()
     assert np.abs(p.astype(np.float64).mean(axis=0) - g2["mean"]).max() < 1e-5
+
+
+def test_cg4096_same_input_same_iteration_count(capi):
+    """bench.py's cg4096 workload -- the 4096^2 tank pressure system with the ANALYTIC input field, i.e.
+    bit-identical labels, u and v on both sides -- solved to 1e-6: the compiled reference (38 minutes of
+    CPU time, golden file cg4096_solve.npz) needs 8 636 iterations; the CUDA path must agree within 1 %
+    (it takes exactly 8 636) and give the same pressure and the same projected velocities."""
+    import bench
+    z = np.load(os.path.join(GOLD, "cg4096_solve.npz"))
+    n, dt = int(z["n"]), float(z["dt"])
+    lab, u0, v0 = bench.tank_fields(n)
+    g = capi.Sim(n, n, 1.0, 1.0, dt, 0.02)
+    g.set_cell_types(lab); g.set_grid(U_FRONT, u0); g.set_grid(V_FRONT, v0)
+    g.set_cg(400000, 1e-6)
+    g.pressure_solve(dt, dt)
+    it, err = g.cg_info()
+    it_ref, err_ref = z["cg"]
+    assert err < 1e-6 and err_ref < 1e-6
+    assert abs(it - it_ref) <= 0.01 * it_ref, (it, it_ref)
+    pr = g.get_pressure()
+    a, b = pr[::16, ::16].astype(np.float64), z["pressure_ds16"].astype(np.float64)
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 2e-3
+    l2 = float(np.sqrt((pr.astype(np.float64) ** 2).sum()))
+    assert abs(l2 - float(z["pressure_l2"])) < 2e-3 * float(z["pressure_l2"])
+    for w, key in ((U_FRONT, "u_ds16"), (V_FRONT, "v_ds16")):
+        assert scenes.field_rel_err(g.get_grid(w)[::16, ::16], z[key]) < 1e-4, key
+
+
+def test_cg8192_first_iterations_match_the_reference(capi):
+    """BASELINE.json configs[3] (8192^2 pressure solve): a full reference solve would take ten hours of CPU
+    time, so the golden file pins the first iterations -- after 1 and after 40 iterations of the same
+    system the iterate x and the relative residual of the CUDA path equal the reference's up to fp32
+    rounding."""
+    import bench
+    z = np.load(os.path.join(GOLD, "cg8192_capped.npz"))
+    n, dt = int(z["n"]), float(z["dt"])
+    lab, u0, v0 = bench.tank_fields(n)
+    g = capi.Sim(n, n, 1.0, 1.0, dt, 0.02)
+    g.set_cell_types(lab)
+    for cap in (1, 40):
+        g.set_grid(U_FRONT, u0); g.set_grid(V_FRONT, v0)
+        g.set_cg(cap, 1e-6)
+        g.pressure_solve(dt, dt)
+        it, err = g.cg_info()
+        it_ref, err_ref = z[f"cg_cap{cap}"]
+        assert it == it_ref == cap
+        assert abs(err - err_ref) <= 1e-5 * err_ref, (cap, err, err_ref)
+        pr = g.get_pressure()
+        a, b = pr[::32, ::32].astype(np.float64), z[f"pressure_cap{cap}_ds32"].astype(np.float64)
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-5, cap
+        l2 = float(np.sqrt((pr.astype(np.float64) ** 2).sum()))
+        assert abs(l2 - float(z[f"pressure_cap{cap}_l2"])) < 1e-5 * float(z[f"pressure_cap{cap}_l2"])
