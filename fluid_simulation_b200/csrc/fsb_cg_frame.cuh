@@ -66,6 +66,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Release / acquire fences.  __threadfence() is a SEQUENTIALLY CONSISTENT fence (SASS: MEMBAR.SC.GPU +
+// CCTL.IVALL); the barrier protocols here only need release before an arrival and acquire after a
+// wait, which fence.acq_rel provides (SASS: MEMBAR.ALL.GPU).
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
 // An arrive that cannot be issued before the value `dep` is available: its address is formed from a
 // term that is always zero (bit 1 of a square) but that the assembler cannot fold away.  Used to
 // release a ring slot as soon as the shared-memory loads that produced `dep` have RETURNED -- an

@@ -150,8 +150,8 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
       // the CTA's global stores (p / r / x rows, peer rows) must be visible to the TMA loads of the
       // next sweep on every SM (and GPU) before the arrival is
       fence_proxy_async_all();
-      if (pushed) __threadfence_system();
-      else __threadfence();
+      if (pushed) fence_acq_rel_sys();
+      else fence_acq_rel_gpu();
       // Who folds the partials: single GPU -- every CTA, as soon as the counter is complete (no
       // broadcast hop); sharded -- the CTA that arrived LAST (it needs no wait at all), which then
       // posts the slab's sums into every rank's mailbox.
@@ -169,7 +169,7 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
         folder = (atomicAdd(&s->bar_count, 1u) + 1u == target) ? 1 : 0;
         FSB_STAMP(1);
       }
-      if (folder) __threadfence();
+      if (folder) fence_acq_rel_gpu();
       s_folder = folder;
       FSB_STAMP(2);
     }
@@ -224,8 +224,8 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
       {
         // every local CTA's arrival (and its peer rows, each fenced at system scope by the CTA that
         // stored them) precedes the entry
-        if (sys_flags & 2) __threadfence();
-        else __threadfence_system();
+        if (sys_flags & 2) fence_acq_rel_gpu();
+        else fence_acq_rel_sys();
         if ((int)lane < sh.world)
         {
           unsigned long long* out = reinterpret_cast<unsigned long long*>(sh.mail[lane]) + kOneMailWord +
@@ -277,7 +277,7 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
       // the peers' boundary rows were stored, and fenced at system scope, before their entries; they
       // live in THIS GPU's memory and the next sweep reads them with TMA loads that the producer issues
       // only after it has seen the release below (FSB_CG_POLL_FENCE_SYS=1: a system-scope fence here)
-      if (!(sys_flags & 1)) __threadfence_system();
+      if (!(sys_flags & 1)) fence_acq_rel_sys();
 #pragma unroll
       for (int n = 0; n < kNSums; ++n)
       {
@@ -416,7 +416,7 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
           SpinGuard g;
           while (*cnt < target) g.tick();
         }
-        __threadfence();
+        fence_acq_rel_gpu();
         fence_proxy_async_all();
         TileWalk tn(blockIdx.x, G, tiles_x, n_walk, serp && ((sweep + 1) & 1) == 0, tile_list, n_prefix, rot);
         const int want = min(stages, tn.count);
