@@ -72,6 +72,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
+// Arrival / wait of the software grid barrier with the ordering attached to the operation itself
+// instead of a separate fence on each side.
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v)
+{
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int atom_acq_rel_gpu_add(unsigned int* p, unsigned int v)
+{
+  unsigned int old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // An arrive that cannot be issued before the value `dep` is available: its address is formed from a
 // term that is always zero (bit 1 of a square) but that the assembler cannot fold away.  Used to
 // release a ring slot as soon as the shared-memory loads that produced `dep` have RETURNED -- an
@@ -277,12 +296,20 @@ constexpr unsigned long long kMailTimeoutNs = 20ull * 1000ull * 1000ull * 1000ul
 // (the mailbox time-out included) traps, so a protocol bug ends the launch with an error instead
 // of occupying the GPU forever.
 constexpr unsigned long long kHangNs = 45ull * 1000ull * 1000ull * 1000ull;
+#ifndef FSB_SPIN_SLEEP_NS
+#define FSB_SPIN_SLEEP_NS 32
+#endif
+constexpr unsigned kSpinSleepNs = FSB_SPIN_SLEEP_NS;
 struct SpinGuard
 {
   unsigned int n = 0;
   unsigned long long t0 = 0;
   __device__ __forceinline__ void tick()
   {
+    // a spinning warp (the producer waiting for a ring slot, warp 0 and the producer waiting at the grid
+    // barrier) takes issue slots from the consumer warps of its scheduler: 21 % of all executed warp
+    // instructions of the solve kernel were these loops (profiles/r02_cg_solve1_ncu_full.md); back off
+    __nanosleep(kSpinSleepNs);
     if ((++n & 4095u) == 0)
     {
       const unsigned long long now = global_ns();

@@ -150,26 +150,25 @@ __device__ __forceinline__ void one_reduce(double (&acc)[kNSums], CgScalars* s,
       // the CTA's global stores (p / r / x rows, peer rows) must be visible to the TMA loads of the
       // next sweep on every SM (and GPU) before the arrival is
       fence_proxy_async_all();
-      if (pushed) fence_acq_rel_sys();
-      else fence_acq_rel_gpu();
+      if (pushed) fence_acq_rel_sys(); // peer rows: acknowledged by the peer before this CTA arrives
       // Who folds the partials: single GPU -- every CTA, as soon as the counter is complete (no
       // broadcast hop); sharded -- the CTA that arrived LAST (it needs no wait at all), which then
-      // posts the slab's sums into every rank's mailbox.
+      // posts the slab's sums into every rank's mailbox.  The arrival is a release (the CTA's stores,
+      // ordered before it by the CTA barrier above, are visible to whoever sees the count), the wait an
+      // acquire -- attached to the atomic / the polling load themselves, no separate fences.
       int folder = 1;
       if (sh.world == 1)
       {
-        atomicAdd(&s->bar_count, 1u); // no return value needed: a reduction, not a round trip
+        red_release_gpu_add(&s->bar_count, 1u); // no return value needed: a reduction, not a round trip
         FSB_STAMP(1);
-        const volatile unsigned int* cnt = &s->bar_count;
         SpinGuard g;
-        while (*cnt < target) g.tick();
+        while (ld_acquire_gpu(&s->bar_count) < target) g.tick();
       }
       else
       {
-        folder = (atomicAdd(&s->bar_count, 1u) + 1u == target) ? 1 : 0;
+        folder = (atom_acq_rel_gpu_add(&s->bar_count, 1u) + 1u == target) ? 1 : 0;
         FSB_STAMP(1);
       }
-      if (folder) fence_acq_rel_gpu();
       s_folder = folder;
       FSB_STAMP(2);
     }
@@ -410,13 +409,11 @@ k_cg_solve1(const __grid_constant__ OneMaps maps, float* __restrict__ x, float* 
       const RingPos pre = rp;
       if (early)
       {
-        const volatile unsigned int* cnt = &s->bar_count;
         const unsigned int target = phase_id * (unsigned int)G;
         {
           SpinGuard g;
-          while (*cnt < target) g.tick();
+          while (ld_acquire_gpu(&s->bar_count) < target) g.tick();
         }
-        fence_acq_rel_gpu();
         fence_proxy_async_all();
         TileWalk tn(blockIdx.x, G, tiles_x, n_walk, serp && ((sweep + 1) & 1) == 0, tile_list, n_prefix, rot);
         const int want = min(stages, tn.count);
