@@ -904,9 +904,15 @@ int fsb_set_rows(fsb_ctx* c, int which, int row_lo, int row_hi, const void* src)
 int fsb_slab_step_a(fsb_ctx* c, int kind)
 {
   CHECK_CTX(c);
-  if (kind < FSB_STEP_PIC || kind > FSB_STEP_PICFLIP)
-    return fsb_fail(c, FSB_ERR_INVALID, "slab steps exist for the particle steps only (kind %d)", kind);
+  if (kind < FSB_STEP_SEMILAGRANGIAN || kind > FSB_STEP_PICFLIP) return fsb_fail(c, FSB_ERR_INVALID, "bad step kind %d", kind);
   FSB_TRY(square_cells(c));
+  if (kind == FSB_STEP_SEMILAGRANGIAN)
+  {
+    // src/FluidSolver.cpp:99-134: the particles only mark cells here (no ghosts needed: a particle marks
+    // its own cell), the velocity lives on the grid, identical on every rank
+    FSB_TRY(flush_diff(c));
+    return fsb_k_classify(c);
+  }
   if (kind == FSB_STEP_PIC) FSB_TRY(flush_diff(c));
   if (c->stage_v1 || c->sort_valid || c->n == 0) FSB_TRY(fsb_k_classify(c));
   else
@@ -921,7 +927,17 @@ int fsb_slab_step_a(fsb_ctx* c, int kind)
 int fsb_slab_step_b(fsb_ctx* c, int kind, float dt)
 {
   CHECK_CTX(c);
-  if (kind < FSB_STEP_PIC || kind > FSB_STEP_PICFLIP) return fsb_fail(c, FSB_ERR_INVALID, "bad step kind %d", kind);
+  if (kind < FSB_STEP_SEMILAGRANGIAN || kind > FSB_STEP_PICFLIP) return fsb_fail(c, FSB_ERR_INVALID, "bad step kind %d", kind);
+  if (kind == FSB_STEP_SEMILAGRANGIAN)
+  {
+    // the deterministic gather form of the velocity advection (fsb_sl.cu) gives every rank the same bits
+    if (c->sl_atomic || c->stage_v1)
+      return fsb_fail(c, FSB_ERR_INVALID, "the float-atomics velocity advection (FSB_SL_ATOMIC / FSB_STAGE_V1: "
+                                          "order-dependent sums) cannot run on slabs");
+    FSB_TRY(fsb_k_advect_velocity_sl(c, dt));
+    FSB_TRY(fsb_k_prev_gravity_dirichlet(c, c->grav_x, c->grav_y, dt, 0));
+    return fsb_k_pressure_solve(c, c->density, dt, true);
+  }
   FSB_TRY(fsb_k_prev_gravity_dirichlet(c, c->grav_x, c->grav_y, dt, kind != FSB_STEP_PIC));
   FSB_TRY(fsb_k_extend_velocity(c, 2));
   if (c->stage_v1)
@@ -935,8 +951,9 @@ int fsb_slab_step_b(fsb_ctx* c, int kind, float dt)
 int fsb_slab_step_c(fsb_ctx* c, int kind, float dt)
 {
   CHECK_CTX(c);
-  if (kind < FSB_STEP_PIC || kind > FSB_STEP_PICFLIP) return fsb_fail(c, FSB_ERR_INVALID, "bad step kind %d", kind);
+  if (kind < FSB_STEP_SEMILAGRANGIAN || kind > FSB_STEP_PICFLIP) return fsb_fail(c, FSB_ERR_INVALID, "bad step kind %d", kind);
   if (c->slab_world > 1) FSB_TRY(fsb_k_slab_mark_ghosts(c));
+  if (kind == FSB_STEP_SEMILAGRANGIAN) return fsb_k_advect_particles_grid(c, dt);
   if (kind == FSB_STEP_PIC) return fsb_k_g2p_advect(c, FSB_G2P_PIC, 0.0f, dt, 0);
   c->diff_pending = true;
   if (kind == FSB_STEP_FLIP) return fsb_k_g2p_advect(c, FSB_G2P_FLIP, 0.0f, dt, 0);

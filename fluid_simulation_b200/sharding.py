@@ -55,7 +55,7 @@ def connect(sim, dist=None, device=None):
 #   * DistSlabs   -- one Sim per process, torch.distributed (gloo / NCCL) moves numpy buffers
 # Because the cell sort's in-cell order goes by global particle id, a slab-partitioned run gives
 # the same bits as the single-GPU run (tests/test_gpu_parity.py::test_particle_slabs_*).
-from .capi import ROWS_LABELS, U_FRONT, V_FRONT  # noqa: E402
+from .capi import ROWS_LABELS, STEP_SL, U_FRONT, V_FRONT  # noqa: E402
 
 
 class LocalSlabs:
@@ -81,8 +81,8 @@ class LocalSlabs:
             if q + 1 < self.world:
                 s.slab_add(*out[q + 1][0])  # the upper neighbour's first row
 
-    def _rows(self):
-        for which in (ROWS_LABELS, U_FRONT, V_FRONT):
+    def _rows(self, labels_only=False):
+        for which in ((ROWS_LABELS,) if labels_only else (ROWS_LABELS, U_FRONT, V_FRONT)):
             slabs = [s.get_rows(which, lo, hi) for s, (lo, hi) in zip(self.sims, self.rows)]
             for s in self.sims:
                 for (lo, hi), a in zip(self.rows, slabs):
@@ -101,10 +101,12 @@ class LocalSlabs:
         return sum(counts[q][d] for q in range(self.world) for d in range(self.world) if d != q)
 
     def step(self, kind, dt):
-        self._ghosts()
+        sl = kind == STEP_SL  # markers only: no ghost rows, label rows only (include/fsb.h)
+        if not sl:
+            self._ghosts()
         for s in self.sims:
             s.slab_step_a(kind)
-        self._rows()
+        self._rows(labels_only=sl)
         for s in self.sims:
             s.slab_step_b(kind, dt)
         for s in self.sims:
@@ -188,11 +190,11 @@ class DistSlabs:
             self.sim.slab_boundary_take_ptr(p.data_ptr(), i.data_ptr())
         return p, i, n
 
-    def _gather_rows(self):
+    def _gather_rows(self, labels_only=False):
         """Every rank's label / u / v rows to every rank.  Slabs differ by a row when ny is not a multiple
         of the world size: the buffers are padded to the tallest slab (all_gather wants equal shapes)."""
         torch, dist, s = self.torch, self.dist, self.sim
-        for which in (ROWS_LABELS, U_FRONT, V_FRONT):
+        for which in ((ROWS_LABELS,) if labels_only else (ROWS_LABELS, U_FRONT, V_FRONT)):
             dtype = torch.uint8 if which == ROWS_LABELS else torch.float32
             mine = torch.zeros((self.max_rows, s.nx), dtype=dtype, device=self.device)
             s.get_rows_ptr(which, self.lo, self.hi, mine.data_ptr())
@@ -205,15 +207,17 @@ class DistSlabs:
 
     def step(self, kind, dt):
         s = self.sim
-        out = [None] * self.world
-        if self.rank > 0:
-            out[self.rank - 1] = self._boundary(0)
-        if self.rank + 1 < self.world:
-            out[self.rank + 1] = self._boundary(1)
-        for p, i, n in self._exchange(out):
-            s.slab_add_ptr(p.data_ptr(), i.data_ptr(), n)
+        sl = kind == STEP_SL  # markers only: no ghost rows, label rows only (include/fsb.h)
+        if not sl:
+            out = [None] * self.world
+            if self.rank > 0:
+                out[self.rank - 1] = self._boundary(0)
+            if self.rank + 1 < self.world:
+                out[self.rank + 1] = self._boundary(1)
+            for p, i, n in self._exchange(out):
+                s.slab_add_ptr(p.data_ptr(), i.data_ptr(), n)
         s.slab_step_a(kind)
-        self._gather_rows()
+        self._gather_rows(labels_only=sl)
         s.slab_step_b(kind, dt)
         s.slab_step_c(kind, dt)
         counts = s.slab_sort_out(self.world)

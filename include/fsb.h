@@ -257,6 +257,14 @@ int fsb_shard_rows(const fsb_ctx* ctx, int* row_lo, int* row_hi);
  *   fsb_slab_step_c(kind, dt)        ghosts retired; G2P + blend + advection of the own particles
  *   fsb_slab_sort_out -> fsb_slab_take(dest) -> send -> fsb_slab_keep_own -> fsb_slab_add (migration)
  *
+ * A semi-Lagrangian step (src/FluidSolver.cpp:99-134) uses the same three phases without ghost rows and with
+ * the label rows only in the exchange: a marker particle labels its own cell, and the velocity lives on the
+ * grid, advected by every rank with identical bits (the gather form of fsb_advect_velocity_sl):
+ *
+ *   fsb_slab_step_a(SL)      labels of the own rows        -> all-gather the label rows
+ *   fsb_slab_step_b(SL, dt)  velocity advection, gravity, walls, pressure solve (optionally sharded)
+ *   fsb_slab_step_c(SL, dt)  RK3 trace of the own particles -> migration
+ *
  * Buffers may be host or device pointers (cudaMemcpyDefault).  Particle ids are the caller's
  * global indices (fsb_set_particles / fsb_emit_source number them 0 .. n-1 identically on all ranks). */
 #define FSB_ROWS_LABELS 8

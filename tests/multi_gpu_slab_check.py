@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"])
     ap.add_argument("--grid", dest="n", type=int, default=128)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--kind", default="picflip", choices=["picflip", "flip", "pic", "sl"],
+                    help="step kind (sl: src/FluidSolver.cpp:99-134 -- label rows only, no ghost rows)")
     ap.add_argument("--shard-cg", action="store_true",
                     help="additionally shard the pressure CG over the ranks (peer memory; nccl only)")
     args = ap.parse_args()
@@ -52,9 +54,10 @@ def main():
     if args.shard_cg:
         sharding.connect(own, dist, device)
     ok, moved = True, 0
+    kind = {"picflip": capi.STEP_PICFLIP, "flip": capi.STEP_FLIP, "pic": capi.STEP_PIC, "sl": capi.STEP_SL}[args.kind]
     for step in range(args.steps):
-        ref.step(capi.STEP_PICFLIP, 0.01)
-        moved += slabs.step(capi.STEP_PICFLIP, 0.01)
+        ref.step(kind, 0.01)
+        moved += slabs.step(kind, 0.01)
         ok = ok and own.cg_info() == ref.cg_info()
         ok = ok and np.array_equal(own.get_cell_types(), ref.get_cell_types())
         for w in (capi.U_FRONT, capi.V_FRONT, capi.U_BACK, capi.V_BACK):
@@ -64,7 +67,7 @@ def main():
     flag = torch.tensor([1 if ok else 0])
     flag = flag.to(device) if device is not None else flag
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    out = {"world": world, "backend": args.backend, "n": n, "steps": args.steps, "cg_sharded": bool(args.shard_cg),
+    out = {"world": world, "backend": args.backend, "n": n, "steps": args.steps, "kind": args.kind, "cg_sharded": bool(args.shard_cg),
            "own_particles": int(own.num_particles()), "all_particles": int(allp.shape[0]),
            "migrated_by_this_rank": int(moved), "ok": bool(flag.item())}
     if rank == 0:

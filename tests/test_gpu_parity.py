@@ -862,7 +862,7 @@ def test_edge_cases_empty_set_tiny_grid_and_particles_in_wall_cells(capi, port, 
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("kind", [STEP_PICFLIP, STEP_FLIP, STEP_PIC])
+@pytest.mark.parametrize("kind", [STEP_PICFLIP, STEP_FLIP, STEP_PIC, STEP_SL])
 def test_particle_slabs_give_the_single_gpu_bits(capi, world, kind):
     """particles partitioned by row slab (ghost rows in, label / u / v rows all-gathered,
     migration after the advection) -- here all ranks as contexts of one process, the transport being

@@ -29,8 +29,9 @@ def test_sharded_cg_two_ranks(built):
 
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
+@pytest.mark.parametrize("kind", ["picflip", "sl"])
 @pytest.mark.parametrize("backend", ["gloo", "nccl"])
-def test_particle_slabs_over_torch_distributed(built, backend):
+def test_particle_slabs_over_torch_distributed(built, backend, kind):
     """DistSlabs (fluid_simulation_b200/sharding.py): the slab-partitioned PIC/FLIP step over
     torch.distributed.  gloo: two ranks share GPU 0 (checks the distributed call sequence on a
     one-GPU box); nccl: one rank per GPU, needs 2 GPUs."""
@@ -40,7 +41,7 @@ def test_particle_slabs_over_torch_distributed(built, backend):
             pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29533" if backend == "gloo" else "29534",
-           os.path.join(ROOT, "tests", "multi_gpu_slab_check.py"), "--backend", backend]
+           os.path.join(ROOT, "tests", "multi_gpu_slab_check.py"), "--backend", backend, "--kind", kind]
     # own process group, killed as a whole on a time-out: a hung rank must not keep the GPU
     p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
                          start_new_session=True)

@@ -122,8 +122,9 @@ class FakeSim:
         for j in range(self.lo, self.hi):
             m = rows == j
             self.labels[j, :] = 0 if m.any() else 1
-            self.grids[0][j, :] = np.float32(m.sum())
-            self.grids[1][j, :] = np.float32(self.ids[m].sum() % 1000)
+            if kind != 0:  # a semi-Lagrangian step (kind 0) has no P2G: labels only
+                self.grids[0][j, :] = np.float32(m.sum())
+                self.grids[1][j, :] = np.float32(self.ids[m].sum() % 1000)
         self.log.append("a")
 
     def slab_step_b(self, kind, dt):
@@ -162,8 +163,9 @@ def expected_rows(parts):
     return np.bincount(rows, minlength=NY).astype(np.float32)
 
 
+@pytest.mark.parametrize("kind", [3, 0])
 @pytest.mark.parametrize("world", [2, 3, 4])
-def test_local_slabs_protocol(world):
+def test_local_slabs_protocol(world, kind):
     import sys
     sys.path.insert(0, ROOT)
     from fluid_simulation_b200 import sharding
@@ -176,16 +178,23 @@ def test_local_slabs_protocol(world):
     moved = 0
     for step in range(8):
         before = expected_rows(cur)
-        moved += slabs.step(3, 0.01)
+        moved += slabs.step(kind, 0.01)
         cur[:, 0] += cur[:, 2] * np.float32(0.01)
         cur[:, 1] += cur[:, 3] * np.float32(0.01)
         for q, s in enumerate(sims):
             assert s.log[-3:] == ["a", "b", "c"]
+            # after the row all-gather every rank holds the labels of the whole grid
+            assert np.array_equal(s.labels[:, 0], (before == 0).astype(np.uint8)), (step, q)
+            if kind == 0:
+                # semi-Lagrangian: no ghost rows travel, and the velocity rows are not exchanged
+                assert s.ghost_rows_seen == [] and not s.grids[0].any()
+                continue
             # every rank saw exactly its neighbours' boundary rows as ghosts ...
             assert set(s.ghost_rows_seen) <= {s.lo - 1, s.hi}
-            # ... and after the row all-gather holds the whole "grid": per-row particle counts
+            # ... and holds the whole "grid": per-row particle counts
             assert np.array_equal(s.grids[0][:, 0], before), (step, q)
             # only own, live particles remain
+        for s in sims:
             rows = s._row(s.parts)
             assert ((rows >= s.lo) & (rows < s.hi)).all() and (s.ids >= 0).all()
     assert moved > 0
@@ -200,7 +209,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, kind=3):
     import sys
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -215,10 +224,14 @@ def _worker(rank, world, port, q):
     cur, ok, moved = p0.copy(), True, 0
     for step in range(8):
         before = me.expected_rows(cur)
-        moved += slabs.step(3, 0.01)
+        moved += slabs.step(kind, 0.01)
         cur[:, 0] += cur[:, 2] * np.float32(0.01)
         cur[:, 1] += cur[:, 3] * np.float32(0.01)
-        ok = ok and np.array_equal(sim.grids[0][:, 0], before)
+        ok = ok and np.array_equal(sim.labels[:, 0], (before == 0).astype(np.uint8))
+        if kind == 0:
+            ok = ok and sim.ghost_rows_seen == [] and not sim.grids[0].any()
+        else:
+            ok = ok and np.array_equal(sim.grids[0][:, 0], before)
         rows = sim._row(sim.parts)
         ok = ok and bool(((rows >= sim.lo) & (rows < sim.hi)).all()) and bool((sim.ids >= 0).all())
     ok = ok and np.array_equal(slabs.particles(), me.reference_run(8, 0.01))
@@ -228,13 +241,13 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.parametrize("world", [2, 3])
-def test_dist_slabs_protocol_gloo(world):
+@pytest.mark.parametrize("world,kind", [(2, 3), (3, 3), (2, 0)])
+def test_dist_slabs_protocol_gloo(world, kind):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, kind)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=150) for _ in procs)
