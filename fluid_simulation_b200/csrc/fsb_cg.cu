@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(256)
 k_cg_build4(const float* __restrict__ uf, const float* __restrict__ vf,
             const uint8_t* __restrict__ cell, uint8_t* __restrict__ code, float* __restrict__ x,
             float* __restrict__ r, const D d, const CgCoef coef, CgScalars* __restrict__ s,
-            double* __restrict__ partials, float tol, int max_iters)
+            double* __restrict__ partials, float tol, int max_iters,
+            int* __restrict__ tile_flags = nullptr, int tiles_x = 0, int tile_rows = 1)
 {
   const int segs = (d.ld + 1023) / 1024;
   const int n_work = segs * d.ny;
@@ -169,14 +170,24 @@ k_cg_build4(const float* __restrict__ uf, const float* __restrict__ vf,
   {
     const int j = w / segs;
     const int i0 = ((w - j * segs) * 256 + threadIdx.x) * 4;
-    if (i0 >= d.ld) continue;
-    const size_t t0 = i0 + (size_t)j * d.ld;
-    uint32_t cd;
-    float4 b;
-    cg_build_group(uf, vf, cell, d, coef.invdiag, i0, j, &cd, &b, &acc_b2, &acc_bz, &acc_n);
-    *reinterpret_cast<uint32_t*>(code + t0) = cd;
-    *reinterpret_cast<float4*>(x + t0) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    *reinterpret_cast<float4*>(r + t0) = b;
+    uint32_t cd = 0u;
+    if (i0 < d.ld)
+    {
+      const size_t t0 = i0 + (size_t)j * d.ld;
+      float4 b;
+      cg_build_group(uf, vf, cell, d, coef.invdiag, i0, j, &cd, &b, &acc_b2, &acc_bz, &acc_n);
+      *reinterpret_cast<uint32_t*>(code + t0) = cd;
+      *reinterpret_cast<float4*>(x + t0) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      *reinterpret_cast<float4*>(r + t0) = b;
+    }
+    // FSB_BUILD_FUSED_FLAGS: a warp's 32 groups are the 128 columns of exactly one solve tile (kTileW),
+    // so the active-tile flags (k_cg_tile_flags) fall out of this pass: the flag array is cleared before
+    // the launch and every writer stores the same 1
+    if (tile_flags)
+    {
+      const bool any = __any_sync(0xffffffffu, cd != 0u);
+      if (any && (threadIdx.x & 31) == 0 && i0 < d.ld) tile_flags[(j / tile_rows) * tiles_x + i0 / kTileW] = 1;
+    }
   }
   const double b2 = block_sum(acc_b2);
   const double bz = block_sum(acc_bz);
@@ -285,16 +296,24 @@ k_cg_tile_compact(const int* __restrict__ flags, int n_tiles, int tiles_x, int* 
   int n_prefix = 0;
   for (int pass = boundary_first ? 0 : 1; pass < 2; ++pass)
   {
-    for (int c0 = 0; c0 < n_tiles; c0 += 1024)
+    for (int c0 = 0; c0 < n_tiles; c0 += 4096)
     {
-      const int t = c0 + (int)threadIdx.x;
-      int f = (t < n_tiles) ? flags[t] : 0;
-      if (boundary_first && t < n_tiles)
+      // four consecutive tiles per thread: a third of the rounds (each costs four CTA barriers)
+      const int t0 = c0 + (int)threadIdx.x * 4;
+      int fq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
       {
-        const int ty = t / tiles_x;
-        const bool edge = (ty == 0 || ty == last_ty);
-        if (edge != (pass == 0)) f = 0;
+        const int t = t0 + q;
+        fq[q] = (t < n_tiles) ? (flags[t] != 0) : 0;
+        if (boundary_first && t < n_tiles)
+        {
+          const int ty = t / tiles_x;
+          const bool edge = (ty == 0 || ty == last_ty);
+          if (edge != (pass == 0)) fq[q] = 0;
+        }
       }
+      const int f = fq[0] + fq[1] + fq[2] + fq[3];
       int incl = f;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1)
@@ -317,10 +336,16 @@ k_cg_tile_compact(const int* __restrict__ flags, int n_tiles, int tiles_x, int* 
       }
       __syncthreads();
       const int base = s_base;
-      const int ex = base + s_warp[wid] + incl - f;
-      if (f) list[ex] = ((t / tiles_x) << 16) | (t % tiles_x);
+      int ex = base + s_warp[wid] + incl - f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (fq[q])
+        {
+          const int t = t0 + q;
+          list[ex++] = ((t / tiles_x) << 16) | (t % tiles_x);
+        }
       __syncthreads();
-      if (threadIdx.x == 1023) s_base = ex + f;
+      if (threadIdx.x == 1023) s_base = ex;
       __syncthreads();
     }
     if (pass == 0) n_prefix = s_base;
@@ -1924,7 +1949,7 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
   // ---- build
   fsb_prof_begin(c, FSB_PROF_RHS);
   const int64_t total = (int64_t)c->ld * c->ny;
-  const int build_blocks = (int)std::min<int64_t>(fsb_div_up(total, 256), c->sm_count * 8);
+  const int build_blocks = (int)std::min<int64_t>(fsb_div_up(total, 256), c->sm_count * c->build_blocks_per_sm);
   FSB_TRY(configure_cg(c));
   const int need = std::max(std::max(std::max(3 * build_blocks, 3 * c->cg_grid_fused),
                                      std::max(c->cg_grid_dir, 2 * c->cg_grid_upd)),
@@ -1937,6 +1962,23 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     c->partials_cap = need;
   }
   auto build = [&]() -> int {
+    // active-tile list of this rank's slab (tiles of the configured height)
+    const int th = c->cg_tile_rows;
+    const int tiles_x = fsb_div_up(c->ld, kTileW);
+    const int n_t = tiles_x * fsb_div_up(c->shard.row_hi - c->shard.row_lo, th);
+    if (c->cg_skip_tiles && n_t > c->cg_tile_cap)
+    {
+      if (c->cg_tile_flags) cudaFree(c->cg_tile_flags);
+      if (c->cg_tile_list) cudaFree(c->cg_tile_list);
+      c->cg_tile_flags = c->cg_tile_list = nullptr;
+      FSB_CUDA(c, cudaMalloc(&c->cg_tile_flags, sizeof(int) * n_t));
+      FSB_CUDA(c, cudaMalloc(&c->cg_tile_list, sizeof(int) * n_t));
+      c->cg_tile_cap = n_t;
+    }
+    // FSB_BUILD_FUSED_FLAGS (one GPU): the set-up kernel marks the active tiles itself
+    const bool fused_flags = c->build_fused_flags && c->cg_skip_tiles && !c->stage_v1 && c->shard.world == 1;
+    int* flags_arg = fused_flags ? c->cg_tile_flags : nullptr;
+    if (fused_flags) FSB_CUDA(c, cudaMemsetAsync(c->cg_tile_flags, 0, sizeof(int) * n_t, c->stream));
     if (c->stage_v1)
       k_cg_build<<<build_blocks, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell, c->cg_code,
                                                       c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
@@ -1944,31 +1986,21 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     else if (d.pow2 == 3)
       k_cg_build4<GridDimsP2><<<build_blocks, 256, 0, c->stream>>>(
           fsb_uf(c), fsb_vf(c), c->cell, c->cg_code, c->cg_x, c->cg_r, as_pow2(d), coef, c->scal,
-          c->partials, c->tol, c->max_iters);
+          c->partials, c->tol, c->max_iters, flags_arg, tiles_x, th);
     else
       k_cg_build4<GridDims><<<build_blocks, 256, 0, c->stream>>>(
           fsb_uf(c), fsb_vf(c), c->cell, c->cg_code, c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
-          c->tol, c->max_iters);
+          c->tol, c->max_iters, flags_arg, tiles_x, th);
     FSB_LAUNCHED(c);
     if (c->cg_skip_tiles)
     {
-      // active-tile list of this rank's slab (tiles of the configured height)
-      const int th = c->cg_tile_rows;
-      const int tiles_x = fsb_div_up(c->ld, kTileW);
-      const int n_t = tiles_x * fsb_div_up(c->shard.row_hi - c->shard.row_lo, th);
-      if (n_t > c->cg_tile_cap)
+      if (!fused_flags)
       {
-        if (c->cg_tile_flags) cudaFree(c->cg_tile_flags);
-        if (c->cg_tile_list) cudaFree(c->cg_tile_list);
-        c->cg_tile_flags = c->cg_tile_list = nullptr;
-        FSB_CUDA(c, cudaMalloc(&c->cg_tile_flags, sizeof(int) * n_t));
-        FSB_CUDA(c, cudaMalloc(&c->cg_tile_list, sizeof(int) * n_t));
-        c->cg_tile_cap = n_t;
+        k_cg_tile_flags<<<n_t, 128, 0, c->stream>>>(c->cg_code, c->ld, tiles_x, th, c->shard.row_lo,
+                                                    c->shard.row_hi, c->cg_tile_flags,
+                                                    c->shard.world > 1 ? 1 : 0);
+        FSB_LAUNCHED(c);
       }
-      k_cg_tile_flags<<<n_t, 128, 0, c->stream>>>(c->cg_code, c->ld, tiles_x, th, c->shard.row_lo,
-                                                  c->shard.row_hi, c->cg_tile_flags,
-                                                  c->shard.world > 1 ? 1 : 0);
-      FSB_LAUNCHED(c);
       k_cg_tile_compact<<<1, 1024, 0, c->stream>>>(c->cg_tile_flags, n_t, tiles_x, c->cg_tile_list,
                                                    c->scal, (c->shard.world > 1 && c->cg_edge_first) ? 1 : 0);
       FSB_LAUNCHED(c);

@@ -164,6 +164,8 @@ struct fsb_ctx
   int precond = 0;
   int mg_max_iters = 200;    // beyond this the multigrid iteration is abandoned for Jacobi
   int mg_sweeps = 3;         // damped-Jacobi pre- and post-sweeps per level (equal: symmetric V-cycle)
+  int mg_stop = 4;        // FSB_MG_STOP: coarsen until both sides are <= this (kMgStopDefault; at most 32)
+  bool mg_renorm = true;  // FSB_MG_RENORM=0: plain bilinear / full-weighting transfers (round-1 behaviour)
   bool last_solve_mg = false;
   fsb_mg_state* mg = nullptr;
   bool cg_persist_miss_normal = false;
@@ -188,6 +190,9 @@ struct fsb_ctx
   int* sl_maxd = nullptr;
   size_t sl_cells = 0;
   int sl_reach = 0;         // reach (source cells) of the last gather
+  bool extend_b16 = false;      // FSB_EXTEND_B16: sixteen-cell early-out in the extension's second pass
+  int build_blocks_per_sm = 8;  // FSB_BUILD_BLOCKS_PER_SM: grid of the pressure set-up kernel
+  bool build_fused_flags = false; // FSB_BUILD_FUSED_FLAGS: the set-up kernel marks the active tiles itself
   bool sl_atomic = false;   // FSB_SL_ATOMIC=1: the first-generation float-atomics scatter
 
   // row-slab sharding (fsb_shard_*); world == 1: not sharded

@@ -6,15 +6,17 @@
 // preconditioner -- not the system, the stopping rule or the result -- by one geometric multigrid
 // V-cycle (after McAdams, Sifakis, Teran: "A parallel multigrid Poisson solver for fluids
 // simulation on large grids", 2010):
-//   * levels: 2x2 cell coarsening down to <= 32 x 32; a coarse cell is AIR (Dirichlet) if any child
+//   * levels: 2x2 cell coarsening down to <= 4 x 4; a coarse cell is AIR (Dirichlet) if any child
 //     is AIR, else LIQUID if any child is LIQUID, else SOLID; the 5-point operator is re-discretised
 //     on the coarse labels with h -> 2h (same matrix-free form as the fine operator: no stored
 //     matrix on any level);
-//   * smoother: damped Jacobi (omega = 2/3), 3 pre- and 3 post-sweeps (FSB_MG_SWEEPS; the numpy study
-//     tools/studies/mgpcg_prototype.py needs 36 iterations at 2048^2 with 2 + 2 and 23 with 3 + 3); restriction = tensor product
-//     of (1 3 3 1)/8, prolongation = 4 x its transpose (cell-centred bilinear); the coarsest level is
-//     solved by 40 Jacobi sweeps inside one CTA's shared memory.  Equal pre/post sweeps and
-//     P = 4 R^T keep the V-cycle symmetric, as CG requires.
+//   * smoother: damped Jacobi (omega = 2/3), 3 pre- and 3 post-sweeps (FSB_MG_SWEEPS); restriction = tensor
+//     product of (1 3 3 1)/8, prolongation = 4 x its transpose (cell-centred bilinear), both with the weights
+//     renormalised over the non-SOLID coarse parents next to walls (fsb_mg_kernels.cuh: without that the
+//     restriction is not conservative at a wall and the iteration count grows with the grid -- 17 / 24 / 50 at
+//     1024^2 / 2048^2 / 4096^2 in round 1, 7 - 8 at every size with it; tools/studies/mg_transfer_study.py);
+//     the coarsest level is solved by 40 Jacobi sweeps inside one CTA's shared memory.  Equal pre/post sweeps
+//     and P = 4 R^T keep the V-cycle symmetric, as CG requires.
 // The outer iteration is Eigen's statement order with z = V(r) in place of z = D^-1 r and the same
 // stopping rule |r|^2 < tol^2 |b|^2.  Every kernel is a memory-bound sweep with four cells per
 // thread; reductions are per-CTA fp64 partials folded in a fixed order by the last CTA.
@@ -32,10 +34,10 @@
 namespace {
 
 constexpr int kMgMaxLevels = 16;
-// coarsening stops at <= 32 x 32: measured at 4096^2 (tank scene) 50 iterations against 59 when
-// coarsened on to 8 x 8 -- the "any AIR child -> AIR" rule misplaces the free surface by up to one
-// coarse cell per level, so very coarse levels add little
-constexpr int kMgStop = 32;
+// coarsening continues to <= 4 x 4 (kMgStopDefault; FSB_MG_STOP): with the wall-conservative transfers of
+// fsb_mg_kernels.cuh the coarse levels represent the smooth modes well, and 40 sweeps solve a 4 x 4 level
+// exactly -- 40 sweeps on a 32 x 32 coarsest level leave its lowest modes almost untouched (per-sweep factor
+// 0.9995 for the fundamental), which showed as a plateau of ~10 PCG iterations.
 constexpr int kMgCoarseSweeps = 40;
 
 struct MgLevel
@@ -275,7 +277,7 @@ int mg_build_hierarchy(fsb_ctx* c)
     FSB_TRY(mg_alloc(c, &L.x[1], cells));
     FSB_TRY(mg_alloc(c, &L.r, cells));
     m->n_levels = l + 1;
-    if (nx <= kMgStop && ny <= kMgStop) break;
+    if (nx <= c->mg_stop && ny <= c->mg_stop) break;
     nx = (nx + 1) / 2; ny = (ny + 1) / 2; inv_h2 *= 0.25f;
   }
   const MgLevel& last = m->lv[m->n_levels - 1];
@@ -330,7 +332,8 @@ int mg_vcycle(fsb_ctx* c, int* cur_out)
     k_mg_residual<<<grid4(L), 256, 0, c->stream>>>(L.x[cur[l]], L.b, L.code, L.r, L.nx, L.ny, L.ld, L.inv_h2);
     FSB_LAUNCHED(c);
     MgLevel& C = m->lv[l + 1];
-    k_mg_restrict<<<grid1(C), 256, 0, c->stream>>>(L.r, L.nx, L.ny, L.ld, C.code, C.b, C.nx, C.ny, C.ld);
+    k_mg_restrict<<<grid1(C), 256, 0, c->stream>>>(L.r, L.nx, L.ny, L.ld, C.code, C.b, C.nx, C.ny, C.ld,
+                                                   c->mg_renorm ? C.lab : nullptr);
     FSB_LAUNCHED(c);
   }
   {
@@ -346,7 +349,8 @@ int mg_vcycle(fsb_ctx* c, int* cur_out)
     MgLevel& C = m->lv[l + 1];
     const MgCoef kf = make_mg_coef(L.inv_h2);
     k_mg_prolong_add<<<grid4(L), 256, 0, c->stream>>>(L.x[cur[l]], L.code, L.nx, L.ny, L.ld,
-                                                      C.x[cur[l + 1]], C.nx, C.ny, C.ld);
+                                                      C.x[cur[l + 1]], C.nx, C.ny, C.ld,
+                                                      c->mg_renorm ? C.lab : nullptr);
     FSB_LAUNCHED(c);
     for (int s = 0; s < c->mg_sweeps; ++s)
     {

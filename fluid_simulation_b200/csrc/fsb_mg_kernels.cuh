@@ -11,6 +11,7 @@
 namespace {
 
 constexpr int kMgCoarsest = 32; // the coarse-solve CTA handles up to 32 x 32 cells
+constexpr int kMgStopDefault = 4; // coarsening continues until both sides are <= this (FSB_MG_STOP)
 constexpr float kMgOmega = 2.0f / 3.0f;
 
 struct MgCoef
@@ -108,11 +109,30 @@ k_mg_residual(const float* __restrict__ x, const float* __restrict__ b,
   *reinterpret_cast<float4*>(r + k) = out;
 }
 
-// b_coarse(I,J) = sum_{a,c} W[a] W[c] r_fine(2I-1+c, 2J-1+a), W = (1 3 3 1)/8; one thread per
-// coarse cell; fine cells outside the grid contribute 0; 0 on non-LIQUID coarse cells
+// Transfer weights next to walls.  The plain operators treat a coarse cell that is SOLID (or lies outside
+// the grid) as a zero: the bilinear prolongation then under-weights the fine cells along a wall, and -- worse --
+// its transpose, the restriction, loses the share of their residuals that would go to the missing coarse
+// cell.  A zero-mean high-frequency residual next to a wall so acquires a net mass, which the coarse levels
+// answer with a smooth correction of size O(n) times the local error: the largest eigenvalue of M A grows
+// like n (1.2 / 1.7 / 3.3 / 6.1 at n = 64 .. 512 on the tank scene, tools/studies/mg_transfer_study.py) and
+// the PCG iteration count with it.  Fix: every fine cell's four bilinear weights are renormalised over its
+// non-SOLID coarse parents (constant extension across a wall; AIR parents stay in the sum -- their value is
+// the Dirichlet zero), P = D^-1 P_bilinear, R = P^T / 4 = R_full-weighting D^-1: conservative at walls and
+// still symmetric.  With it (and the hierarchy continued to <= 4 x 4) the count is 7 - 8 from 512^2 to 4096^2.
+//
+// mg_parent_norm: D for the fine cell whose own parent has the flag `oo`, the parent's neighbour on the
+// child's side in x `on`, in y `no`, diagonal `nn` (1.0f = non-SOLID and inside, else 0.0f).
+__device__ __forceinline__ float mg_parent_norm(float oo, float on, float no, float nn)
+{
+  return 0.75f * (0.75f * oo + 0.25f * on) + 0.25f * (0.75f * no + 0.25f * nn);
+}
+
+// b_coarse(I,J) = sum_{a,c} W[a] W[c] r_fine(2I-1+c, 2J-1+a) / D_fine, W = (1 3 3 1)/8; one thread per
+// coarse cell; fine cells outside the grid contribute 0; 0 on non-LIQUID coarse cells.  clab: labels of the
+// COARSE level (nullptr: plain full weighting, D = 1).
 __global__ void k_mg_restrict(const float* __restrict__ rf, int fnx, int fny, int fld,
                               const uint8_t* __restrict__ ccode, float* __restrict__ bc, int cnx,
-                              int cny, int cld)
+                              int cny, int cld, const uint8_t* __restrict__ clab)
 {
   const int I = blockIdx.x * blockDim.x + threadIdx.x;
   const int J = blockIdx.y;
@@ -121,6 +141,22 @@ __global__ void k_mg_restrict(const float* __restrict__ rf, int fnx, int fny, in
   if (I < cnx && ccode[I + (size_t)J * cld] != 0)
   {
     const float W[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+    // non-SOLID flags of the 3 x 3 coarse neighbourhood; s[1][1] is this (LIQUID) cell
+    float s[3][3];
+    bool all = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+      {
+        const int II = I - 1 + q, JJ = J - 1 + a;
+        const bool ok = !clab || (II >= 0 && II < cnx && JJ >= 0 && JJ < cny && clab[II + (size_t)JJ * cld] != FSB_SOLID);
+        s[a][q] = ok ? 1.0f : 0.0f;
+        all = all && ok;
+      }
+    // fine offset 0..3 (row 2J-1+a / column 2I-1+q): own parent and the neighbour on the child's side,
+    // as indices into the 3 x 3 window
+    const int own[4] = {0, 1, 1, 2}, nb[4] = {1, 0, 2, 1};
 #pragma unroll
     for (int a = 0; a < 4; ++a)
     {
@@ -131,7 +167,16 @@ __global__ void k_mg_restrict(const float* __restrict__ rf, int fnx, int fny, in
       for (int q = 0; q < 4; ++q)
       {
         const int fi = 2 * I - 1 + q;
-        if (fi >= 0 && fi < fnx) row += W[q] * rf[fi + (size_t)fj * fld];
+        if (fi >= 0 && fi < fnx)
+        {
+          float v = rf[fi + (size_t)fj * fld];
+          if (!all)
+          {
+            const float d = mg_parent_norm(s[own[a]][own[q]], s[own[a]][nb[q]], s[nb[a]][own[q]], s[nb[a]][nb[q]]);
+            v = (d > 0.0f) ? v / d : 0.0f; // d = 0: no non-SOLID parent, the fine cell is SOLID and v is 0
+          }
+          row += W[q] * v;
+        }
       }
       out += W[a] * row;
     }
@@ -139,11 +184,12 @@ __global__ void k_mg_restrict(const float* __restrict__ rf, int fnx, int fny, in
   bc[I + (size_t)J * cld] = out;
 }
 
-// x_fine += P e_coarse on LIQUID fine cells (P = 4 R^T: per dimension 3/4 of the parent and 1/4 of
-// the parent's neighbour on the child's side); four fine cells per thread
+// x_fine += D^-1 P e_coarse on LIQUID fine cells (P = 4 R^T: per dimension 3/4 of the parent and 1/4 of
+// the parent's neighbour on the child's side); four fine cells per thread.  clab as in k_mg_restrict.
 __global__ void __launch_bounds__(256)
 k_mg_prolong_add(float* __restrict__ xf, const uint8_t* __restrict__ fcode, int fnx, int fny,
-                 int fld, const float* __restrict__ ec, int cnx, int cny, int cld)
+                 int fld, const float* __restrict__ ec, int cnx, int cny, int cld,
+                 const uint8_t* __restrict__ clab)
 {
   const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int j = blockIdx.y;
@@ -154,27 +200,44 @@ k_mg_prolong_add(float* __restrict__ xf, const uint8_t* __restrict__ fcode, int 
   const int J = j >> 1;
   const int Jn = (j & 1) ? J + 1 : J - 1; // the neighbour row on this child's side
   const int I0 = i0 >> 1;                 // parents of columns i0..i0+3: I0, I0, I0+1, I0+1
-  auto row_vals = [&](int JJ, float* v) { // coarse values at columns I0-1 .. I0+2 of row JJ
+  bool all = true;
+  auto row_vals = [&](int JJ, float* v, float* f) { // coarse values / non-SOLID flags at columns I0-1 .. I0+2 of row JJ
 #pragma unroll
     for (int q = 0; q < 4; ++q)
     {
       const int II = I0 - 1 + q;
-      v[q] = (JJ >= 0 && JJ < cny && II >= 0 && II < cnx) ? ec[II + (size_t)JJ * cld] : 0.0f;
+      const bool in = JJ >= 0 && JJ < cny && II >= 0 && II < cnx;
+      v[q] = in ? ec[II + (size_t)JJ * cld] : 0.0f;
+      const bool ok = !clab || (in && clab[II + (size_t)JJ * cld] != FSB_SOLID);
+      f[q] = ok ? 1.0f : 0.0f;
+      all = all && ok;
     }
   };
-  float p[4], n[4];
-  row_vals(J, p);
-  row_vals(Jn, n);
+  float p[4], n[4], fp[4], fn[4];
+  row_vals(J, p, fp);
+  row_vals(Jn, n, fn);
   float m[4]; // blended in y
 #pragma unroll
   for (int q = 0; q < 4; ++q) m[q] = 0.75f * p[q] + 0.25f * n[q];
   // columns: i0 (even child of I0: neighbour I0-1), i0+1 (odd child of I0: neighbour I0+1),
   //          i0+2 (even child of I0+1: neighbour I0), i0+3 (odd child of I0+1: neighbour I0+2)
+  float a0 = 0.75f * m[1] + 0.25f * m[0], a1 = 0.75f * m[1] + 0.25f * m[2];
+  float a2 = 0.75f * m[2] + 0.25f * m[1], a3 = 0.75f * m[2] + 0.25f * m[3];
+  if (!all)
+  {
+    // a LIQUID fine cell's own parent is never SOLID, so every D below is at least 9/16
+    // (pad columns beyond the grid may have none: their value is not stored)
+    auto scaled = [](float a, float d) { return d > 0.0f ? a / d : 0.0f; };
+    a0 = scaled(a0, mg_parent_norm(fp[1], fp[0], fn[1], fn[0]));
+    a1 = scaled(a1, mg_parent_norm(fp[1], fp[2], fn[1], fn[2]));
+    a2 = scaled(a2, mg_parent_norm(fp[2], fp[1], fn[2], fn[1]));
+    a3 = scaled(a3, mg_parent_norm(fp[2], fp[3], fn[2], fn[3]));
+  }
   float4 x4 = *reinterpret_cast<const float4*>(xf + k);
-  if (c4 & 0xff) x4.x += 0.75f * m[1] + 0.25f * m[0];
-  if ((c4 >> 8) & 0xff) x4.y += 0.75f * m[1] + 0.25f * m[2];
-  if ((c4 >> 16) & 0xff) x4.z += 0.75f * m[2] + 0.25f * m[1];
-  if (c4 >> 24) x4.w += 0.75f * m[2] + 0.25f * m[3];
+  if (c4 & 0xff) x4.x += a0;
+  if ((c4 >> 8) & 0xff) x4.y += a1;
+  if ((c4 >> 16) & 0xff) x4.z += a2;
+  if (c4 >> 24) x4.w += a3;
   *reinterpret_cast<float4*>(xf + k) = x4;
 }
 

@@ -103,6 +103,17 @@ void emul_extend2(float* uf, const float* vf, float* ub, float* vb, uint8_t* m1,
          [&] { k_extend2_b(uf, ub, vb, m1, cell, d); });
 }
 
+// the same with the sixteen-cell form of the second pass (FSB_EXTEND_B16)
+void emul_extend2_b16(float* uf, const float* vf, float* ub, float* vb, uint8_t* m1,
+                      const uint8_t* cell, int nx, int ny, int ld, float dx, float dy)
+{
+  const GridDims d = make_grid_dims(nx, ny, ld, dx, dy);
+  launch(div_up(ld, 1024), div_up(ny, kExtendRows), 256,
+         [&] { k_extend2_a(uf, vf, ub, vb, m1, cell, d); });
+  launch(div_up(ld, 16 * 256), div_up(ny, kExtendRows), 256,
+         [&] { k_extend2_b16(uf, ub, vb, m1, cell, d); });
+}
+
 void emul_pressure_patch(const float* uf, const float* vf, float* ub, float* vb, const float* x,
                          const uint8_t* cell, int nx, int ny, int ld, float dx, float dy, float dt,
                          float density, int dirichlet)
@@ -148,11 +159,11 @@ void emul_cg_build(const float* uf, const float* vf, const uint8_t* cell, uint8_
 }
 
 // One V-cycle z = V(r) of the multigrid preconditioner, the launch sequence of mg_vcycle() in
-// fsb_mg.cu (`sweeps` + `sweeps` damped-Jacobi sweeps, restriction, 40 sweeps on the coarsest level, prolongation)
-// on host arrays.  lab / code0 / r are pitched (ld = nx rounded up to 32); z receives the result.
+// fsb_mg.cu (`sweeps` + `sweeps` damped-Jacobi sweeps, restriction, 40 sweeps on the coarsest level, prolongation;
+// coarsening until both sides are <= `stop`; `renorm`: wall-conservative transfer weights) on host arrays.  lab / code0 / r are pitched (ld = nx rounded up to 32); z receives the result.
 // Returns the number of levels.
 int emul_mg_vcycle(const uint8_t* lab0, const uint8_t* code0, const float* r0, int nx0, int ny0,
-                   float inv_h2_0, float* z, int sweeps)
+                   float inv_h2_0, float* z, int sweeps, int stop, int renorm)
 {
   struct Lv
   {
@@ -172,7 +183,7 @@ int emul_mg_vcycle(const uint8_t* lab0, const uint8_t* code0, const float* r0, i
     L.lab.assign(cells, FSB_SOLID); L.code.assign(cells, 0);
     L.x[0].assign(cells, 0.f); L.x[1].assign(cells, 0.f); L.b.assign(cells, 0.f); L.r.assign(cells, 0.f);
     lv.push_back(std::move(L));
-    if (nx <= 32 && ny <= 32) break;
+    if (nx <= stop && ny <= stop) break;
     nx = (nx + 1) / 2; ny = (ny + 1) / 2; inv_h2 *= 0.25f;
   }
   {
@@ -223,7 +234,8 @@ int emul_mg_vcycle(const uint8_t* lab0, const uint8_t* code0, const float* r0, i
     });
     Lv& C = lv[l + 1];
     launch(div_up(C.ld, 256), C.ny, 256, [&] {
-      k_mg_restrict(L.r.data(), L.nx, L.ny, L.ld, C.code.data(), C.b.data(), C.nx, C.ny, C.ld);
+      k_mg_restrict(L.r.data(), L.nx, L.ny, L.ld, C.code.data(), C.b.data(), C.nx, C.ny, C.ld,
+                    renorm ? C.lab.data() : nullptr);
     });
   }
   {
@@ -238,7 +250,7 @@ int emul_mg_vcycle(const uint8_t* lab0, const uint8_t* code0, const float* r0, i
     Lv& C = lv[l + 1];
     launch(div_up(L.ld, 1024), L.ny, 256, [&] {
       k_mg_prolong_add(L.x[cur[l]].data(), L.code.data(), L.nx, L.ny, L.ld, C.x[cur[l + 1]].data(), C.nx,
-                       C.ny, C.ld);
+                       C.ny, C.ld, renorm ? C.lab.data() : nullptr);
     });
     for (int s = 0; s < sweeps; ++s) smooth(L, cur[l]); // post-smoothing
   }

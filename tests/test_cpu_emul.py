@@ -89,11 +89,12 @@ def test_enforce_dirichlet(emul, checkers, nx, ny):
 
 @pytest.mark.parametrize("nx,ny", SIZES)
 @pytest.mark.parametrize("p_liquid", [0.5, 0.08])
-def test_extend_velocity_two_sweeps(emul, checkers, nx, ny, p_liquid):
+@pytest.mark.parametrize("b16", [0, 1])
+def test_extend_velocity_two_sweeps(emul, checkers, nx, ny, p_liquid, b16):
     rng = np.random.default_rng(22)
     for chk in checkers:
         c = make_sim(chk, nx, ny)
-        lab = scenes.random_labels(nx, ny, rng, p_liquid=p_liquid, p_solid=0.05)
+        lab = scenes.random_labels(nx, ny, rng, p_liquid=p_liquid, p_solid=0.01 if b16 else 0.05)
         f = {w: scenes.random_field(nx, ny, rng) for w in (U_FRONT, V_FRONT, U_BACK, V_BACK)}
         c.set_cell_types(lab)
         for w, a in f.items():
@@ -103,7 +104,9 @@ def test_extend_velocity_two_sweeps(emul, checkers, nx, ny, p_liquid):
         pub, pvb = pitched(f[U_BACK]), pitched(f[V_BACK])
         pl = pitched(lab, scenes.SOLID)
         m1 = np.zeros_like(pl)
-        emul.emul_extend2(ptr(pu), ptr(pv), ptr(pub), ptr(pvb), ptr(m1), ptr(pl), *dims(c, nx, ny))
+        # p_solid below: long all-LIQUID runs exist, so the sixteen-cell early-out of pass B is taken
+        (emul.emul_extend2_b16 if b16 else emul.emul_extend2)(ptr(pu), ptr(pv), ptr(pub), ptr(pvb), ptr(m1),
+                                                              ptr(pl), *dims(c, nx, ny))
         assert np.array_equal(pub[:, :nx], c.get_grid(U_FRONT))
         assert np.array_equal(pvb[:, :nx], c.get_grid(V_FRONT))
         assert np.array_equal(pu[:, :nx], c.get_grid(U_BACK))  # incl. the :527 typo
@@ -171,13 +174,15 @@ def test_cg_build_group(emul, nx, ny):
 
 
 @pytest.mark.parametrize("sweeps", [2, 3])
+@pytest.mark.parametrize("stop,renorm", [(4, 1), (32, 0)])
 @pytest.mark.parametrize("scene,n", [("tank", 64), ("tank", 128), ("blobs", 96), ("blobs", 130)])
-def test_multigrid_vcycle_matches_the_numpy_prototype(emul, scene, n, sweeps):
+def test_multigrid_vcycle_matches_the_numpy_prototype(emul, scene, n, sweeps, stop, renorm):
     """One V-cycle of the opt-in multigrid preconditioner -- the level kernels of
     fsb_mg_kernels.cuh run on the host in the launch order of fsb_mg.cu -- against the independent
     numpy statement the device code was derived from (tools/studies/mgpcg_prototype.py): coarsening
-    rule, damped-Jacobi sweeps, (1 3 3 1)/8 restriction, 4 R^T prolongation.  Both are fp32 with
-    different summation orders, hence a tolerance."""
+    rule, damped-Jacobi sweeps, (1 3 3 1)/8 restriction, 4 R^T prolongation -- with the wall-conservative
+    weights and the hierarchy down to 4 x 4 (the default), and in the plain round-1 form (FSB_MG_RENORM=0,
+    FSB_MG_STOP=32).  Both are fp32 with different summation orders, hence a tolerance."""
     import sys
     sys.path.insert(0, os.path.join(ROOT, "tools", "studies"))
     import mgpcg_prototype as proto
@@ -191,14 +196,15 @@ def test_multigrid_vcycle_matches_the_numpy_prototype(emul, scene, n, sweeps):
     inv_h2 = np.float32(1.0) / (dx * dx)
     liq = lab == scenes.LIQUID
     r = np.where(liq, rng.standard_normal((n, n)), 0.0).astype(np.float32)
-    mg = proto.MG(lab, dx, nmin=32, pre=sweeps, post=sweeps)
+    mg = proto.MG(lab, dx, nmin=stop, pre=sweeps, post=sweeps, renorm=bool(renorm))
     z_ref = mg.vcycle(r)
     code = np.where(liq, 1 + proto.make_level(lab)["cnt"], 0).astype(np.uint8)
     pl, pc, pr = pitched(lab, scenes.SOLID), pitched(code), pitched(r)
     z = np.zeros_like(pr)
     emul.emul_mg_vcycle.restype = ctypes.c_int
     levels = emul.emul_mg_vcycle(ptr(pl), ptr(pc), ptr(pr), ctypes.c_int(n), ctypes.c_int(n),
-                                 ctypes.c_float(inv_h2), ptr(z), ctypes.c_int(sweeps))
+                                 ctypes.c_float(inv_h2), ptr(z), ctypes.c_int(sweeps), ctypes.c_int(stop),
+                                 ctypes.c_int(renorm))
     assert levels == len(mg.levels)
     assert not z[:, n:].any() and not z[:, :n][~liq].any()
     err = np.abs(z[:, :n].astype(np.float64) - z_ref).max() / np.abs(z_ref).max()

@@ -304,6 +304,59 @@ CG_KNOBS = ("FSB_CG_SKIP_TILES", "FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH"
             "FSB_CG_STAGES", "FSB_CG_XDEFER", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB")
 
 
+STAGE_KNOBS = [dict(FSB_EXTEND_B16="1"), dict(FSB_BUILD_FUSED_FLAGS="1"), dict(FSB_BUILD_BLOCKS_PER_SM="5"),
+               dict(FSB_EXTEND_B16="1", FSB_BUILD_FUSED_FLAGS="1", FSB_BUILD_BLOCKS_PER_SM="16")]
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 64), (130, 67), (700, 300), (1030, 520)])
+def test_stage_knobs_leave_every_bit_alone(capi, monkeypatch, nx, ny):
+    """The stage-kernel knobs (sixteen-cell early-out in the extension's second pass, active-tile flags
+    from the pressure set-up kernel, its grid size) change launch geometry and fusion only: extension,
+    pressure solve and whole steps give the bits of the default configuration (which the tests above
+    compare with the reference)."""
+    rng = np.random.default_rng(77)
+    lab = _no_isolated_liquid(scenes.random_labels(nx, ny, rng, p_liquid=0.6, p_solid=0.01))
+    f = {w: scenes.random_field(nx, ny, rng) for w in (U_FRONT, V_FRONT, U_BACK, V_BACK)}
+    parts = scenes.particles_in_liquid(lab, 1.0 / nx, rng, 3)
+
+    def run():
+        g = capi.Sim(nx, ny, 1.0, float(ny) / nx, 0.01, 0.05)
+        out = []
+        g.set_cell_types(lab)
+        for w, a in f.items():
+            g.set_grid(w, a)
+        g.extend_velocity(2)
+        out += [g.get_grid(w) for w in (U_FRONT, V_FRONT, U_BACK, V_BACK)]
+        g.set_cg(300, 1e-6)
+        g.pressure_solve(0.01, 0.01)
+        out += [g.get_pressure(), np.array(g.cg_info()), g.get_grid(U_FRONT), g.get_grid(V_FRONT)]
+        g.set_particles(parts)
+        for _ in range(2):
+            g.step(STEP_PICFLIP, 0.002)
+        out += [g.get_cell_types(), g.get_particles(), g.get_grid(U_FRONT), g.get_grid(V_FRONT), np.array(g.cg_info())]
+        g.close()
+        return out
+
+    names = sorted({k for env in STAGE_KNOBS for k in env})
+    for k in names:
+        monkeypatch.delenv(k, raising=False)
+    ref = run()
+    for env in STAGE_KNOBS:
+        for k in names:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got = run()
+        for q, (a, b) in enumerate(zip(ref, got)):
+            if "FSB_BUILD_BLOCKS_PER_SM" in env and not np.array_equal(a, b):
+                # another grid folds the fp64 partial sums of |b|^2 and b.z in another order: the last bit of a
+                # double may differ, and with it (rarely) a rounding of the first fp32 step length
+                assert a.shape == b.shape and a.dtype == b.dtype and a.dtype != np.uint8, (env, q)
+                assert np.abs(a.astype(np.float64) - b).max() <= 1e-5 * max(1.0, np.abs(a).max()), (env, q)
+                continue
+            assert np.array_equal(a, b), (env, q)
+
+
 @pytest.mark.parametrize("nx,ny", [(64, 64), (130, 67), (700, 300)])
 def test_pressure_solve_launch_modes(capi, port, monkeypatch, nx, ny):
     """Every launch mode of the CG (the default one-sweep persistent kernel; the two-sweep persistent
@@ -411,15 +464,24 @@ def test_multigrid_preconditioner_same_solution_far_fewer_iterations(capi, nx, n
     assert scenes.field_rel_err(um, uj) < 1e-3
 
 
-def test_multigrid_tank_iteration_count_is_grid_independent(capi):
+def test_multigrid_tank_iteration_count_is_grid_independent(capi, monkeypatch):
+    """With the wall-conservative transfer weights and the hierarchy continued to 4 x 4 the count does not
+    grow with the grid (numpy statement of the same V-cycle, tools/studies/mg_transfer_study.py: 7 / 7 / 8 / 8
+    at 512^2 .. 4096^2); the round-1 form (plain weights, coarsest level 32 x 32: 17 / 24 / 50 at 1024^2 /
+    2048^2 / 4096^2) stays available behind FSB_MG_RENORM=0 FSB_MG_STOP=32."""
     import bench
     its = []
-    for n in (256, 1024):
+    for n in (256, 1024, 2048):
         lab, u, v = bench.tank_fields(n)
         (im, em), _, _, mm = _solve(capi, n, n, lab, u, v, capi.PRECOND_MULTIGRID)
         assert mm == 3 and em < 1e-6
         its.append(im)
-    assert its[1] <= its[0] + 15 and its[1] <= 45, its
+    assert max(its) <= 12 and max(its) - min(its) <= 3, its
+    monkeypatch.setenv("FSB_MG_RENORM", "0")
+    monkeypatch.setenv("FSB_MG_STOP", "32")
+    lab, u, v = bench.tank_fields(1024)
+    (io, eo), _, _, mo = _solve(capi, 1024, 1024, lab, u, v, capi.PRECOND_MULTIGRID)
+    assert mo == 3 and eo < 1e-6 and its[1] < io <= 45, (io, its)
 
 
 def _no_isolated_liquid(lab):

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Stage-kernel knobs on the default workload (4096^2 PIC/FLIP tank step), one process, one GPU.
+
+Every configuration gets its own context (the knobs are read when a context is created), the same
+particle set, one untimed and `--steps` timed steps with the CG capped (the stages around the solve do not
+depend on how long it iterates), and must leave the SAME labels, velocity grids and particles as the first
+configuration -- the knobs change launch geometry and fusion, never arithmetic.  Prints ms per step of
+every stage (CUDA events of fsb_profile_read).
+
+    python tools/stage_knobs.py [--grid 4096] [--steps 3] [--cap 20]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONFIGS = [
+    ("default", {}),
+    ("extend: 16-cell early-out in pass B", {"FSB_EXTEND_B16": "1"}),
+    ("rhs: tile flags from the set-up kernel", {"FSB_BUILD_FUSED_FLAGS": "1"}),
+    ("rhs: 4 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "4"}),
+    ("rhs: 5 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "5"}),
+    ("rhs: 6 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "6"}),
+    ("rhs: 10 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "10"}),
+    ("rhs: 16 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "16"}),
+    ("rhs: 32 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "32"}),
+    ("all: b16 + fused flags + 5 CTAs/SM", {"FSB_EXTEND_B16": "1", "FSB_BUILD_FUSED_FLAGS": "1",
+                                           "FSB_BUILD_BLOCKS_PER_SM": "5"}),
+]
+KNOBS = sorted({k for _, env in CONFIGS for k in env})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grid", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--cap", type=int, default=20)
+    args = ap.parse_args()
+    import torch
+    import bench
+    from fluid_simulation_b200 import capi
+    n = args.grid
+    dt = float(np.float32(0.01 * 64.0 / n))
+    parts = bench.tank_particles(n, 2)
+    host = torch.empty(parts.shape, dtype=torch.float32, pin_memory=True)
+    host.numpy()[:] = parts
+    n_part = parts.shape[0]
+    del parts
+    first, rows = None, []
+    for name, env in CONFIGS:
+        for k in KNOBS:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        sim = capi.Sim(n, n, 1.0, 1.0, dt, 0.02)
+        sim.set_cg(args.cap, 1e-6)
+        sim.set_particles_ptr(host.data_ptr(), n_part)
+        sim.step(capi.STEP_PICFLIP, dt)
+        sim.synchronize()
+        sim.profile_enable(True)
+        for _ in range(args.steps):
+            sim.step(capi.STEP_PICFLIP, dt)
+        sim.synchronize()
+        prof = sim.profile_read()
+        ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]}
+        state = [sim.get_cell_types(), sim.get_grid(capi.U_FRONT), sim.get_grid(capi.V_FRONT),
+                 sim.get_grid(capi.U_BACK), sim.get_grid(capi.V_BACK), sim.get_pressure(), sim.get_particles()]
+        tiles = sim.cg_info()
+        if first is None:
+            first = state
+            same = True
+        else:
+            same = all(np.array_equal(a, b) for a, b in zip(first, state))
+        rows.append({"config": name, "env": env, "identical_to_default": bool(same), "cg": list(tiles), "ms": ms})
+        print(json.dumps(rows[-1]), flush=True)
+        sim.close()
+        del sim, state
+    bad = [r["config"] for r in rows if not r["identical_to_default"]]
+    print("ALL IDENTICAL" if not bad else f"DIFFERENT RESULTS: {bad}", flush=True)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -59,14 +59,28 @@ def prolong(Lf,Lc,e):
     out=out[1:ny+1,1:nx+1]
     return np.where(Lf['liq'],out,f32(0)).astype(f32)
 
+def parent_norm(Lf,Lc):
+    """Sum of a fine cell's bilinear weights over its non-SOLID coarse parents (outside the grid = SOLID):
+    1 away from walls, < 1 next to them.  Dividing by it makes the prolongation a constant extension across
+    walls and its transpose, the restriction, conservative there (tools/studies/mg_transfer_study.py)."""
+    nons=(Lc['lab']!=SOL).astype(f32)
+    ny,nx=Lf['ny'],Lf['nx']; NY,NX=Lc['ny'],Lc['nx']
+    out=np.zeros((2*NY+2,2*NX+2),dtype=f32)
+    for a in range(4):
+        for c in range(4):
+            out[a:a+2*NY:2,c:c+2*NX:2]+=f32(4)*W[a]*W[c]*nons
+    w=out[1:ny+1,1:nx+1]
+    return np.where(w>0,w,f32(1)).astype(f32)
+
 class MG:
-    def __init__(self,lab,dx,nmin=8,pre=2,post=2,coarse_sweeps=40,scale=1.0):
+    def __init__(self,lab,dx,nmin=8,pre=2,post=2,coarse_sweeps=40,scale=1.0,renorm=False):
         self.levels=[make_level(lab)]; self.h2=[f32(1)/(f32(dx)*f32(dx))]
-        while min(self.levels[-1]['lab'].shape)>nmin:
+        while max(self.levels[-1]['lab'].shape)>nmin:
             cl=coarsen(self.levels[-1]['lab'])
             self.levels.append(make_level(cl)); self.h2.append(self.h2[-1]/f32(4))
         self.pre,self.post,self.cs=pre,post,coarse_sweeps
         self.scale=f32(scale)
+        self.norm=[parent_norm(self.levels[l],self.levels[l+1]) if renorm else None for l in range(len(self.levels)-1)]
     def vcycle(self,b,l=0):
         L=self.levels[l]; h2=self.h2[l]
         x=np.zeros_like(b)
@@ -74,9 +88,12 @@ class MG:
             return smooth(L,x,b,h2,self.cs)
         x=smooth(L,x,b,h2,self.pre)
         r=b-applyA(L,x,h2); r=np.where(L['liq'],r,f32(0))
+        if self.norm[l] is not None: r=(r/self.norm[l]).astype(f32)
         rc=restrict(L,self.levels[l+1],r)
         ec=self.vcycle(rc,l+1)
-        x=(x+self.scale*prolong(L,self.levels[l+1],ec)).astype(f32)
+        e=prolong(L,self.levels[l+1],ec)
+        if self.norm[l] is not None: e=(e/self.norm[l]).astype(f32)
+        x=(x+self.scale*e).astype(f32)
         x=smooth(L,x,b,h2,self.post)
         return x
 
