@@ -238,9 +238,8 @@ int fsb_create(fsb_ctx** out, int size_x, int size_y, float length_x, float leng
   c->grav_y = (float)-9.82; // src/FluidSolver.cpp:232
   if (const char* e = getenv("FSB_STAGE_KERNELS")) c->stage_v1 = (strcmp(e, "v1") == 0);
   if (const char* e = getenv("FSB_SL_ATOMIC")) c->sl_atomic = atoi(e) != 0;
-  if (const char* e = getenv("FSB_EXTEND_B16")) c->extend_b16 = atoi(e) != 0;
   if (const char* e = getenv("FSB_BUILD_BLOCKS_PER_SM")) c->build_blocks_per_sm = std::max(1, std::min(32, atoi(e)));
-  if (const char* e = getenv("FSB_BUILD_FUSED_FLAGS")) c->build_fused_flags = atoi(e) != 0;
+
   if (const char* e = getenv("FSB_MG_MAX_ITERS")) c->mg_max_iters = std::max(1, atoi(e));
   if (const char* e = getenv("FSB_MG_SWEEPS")) c->mg_sweeps = std::max(1, std::min(8, atoi(e)));
   if (const char* e = getenv("FSB_MG_STOP")) c->mg_stop = std::max(1, std::min(32, atoi(e)));

@@ -160,8 +160,7 @@ __global__ void __launch_bounds__(256)
 k_cg_build4(const float* __restrict__ uf, const float* __restrict__ vf,
             const uint8_t* __restrict__ cell, uint8_t* __restrict__ code, float* __restrict__ x,
             float* __restrict__ r, const D d, const CgCoef coef, CgScalars* __restrict__ s,
-            double* __restrict__ partials, float tol, int max_iters,
-            int* __restrict__ tile_flags = nullptr, int tiles_x = 0, int tile_rows = 1)
+            double* __restrict__ partials, float tol, int max_iters)
 {
   const int segs = (d.ld + 1023) / 1024;
   const int n_work = segs * d.ny;
@@ -170,24 +169,14 @@ k_cg_build4(const float* __restrict__ uf, const float* __restrict__ vf,
   {
     const int j = w / segs;
     const int i0 = ((w - j * segs) * 256 + threadIdx.x) * 4;
-    uint32_t cd = 0u;
-    if (i0 < d.ld)
-    {
-      const size_t t0 = i0 + (size_t)j * d.ld;
-      float4 b;
-      cg_build_group(uf, vf, cell, d, coef.invdiag, i0, j, &cd, &b, &acc_b2, &acc_bz, &acc_n);
-      *reinterpret_cast<uint32_t*>(code + t0) = cd;
-      *reinterpret_cast<float4*>(x + t0) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      *reinterpret_cast<float4*>(r + t0) = b;
-    }
-    // FSB_BUILD_FUSED_FLAGS: a warp's 32 groups are the 128 columns of exactly one solve tile (kTileW),
-    // so the active-tile flags (k_cg_tile_flags) fall out of this pass: the flag array is cleared before
-    // the launch and every writer stores the same 1
-    if (tile_flags)
-    {
-      const bool any = __any_sync(0xffffffffu, cd != 0u);
-      if (any && (threadIdx.x & 31) == 0 && i0 < d.ld) tile_flags[(j / tile_rows) * tiles_x + i0 / kTileW] = 1;
-    }
+    if (i0 >= d.ld) continue;
+    const size_t t0 = i0 + (size_t)j * d.ld;
+    uint32_t cd;
+    float4 b;
+    cg_build_group(uf, vf, cell, d, coef.invdiag, i0, j, &cd, &b, &acc_b2, &acc_bz, &acc_n);
+    *reinterpret_cast<uint32_t*>(code + t0) = cd;
+    *reinterpret_cast<float4*>(x + t0) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    *reinterpret_cast<float4*>(r + t0) = b;
   }
   const double b2 = block_sum(acc_b2);
   const double bz = block_sum(acc_bz);
@@ -1949,6 +1938,17 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
   // ---- build
   fsb_prof_begin(c, FSB_PROF_RHS);
   const int64_t total = (int64_t)c->ld * c->ny;
+  // one resident wave of the set-up kernel (5 CTAs per SM at 48 registers): its grid-stride loop then has no
+  // second, partly filled wave -- 0.114 -> 0.104 ms at 4096^2 against the former 8 per SM (4: 0.113, 6: 0.106,
+  // 16: 0.113, 32: 0.128; tools/stage_knobs.py).  FSB_BUILD_BLOCKS_PER_SM overrides.
+  if (c->build_blocks_per_sm == 0)
+  {
+    int per_sm = 0;
+    const cudaError_t e = (d.pow2 == 3)
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_build4<GridDimsP2>, 256, 0)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_build4<GridDims>, 256, 0);
+    c->build_blocks_per_sm = (e == cudaSuccess && per_sm > 0) ? per_sm : 5;
+  }
   const int build_blocks = (int)std::min<int64_t>(fsb_div_up(total, 256), c->sm_count * c->build_blocks_per_sm);
   FSB_TRY(configure_cg(c));
   const int need = std::max(std::max(std::max(3 * build_blocks, 3 * c->cg_grid_fused),
@@ -1975,10 +1975,6 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
       FSB_CUDA(c, cudaMalloc(&c->cg_tile_list, sizeof(int) * n_t));
       c->cg_tile_cap = n_t;
     }
-    // FSB_BUILD_FUSED_FLAGS (one GPU): the set-up kernel marks the active tiles itself
-    const bool fused_flags = c->build_fused_flags && c->cg_skip_tiles && !c->stage_v1 && c->shard.world == 1;
-    int* flags_arg = fused_flags ? c->cg_tile_flags : nullptr;
-    if (fused_flags) FSB_CUDA(c, cudaMemsetAsync(c->cg_tile_flags, 0, sizeof(int) * n_t, c->stream));
     if (c->stage_v1)
       k_cg_build<<<build_blocks, 256, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), c->cell, c->cg_code,
                                                       c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
@@ -1986,21 +1982,18 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
     else if (d.pow2 == 3)
       k_cg_build4<GridDimsP2><<<build_blocks, 256, 0, c->stream>>>(
           fsb_uf(c), fsb_vf(c), c->cell, c->cg_code, c->cg_x, c->cg_r, as_pow2(d), coef, c->scal,
-          c->partials, c->tol, c->max_iters, flags_arg, tiles_x, th);
+          c->partials, c->tol, c->max_iters);
     else
       k_cg_build4<GridDims><<<build_blocks, 256, 0, c->stream>>>(
           fsb_uf(c), fsb_vf(c), c->cell, c->cg_code, c->cg_x, c->cg_r, d, coef, c->scal, c->partials,
-          c->tol, c->max_iters, flags_arg, tiles_x, th);
+          c->tol, c->max_iters);
     FSB_LAUNCHED(c);
     if (c->cg_skip_tiles)
     {
-      if (!fused_flags)
-      {
-        k_cg_tile_flags<<<n_t, 128, 0, c->stream>>>(c->cg_code, c->ld, tiles_x, th, c->shard.row_lo,
-                                                    c->shard.row_hi, c->cg_tile_flags,
-                                                    c->shard.world > 1 ? 1 : 0);
-        FSB_LAUNCHED(c);
-      }
+      k_cg_tile_flags<<<n_t, 128, 0, c->stream>>>(c->cg_code, c->ld, tiles_x, th, c->shard.row_lo,
+                                                  c->shard.row_hi, c->cg_tile_flags,
+                                                  c->shard.world > 1 ? 1 : 0);
+      FSB_LAUNCHED(c);
       k_cg_tile_compact<<<1, 1024, 0, c->stream>>>(c->cg_tile_flags, n_t, tiles_x, c->cg_tile_list,
                                                    c->scal, (c->shard.world > 1 && c->cg_edge_first) ? 1 : 0);
       FSB_LAUNCHED(c);

@@ -369,14 +369,8 @@ int fsb_k_extend_velocity(fsb_ctx* c, int n_iter)
     k_extend2_a<<<grid, kBlock, 0, c->stream>>>(fsb_uf(c), fsb_vf(c), fsb_ub(c), fsb_vb(c), m1,
                                                 c->cell, dims(c));
     FSB_LAUNCHED(c);
-    if (c->extend_b16)
-    {
-      const dim3 grid16(fsb_div_up(c->ld, 16 * kBlock), fsb_div_up(c->ny, kExtendRows));
-      k_extend2_b16<<<grid16, kBlock, 0, c->stream>>>(fsb_uf(c), fsb_ub(c), fsb_vb(c), m1, c->cell, dims(c));
-    }
-    else
-      k_extend2_b<<<grid, kBlock, 0, c->stream>>>(fsb_uf(c), fsb_ub(c), fsb_vb(c), m1, c->cell,
-                                                  dims(c));
+    k_extend2_b<<<grid, kBlock, 0, c->stream>>>(fsb_uf(c), fsb_ub(c), fsb_vb(c), m1, c->cell,
+                                                dims(c));
     FSB_LAUNCHED(c);
     c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:621
     fsb_prof_end(c, FSB_PROF_EXTEND);

@@ -190,9 +190,7 @@ struct fsb_ctx
   int* sl_maxd = nullptr;
   size_t sl_cells = 0;
   int sl_reach = 0;         // reach (source cells) of the last gather
-  bool extend_b16 = false;      // FSB_EXTEND_B16: sixteen-cell early-out in the extension's second pass
-  int build_blocks_per_sm = 8;  // FSB_BUILD_BLOCKS_PER_SM: grid of the pressure set-up kernel
-  bool build_fused_flags = false; // FSB_BUILD_FUSED_FLAGS: the set-up kernel marks the active tiles itself
+  int build_blocks_per_sm = 0;  // grid of the pressure set-up kernel: 0 = one resident wave (FSB_BUILD_BLOCKS_PER_SM)
   bool sl_atomic = false;   // FSB_SL_ATOMIC=1: the first-generation float-atomics scatter
 
   // row-slab sharding (fsb_shard_*); world == 1: not sharded

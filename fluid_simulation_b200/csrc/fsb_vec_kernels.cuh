@@ -263,34 +263,6 @@ k_extend2_b(float* __restrict__ uf, float* __restrict__ ub, float* __restrict__ 
   }
 }
 
-// Pass B with sixteen cells per thread in front of the four-cell groups: in a tank nearly every thread's
-// cells are LIQUID and the pass has nothing to do for them, so the test is made on one 16-byte label load
-// instead of four threads' 4-byte loads (the pass was bound by its thread count: 38 us at 4096^2 for
-// 27 MB of DRAM traffic, profiles/r02_stage_kernels_ncu_full.md).  Same groups, same arithmetic.
-__global__ void __launch_bounds__(256)
-k_extend2_b16(float* __restrict__ uf, float* __restrict__ ub, float* __restrict__ vb,
-              const uint8_t* __restrict__ m1, const uint8_t* __restrict__ cell, const GridDims d)
-{
-  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-  if (i0 >= d.nx) return;
-#pragma unroll
-  for (int r = 0; r < kExtendRows; ++r)
-  {
-    const int j = blockIdx.y * kExtendRows + r;
-    if (j >= d.ny) continue;
-    if (i0 + 16 <= d.nx)
-    {
-      const uint4 w = *reinterpret_cast<const uint4*>(cell + i0 + (size_t)j * d.ld);
-      if (((w.x ^ (FSB_LIQUID * 0x01010101u)) | (w.y ^ (FSB_LIQUID * 0x01010101u)) |
-           (w.z ^ (FSB_LIQUID * 0x01010101u)) | (w.w ^ (FSB_LIQUID * 0x01010101u))) == 0u)
-        continue;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (i0 + 4 * q < d.nx) extend2_b_group(uf, ub, vb, m1, cell, d, i0 + 4 * q, j);
-  }
-}
-
 #endif // FSB_VEC_WANT_GRID
 
 #ifdef FSB_VEC_WANT_CG

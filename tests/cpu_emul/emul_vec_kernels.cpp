@@ -103,17 +103,6 @@ void emul_extend2(float* uf, const float* vf, float* ub, float* vb, uint8_t* m1,
          [&] { k_extend2_b(uf, ub, vb, m1, cell, d); });
 }
 
-// the same with the sixteen-cell form of the second pass (FSB_EXTEND_B16)
-void emul_extend2_b16(float* uf, const float* vf, float* ub, float* vb, uint8_t* m1,
-                      const uint8_t* cell, int nx, int ny, int ld, float dx, float dy)
-{
-  const GridDims d = make_grid_dims(nx, ny, ld, dx, dy);
-  launch(div_up(ld, 1024), div_up(ny, kExtendRows), 256,
-         [&] { k_extend2_a(uf, vf, ub, vb, m1, cell, d); });
-  launch(div_up(ld, 16 * 256), div_up(ny, kExtendRows), 256,
-         [&] { k_extend2_b16(uf, ub, vb, m1, cell, d); });
-}
-
 void emul_pressure_patch(const float* uf, const float* vf, float* ub, float* vb, const float* x,
                          const uint8_t* cell, int nx, int ny, int ld, float dx, float dy, float dt,
                          float density, int dirichlet)

@@ -89,12 +89,11 @@ def test_enforce_dirichlet(emul, checkers, nx, ny):
 
 @pytest.mark.parametrize("nx,ny", SIZES)
 @pytest.mark.parametrize("p_liquid", [0.5, 0.08])
-@pytest.mark.parametrize("b16", [0, 1])
-def test_extend_velocity_two_sweeps(emul, checkers, nx, ny, p_liquid, b16):
+def test_extend_velocity_two_sweeps(emul, checkers, nx, ny, p_liquid):
     rng = np.random.default_rng(22)
     for chk in checkers:
         c = make_sim(chk, nx, ny)
-        lab = scenes.random_labels(nx, ny, rng, p_liquid=p_liquid, p_solid=0.01 if b16 else 0.05)
+        lab = scenes.random_labels(nx, ny, rng, p_liquid=p_liquid, p_solid=0.05)
         f = {w: scenes.random_field(nx, ny, rng) for w in (U_FRONT, V_FRONT, U_BACK, V_BACK)}
         c.set_cell_types(lab)
         for w, a in f.items():
@@ -104,9 +103,7 @@ def test_extend_velocity_two_sweeps(emul, checkers, nx, ny, p_liquid, b16):
         pub, pvb = pitched(f[U_BACK]), pitched(f[V_BACK])
         pl = pitched(lab, scenes.SOLID)
         m1 = np.zeros_like(pl)
-        # p_solid below: long all-LIQUID runs exist, so the sixteen-cell early-out of pass B is taken
-        (emul.emul_extend2_b16 if b16 else emul.emul_extend2)(ptr(pu), ptr(pv), ptr(pub), ptr(pvb), ptr(m1),
-                                                              ptr(pl), *dims(c, nx, ny))
+        emul.emul_extend2(ptr(pu), ptr(pv), ptr(pub), ptr(pvb), ptr(m1), ptr(pl), *dims(c, nx, ny))
         assert np.array_equal(pub[:, :nx], c.get_grid(U_FRONT))
         assert np.array_equal(pvb[:, :nx], c.get_grid(V_FRONT))
         assert np.array_equal(pu[:, :nx], c.get_grid(U_BACK))  # incl. the :527 typo

@@ -304,16 +304,14 @@ CG_KNOBS = ("FSB_CG_SKIP_TILES", "FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH"
             "FSB_CG_STAGES", "FSB_CG_XDEFER", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB")
 
 
-STAGE_KNOBS = [dict(FSB_EXTEND_B16="1"), dict(FSB_BUILD_FUSED_FLAGS="1"), dict(FSB_BUILD_BLOCKS_PER_SM="5"),
-               dict(FSB_EXTEND_B16="1", FSB_BUILD_FUSED_FLAGS="1", FSB_BUILD_BLOCKS_PER_SM="16")]
+STAGE_KNOBS = [dict(FSB_BUILD_BLOCKS_PER_SM="8"), dict(FSB_BUILD_BLOCKS_PER_SM="16")]
 
 
 @pytest.mark.parametrize("nx,ny", [(64, 64), (130, 67), (700, 300), (1030, 520)])
 def test_stage_knobs_leave_every_bit_alone(capi, monkeypatch, nx, ny):
-    """The stage-kernel knobs (sixteen-cell early-out in the extension's second pass, active-tile flags
-    from the pressure set-up kernel, its grid size) change launch geometry and fusion only: extension,
-    pressure solve and whole steps give the bits of the default configuration (which the tests above
-    compare with the reference)."""
+    """The grid size of the pressure set-up kernel (default: one resident wave) changes launch geometry
+    only: extension, pressure solve and whole steps give the results of the default configuration (which
+    the tests above compare with the reference)."""
     rng = np.random.default_rng(77)
     lab = _no_isolated_liquid(scenes.random_labels(nx, ny, rng, p_liquid=0.6, p_solid=0.01))
     f = {w: scenes.random_field(nx, ny, rng) for w in (U_FRONT, V_FRONT, U_BACK, V_BACK)}

@@ -20,6 +20,7 @@ PY
 if [ "$N" = 1 ]; then
   timeout 1700 python -m pytest tests -q -m gpu > gpurun_out/checks_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/checks_pytest.log
   timeout 900 python bench.py --no-cpu-baseline > gpurun_out/checks_bench_n1.json 2> gpurun_out/checks_bench_n1.err; line gpurun_out/checks_bench_n1.json
+  timeout 400 python tools/stage_knobs.py > gpurun_out/checks_stage_knobs.log 2>&1; echo "stage knobs rc=$?"; tail -1 gpurun_out/checks_stage_knobs.log
   for wl in cg4096 cg1024 cg8192; do
     timeout 300 python bench.py --workload $wl --steps 2 --warmup 1 --no-cpu-baseline --no-optin --no-e2e --no-scale > gpurun_out/checks_$wl.json 2> gpurun_out/checks_$wl.err; line gpurun_out/checks_$wl.json
   done
@@ -30,5 +31,7 @@ else
   echo "sharded CG vs single GPU rc=$? $(grep '^{' gpurun_out/checks_cg_$N.log | tail -1 | cut -c1-300)"
   timeout 300 $TR --master-port 29551 tests/multi_gpu_slab_check.py --backend nccl --grid 515 --steps 4 --shard-cg > gpurun_out/checks_slab_$N.log 2>&1
   echo "particle slabs + sharded CG vs single GPU rc=$? $(grep '^{' gpurun_out/checks_slab_$N.log | tail -1)"
+  timeout 200 $TR --master-port 29552 tests/multi_gpu_slab_check.py --backend nccl --grid 515 --steps 4 --kind sl --shard-cg > gpurun_out/checks_slab_sl_$N.log 2>&1
+  echo "semi-Lagrangian slabs + sharded CG vs single GPU rc=$? $(grep '^{' gpurun_out/checks_slab_sl_$N.log | tail -1)"
   timeout 900 $TR --master-port 29553 bench.py --gpus $N --no-cpu-baseline --no-optin > gpurun_out/checks_bench_n$N.json 2> gpurun_out/checks_bench_n$N.err; line gpurun_out/checks_bench_n$N.json
 fi

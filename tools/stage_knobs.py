@@ -21,17 +21,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CONFIGS = [
-    ("default", {}),
-    ("extend: 16-cell early-out in pass B", {"FSB_EXTEND_B16": "1"}),
-    ("rhs: tile flags from the set-up kernel", {"FSB_BUILD_FUSED_FLAGS": "1"}),
+    ("default (one resident wave of the set-up kernel)", {}),
     ("rhs: 4 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "4"}),
-    ("rhs: 5 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "5"}),
     ("rhs: 6 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "6"}),
-    ("rhs: 10 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "10"}),
+    ("rhs: 8 CTAs/SM (rounds 1 - 2)", {"FSB_BUILD_BLOCKS_PER_SM": "8"}),
     ("rhs: 16 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "16"}),
-    ("rhs: 32 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "32"}),
-    ("all: b16 + fused flags + 5 CTAs/SM", {"FSB_EXTEND_B16": "1", "FSB_BUILD_FUSED_FLAGS": "1",
-                                           "FSB_BUILD_BLOCKS_PER_SM": "5"}),
 ]
 KNOBS = sorted({k for _, env in CONFIGS for k in env})
 
