@@ -238,6 +238,10 @@ int fsb_create(fsb_ctx** out, int size_x, int size_y, float length_x, float leng
   c->grav_y = (float)-9.82; // src/FluidSolver.cpp:232
   if (const char* e = getenv("FSB_STAGE_KERNELS")) c->stage_v1 = (strcmp(e, "v1") == 0);
   if (const char* e = getenv("FSB_SL_ATOMIC")) c->sl_atomic = atoi(e) != 0;
+  if (const char* e = getenv("FSB_CANON_PER")) c->canon_per = atoi(e) == 1 ? 1 : 2;
+  if (const char* e = getenv("FSB_P2G_PIPE")) c->p2g_pipe = atoi(e) != 0;
+  if (const char* e = getenv("FSB_SORT_PER")) { const int v = atoi(e); c->sort_per = (v == 1 || v == 4) ? v : 2; }
+  if (const char* e = getenv("FSB_G2P_PER")) { const int v = atoi(e); c->g2p_per = (v == 1 || v == 4) ? v : 2; }
   if (const char* e = getenv("FSB_BUILD_BLOCKS_PER_SM")) c->build_blocks_per_sm = std::max(1, std::min(32, atoi(e)));
 
   if (const char* e = getenv("FSB_MG_MAX_ITERS")) c->mg_max_iters = std::max(1, atoi(e));

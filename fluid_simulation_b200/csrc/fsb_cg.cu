@@ -1940,7 +1940,8 @@ int fsb_k_pressure_solve(fsb_ctx* c, float density, float dt, bool fuse_dirichle
   const int64_t total = (int64_t)c->ld * c->ny;
   // one resident wave of the set-up kernel (5 CTAs per SM at 48 registers): its grid-stride loop then has no
   // second, partly filled wave -- 0.114 -> 0.104 ms at 4096^2 against the former 8 per SM (4: 0.113, 6: 0.106,
-  // 16: 0.113, 32: 0.128; tools/stage_knobs.py).  FSB_BUILD_BLOCKS_PER_SM overrides.
+  // 16: 0.113, 32: 0.128; tools/stage_knobs.py).  FSB_BUILD_BLOCKS_PER_SM overrides.  (Requesting the next
+  // group's label rows early with prefetch.global.L1 made the pass slower: 0.106 -> 0.111 ms.)
   if (c->build_blocks_per_sm == 0)
   {
     int per_sm = 0;

@@ -190,6 +190,10 @@ struct fsb_ctx
   int* sl_maxd = nullptr;
   size_t sl_cells = 0;
   int sl_reach = 0;         // reach (source cells) of the last gather
+  int canon_per = 2;            // FSB_CANON_PER: cells per thread of the sort's in-cell ordering pass (1, 2)
+  int p2g_pipe = 1;             // FSB_P2G_PIPE: particle-to-grid kernel requests the next record before computing this one
+  int sort_per = 2;             // FSB_SORT_PER: particles per thread of the sort's counting and gather passes (1, 2, 4)
+  int g2p_per = 2;              // FSB_G2P_PER: particles per thread of the grid-to-particle kernel (1, 2, 4)
   int build_blocks_per_sm = 0;  // grid of the pressure set-up kernel: 0 = one resident wave (FSB_BUILD_BLOCKS_PER_SM)
   bool sl_atomic = false;   // FSB_SL_ATOMIC=1: the first-generation float-atomics scatter
 

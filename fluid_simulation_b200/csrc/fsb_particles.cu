@@ -25,44 +25,66 @@ inline GridDims pool_dims(const fsb_ctx* c)
 // MARK: the same pass also performs FluidDomain::classifyCells' marking (src/FluidDomain.cpp:
 // 157-167, the formula of k_mark_liquid: (int)((pos / length) * size), clamped, border skipped),
 // so that a step reads the particle set once for both.
-template <bool MARK, class D>
-__global__ void k_sort_count(const float4* __restrict__ part, int64_t n, const D d,
-                             int* __restrict__ count, int* __restrict__ key_out,
-                             int* __restrict__ rank_out, uint8_t* __restrict__ cell,
-                             const GridDims gd, const D glen)
+//
+// PER particles per thread (block-strided, every access coalesced): a particle is a chain of dependent
+// round trips -- its record, then the counter atomic whose return value is its rank -- and with one
+// particle per thread the pass is bound by that chain times the number of thread waves.  The records of
+// all PER particles are requested first, then all atomics are issued, then everything is stored.
+template <bool MARK, class D, int PER>
+__global__ void __launch_bounds__(256)
+k_sort_count(const float4* __restrict__ part, int64_t n, const D d,
+             int* __restrict__ count, int* __restrict__ key_out,
+             int* __restrict__ rank_out, uint8_t* __restrict__ cell,
+             const GridDims gd, const D glen)
 {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t k0 = (int64_t)blockIdx.x * (blockDim.x * PER) + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
-  const bool live = k < n;
-  int key = -1 - (int)lane; // distinct per lane, never equal to a real key
-  if (live)
+  float4 p[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
   {
-    const float4 p = part[k];
-    const int ci = clampi((int)div_dx(d, p.x), 0, d.nx - 1);
-    const int cj = clampi((int)div_dy(d, p.y), 0, d.ny - 1);
-    key = ci + cj * d.nx;
-    if (MARK)
-    {
-      const int x = clampi((int)(div_dx(glen, p.x) * (float)gd.nx), 0, gd.nx - 1);
-      const int y = clampi((int)(div_dy(glen, p.y) * (float)gd.ny), 0, gd.ny - 1);
-      if (!(x == 0 || y == 0 || x == gd.nx - 1 || y == gd.ny - 1))
-        cell[x + (size_t)y * gd.ld] = FSB_LIQUID;
-    }
+    const int64_t k = k0 + (int64_t)q * blockDim.x;
+    p[q] = (k < n) ? part[k] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const int prev = __shfl_up_sync(0xffffffffu, key, 1);
-  const bool head = (lane == 0) || (key != prev);
-  const unsigned heads = __ballot_sync(0xffffffffu, head);
-  const unsigned below = heads & (0xffffffffu >> (31 - lane)); // heads at lanes <= mine
-  const int start = 31 - __clz(below);
-  const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
-  const int len = above ? __ffs(above) : (32 - (int)lane); // run length seen from a head
-  int base = 0;
-  if (head && live) base = atomicAdd(count + key, len);
-  base = __shfl_sync(0xffffffffu, base, start);
-  if (live)
+  int key[PER], base[PER], start[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
   {
-    key_out[k] = key;
-    rank_out[k] = base + ((int)lane - start);
+    const bool live = k0 + (int64_t)q * blockDim.x < n;
+    key[q] = -1 - (int)lane; // distinct per lane, never equal to a real key
+    if (live)
+    {
+      const int ci = clampi((int)div_dx(d, p[q].x), 0, d.nx - 1);
+      const int cj = clampi((int)div_dy(d, p[q].y), 0, d.ny - 1);
+      key[q] = ci + cj * d.nx;
+      if (MARK)
+      {
+        const int x = clampi((int)(div_dx(glen, p[q].x) * (float)gd.nx), 0, gd.nx - 1);
+        const int y = clampi((int)(div_dy(glen, p[q].y) * (float)gd.ny), 0, gd.ny - 1);
+        if (!(x == 0 || y == 0 || x == gd.nx - 1 || y == gd.ny - 1))
+          cell[x + (size_t)y * gd.ld] = FSB_LIQUID;
+      }
+    }
+    const int prev = __shfl_up_sync(0xffffffffu, key[q], 1);
+    const bool head = (lane == 0) || (key[q] != prev);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned below = heads & (0xffffffffu >> (31 - lane)); // heads at lanes <= mine
+    start[q] = 31 - __clz(below);
+    const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
+    const int len = above ? __ffs(above) : (32 - (int)lane); // run length seen from a head
+    base[q] = 0;
+    if (head && live) base[q] = atomicAdd(count + key[q], len);
+  }
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+  {
+    const int64_t k = k0 + (int64_t)q * blockDim.x;
+    const int b = __shfl_sync(0xffffffffu, base[q], start[q]);
+    if (k < n)
+    {
+      key_out[k] = key[q];
+      rank_out[k] = b + ((int)lane - start[q]);
+    }
   }
 }
 
@@ -203,72 +225,119 @@ __global__ void k_sort_place(const int* __restrict__ key, const int* __restrict_
 // deterministic sort whose result does not depend on the order the particles were stored in
 // before: every floating-point sum over a cell's particles is reproducible across runs, across
 // state files and across particle partitions.
-__global__ void k_sort_canon(const int* __restrict__ start, int m, int* __restrict__ idx,
-                             const int* __restrict__ orig)
+//
+// PER cells per thread (block-strided): a cell is three dependent round trips (its bounds, its entries,
+// their keys); the loads of all PER cells are issued level by level so that the chains overlap.
+template <int PER>
+__global__ void __launch_bounds__(256)
+k_sort_canon(const int* __restrict__ start, int m, int* __restrict__ idx, const int* __restrict__ orig)
 {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= m) return;
-  const int a = start[c], b = start[c + 1];
-  const int n = b - a;
-  if (n <= 1) return;
-  if (n <= 8)
+  const int c0 = blockIdx.x * (blockDim.x * PER) + threadIdx.x;
+  int a[PER], n[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
   {
-    // the common case: all entries and their keys loaded at once (independent loads), a fixed
-    // 19-exchange sorting network in registers, and a write-back only where the order changed
-    int v[8], key[8], w[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) v[t] = (t < n) ? idx[a + t] : -1;
-#pragma unroll
-    for (int t = 0; t < 8; ++t)
+    const int c = c0 + q * (int)blockDim.x;
+    a[q] = 0;
+    n[q] = 0;
+    if (c < m)
     {
-      key[t] = (t < n) ? __ldg(orig + v[t]) : 0x7fffffff;
-      w[t] = v[t];
+      a[q] = start[c];
+      n[q] = start[c + 1] - a[q];
     }
-#define FSB_CX(p, q)                                  \
-  {                                                   \
-    const bool sw = key[p] > key[q];                  \
-    const int klo = sw ? key[q] : key[p];             \
-    const int khi = sw ? key[p] : key[q];             \
-    const int wlo = sw ? w[q] : w[p];                 \
-    const int whi = sw ? w[p] : w[q];                 \
-    key[p] = klo; key[q] = khi; w[p] = wlo; w[q] = whi; \
   }
-    FSB_CX(0, 1) FSB_CX(2, 3) FSB_CX(4, 5) FSB_CX(6, 7)
-    FSB_CX(0, 2) FSB_CX(1, 3) FSB_CX(4, 6) FSB_CX(5, 7)
-    FSB_CX(1, 2) FSB_CX(5, 6) FSB_CX(0, 4) FSB_CX(3, 7)
-    FSB_CX(1, 5) FSB_CX(2, 6)
-    FSB_CX(1, 4) FSB_CX(3, 6)
-    FSB_CX(2, 4) FSB_CX(3, 5)
-    FSB_CX(3, 4)
+  // the common case (2 .. 8 entries): all entries and their keys loaded at once (independent loads), a
+  // fixed 19-exchange sorting network in registers, and a write-back only where the order changed
+  int v[PER][8], key[PER][8];
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[q][t] = (n[q] >= 2 && n[q] <= 8 && t < n[q]) ? idx[a[q] + t] : -1;
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) key[q][t] = (v[q][t] >= 0) ? __ldg(orig + v[q][t]) : 0x7fffffff;
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+  {
+    if (n[q] <= 1) continue;
+    if (n[q] <= 8)
+    {
+      int w[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) w[t] = v[q][t];
+#define FSB_CX(p, r)                                              \
+  {                                                               \
+    const bool sw = key[q][p] > key[q][r];                        \
+    const int klo = sw ? key[q][r] : key[q][p];                   \
+    const int khi = sw ? key[q][p] : key[q][r];                   \
+    const int wlo = sw ? w[r] : w[p];                             \
+    const int whi = sw ? w[p] : w[r];                             \
+    key[q][p] = klo; key[q][r] = khi; w[p] = wlo; w[r] = whi;     \
+  }
+      FSB_CX(0, 1) FSB_CX(2, 3) FSB_CX(4, 5) FSB_CX(6, 7)
+      FSB_CX(0, 2) FSB_CX(1, 3) FSB_CX(4, 6) FSB_CX(5, 7)
+      FSB_CX(1, 2) FSB_CX(5, 6) FSB_CX(0, 4) FSB_CX(3, 7)
+      FSB_CX(1, 5) FSB_CX(2, 6)
+      FSB_CX(1, 4) FSB_CX(3, 6)
+      FSB_CX(2, 4) FSB_CX(3, 5)
+      FSB_CX(3, 4)
 #undef FSB_CX
 #pragma unroll
-    for (int t = 0; t < 8; ++t)
-      if (t < n && w[t] != v[t]) idx[a + t] = w[t];
-    return;
-  }
-  for (int s = a + 1; s < b; ++s)
-  {
-    const int v = idx[s];
-    const int kv = orig[v];
-    int t = s - 1;
-    while (t >= a && orig[idx[t]] > kv)
-    {
-      idx[t + 1] = idx[t];
-      --t;
+      for (int t = 0; t < 8; ++t)
+        if (t < n[q] && w[t] != v[q][t]) idx[a[q] + t] = w[t];
+      continue;
     }
-    idx[t + 1] = v;
+    const int lo = a[q], hi = a[q] + n[q];
+    for (int s = lo + 1; s < hi; ++s)
+    {
+      const int vv = idx[s];
+      const int kv = orig[vv];
+      int t = s - 1;
+      while (t >= lo && orig[idx[t]] > kv)
+      {
+        idx[t + 1] = idx[t];
+        --t;
+      }
+      idx[t + 1] = vv;
+    }
   }
 }
 
-__global__ void k_sort_gather(const float4* __restrict__ src, const int* __restrict__ src_orig,
-                              const int* __restrict__ idx, int64_t n, float4* __restrict__ dst,
-                              int* __restrict__ dst_orig)
+template <int PER>
+__global__ void __launch_bounds__(256)
+k_sort_gather(const float4* __restrict__ src, const int* __restrict__ src_orig,
+              const int* __restrict__ idx, int64_t n, float4* __restrict__ dst,
+              int* __restrict__ dst_orig)
 {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const int s = idx[k];
-  dst[k] = src[s];
-  dst_orig[k] = src_orig[s];
+  // PER destinations per thread, block-strided: all permutation entries first, then all records, then the stores
+  const int64_t k0 = (int64_t)blockIdx.x * (blockDim.x * PER) + threadIdx.x;
+  int sidx[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+  {
+    const int64_t k = k0 + (int64_t)q * blockDim.x;
+    sidx[q] = (k < n) ? idx[k] : 0;
+  }
+  float4 v[PER];
+  int o[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+  {
+    const bool live = k0 + (int64_t)q * blockDim.x < n;
+    v[q] = live ? src[sidx[q]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    o[q] = live ? src_orig[sidx[q]] : 0;
+  }
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+  {
+    const int64_t k = k0 + (int64_t)q * blockDim.x;
+    if (k < n)
+    {
+      dst[k] = v[q];
+      dst_orig[k] = o[q];
+    }
+  }
 }
 
 // ------------------------------------------------------------------- P2G --
@@ -393,7 +462,7 @@ __device__ __forceinline__ void p2g_particle(P2gAcc& a, const float4 p, const D&
   }
 }
 
-template <class D>
+template <class D, bool PIPE>
 __global__ void __launch_bounds__(256)
 k_p2g_stream(const float4* __restrict__ part, const int* __restrict__ cell_start,
              float* __restrict__ ub, float* __restrict__ vb, const D d, float half_dx,
@@ -426,7 +495,22 @@ k_p2g_stream(const float4* __restrict__ part, const int* __restrict__ cell_start
     {
       const int p0 = __ldg(cell_start + ci + c * d.nx);
       const int p1 = __ldg(cell_start + ci + c * d.nx + 1);
-      for (int k = p0; k < p1; ++k) p2g_particle(a, __ldg(part + k), d, ci, c, half_dx, half_dy);
+      if (PIPE)
+      {
+        // the next particle's record is requested before this one's splats are computed
+        if (p0 < p1)
+        {
+          float4 cur = __ldg(part + p0);
+          for (int k = p0; k < p1; ++k)
+          {
+            const float4 nxt = __ldg(part + min(k + 1, p1 - 1));
+            p2g_particle(a, cur, d, ci, c, half_dx, half_dy);
+            cur = nxt;
+          }
+        }
+      }
+      else
+        for (int k = p0; k < p1; ++k) p2g_particle(a, __ldg(part + k), d, ci, c, half_dx, half_dy);
     }
     // u nodes of row c-1: own column + the part the west neighbour lane holds for us
     {
@@ -550,15 +634,13 @@ __global__ void k_g2p_advect(float4* __restrict__ part, int64_t n, const float* 
 // compile-time, the (front - previous) difference is taken per tap (src/MacGrid.cpp:64-67), and
 // all sixteen taps are independent loads the compiler can issue back to back.  Per particle the
 // arithmetic is that of k_g2p_advect<true, true> with diff_is_prev (bit-identical).
+// one particle of the fused transfer + blend + advection
 template <int MODE, class D>
-__global__ void __launch_bounds__(256)
-k_g2p_step(float4* __restrict__ part, int64_t n, const float* __restrict__ uf,
-           const float* __restrict__ vf, const float* __restrict__ up, const float* __restrict__ vp,
-           const uint8_t* __restrict__ cell, const D d, float pic_ratio, float dt, int ensure_outside)
+__device__ __forceinline__ float4 g2p_one(float4 p, const float* __restrict__ uf, const float* __restrict__ vf,
+                                          const float* __restrict__ up, const float* __restrict__ vp,
+                                          const uint8_t* __restrict__ cell, const D& d, float pic_ratio,
+                                          float dt, int ensure_outside)
 {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  float4 p = part[k];
   float nvx, nvy;
   if (MODE == FSB_G2P_PIC)
   {
@@ -597,7 +679,37 @@ k_g2p_step(float4* __restrict__ part, int64_t n, const float* __restrict__ uf,
       p.y += p.w * mdt;
     }
   }
-  part[k] = p;
+  return p;
+}
+
+// PER particles per thread, block-strided so that every access stays coalesced: a particle is two
+// dependent rounds of loads (its record, then the 16 grid taps its position selects); with one particle per
+// thread the kernel is bound by that chain times the number of thread waves (207 at 6.3e7 particles), not by
+// bandwidth.  All records are loaded first, all stores come last, so the PER chains overlap.
+template <int MODE, class D, int PER>
+__global__ void __launch_bounds__(256)
+k_g2p_step(float4* __restrict__ part, int64_t n, const float* __restrict__ uf,
+           const float* __restrict__ vf, const float* __restrict__ up, const float* __restrict__ vp,
+           const uint8_t* __restrict__ cell, const D d, float pic_ratio, float dt, int ensure_outside)
+{
+  const int64_t k0 = (int64_t)blockIdx.x * (blockDim.x * PER) + threadIdx.x;
+  float4 p[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+  {
+    const int64_t k = k0 + (int64_t)q * blockDim.x;
+    p[q] = (k < n) ? part[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+    if (k0 + (int64_t)q * blockDim.x < n)
+      p[q] = g2p_one<MODE, D>(p[q], uf, vf, up, vp, cell, d, pic_ratio, dt, ensure_outside);
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+  {
+    const int64_t k = k0 + (int64_t)q * blockDim.x;
+    if (k < n) part[k] = p[q];
+  }
 }
 
 // src/FluidSolver.cpp:774-791
@@ -898,17 +1010,25 @@ int fsb_k_sort_particles(fsb_ctx* c, bool mark_labels)
     const GridDims len =
         make_grid_dims(c->nx, c->ny, c->ld, (float)c->nx * c->dx, (float)c->ny * c->dy);
     const GridDims pd = pool_dims(c);
-    const dim3 grid(fsb_div_up(c->n, kBlock));
-#define FSB_COUNT(MARK, D, pd_, len_)                                                              \
-  k_sort_count<MARK, D><<<grid, kBlock, 0, c->stream>>>(c->part[c->pcur], c->n, pd_, c->cell_count, \
-                                                        c->sort_key, c->sort_rank, c->cell, dims(c), \
-                                                        len_)
+    const int per = c->sort_per; // particles per thread (FSB_SORT_PER: 1, 2 or 4)
+    const dim3 grid(fsb_div_up(c->n, (int64_t)kBlock * per));
+#define FSB_COUNT_N(MARK, D, pd_, len_, PER)                                                             \
+  k_sort_count<MARK, D, PER><<<grid, kBlock, 0, c->stream>>>(c->part[c->pcur], c->n, pd_, c->cell_count, \
+                                                             c->sort_key, c->sort_rank, c->cell, dims(c), \
+                                                             len_)
+#define FSB_COUNT(MARK, D, pd_, len_)                       \
+  do {                                                      \
+    if (per == 4) FSB_COUNT_N(MARK, D, pd_, len_, 4);       \
+    else if (per == 2) FSB_COUNT_N(MARK, D, pd_, len_, 2);  \
+    else FSB_COUNT_N(MARK, D, pd_, len_, 1);                \
+  } while (0)
     const bool p2 = pd.pow2 == 3 && (!mark_labels || len.pow2 == 3);
     if (p2 && mark_labels) FSB_COUNT(true, GridDimsP2, as_pow2(pd), as_pow2(len));
     else if (p2) FSB_COUNT(false, GridDimsP2, as_pow2(pd), as_pow2(len));
     else if (mark_labels) FSB_COUNT(true, GridDims, pd, len);
     else FSB_COUNT(false, GridDims, pd, len);
 #undef FSB_COUNT
+#undef FSB_COUNT_N
     FSB_LAUNCHED(c);
   }
   const int nb = fsb_div_up(m, kScanTile);
@@ -923,12 +1043,22 @@ int fsb_k_sort_particles(fsb_ctx* c, bool mark_labels)
     k_sort_place<<<fsb_div_up(fsb_div_up(c->n, 4), kBlock), kBlock, 0, c->stream>>>(
         c->sort_key, c->sort_rank, c->n, c->cell_start, c->sort_idx);
     FSB_LAUNCHED(c);
-    k_sort_canon<<<fsb_div_up(m, kBlock), kBlock, 0, c->stream>>>(c->cell_start, m, c->sort_idx,
-                                                                  c->orig[c->pcur]);
+    if (c->canon_per == 2)
+      k_sort_canon<2><<<fsb_div_up(m, kBlock * 2), kBlock, 0, c->stream>>>(c->cell_start, m, c->sort_idx, c->orig[c->pcur]);
+    else
+      k_sort_canon<1><<<fsb_div_up(m, kBlock), kBlock, 0, c->stream>>>(c->cell_start, m, c->sort_idx, c->orig[c->pcur]);
     FSB_LAUNCHED(c);
-    k_sort_gather<<<fsb_div_up(c->n, kBlock), kBlock, 0, c->stream>>>(
-        c->part[c->pcur], c->orig[c->pcur], c->sort_idx, c->n, c->part[c->pcur ^ 1],
-        c->orig[c->pcur ^ 1]);
+    const int per = c->sort_per;
+    const int gather_grid = fsb_div_up(c->n, (int64_t)kBlock * per);
+    if (per == 4)
+      k_sort_gather<4><<<gather_grid, kBlock, 0, c->stream>>>(c->part[c->pcur], c->orig[c->pcur], c->sort_idx, c->n,
+                                                              c->part[c->pcur ^ 1], c->orig[c->pcur ^ 1]);
+    else if (per == 2)
+      k_sort_gather<2><<<gather_grid, kBlock, 0, c->stream>>>(c->part[c->pcur], c->orig[c->pcur], c->sort_idx, c->n,
+                                                              c->part[c->pcur ^ 1], c->orig[c->pcur ^ 1]);
+    else
+      k_sort_gather<1><<<gather_grid, kBlock, 0, c->stream>>>(c->part[c->pcur], c->orig[c->pcur], c->sort_idx, c->n,
+                                                              c->part[c->pcur ^ 1], c->orig[c->pcur ^ 1]);
     FSB_LAUNCHED(c);
     c->pcur ^= 1;
   }
@@ -946,14 +1076,13 @@ int fsb_k_p2g(fsb_ctx* c)
   // slab-partitioned particles: only the faces of this rank's rows (the other rows come from their owners)
   const int row_lo = c->slab_world > 1 ? c->slab_lo : 0, row_hi = c->slab_world > 1 ? c->slab_hi : c->ny;
   const int64_t n_warps = (int64_t)strips_x * fsb_div_up(row_hi - row_lo, kP2gRows);
-  if (d.pow2 == 3)
-    k_p2g_stream<GridDimsP2><<<fsb_div_up(n_warps * 32, 256), 256, 0, c->stream>>>(
-        c->part[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), as_pow2(d), 0.5f * c->dx,
-        0.5f * c->dy, strips_x, (int)n_warps, row_lo, row_hi);
-  else
-    k_p2g_stream<GridDims><<<fsb_div_up(n_warps * 32, 256), 256, 0, c->stream>>>(
-        c->part[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), d, 0.5f * c->dx, 0.5f * c->dy,
-        strips_x, (int)n_warps, row_lo, row_hi);
+#define FSB_P2G(D, d_, PIPE)                                                                         \
+  k_p2g_stream<D, PIPE><<<fsb_div_up(n_warps * 32, 256), 256, 0, c->stream>>>(                        \
+      c->part[c->pcur], c->cell_start, fsb_ub(c), fsb_vb(c), d_, 0.5f * c->dx, 0.5f * c->dy, strips_x, \
+      (int)n_warps, row_lo, row_hi)
+  if (d.pow2 == 3) { if (c->p2g_pipe) FSB_P2G(GridDimsP2, as_pow2(d), true); else FSB_P2G(GridDimsP2, as_pow2(d), false); }
+  else { if (c->p2g_pipe) FSB_P2G(GridDims, d, true); else FSB_P2G(GridDims, d, false); }
+#undef FSB_P2G
   FSB_LAUNCHED(c);
   c->front ^= 1; // swapVelocityBuffers, src/FluidSolver.cpp:918
   fsb_prof_end(c, FSB_PROF_P2G);
@@ -993,21 +1122,30 @@ int fsb_k_g2p_advect(fsb_ctx* c, int mode, float pic_ratio, float dt, int ensure
   fsb_prof_begin(c, FSB_PROF_G2P);
   const GridDims d = dims(c);
   const dim3 grid(fsb_div_up(c->n, kBlock));
+  const int per = c->g2p_per; // particles per thread (FSB_G2P_PER: 1, 2 or 4)
+  const dim3 grid_per(fsb_div_up(c->n, (int64_t)kBlock * per));
   if (c->stage_v1)
     k_g2p_advect<true, true><<<grid, kBlock, 0, c->stream>>>(
         c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c), c->u_prev, c->v_prev, 1, c->cell, d, mode,
         pic_ratio, dt, ensure_outside);
   else
   {
-#define FSB_G2P(MODE, D, d_)                                                                        \
-  k_g2p_step<MODE, D><<<grid, kBlock, 0, c->stream>>>(c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c),  \
-                                                      c->u_prev, c->v_prev, c->cell, d_, pic_ratio,  \
-                                                      dt, ensure_outside)
+#define FSB_G2P_N(MODE, D, d_, PER)                                                                 \
+  k_g2p_step<MODE, D, PER><<<grid_per, kBlock, 0, c->stream>>>(                                      \
+      c->part[c->pcur], c->n, fsb_uf(c), fsb_vf(c), c->u_prev, c->v_prev, c->cell, d_, pic_ratio, dt, \
+      ensure_outside)
+#define FSB_G2P(MODE, D, d_)                          \
+  do {                                                \
+    if (per == 4) FSB_G2P_N(MODE, D, d_, 4);          \
+    else if (per == 2) FSB_G2P_N(MODE, D, d_, 2);     \
+    else FSB_G2P_N(MODE, D, d_, 1);                   \
+  } while (0)
     const bool p2 = d.pow2 == 3;
     if (mode == FSB_G2P_PIC) { if (p2) FSB_G2P(FSB_G2P_PIC, GridDimsP2, as_pow2(d)); else FSB_G2P(FSB_G2P_PIC, GridDims, d); }
     else if (mode == FSB_G2P_FLIP) { if (p2) FSB_G2P(FSB_G2P_FLIP, GridDimsP2, as_pow2(d)); else FSB_G2P(FSB_G2P_FLIP, GridDims, d); }
     else { if (p2) FSB_G2P(FSB_G2P_PICFLIP, GridDimsP2, as_pow2(d)); else FSB_G2P(FSB_G2P_PICFLIP, GridDims, d); }
 #undef FSB_G2P
+#undef FSB_G2P_N
   }
   FSB_LAUNCHED(c);
   c->sort_valid = false;

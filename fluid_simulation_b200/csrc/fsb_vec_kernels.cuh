@@ -104,12 +104,11 @@ __device__ __forceinline__ void extend2_a_group(const float* __restrict__ uf,
                                                 float* __restrict__ ub, float* __restrict__ vb,
                                                 uint8_t* __restrict__ m1,
                                                 const uint8_t* __restrict__ cell, const GridDims& d,
-                                                int i0, int j)
+                                                int i0, int j, const float4 u4, const float4 v4,
+                                                const uint32_t lab4)
 {
   const size_t k = i0 + (size_t)j * d.ld;
-  const float4 u4 = *reinterpret_cast<const float4*>(uf + k);
-  const float4 v4 = *reinterpret_cast<const float4*>(vf + k);
-  if (i0 + 4 <= d.nx && *reinterpret_cast<const uint32_t*>(cell + k) == FSB_LIQUID * 0x01010101u)
+  if (i0 + 4 <= d.nx && lab4 == FSB_LIQUID * 0x01010101u)
   {
     // four LIQUID cells (the bulk of a full tank): every face is valid, the pass is a copy
     *reinterpret_cast<float4*>(ub + k) = u4;
@@ -174,11 +173,24 @@ k_extend2_a(const float* __restrict__ uf, const float* __restrict__ vf, float* _
 {
   const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i0 >= d.nx) return;
+  // the loads of all rows first: the rows are independent, but each row's stores would otherwise keep the
+  // next row's loads behind them (one DRAM round trip per row instead of one per thread)
+  float4 u4[kExtendRows], v4[kExtendRows];
+  uint32_t lab4[kExtendRows];
+#pragma unroll
+  for (int r = 0; r < kExtendRows; ++r)
+  {
+    const int j = min((int)blockIdx.y * kExtendRows + r, d.ny - 1);
+    const size_t k = i0 + (size_t)j * d.ld;
+    u4[r] = *reinterpret_cast<const float4*>(uf + k);
+    v4[r] = *reinterpret_cast<const float4*>(vf + k);
+    lab4[r] = *reinterpret_cast<const uint32_t*>(cell + k);
+  }
 #pragma unroll
   for (int r = 0; r < kExtendRows; ++r)
   {
     const int j = blockIdx.y * kExtendRows + r;
-    if (j < d.ny) extend2_a_group(uf, vf, ub, vb, m1, cell, d, i0, j);
+    if (j < d.ny) extend2_a_group(uf, vf, ub, vb, m1, cell, d, i0, j, u4[r], v4[r], lab4[r]);
   }
 }
 
@@ -255,11 +267,25 @@ k_extend2_b(float* __restrict__ uf, float* __restrict__ ub, float* __restrict__ 
 {
   const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i0 >= d.nx) return;
+  // Row groups from the top of the grid down: the rows with work in this pass (free surface, AIR above it)
+  // are the upper ones in a tank, and their CTAs -- dependent label / mask / value loads, four rows in turn
+  // -- are the long ones; started first they overlap the all-LIQUID rows instead of forming the tail.
+  const int jy = (int)gridDim.y - 1 - (int)blockIdx.y;
+  // the label words of all rows first (independent loads); an all-LIQUID group has nothing to do
+  uint32_t lab4[kExtendRows];
 #pragma unroll
   for (int r = 0; r < kExtendRows; ++r)
   {
-    const int j = blockIdx.y * kExtendRows + r;
-    if (j < d.ny) extend2_b_group(uf, ub, vb, m1, cell, d, i0, j);
+    const int j = min(jy * kExtendRows + r, d.ny - 1);
+    lab4[r] = *reinterpret_cast<const uint32_t*>(cell + i0 + (size_t)j * d.ld);
+  }
+#pragma unroll
+  for (int r = 0; r < kExtendRows; ++r)
+  {
+    const int j = jy * kExtendRows + r;
+    if (j >= d.ny) continue;
+    if (i0 + 4 <= d.nx && lab4[r] == FSB_LIQUID * 0x01010101u) continue;
+    extend2_b_group(uf, ub, vb, m1, cell, d, i0, j);
   }
 }
 

@@ -304,14 +304,16 @@ CG_KNOBS = ("FSB_CG_SKIP_TILES", "FSB_CG_MODE", "FSB_CG_SERP", "FSB_CG_PREFETCH"
             "FSB_CG_STAGES", "FSB_CG_XDEFER", "FSB_CG_KEEP", "FSB_CG_PHINT", "FSB_CG_PERSIST_MB")
 
 
-STAGE_KNOBS = [dict(FSB_BUILD_BLOCKS_PER_SM="8"), dict(FSB_BUILD_BLOCKS_PER_SM="16")]
+STAGE_KNOBS = [dict(FSB_BUILD_BLOCKS_PER_SM="8"), dict(FSB_BUILD_BLOCKS_PER_SM="16"),
+               dict(FSB_SORT_PER="1", FSB_CANON_PER="1", FSB_G2P_PER="1", FSB_P2G_PIPE="0"),
+               dict(FSB_SORT_PER="4", FSB_G2P_PER="4")]
 
 
 @pytest.mark.parametrize("nx,ny", [(64, 64), (130, 67), (700, 300), (1030, 520)])
 def test_stage_knobs_leave_every_bit_alone(capi, monkeypatch, nx, ny):
-    """The grid size of the pressure set-up kernel (default: one resident wave) changes launch geometry
-    only: extension, pressure solve and whole steps give the results of the default configuration (which
-    the tests above compare with the reference)."""
+    """The launch-geometry knobs of the stage kernels (grid of the pressure set-up kernel; items per thread of
+    the sort passes and of G2P; early record loads in P2G) change no arithmetic: extension, pressure solve and
+    whole steps give the results of the default configuration (which the tests above compare with the reference)."""
     rng = np.random.default_rng(77)
     lab = _no_isolated_liquid(scenes.random_labels(nx, ny, rng, p_liquid=0.6, p_solid=0.01))
     f = {w: scenes.random_field(nx, ny, rng) for w in (U_FRONT, V_FRONT, U_BACK, V_BACK)}

@@ -21,13 +21,18 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CONFIGS = [
-    ("default (one resident wave of the set-up kernel)", {}),
-    ("rhs: 4 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "4"}),
-    ("rhs: 6 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "6"}),
+    ("default", {}),
+    ("sort: 1 particle per thread in the counting and gather passes (rounds 1 - 2)", {"FSB_SORT_PER": "1"}),
+    ("sort: 4 particles per thread", {"FSB_SORT_PER": "4"}),
+    ("sort: 1 cell per thread in the in-cell ordering pass (rounds 1 - 2)", {"FSB_CANON_PER": "1"}),
+    ("p2g: record loaded when needed (rounds 1 - 2)", {"FSB_P2G_PIPE": "0"}),
+    ("g2p: 1 particle per thread (rounds 1 - 2)", {"FSB_G2P_PER": "1"}),
+    ("g2p: 4 particles per thread", {"FSB_G2P_PER": "4"}),
     ("rhs: 8 CTAs/SM (rounds 1 - 2)", {"FSB_BUILD_BLOCKS_PER_SM": "8"}),
-    ("rhs: 16 CTAs/SM", {"FSB_BUILD_BLOCKS_PER_SM": "16"}),
 ]
 KNOBS = sorted({k for _, env in CONFIGS for k in env})
+if os.environ.get("FSB_KNOBS_ONLY_DEFAULT"):
+    CONFIGS = CONFIGS[:1]
 
 
 def main():
