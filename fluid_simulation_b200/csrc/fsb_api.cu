@@ -246,6 +246,7 @@ int fsb_create(fsb_ctx** out, int size_x, int size_y, float length_x, float leng
 
   if (const char* e = getenv("FSB_MG_MAX_ITERS")) c->mg_max_iters = std::max(1, atoi(e));
   if (const char* e = getenv("FSB_MG_SWEEPS")) c->mg_sweeps = std::max(1, std::min(8, atoi(e)));
+  if (const char* e = getenv("FSB_MG_GRAPH")) c->mg_graph = atoi(e) != 0;
   if (const char* e = getenv("FSB_MG_STOP")) c->mg_stop = std::max(1, std::min(32, atoi(e)));
   if (const char* e = getenv("FSB_MG_RENORM")) c->mg_renorm = atoi(e) != 0;
   memset(c->prof_ms, 0, sizeof c->prof_ms);

@@ -164,6 +164,7 @@ struct fsb_ctx
   int precond = 0;
   int mg_max_iters = 200;    // beyond this the multigrid iteration is abandoned for Jacobi
   int mg_sweeps = 3;         // damped-Jacobi pre- and post-sweeps per level (equal: symmetric V-cycle)
+  bool mg_graph = true;   // FSB_MG_GRAPH=0: the V-cycle as plain launches instead of one captured CUDA graph
   int mg_stop = 4;        // FSB_MG_STOP: coarsen until both sides are <= this (kMgStopDefault; at most 32)
   bool mg_renorm = true;  // FSB_MG_RENORM=0: plain bilinear / full-weighting transfers (round-1 behaviour)
   bool last_solve_mg = false;

@@ -70,6 +70,13 @@ struct fsb_mg_state
   double* partials = nullptr;
   int partials_cap = 0;
   int nx = 0, ny = 0;
+  // the V-cycle as one CUDA graph (about 90 launches, most of them on levels of a few thousand cells whose
+  // cost is the launch itself): captured on first use -- buffers, sizes and the sweep count are fixed for
+  // the life of the hierarchy -- and replayed for every application of the preconditioner
+  cudaGraphExec_t vexec = nullptr;
+  int vexec_cur = 0;      // which of lv[0].x[] holds the result
+  int vexec_launches = 0; // kernels inside the graph (for the launch counter)
+  bool vexec_failed = false;
 };
 
 namespace {
@@ -363,12 +370,49 @@ int mg_vcycle(fsb_ctx* c, int* cur_out)
   return FSB_OK;
 }
 
+// z = V(r) through the captured graph (FSB_MG_GRAPH=0: plain launches)
+int mg_vcycle_run(fsb_ctx* c, int* cur_out)
+{
+  fsb_mg_state* m = c->mg;
+  if (!c->mg_graph || m->vexec_failed) return mg_vcycle(c, cur_out);
+  if (!m->vexec)
+  {
+    const long long before = c->launches;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+    {
+      cudaGetLastError();
+      m->vexec_failed = true;
+      return mg_vcycle(c, cur_out);
+    }
+    const int rc = mg_vcycle(c, &m->vexec_cur);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    m->vexec_launches = (int)(c->launches - before);
+    c->launches = before;
+    if (rc != FSB_OK || e != cudaSuccess || !g ||
+        cudaGraphInstantiate(&m->vexec, g, 0) != cudaSuccess)
+    {
+      cudaGetLastError();
+      if (g) cudaGraphDestroy(g);
+      m->vexec = nullptr;
+      m->vexec_failed = true;
+      return mg_vcycle(c, cur_out);
+    }
+    cudaGraphDestroy(g);
+  }
+  FSB_CUDA(c, cudaGraphLaunch(m->vexec, c->stream));
+  c->launches += m->vexec_launches;
+  *cur_out = m->vexec_cur;
+  return FSB_OK;
+}
+
 } // namespace
 
 void fsb_mg_free(fsb_ctx* c)
 {
   if (!c->mg) return;
   fsb_mg_state* m = c->mg;
+  if (m->vexec) cudaGraphExecDestroy(m->vexec);
   for (int l = 0; l < m->n_levels; ++l)
   {
     MgLevel& L = m->lv[l];
@@ -403,7 +447,7 @@ int fsb_k_mg_solve(fsb_ctx* c, int* converged)
   float* p = c->cg_p[0];
   float* q = c->cg_p[1];
   int zc = 0;
-  FSB_TRY(mg_vcycle(c, &zc));
+  FSB_TRY(mg_vcycle_run(c, &zc));
   k_mg_dot_rz<<<blocks, 256, 0, c->stream>>>(c->cg_r, L0.x[zc], L0.ny, L0.ld, m->scal, m->partials, 1);
   FSB_LAUNCHED(c);
   FSB_CUDA(c, cudaMemcpyAsync(p, L0.x[zc], sizeof(float) * (size_t)L0.ld * L0.ny,
@@ -421,7 +465,7 @@ int fsb_k_mg_solve(fsb_ctx* c, int* converged)
     FSB_CUDA(c, cudaStreamSynchronize(c->stream));
     fin = *m->scal_h;
     if (fin.fail || fin.done) break;
-    FSB_TRY(mg_vcycle(c, &zc));
+    FSB_TRY(mg_vcycle_run(c, &zc));
     k_mg_dot_rz<<<blocks, 256, 0, c->stream>>>(c->cg_r, L0.x[zc], L0.ny, L0.ld, m->scal, m->partials, 0);
     FSB_LAUNCHED(c);
     k_mg_direction<<<blocks, 256, 0, c->stream>>>(p, L0.x[zc], L0.ny, L0.ld, m->scal);
